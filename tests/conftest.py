@@ -1,0 +1,23 @@
+"""pytest configuration: registers the `gpu` marker and puts the package + oracle on sys.path."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200")
+for p in (PKG_DIR, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    path = os.path.join(ROOT, "tests", "golden", "reference_outputs.npz")
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
