@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the fused polarization-cue pipeline (BASELINE.json configs[1] per GPU, weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [...]                          # the reference's CPU algorithm (oracle port)
+
+A step is ONE pass of the hot path over one batch: `--frames` (64) synthetic 2448x2048 polarizer mosaics per GPU
+-> quadrant split -> Stokes -> DoLP/AoLP -> three physics normal candidates, one kernel launch.
+  value     whole-job mosaic-Mpix/s with inputs and outputs resident in HBM (CUDA events, max over ranks)
+  e2e       the same metric through the host-buffer C-ABI call (pinned host mosaics in, pinned host XOLP +
+            normals out; H2D and D2H inside the timed region)
+  roofline  algorithmic bytes (48 B per output pixel) / mean launch time vs the measured HBM copy peak
+  cpu_baseline  the oracle's restatement of the reference chain (lstsq + table interpolation, numpy float64)
+            timed on this box's host cores over a bounded sample of the same frames
+Under torchrun every rank processes its own `--frames` frames (weak scaling); the only collective is the
+all-reduce of an output checksum + the max-over-ranks of the timings.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200")
+for _p in (PKG_DIR, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+FRAME_H, FRAME_W = 2048, 2448
+MPIX_PER_FRAME = FRAME_H * FRAME_W / 1e6
+BYTES_PER_OUT_PX = 48            # 4 B read + 8 B XOLP + 36 B normals (SURVEY 8d / BASELINE.md 3)
+HBM_FALLBACK_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def baseline_metric():
+    try:
+        with open(os.path.join(ROOT, "BASELINE.json")) as f:
+            return json.load(f)["metric"]
+    except Exception:
+        return "Mpix/s (frames/s) fused pol-cue+normals at 1/2/4/8 B200; % of HBM roofline"
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
+            d = json.load(f)
+        return d
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU leg: the reference's algorithm (oracle port) on the host cores
+# --------------------------------------------------------------------------------------------------
+def _cpu_frame(frame_index):
+    os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from oracle import polcue_oracle as O     # test infrastructure; allowed here as the measured CPU baseline only
+    mosaic = _CPU_FRAMES[frame_index % len(_CPU_FRAMES)]
+    t0 = time.perf_counter()
+    _, rho, _, normals = O.frame_chain_reference(mosaic, 1.5)
+    return time.perf_counter() - t0, float(rho.sum()) + float(normals[2].sum())
+
+
+_CPU_FRAMES = []
+
+
+def cpu_reference_run(frames_per_step, steps, warmup):
+    """Times `steps` passes of `frames_per_step` frames through the reference chain on all host cores.
+
+    One worker process per core with BLAS pinned to one thread, as the reference pins it (trainer.py:9-11) and as its
+    DataLoader workers run (num_workers, options.py:299-302).  Returns (Mpix/s, cores, seconds per step).
+    """
+    import multiprocessing as mp
+    from polcue import synth
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, frames_per_step))
+    _CPU_FRAMES.extend(synth.gen_p_mosaic(i) for i in range(min(frames_per_step, 4)))   # inherited by fork
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        for _ in range(warmup):
+            pool.map(_cpu_frame, range(workers))
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_frame, range(frames_per_step))
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return frames_per_step * MPIX_PER_FRAME / sec, workers, sec
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = max(1, min(cores, args.frames))            # bounded sample: one frame per core and step (~1-2 s each)
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    value, workers, sec = cpu_reference_run(frames, steps, warmup)
+    line = {
+        "impl": "reference", "metric": baseline_metric(), "value": value, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: fused split+XOLP+3 physics normal candidates on synthetic 2448x2048 mosaics (Gen-P), n=1.5",
+                   "frames_per_step": frames, "frame": [FRAME_H, FRAME_W], "frames_per_s": frames / sec},
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": workers, "kind": "port",
+                         "sample": f"{frames} frames per step x {steps} steps, one process per core, BLAS threads=1; "
+                                   "oracle/polcue_oracle.frame_chain_reference (lstsq XOLP + 3 table interpolations + normals)"},
+        "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU leg
+# --------------------------------------------------------------------------------------------------
+def run_polcue_arm(args, rank, local_rank, world):
+    import torch
+    from polcue import _lib, dist as D, ops, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (polcue has no CPU path); use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    D.init("nccl")
+    _lib.lib().polcue_debug_set_trig(1 if args.trig == "mufu" else 0)
+
+    B, H, W = args.frames, FRAME_H, FRAME_W
+    hs, ws = H // 2, W // 2
+    out_px = B * hs * ws
+    first = rank * B                                            # every rank owns its own frames of the sequence
+    if args.gen == "P":
+        mosaic = synth.gen_p_batch_torch(first, B, H, W, device=dev)
+    else:
+        mosaic = torch.stack([torch.from_numpy(synth.gen_u_mosaic(first + i, H, W)) for i in range(B)]).to(dev)
+    out = {"xolp": torch.empty((B, 2, hs, ws), dtype=torch.float32, device=dev),
+           "normals": torch.empty((B, 9, hs, ws), dtype=torch.float32, device=dev)}
+    ops.lut_for(1.5, dev)
+    torch.cuda.synchronize()
+
+    def step():
+        ops.fused_mosaic(mosaic, 1.5, out=out)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    D.barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize()
+    events[0].record()
+    for i in range(args.steps):
+        step()
+        events[i + 1].record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - launches0
+    D.barrier()
+    total_ms = events[0].elapsed_time(events[-1])
+    per_launch_ms = [events[i].elapsed_time(events[i + 1]) for i in range(args.steps)]
+    ms_per_step = D.max_over_ranks(total_ms / args.steps, dev)
+    clocks = sampler.stop() if sampler else None
+
+    # output checksum: the one collective of the sequence benchmark
+    chk = torch.stack((out["xolp"].double().sum(), out["normals"].double().sum()))
+    D.all_reduce_sums(chk)
+
+    # ---- e2e: host buffers through the public host entry point -------------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h_mosaic = mosaic.cpu().pin_memory()
+    h_out = {"xolp": torch.empty((B, 2, hs, ws), dtype=torch.float32).pin_memory(),
+             "normals": torch.empty((B, 9, hs, ws), dtype=torch.float32).pin_memory()}
+    ops.fused_mosaic_host(h_mosaic, 1.5, out=h_out)             # warm-up: allocates the device ring
+    torch.cuda.synchronize()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ops.fused_mosaic_host(h_mosaic, 1.5, out=h_out)         # blocks until the results are in host memory
+    e2e_ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps, dev)
+    same = bool(torch.equal(h_out["normals"][0], out["normals"][0].cpu()))
+
+    if rank != 0:
+        return
+    peak, peak_src = hbm_peak()
+    mean_launch_ms = sum(per_launch_ms) / len(per_launch_ms)
+    achieved = BYTES_PER_OUT_PX * out_px / (mean_launch_ms * 1e-3) / 1e9
+    traffic = recorded_traffic()
+    value = world * B * MPIX_PER_FRAME / (ms_per_step * 1e-3)
+    line = {
+        "metric": baseline_metric(), "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: fused split+XOLP+3 physics normal candidates on synthetic 2448x2048 mosaics "
+                               f"(Gen-{args.gen}), n=1.5", "frames_per_gpu_per_step": B, "frame": [H, W],
+                   "frames_per_s": world * B / (ms_per_step * 1e-3), "outputs": "xolp f32 [B,2,Hs,Ws] + normals f32 [B,9,Hs,Ws]",
+                   "l2_policy": f"working set {BYTES_PER_OUT_PX * out_px / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)",
+                   "trig": args.trig, "checksum": [float(chk[0]), float(chk[1])]},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": BYTES_PER_OUT_PX * out_px, "kernel": "fused_mosaic_kernel<4>",
+                     "launch_ms": mean_launch_ms},
+        "e2e": {"value": world * B * MPIX_PER_FRAME / (e2e_ms * 1e-3), "unit": "Mpix/s", "ms_per_step": e2e_ms,
+                "steps": e2e_steps, "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": 44 * out_px,
+                "api": "polcue.ops.fused_mosaic_host -> polcue_fused_mosaic_u8_host (pinned host buffers)",
+                "matches_device_path": same},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        frames = max(1, min(cores, 32))
+        v, workers, sec = cpu_reference_run(frames, 2, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "Mpix/s", "cores": workers, "kind": "port",
+                                "sample": f"{frames} Gen-P frames per pass x 2 passes ({sec:.1f} s per pass), one process per core, "
+                                          "BLAS threads=1; oracle/polcue_oracle.frame_chain_reference"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("polcue", "reference"), default="polcue")
+    ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step (BASELINE configs[1]: 64)")
+    ap.add_argument("--gen", choices=("P", "U"), default="P", help="synthetic generator: physical (P) or uniform stress (U)")
+    ap.add_argument("--trig", choices=("poly", "mufu"), default="poly")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+    else:
+        run_polcue_arm(args, rank, local_rank, world)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

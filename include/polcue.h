@@ -1,0 +1,180 @@
+/*
+ * polcue.h -- C ABI of libpolcue.so: the per-pixel polarization hot path on B200 (sm_100a).
+ *
+ * The reference (kkaytekin/Supervised-Depth-Estimation-from-Polarized-Images) is pure Python and has
+ * no FFI; its boundary for this path is a set of Python function signatures.  Every
+ * entry point below names the reference function (file:line, relative to the reference root) whose
+ * arithmetic it replaces.  The Python mirror of those signatures lives in
+ * supervised-depth-estimation-from-polarized-images_b200/polcue/ and binds this header with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - All image pointers are DEVICE pointers owned by the caller unless the function name ends in
+ *     `_host`; tensors are dense, row-major, batch outermost.  Nothing is allocated per call.
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and never synchronise.
+ *   - Return value: 0 on success; a NEGATIVE errno-style code for a rejected argument (nothing was
+ *     launched); a POSITIVE value is the cudaError_t reported by the launch.
+ *   - Re-entrant for distinct streams/outputs.  Not for use from forked DataLoader workers.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef POLCUE_H_
+#define POLCUE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define POLCUE_API __attribute__((visibility("default")))
+#else
+#define POLCUE_API
+#endif
+
+#define POLCUE_OK 0
+#define POLCUE_EINVAL (-22)  /* null pointer, non-positive or odd size, misaligned buffer */
+#define POLCUE_ENOMEM (-12)  /* device / pinned allocation failed */
+#define POLCUE_ERANGE (-34)  /* refractive index whose tables cannot be represented */
+#define POLCUE_E2BIG (-7)    /* problem exceeds the 32-bit work-item range of one launch */
+
+typedef void* polcue_stream_t;      /* cudaStream_t */
+typedef struct polcue_lut polcue_lut; /* opaque: zenith-angle lookup tables for one refractive index */
+
+POLCUE_API const char* polcue_version(void);
+POLCUE_API const char* polcue_error_string(int code);
+/* Tuning knob: 0 = polynomial sincos (1.4e-7 abs, default), 1 = MUFU sin/cos (3.6e-7 abs). */
+POLCUE_API int polcue_debug_set_trig(int mufu);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+POLCUE_API unsigned long long polcue_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Zenith-angle tables.  Replaces the table construction + scipy interp1d(linear, extrapolate) of
+ *   manydepth/normals_vec.py:11-22 (rho_diffuse) and :25-50 (rho_spec),
+ *   polarisation/xolp_and_normals.py:41-83, ppp_code/physical_normals_channels.py:39-72.
+ * The three 1000-knot piecewise-linear tables are built on the host in float64 and re-indexed into
+ * uniform cells of g(rho) (one knot per cell) so the device needs no search; see DESIGN.md.
+ * `polcue_lut_create` allocates on the CURRENT device.  Returns POLCUE_ERANGE if no cell grid
+ * reproduces the reference interpolant to 1e-6 rad inside its shared-memory budget.
+ * ------------------------------------------------------------------------------------------- */
+POLCUE_API int polcue_lut_create(double n, polcue_lut** out);
+POLCUE_API void polcue_lut_destroy(polcue_lut* lut);
+/* Host-side introspection (no GPU needed): cell counts / knot counts of table t (0 diffuse, 1 spec1, 2 spec2). */
+POLCUE_API int polcue_lut_host_build(double n, polcue_lut** out); /* same tables, no device copy (CPU tests) */
+POLCUE_API int polcue_lut_cells(const polcue_lut* lut, int table);
+POLCUE_API int polcue_lut_knots(const polcue_lut* lut, int table, double* x, double* y, int capacity);
+/* Evaluates the float32 cell tables on the host exactly as the kernels do (float32 arithmetic). */
+POLCUE_API int polcue_lut_eval_host(const polcue_lut* lut, int table, const float* rho, size_t count, float* theta);
+
+/* ---------------------------------------------------------------------------------------------
+ * Quadrant split ("demosaic" of the stored 2x2-tiled polarizer image), bit-exact.
+ *   polarisation/pol_split_and_save.py:10-27  split_pol(img) -> (im00, im10, im01, im11)
+ * img: B x H x W pixels of px_bytes bytes each; H and W even.  Each output: B x H/2 x W/2.
+ * ------------------------------------------------------------------------------------------- */
+POLCUE_API int polcue_split_pol(const void* img, int B, int H, int W, int px_bytes,
+                     void* im00, void* im10, void* im01, void* im11, polcue_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused pipeline: quadrant split -> Stokes -> Iun/DoLP/AoLP -> three physics normal candidates.
+ * One launch replaces the chain of polarisation/xolp_and_normals.py:107-121:
+ *   split_pol (pol_split_and_save.py:10-27), np.stack order (indoor_dataset.py:435-439),
+ *   Iun_and_xolp (polarisation/xolp.py:8-34, canonical angles, closed form of the 4x3 least squares),
+ *   rho_diffuse / rho_spec (normals_vec.py:11-50), calc_normals x3 (normals_vec.py:53-60) in the
+ *   channel order of ShallowNormalsEncoder.get_normals (networks/pre_encoders.py:99-113).
+ * mosaic : B x H x W uint8, quadrants TL/TR/BL/BR = 0/45/90/135 degrees.  Hs = H/2, Ws = W/2.
+ * planes : B x 4 x Hs x Ws uint8 (I0, I45, I90, I135) or NULL
+ * iun    : B x Hs x Ws float32 or NULL
+ * xolp   : B x 2 x Hs x Ws float32 (DoLP, AoLP)                      [required]
+ * normals: B x 9 x Hs x Ws float32 (diffuse xyz, spec1 xyz, spec2 xyz) or NULL
+ * ------------------------------------------------------------------------------------------- */
+POLCUE_API int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W, const polcue_lut* lut,
+                           uint8_t* planes, float* iun, float* xolp, float* normals,
+                           polcue_stream_t stream);
+
+/* Same pipeline with HOST buffers (pinned or pageable): chunks of frames are copied in, processed
+ * and copied out on three streams so H2D, the kernel and D2H overlap.  Blocks until done.
+ * `chunk_frames` <= 0 picks a default.  This is the call bench.py's `e2e` figure times. */
+POLCUE_API int polcue_fused_mosaic_u8_host(const uint8_t* h_mosaic, int B, int H, int W, const polcue_lut* lut,
+                                float* h_iun, float* h_xolp, float* h_normals, int chunk_frames);
+/* Pinned host memory helpers for the callers of the *_host entry point. */
+POLCUE_API int polcue_host_alloc(void** ptr, size_t bytes);
+POLCUE_API int polcue_host_free(void* ptr);
+
+/* ---------------------------------------------------------------------------------------------
+ * XOLP only.   polarisation/xolp.py:8-34   Iun_and_xolp(images[H,W,4], angles[4]) -> Iun, rho, phi
+ * stack : B x H x W x 4 interleaved samples in angle order (the np.stack of indoor_dataset.py:439).
+ * pinv  : NULL for the canonical angles (0,45,90,135 deg; closed form), else the 3x4 row-major
+ *         pseudo-inverse of [1, cos 2a, sin 2a] (what np.linalg.lstsq applies), 12 HOST floats.
+ * iun   : B x H x W or NULL;  xolp : B x 2 x H x W (rho, phi).
+ * inf/nan scrub as xolp.py:26-29 (+inf -> 0, nan -> 0, -inf -> -FLT_MAX).
+ * ------------------------------------------------------------------------------------------- */
+POLCUE_API int polcue_xolp_stack_u8(const uint8_t* stack, int B, int H, int W, const float* pinv,
+                         float* iun, float* xolp, polcue_stream_t stream);
+POLCUE_API int polcue_xolp_stack_f32(const float* stack, int B, int H, int W, const float* pinv,
+                          float* iun, float* xolp, polcue_stream_t stream);
+/* Loader path: four separate B x H x W uint8 planes (indoor_dataset.py:435-438), canonical angles. */
+POLCUE_API int polcue_xolp_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t* i90, const uint8_t* i135,
+                          int B, int H, int W, float* iun, float* xolp, polcue_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Physics normals from XOLP.
+ *   manydepth/networks/pre_encoders.py:99-113  ShallowNormalsEncoder.get_normals(x, n)
+ * xolp: B x 2 x H x W float32 -> normals: B x 9 x H x W float32.
+ * ------------------------------------------------------------------------------------------- */
+POLCUE_API int polcue_normals_from_xolp_f32(const float* xolp, int B, int H, int W, const polcue_lut* lut,
+                                 float* normals, polcue_stream_t stream);
+/* The three fine-grained functions of manydepth/normals_vec.py (count = number of elements).
+ *   rho_diffuse :11-22, rho_spec :25-50, calc_normals :53-60 (phi, theta: B x HW -> B x 3 x HW). */
+POLCUE_API int polcue_rho_diffuse_f32(const float* rho, size_t count, const polcue_lut* lut, float* theta,
+                           polcue_stream_t stream);
+POLCUE_API int polcue_rho_spec_f32(const float* rho, size_t count, const polcue_lut* lut, float* theta1, float* theta2,
+                        polcue_stream_t stream);
+POLCUE_API int polcue_calc_normals_f32(const float* phi, const float* theta, int B, size_t hw, float* normals,
+                            polcue_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Masked direct-Stokes "channel" variant.
+ *   ppp_code/physical_normals_channels.py:15-36  PolarisationImage_channel (s0 = I0 + I90, no nan scrub)
+ *   ppp_code/physical_normals_channels.py:75-83  calc_normals_channel (H x W x 3, zero outside mask)
+ * stack: H x W x 4 float32; mask: H x W uint8 (non-zero = inside); rho/phi/iun: H x W float32.
+ * ------------------------------------------------------------------------------------------- */
+POLCUE_API int polcue_stokes_channel_f32(const float* stack, const uint8_t* mask, int H, int W,
+                              float* rho, float* phi, float* iun, polcue_stream_t stream);
+POLCUE_API int polcue_calc_normals_channel_f32(const float* phi, const float* theta, const uint8_t* mask, size_t hw,
+                                    float phi_offset, float* normals_hw3, polcue_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Depth -> surface normals 3x3 stencil.
+ *   kornia.geometry.depth.depth_to_normals (kornia 0.5.11, environment.yml:41), called at
+ *   manydepth/trainer.py:1305-1306,1477,1484.
+ * depth: B x 1 x H x W float32; K: B x 3 x 3 float32 (pixel units); normals: B x 3 x H x W float32.
+ * Forward only (the GT branch); see DESIGN.md for the autograd note.
+ * ------------------------------------------------------------------------------------------- */
+POLCUE_API int polcue_depth_to_normals_f32(const float* depth, const float* K, int B, int H, int W, float* normals,
+                                polcue_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Depth error metrics.
+ *   manydepth/layers.py:539-557 compute_depth_errors / :559-577 compute_depth_errors_numpy
+ * sums8   : 8 doubles (device): count, n[t<1.25], n[t<1.25^2], n[t<1.25^3], S d^2, S dlog^2, S |d|/gt, S d^2/gt
+ * metrics7: 7 floats (device) in the reference order abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3; or NULL
+ * workspace: device scratch of polcue_depth_errors_workspace_bytes() bytes (contents irrelevant, but its
+ *            first 8 bytes must be ZERO before the first use; the kernel re-zeroes them itself).
+ * The sums are additive across ranks (NCCL all-reduce of 8 doubles).
+ * ------------------------------------------------------------------------------------------- */
+POLCUE_API size_t polcue_depth_errors_workspace_bytes(void);
+POLCUE_API int polcue_depth_errors_f32(const float* gt, const float* pred, size_t count, void* workspace,
+                            double* sums8, float* metrics7, polcue_stream_t stream);
+/* Per-image masked evaluation of Trainer.compute_depth_losses_from_list (manydepth/trainer.py:1376-1428):
+ * mask = gt > min_d && gt < max_d [&& inst == inst_id], pred clamped to [min_d, max_d].
+ * inst: B x px uint8 instance-id map or NULL (then inst_id is ignored).
+ * sums: B x 8 doubles; metrics: B x 7 floats or NULL.  One block-group per image, no workspace. */
+POLCUE_API int polcue_depth_errors_images_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px,
+                                   float min_d, float max_d, int inst_id, double* sums, float* metrics,
+                                   polcue_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLCUE_H_ */

@@ -1,0 +1,580 @@
+// Fused polarization-cue kernels: quadrant split -> Stokes -> Iun/DoLP/AoLP -> normal candidates,
+// plus the XOLP-only and normals-only members of the same family.
+//
+// Roofline: HBM.  Algorithmic bytes per output pixel: fused 4 R + 44 W = 48 B
+// (+4 Iun, +4 planes); XOLP-only 4 R + 8 W; normals-from-XOLP 8 R + 36 W.  Nothing here is a
+// contraction, so no tensor cores: the work is MUFU/FMA per pixel and coalesced 128-bit stores.
+//
+// Layout: every output is planar (B x C x Hs x Ws) so each of the 11 float planes is written as
+// one contiguous 512-byte run per warp instruction.  A thread owns VEC consecutive pixels of one
+// row: it reads VEC bytes from each of the four quadrants (one 32-bit load each for VEC = 4) and
+// writes one 16-byte vector per plane.  The grid is persistent (resident CTAs x SMs) and strides
+// over the flat list of pixel groups; the zenith tables (~85 KB for n = 1.5) are staged once per
+// CTA into shared memory with a single bulk-async (TMA) copy.
+#include <cfloat>
+
+#include "polcue_device.cuh"
+#include "polcue_host.h"
+
+namespace polcue {
+
+std::atomic<unsigned long long> g_launches{0};
+
+const DeviceInfo& device_info() {
+    static DeviceInfo cache[64];
+    static std::atomic<int> ready[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev = (dev < 0 || dev >= 64) ? 0 : dev;
+    if (!ready[dev].load(std::memory_order_acquire)) {
+        DeviceInfo d;
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cache[dev] = d;
+        ready[dev].store(1, std::memory_order_release);
+    }
+    return cache[dev];
+}
+
+namespace {
+
+constexpr int kFusedThreads = 512;
+
+struct LutArgs {
+    const float4* blob;
+    uint32_t bytes;
+    int offset[3];
+    float scale[3];
+    int last[3];
+};
+
+LutArgs lut_args(const polcue_lut* lut) {
+    LutArgs a;
+    a.blob = lut->d_blob;
+    a.bytes = (uint32_t)lut->bytes();
+    for (int t = 0; t < 3; ++t) {
+        a.offset[t] = lut->offset[t];
+        a.scale[t] = lut->scale[t];
+        a.last[t] = lut->cells[t] - 1;
+    }
+    return a;
+}
+
+__device__ __forceinline__ LutView lut_view(const float4* base, const LutArgs& a) {
+    LutView v;
+    for (int t = 0; t < 3; ++t) {
+        v.cells[t] = base + a.offset[t];
+        v.scale[t] = a.scale[t];
+        v.last[t] = a.last[t];
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused kernel
+// ---------------------------------------------------------------------------------------------
+struct FusedParams {
+    const uint8_t* mosaic;
+    uint8_t* planes;   // may be null
+    float* iun;        // may be null
+    float* xolp;
+    float* normals;    // may be null
+    LutArgs lut;
+    uint32_t groups_total;   // B * Hs * (Ws / VEC)
+    FastDiv groups_per_frame, groups_per_row;
+    uint32_t W, Ws;
+    size_t frame_bytes;      // H * W
+    size_t quad_down;        // Hs * W : byte offset from a top quadrant to the one below it
+    size_t plane;            // Hs * Ws
+};
+
+template <int VEC>
+struct Packed;
+template <>
+struct Packed<4> {
+    using type = uint32_t;
+    static __device__ __forceinline__ type load(const uint8_t* p) { return ld_stream_u32(p); }
+};
+template <>
+struct Packed<2> {
+    using type = uint16_t;
+    static __device__ __forceinline__ type load(const uint8_t* p) { return ld_stream_u16(p); }
+};
+template <>
+struct Packed<1> {
+    using type = uint8_t;
+    static __device__ __forceinline__ type load(const uint8_t* p) { return ld_stream_u8(p); }
+};
+
+template <int VEC, bool MUFU>
+__global__ void __launch_bounds__(kFusedThreads, 2) fused_mosaic_kernel(const FusedParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    const float4* s_lut = reinterpret_cast<const float4*>(smem_raw);
+    const bool want_normals = p.normals != nullptr;
+    if (want_normals) {
+        lut_stage_begin(smem_raw, p.lut.blob, p.lut.bytes, &bar);
+        lut_stage_wait(&bar);
+    }
+    const LutView lut = lut_view(s_lut, p.lut);
+    using PK = Packed<VEC>;
+
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < p.groups_total; gid += stride) {
+        const uint32_t b = fastdiv(gid, p.groups_per_frame);
+        const uint32_t rem = gid - b * p.groups_per_frame.div;   // group index inside the frame
+        const uint32_t y = fastdiv(rem, p.groups_per_row);
+        const uint32_t xg = rem - y * p.groups_per_row.div;
+
+        const uint8_t* src = p.mosaic + (size_t)b * p.frame_bytes + (size_t)y * p.W + (size_t)xg * VEC;
+        const typename PK::type w0 = PK::load(src);                     // TL:   0 deg
+        const typename PK::type w45 = PK::load(src + p.Ws);             // TR:  45 deg
+        const typename PK::type w90 = PK::load(src + p.quad_down);      // BL:  90 deg
+        const typename PK::type w135 = PK::load(src + p.quad_down + p.Ws);  // BR: 135 deg
+
+        const size_t pix = (size_t)rem * VEC;   // first pixel inside the Hs x Ws plane (Ws = groups_per_row * VEC)
+
+        if (p.planes) {
+            typename PK::type* dst = reinterpret_cast<typename PK::type*>(p.planes + (size_t)b * 4 * p.plane + pix);
+            const size_t ps = p.plane / VEC;    // plane stride in packed words
+            dst[0] = w0;
+            dst[ps] = w45;
+            dst[2 * ps] = w90;
+            dst[3 * ps] = w135;
+        }
+
+        float rho[VEC], phi[VEC], iun[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const Cues q = cues_from_u8((w0 >> (8 * j)) & 0xff, (w45 >> (8 * j)) & 0xff, (w90 >> (8 * j)) & 0xff,
+                                        (w135 >> (8 * j)) & 0xff);
+            rho[j] = q.rho;
+            phi[j] = q.phi;
+            iun[j] = q.iun;
+        }
+        float* xo = p.xolp + (size_t)b * 2 * p.plane + pix;
+        st_stream_vec<VEC>(xo, rho);
+        st_stream_vec<VEC>(xo + p.plane, phi);
+        if (p.iun) st_stream_vec<VEC>(p.iun + (size_t)b * p.plane + pix, iun);
+
+        if (want_normals) {
+            float nrm[9][VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float n9[9];
+                normals_from_cues<MUFU>(lut, rho[j], phi[j], n9);
+#pragma unroll
+                for (int c = 0; c < 9; ++c) nrm[c][j] = n9[c];
+            }
+            float* no = p.normals + (size_t)b * 9 * p.plane + pix;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) st_stream_vec<VEC>(no + (size_t)c * p.plane, nrm[c]);
+        }
+    }
+}
+
+int g_trig_mufu = 0;  // 0: polynomial sincos (1.4e-7), 1: MUFU sin/cos (3.6e-7).  Tuning knob, see DESIGN.md.
+
+template <int VEC>
+int launch_fused(const FusedParams& p, size_t smem, cudaStream_t stream) {
+    auto kern = g_trig_mufu ? fused_mosaic_kernel<VEC, true> : fused_mosaic_kernel<VEC, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) return POLCUE_ERANGE;
+    const uint32_t want = (p.groups_total + kFusedThreads - 1) / kFusedThreads;
+    const uint32_t resident = (uint32_t)(per_sm * device_info().sms);
+    const uint32_t grid = want < resident ? want : resident;
+    kern<<<grid, kFusedThreads, smem, stream>>>(p);
+    return launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------
+// XOLP-only kernels (loader path): interleaved H x W x 4 stacks or four planes.
+// ---------------------------------------------------------------------------------------------
+struct Pinv {
+    float m[12];
+};
+
+// General angles: x = pinv(A) I, then xolp.py:22-30 with its inf/nan scrub.
+__device__ __forceinline__ Cues cues_general(const float (&i)[4], const Pinv& pv) {
+    const float x0 = fmaf(pv.m[3], i[3], fmaf(pv.m[2], i[2], fmaf(pv.m[1], i[1], pv.m[0] * i[0])));
+    const float x1 = fmaf(pv.m[7], i[3], fmaf(pv.m[6], i[2], fmaf(pv.m[5], i[1], pv.m[4] * i[0])));
+    const float x2 = fmaf(pv.m[11], i[3], fmaf(pv.m[10], i[2], fmaf(pv.m[9], i[1], pv.m[8] * i[0])));
+    const float amp = sqrtf(fmaf(x1, x1, x2 * x2));
+    float rho = amp / x0;                             // IEEE: 0/0 = nan, a/0 = +-inf like numpy
+    if (isnan(rho) || rho == INFINITY) rho = 0.0f;    // xolp.py:28-29
+    else if (rho == -INFINITY) rho = -FLT_MAX;        // np.nan_to_num(-inf)
+    Cues q;
+    q.iun = x0;
+    q.rho = rho;
+    q.phi = 0.5f * atan2_poly(x2, x1);
+    return q;
+}
+
+// Canonical angles, float samples.
+__device__ __forceinline__ Cues cues_canonical_f32(const float (&i)[4]) {
+    const float s1 = i[0] - i[2], s2 = i[1] - i[3];
+    const float x0 = 0.25f * ((i[0] + i[2]) + (i[1] + i[3]));
+    const float amp = 0.5f * sqrtf(fmaf(s1, s1, s2 * s2));
+    float rho = amp / x0;
+    if (isnan(rho) || rho == INFINITY) rho = 0.0f;
+    else if (rho == -INFINITY) rho = -FLT_MAX;
+    Cues q;
+    q.iun = x0;
+    q.rho = rho;
+    q.phi = 0.5f * atan2_poly(s2, s1);
+    return q;
+}
+
+template <typename T>
+__device__ __forceinline__ void load_stack_px(const T* stack, size_t px, float (&v)[4], int (&iv)[4]);
+template <>
+__device__ __forceinline__ void load_stack_px<uint8_t>(const uint8_t* stack, size_t px, float (&v)[4], int (&iv)[4]) {
+    const uint32_t w = ld_stream_u32(stack + 4 * px);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        iv[k] = (w >> (8 * k)) & 0xff;
+        v[k] = (float)iv[k];
+    }
+}
+template <>
+__device__ __forceinline__ void load_stack_px<float>(const float* stack, size_t px, float (&v)[4], int (&iv)[4]) {
+    const float4 w = ld_stream_f32x4(stack + 4 * px);
+    v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+    iv[0] = iv[1] = iv[2] = iv[3] = 0;
+}
+
+// One thread per pixel: a warp reads 128 (u8) or 512 (f32) contiguous bytes and writes 128 per plane.
+template <typename T, bool GENERAL>
+__global__ void __launch_bounds__(256) xolp_stack_kernel(const T* __restrict__ stack, size_t hw, size_t total, Pinv pv,
+                                                          float* __restrict__ iun, float* __restrict__ xolp) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        float v[4];
+        int iv[4];
+        load_stack_px<T>(stack, i, v, iv);
+        Cues q;
+        if constexpr (GENERAL) q = cues_general(v, pv);
+        else if constexpr (sizeof(T) == 1) q = cues_from_u8(iv[0], iv[1], iv[2], iv[3]);
+        else q = cues_canonical_f32(v);
+        const size_t b = i / hw, r = i - b * hw;
+        float* xo = xolp + b * 2 * hw + r;
+        st_stream_f32(xo, q.rho);
+        st_stream_f32(xo + hw, q.phi);
+        if (iun) st_stream_f32(iun + i, q.iun);
+    }
+}
+
+__global__ void __launch_bounds__(256) xolp_planes_kernel(const uint8_t* __restrict__ i0, const uint8_t* __restrict__ i45,
+                                                           const uint8_t* __restrict__ i90, const uint8_t* __restrict__ i135,
+                                                           size_t hw, size_t total, float* __restrict__ iun,
+                                                           float* __restrict__ xolp) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const Cues q = cues_from_u8(ld_stream_u8(i0 + i), ld_stream_u8(i45 + i), ld_stream_u8(i90 + i), ld_stream_u8(i135 + i));
+        const size_t b = i / hw, r = i - b * hw;
+        float* xo = xolp + b * 2 * hw + r;
+        st_stream_f32(xo, q.rho);
+        st_stream_f32(xo + hw, q.phi);
+        if (iun) st_stream_f32(iun + i, q.iun);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Normals from XOLP (get_normals) and the fine-grained normals_vec functions.
+// ---------------------------------------------------------------------------------------------
+struct NormalsParams {
+    const float* xolp;
+    float* normals;
+    LutArgs lut;
+    uint32_t groups_total;    // B * HW / VEC
+    FastDiv groups_per_image;
+    size_t hw;
+};
+
+template <int VEC, bool MUFU>
+__global__ void __launch_bounds__(kFusedThreads, 2) normals_from_xolp_kernel(const NormalsParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    lut_stage_begin(smem_raw, p.lut.blob, p.lut.bytes, &bar);
+    lut_stage_wait(&bar);
+    const LutView lut = lut_view(reinterpret_cast<const float4*>(smem_raw), p.lut);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < p.groups_total; gid += stride) {
+        const uint32_t b = fastdiv(gid, p.groups_per_image);
+        const size_t pix = (size_t)(gid - b * p.groups_per_image.div) * VEC;
+        const float* xi = p.xolp + (size_t)b * 2 * p.hw + pix;
+        float rho[VEC], phi[VEC];
+        if constexpr (VEC == 4) {
+            const float4 r = ld_stream_f32x4(xi), f = ld_stream_f32x4(xi + p.hw);
+            rho[0] = r.x; rho[1] = r.y; rho[2] = r.z; rho[3] = r.w;
+            phi[0] = f.x; phi[1] = f.y; phi[2] = f.z; phi[3] = f.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                rho[j] = ld_stream_f32(xi + j);
+                phi[j] = ld_stream_f32(xi + p.hw + j);
+            }
+        }
+        float nrm[9][VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float n9[9];
+            normals_from_cues<MUFU>(lut, rho[j], phi[j], n9);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) nrm[c][j] = n9[c];
+        }
+        float* no = p.normals + (size_t)b * 9 * p.hw + pix;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) st_stream_vec<VEC>(no + (size_t)c * p.hw, nrm[c]);
+    }
+}
+
+// theta lookups straight from the global-memory blob (L1-resident after first touch).
+template <int WHICH>  // 0: diffuse, 1: both specular branches
+__global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ rho, size_t count, LutArgs a,
+                                                     float* __restrict__ out0, float* __restrict__ out1) {
+    const LutView lut = lut_view(a.blob, a);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const float r = ld_stream_f32(rho + i);
+        const float g = lut_coord(r);
+        if constexpr (WHICH == 0) {
+            st_stream_f32(out0 + i, lut_eval(lut.cells[0], lut.scale[0], lut.last[0], r, g));
+        } else {
+            st_stream_f32(out0 + i, lut_eval(lut.cells[1], lut.scale[1], lut.last[1], r, g));
+            st_stream_f32(out1 + i, lut_eval(lut.cells[2], lut.scale[2], lut.last[2], r, g));
+        }
+    }
+}
+
+// calc_normals: (phi, theta)[B, HW] -> [B, 3, HW]   (normals_vec.py:53-60)
+__global__ void __launch_bounds__(256) calc_normals_kernel(const float* __restrict__ phi, const float* __restrict__ theta,
+                                                            size_t hw, size_t total, float* __restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        float sp, cp, st, ct;
+        sincos_poly(ld_stream_f32(phi + i), sp, cp);
+        sincos_poly(ld_stream_f32(theta + i), st, ct);
+        const size_t b = i / hw, r = i - b * hw;
+        float* o = out + b * 3 * hw + r;
+        st_stream_f32(o, cp * st);
+        st_stream_f32(o + hw, sp * st);
+        st_stream_f32(o + 2 * hw, ct);
+    }
+}
+
+// ppp "channel" variant (physical_normals_channels.py:15-36): s0 = I0 + I90, no nan scrub, masked.
+__global__ void __launch_bounds__(256) stokes_channel_kernel(const float* __restrict__ stack, const uint8_t* __restrict__ mask,
+                                                              size_t total, float* __restrict__ rho, float* __restrict__ phi,
+                                                              float* __restrict__ iun) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const float4 w = ld_stream_f32x4(stack + 4 * i);
+        const bool in = mask[i] != 0;
+        const float s0 = w.x + w.z, s1 = w.x - w.z, s2 = w.y - w.w;
+        const float r = sqrtf(fmaf(s1, s1, s2 * s2)) / s0;   // 0/0 stays NaN, as np.divide
+        rho[i] = in ? r : 0.0f;
+        phi[i] = in ? 0.5f * atan2_poly(s2, s1) : 0.0f;
+        iun[i] = in ? 0.5f * s0 : 0.0f;
+    }
+}
+
+// calc_normals_channel (physical_normals_channels.py:75-83): H x W x 3 interleaved, zero outside mask.
+__global__ void __launch_bounds__(256) calc_normals_channel_kernel(const float* __restrict__ phi, const float* __restrict__ theta,
+                                                                    const uint8_t* __restrict__ mask, size_t total,
+                                                                    float phi_offset, float* __restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        float sp, cp, st, ct;
+        sincos_poly(phi[i] + phi_offset, sp, cp);
+        sincos_poly(theta[i], st, ct);
+        const bool in = mask[i] != 0;
+        out[3 * i + 0] = in ? cp * st : 0.0f;
+        out[3 * i + 1] = in ? sp * st : 0.0f;
+        out[3 * i + 2] = in ? ct : 0.0f;
+    }
+}
+
+inline unsigned grid_for(size_t total, int threads) {
+    const size_t want = (total + threads - 1) / threads;
+    const size_t cap = (size_t)device_info().sms * 16;
+    return (unsigned)(want < cap ? (want ? want : 1) : cap);
+}
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+}  // namespace
+}  // namespace polcue
+
+using namespace polcue;
+
+extern "C" {
+
+int polcue_debug_set_trig(int mufu) {
+    g_trig_mufu = mufu ? 1 : 0;
+    return POLCUE_OK;
+}
+
+int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W, const polcue_lut* lut, uint8_t* planes,
+                           float* iun, float* xolp, float* normals, polcue_stream_t stream) {
+    if (!mosaic || !xolp || B < 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return POLCUE_EINVAL;
+    if (normals && (!lut || !lut->d_blob)) return POLCUE_EINVAL;
+    if (B == 0) return POLCUE_OK;
+    const int Hs = H / 2, Ws = W / 2;
+    int vec = 1;
+    if (Ws % 4 == 0 && aligned(mosaic, 4) && aligned(xolp, 16) && aligned(normals, 16) && aligned(iun, 16) && aligned(planes, 4))
+        vec = 4;
+    else if (Ws % 2 == 0 && aligned(mosaic, 2) && aligned(xolp, 8) && aligned(normals, 8) && aligned(iun, 8) && aligned(planes, 2))
+        vec = 2;
+    else if (!aligned(xolp, 4) || !aligned(normals, 4) || !aligned(iun, 4))
+        return POLCUE_EINVAL;
+    const unsigned long long groups = (unsigned long long)B * Hs * (Ws / vec);
+    if (groups >= (1ull << 31)) return POLCUE_E2BIG;
+    FusedParams p;
+    p.mosaic = mosaic;
+    p.planes = planes;
+    p.iun = iun;
+    p.xolp = xolp;
+    p.normals = normals;
+    if (normals) p.lut = lut_args(lut);
+    else p.lut = LutArgs{};
+    p.groups_total = (uint32_t)groups;
+    p.groups_per_frame.div = (uint32_t)Hs * (Ws / vec);
+    make_fastdiv(p.groups_per_frame.div, p.groups_per_frame.mul, p.groups_per_frame.shift);
+    p.groups_per_row.div = (uint32_t)(Ws / vec);
+    make_fastdiv(p.groups_per_row.div, p.groups_per_row.mul, p.groups_per_row.shift);
+    p.W = (uint32_t)W;
+    p.Ws = (uint32_t)Ws;
+    p.frame_bytes = (size_t)H * W;
+    p.quad_down = (size_t)Hs * W;
+    p.plane = (size_t)Hs * Ws;
+    const size_t smem = normals ? lut->bytes() : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (vec) {
+        case 4: return launch_fused<4>(p, smem, s);
+        case 2: return launch_fused<2>(p, smem, s);
+        default: return launch_fused<1>(p, smem, s);
+    }
+}
+
+static int xolp_stack_common(const void* stack, bool is_u8, int B, int H, int W, const float* pinv, float* iun, float* xolp,
+                             polcue_stream_t stream) {
+    if (!stack || !xolp || B < 0 || H <= 0 || W <= 0) return POLCUE_EINVAL;
+    if (!aligned(stack, is_u8 ? 4 : 16) || !aligned(xolp, 4) || !aligned(iun, 4)) return POLCUE_EINVAL;
+    if (B == 0) return POLCUE_OK;
+    const size_t hw = (size_t)H * W, total = hw * B;
+    Pinv pv{};
+    if (pinv)
+        for (int k = 0; k < 12; ++k) pv.m[k] = pinv[k];
+    const unsigned grid = grid_for(total, 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (is_u8) {
+        if (pinv) xolp_stack_kernel<uint8_t, true><<<grid, 256, 0, s>>>((const uint8_t*)stack, hw, total, pv, iun, xolp);
+        else xolp_stack_kernel<uint8_t, false><<<grid, 256, 0, s>>>((const uint8_t*)stack, hw, total, pv, iun, xolp);
+    } else {
+        if (pinv) xolp_stack_kernel<float, true><<<grid, 256, 0, s>>>((const float*)stack, hw, total, pv, iun, xolp);
+        else xolp_stack_kernel<float, false><<<grid, 256, 0, s>>>((const float*)stack, hw, total, pv, iun, xolp);
+    }
+    return launch_status();
+}
+
+int polcue_xolp_stack_u8(const uint8_t* stack, int B, int H, int W, const float* pinv, float* iun, float* xolp,
+                         polcue_stream_t stream) {
+    return xolp_stack_common(stack, true, B, H, W, pinv, iun, xolp, stream);
+}
+
+int polcue_xolp_stack_f32(const float* stack, int B, int H, int W, const float* pinv, float* iun, float* xolp,
+                          polcue_stream_t stream) {
+    return xolp_stack_common(stack, false, B, H, W, pinv, iun, xolp, stream);
+}
+
+int polcue_xolp_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t* i90, const uint8_t* i135, int B, int H, int W,
+                          float* iun, float* xolp, polcue_stream_t stream) {
+    if (!i0 || !i45 || !i90 || !i135 || !xolp || B < 0 || H <= 0 || W <= 0) return POLCUE_EINVAL;
+    if (!aligned(xolp, 4) || !aligned(iun, 4)) return POLCUE_EINVAL;
+    if (B == 0) return POLCUE_OK;
+    const size_t hw = (size_t)H * W, total = hw * B;
+    xolp_planes_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(i0, i45, i90, i135, hw, total, iun, xolp);
+    return launch_status();
+}
+
+int polcue_normals_from_xolp_f32(const float* xolp, int B, int H, int W, const polcue_lut* lut, float* normals,
+                                 polcue_stream_t stream) {
+    if (!xolp || !normals || !lut || !lut->d_blob || B < 0 || H <= 0 || W <= 0) return POLCUE_EINVAL;
+    if (!aligned(xolp, 4) || !aligned(normals, 4)) return POLCUE_EINVAL;
+    if (B == 0) return POLCUE_OK;
+    const size_t hw = (size_t)H * W;
+    const int vec = (hw % 4 == 0 && aligned(xolp, 16) && aligned(normals, 16)) ? 4 : 1;
+    const unsigned long long groups = (unsigned long long)B * (hw / vec);
+    if (groups >= (1ull << 31)) return POLCUE_E2BIG;
+    NormalsParams p;
+    p.xolp = xolp;
+    p.normals = normals;
+    p.lut = lut_args(lut);
+    p.groups_total = (uint32_t)groups;
+    p.groups_per_image.div = (uint32_t)(hw / vec);
+    make_fastdiv(p.groups_per_image.div, p.groups_per_image.mul, p.groups_per_image.shift);
+    p.hw = hw;
+    const size_t smem = lut->bytes();
+    auto launch = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (per_sm < 1) return POLCUE_ERANGE;
+        const uint32_t want = (p.groups_total + kFusedThreads - 1) / kFusedThreads;
+        const uint32_t resident = (uint32_t)(per_sm * device_info().sms);
+        kern<<<want < resident ? want : resident, kFusedThreads, smem, (cudaStream_t)stream>>>(p);
+        return launch_status();
+    };
+    if (vec == 4) return g_trig_mufu ? launch(normals_from_xolp_kernel<4, true>) : launch(normals_from_xolp_kernel<4, false>);
+    return g_trig_mufu ? launch(normals_from_xolp_kernel<1, true>) : launch(normals_from_xolp_kernel<1, false>);
+}
+
+int polcue_rho_diffuse_f32(const float* rho, size_t count, const polcue_lut* lut, float* theta, polcue_stream_t stream) {
+    if ((!rho || !theta) && count) return POLCUE_EINVAL;
+    if (!lut || !lut->d_blob) return POLCUE_EINVAL;
+    if (!count) return POLCUE_OK;
+    theta_kernel<0><<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(rho, count, lut_args(lut), theta, nullptr);
+    return launch_status();
+}
+
+int polcue_rho_spec_f32(const float* rho, size_t count, const polcue_lut* lut, float* theta1, float* theta2,
+                        polcue_stream_t stream) {
+    if ((!rho || !theta1 || !theta2) && count) return POLCUE_EINVAL;
+    if (!lut || !lut->d_blob) return POLCUE_EINVAL;
+    if (!count) return POLCUE_OK;
+    theta_kernel<1><<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(rho, count, lut_args(lut), theta1, theta2);
+    return launch_status();
+}
+
+int polcue_calc_normals_f32(const float* phi, const float* theta, int B, size_t hw, float* normals, polcue_stream_t stream) {
+    if (!phi || !theta || !normals || B < 0) return POLCUE_EINVAL;
+    const size_t total = hw * (size_t)B;
+    if (!total) return POLCUE_OK;
+    calc_normals_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(phi, theta, hw, total, normals);
+    return launch_status();
+}
+
+int polcue_stokes_channel_f32(const float* stack, const uint8_t* mask, int H, int W, float* rho, float* phi, float* iun,
+                              polcue_stream_t stream) {
+    if (!stack || !mask || !rho || !phi || !iun || H <= 0 || W <= 0 || !aligned(stack, 16)) return POLCUE_EINVAL;
+    const size_t total = (size_t)H * W;
+    stokes_channel_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(stack, mask, total, rho, phi, iun);
+    return launch_status();
+}
+
+int polcue_calc_normals_channel_f32(const float* phi, const float* theta, const uint8_t* mask, size_t hw, float phi_offset,
+                                    float* normals_hw3, polcue_stream_t stream) {
+    if (!phi || !theta || !mask || !normals_hw3) return POLCUE_EINVAL;
+    if (!hw) return POLCUE_OK;
+    calc_normals_channel_kernel<<<grid_for(hw, 256), 256, 0, (cudaStream_t)stream>>>(phi, theta, mask, hw, phi_offset, normals_hw3);
+    return launch_status();
+}
+
+}  // extern "C"

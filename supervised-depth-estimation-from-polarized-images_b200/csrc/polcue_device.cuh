@@ -1,0 +1,267 @@
+// Device-side building blocks shared by the polcue kernels (sm_100a).
+//   - approximate-unit math wrappers (MUFU) with known error bounds
+//   - atan2 / sincos polynomials accurate to ~1.5e-7 abs (fitted for this project)
+//   - the search-free zenith-angle table lookup
+//   - the per-pixel Stokes -> XOLP -> normal-candidate pipeline
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace polcue {
+
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kHalfPi = 1.57079632679489661923f;
+constexpr float kSqrt2 = 1.41421356237309504880f;
+
+// ------------------------------------------------------------------------------------------
+// MUFU wrappers.  rel. error: rcp 1 ulp, sqrt 1 ulp, rsqrt 2 ulp (PTX ISA approx variants).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Streaming global access: inputs are read once, outputs written once (no reuse in L1/L2).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint16_t ld_stream_u16(const void* p) {
+    uint16_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint8_t ld_stream_u8(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return (uint8_t)v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_stream_f32x4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f32(float* p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_f32x2(float* p, float a, float b) {
+    asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void st_stream_f32x4(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Vector store of V consecutive floats (V in {1,2,4}); p is V*4-byte aligned.
+template <int V>
+__device__ __forceinline__ void st_stream_vec(float* p, const float (&v)[V]) {
+    if constexpr (V == 4) st_stream_f32x4(p, v[0], v[1], v[2], v[3]);
+    else if constexpr (V == 2) st_stream_f32x2(p, v[0], v[1]);
+    else st_stream_f32(p, v[0]);
+}
+
+// ------------------------------------------------------------------------------------------
+// atan2(y, x) in [-pi, pi].  a = min/max in [0,1]; atan(a) = a + a s P7(s), s = a^2.
+// Max abs error 1.2e-7 rad (float32 evaluation, fitted on [0,1]).  atan2(0,0) = 0, atan2(+0, x<0) = +pi
+// -- the closed-form tie behaviour DESIGN.md documents (the reference's lstsq leaves it to round-off).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float atan2_poly(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float a = mn * rcp_approx(mx);
+    a = (mx == 0.0f) ? 0.0f : a;  // 0 * inf
+    const float s = a * a;
+    float p = 0.004059889819473028f;
+    p = fmaf(p, s, -0.020706569775938988f);
+    p = fmaf(p, s, 0.049855392426252365f);
+    p = fmaf(p, s, -0.08074377477169037f);
+    p = fmaf(p, s, 0.10888639092445374f);
+    p = fmaf(p, s, -0.142609104514122f);
+    p = fmaf(p, s, 0.19998927414417267f);
+    p = fmaf(p, s, -0.33333325386047363f);
+    float r = fmaf(a * s, p, a);
+    r = (ay > ax) ? kHalfPi - r : r;
+    r = (x < 0.0f) ? kPi - r : r;
+    return copysignf(r, y);
+}
+
+// ------------------------------------------------------------------------------------------
+// sincos.  Polynomials fitted on |x| <= 1.60 (covers every in-table zenith angle and every AoLP
+// without reduction): abs error 1.4e-7.  Larger arguments (extrapolated zenith angles reach
+// +-140 rad) take a 3-term Cody-Waite reduction by pi/2 first; valid to |x| ~ 1e5.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sincos_core(float r, float& s, float& c) {
+    const float t = r * r;
+    float ps = 2.6301038360543316e-06f;
+    ps = fmaf(ps, t, -0.00019821283058263361f);
+    ps = fmaf(ps, t, 0.008333231322467327f);
+    ps = fmaf(ps, t, -0.1666666567325592f);
+    s = fmaf(r * t, ps, r);
+    float pc = -2.624870205636398e-07f;
+    pc = fmaf(pc, t, 2.4772434699116275e-05f);
+    pc = fmaf(pc, t, -0.0013888622634112835f);
+    pc = fmaf(pc, t, 0.041666656732559204f);
+    pc = fmaf(pc, t, -0.5f);
+    c = fmaf(t, pc, 1.0f);
+}
+
+__device__ __forceinline__ void sincos_poly(float x, float& s, float& c) {
+    float r = x;
+    int q = 0;
+    if (fabsf(x) > 1.6f) {  // rare: only extrapolated zenith angles
+        const float k = rintf(x * 0.636619772367581343f);
+        r = fmaf(k, -1.57079601e+00f, x);
+        r = fmaf(k, -3.13916473e-07f, r);
+        r = fmaf(k, -5.39030253e-15f, r);
+        q = (int)k;
+    }
+    float ss, cc;
+    sincos_core(r, ss, cc);
+    const float s1 = (q & 1) ? cc : ss;
+    const float c1 = (q & 1) ? ss : cc;
+    s = (q & 2) ? -s1 : s1;
+    c = ((q + 1) & 2) ? -c1 : c1;
+}
+
+// MUFU variant: sin.approx/cos.approx, abs error 2^-21.4 = 3.6e-7 on [-pi, pi].  Arguments beyond
+// that are first reduced by 2 pi (2-term Cody-Waite) so the error stays flat out to |x| ~ 1e4.
+__device__ __forceinline__ void sincos_mufu(float x, float& s, float& c) {
+    float r = x;
+    if (fabsf(x) > kPi) {
+        const float k = rintf(x * 0.159154943091895336f);
+        r = fmaf(k, -6.28318548202514648f, x);       // 2 pi rounded to float32
+        r = fmaf(k, 1.74845553146951715e-07f, r);    // (float32(2 pi) - 2 pi)
+    }
+    s = __sinf(r);
+    c = __cosf(r);
+}
+
+template <bool kMufu>
+__device__ __forceinline__ void sincos_sel(float x, float& s, float& c) {
+    if constexpr (kMufu) sincos_mufu(x, s, c);
+    else sincos_poly(x, s, c);
+}
+
+// ------------------------------------------------------------------------------------------
+// Zenith-angle tables.  Each table is a uniform grid of cells over g(rho) in [0, sqrt 2]:
+//     g = sqrt(rho)                for rho <  0.5   (knots of rho_d, rho_s crowd quadratically at 0)
+//     g = sqrt 2 - sqrt(1 - rho)   for rho >= 0.5   (... and at the specular peak rho -> 1)
+// A cell holds (x_k, y_k, slope_left, slope_right) of the single knot it contains (or of the next
+// knot to the right); theta = y_k + (rho - x_k) * (rho <= x_k ? slope_left : slope_right), which is the
+// same line scipy's interp1d(linear, extrapolate) evaluates on that segment.  Built in lut.cu.
+// ------------------------------------------------------------------------------------------
+struct LutView {
+    const float4* cells[3];  // diffuse, spec1, spec2 (shared memory in the hot kernels)
+    float scale[3];          // cells per unit g
+    int last[3];             // cell count - 1
+};
+
+__device__ __forceinline__ float lut_coord(float rho) {
+    const bool low = rho < 0.5f;
+    const float t = fmaxf(low ? rho : 1.0f - rho, 0.0f);
+    const float g = sqrt_approx(t);
+    return low ? g : kSqrt2 - g;
+}
+
+__device__ __forceinline__ float lut_eval(const float4* __restrict__ cells, float scale, int last, float rho, float g) {
+    const int c = min((int)(g * scale), last);
+    const float4 e = cells[c];
+    const float d = rho - e.x;
+    return fmaf(d, (d <= 0.0f) ? e.z : e.w, e.y);
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-pixel pipeline pieces.
+// ------------------------------------------------------------------------------------------
+struct Cues {
+    float iun, rho, phi;
+};
+
+// Canonical angles, integer samples: polarisation/xolp.py:8-34 in closed form.
+//   x0 = (I0+I45+I90+I135)/4, x1 = (I0-I90)/2, x2 = (I45-I135)/2
+//   rho = sqrt(x1^2+x2^2)/x0 (x0 == 0 -> 0, the inf/nan scrub of xolp.py:26-29), phi = atan2(x2,x1)/2
+__device__ __forceinline__ Cues cues_from_u8(int i0, int i45, int i90, int i135) {
+    const int s1 = i0 - i90, s2 = i45 - i135, sum = i0 + i45 + i90 + i135;
+    const float fs1 = (float)s1, fs2 = (float)s2, fsum = (float)sum;
+    const float amp = sqrt_approx((float)(s1 * s1 + s2 * s2));  // exact integer under the root
+    Cues q;
+    q.iun = 0.25f * fsum;
+    q.rho = (sum == 0) ? 0.0f : (2.0f * amp) * rcp_approx(fsum);
+    q.phi = 0.5f * atan2_poly(fs2, fs1);
+    return q;
+}
+
+// Three normal candidates in the channel order of get_normals (pre_encoders.py:99-113):
+//   N_diff = (cos phi sin td, sin phi sin td, cos td)
+//   N_spec = (cos(phi+pi/2) sin ts, sin(phi+pi/2) sin ts, cos ts) = (-sin phi sin ts, cos phi sin ts, cos ts)
+template <bool kMufu>
+__device__ __forceinline__ void normals_from_cues(const LutView& lut, float rho, float phi, float (&n)[9]) {
+    float sp, cp;
+    sincos_sel<kMufu>(phi, sp, cp);
+    const float g = lut_coord(rho);
+    const float td = lut_eval(lut.cells[0], lut.scale[0], lut.last[0], rho, g);
+    const float t1 = lut_eval(lut.cells[1], lut.scale[1], lut.last[1], rho, g);
+    const float t2 = lut_eval(lut.cells[2], lut.scale[2], lut.last[2], rho, g);
+    float s, c;
+    sincos_sel<kMufu>(td, s, c);
+    n[0] = cp * s; n[1] = sp * s; n[2] = c;
+    sincos_sel<kMufu>(t1, s, c);
+    n[3] = -sp * s; n[4] = cp * s; n[5] = c;
+    sincos_sel<kMufu>(t2, s, c);
+    n[6] = -sp * s; n[7] = cp * s; n[8] = c;
+}
+
+// ------------------------------------------------------------------------------------------
+// Bulk (TMA) copy of the table blob into shared memory, completion on an mbarrier.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void lut_stage_begin(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+            "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+            : "memory");
+    }
+}
+
+__device__ __forceinline__ void lut_stage_wait(uint64_t* bar) {
+    __syncthreads();  // orders the init by thread 0 before anyone polls
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar))
+            : "memory");
+    }
+}
+
+// Exact unsigned division by a runtime constant (d >= 1, n < 2^31): q = (n * mul) >> 32 >> shift.
+struct FastDiv {
+    uint32_t mul, shift, div;
+};
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& d) {
+    return (d.div == 1) ? n : (__umulhi(n, d.mul) >> d.shift);
+}
+
+}  // namespace polcue

@@ -1,0 +1,50 @@
+// Host-side internals shared by the translation units of libpolcue.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../include/polcue.h"
+
+struct polcue_lut {
+    double n = 0.0;
+    int cells[3] = {0, 0, 0};      // cell count per table (diffuse, spec1, spec2)
+    int offset[3] = {0, 0, 0};     // first cell of each table inside the blob (float4 units)
+    float scale[3] = {0, 0, 0};    // cells per unit g
+    std::vector<float4> blob;      // host copy of the device blob
+    std::vector<double> kx[3], ky[3];  // sorted knots as scipy's interp1d holds them
+    float4* d_blob = nullptr;      // device copy (null for host-only builds)
+    int device = -1;
+    size_t bytes() const { return blob.size() * sizeof(float4); }
+};
+
+namespace polcue {
+
+extern std::atomic<unsigned long long> g_launches;
+
+inline int launch_status() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+struct DeviceInfo {
+    int sms = 0;
+    int smem_optin = 0;
+};
+const DeviceInfo& device_info();  // of the current device (cached per device)
+
+// magic numbers for polcue::FastDiv (exact for numerators < 2^31)
+inline void make_fastdiv(uint32_t d, uint32_t& mul, uint32_t& shift) {
+    if (d <= 1) {
+        mul = 0;
+        shift = 0;
+        return;
+    }
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;  // s = ceil(log2 d) >= 1
+    mul = (uint32_t)(((1ull << (31 + s)) / d) + 1);
+    shift = s - 1;
+}
+
+}  // namespace polcue

@@ -1,0 +1,130 @@
+// Depth -> surface-normal 3x3 stencil (forward).
+//
+// Replaces kornia.geometry.depth.depth_to_normals (kornia 0.5.11, environment.yml:41) as called at
+// manydepth/trainer.py:1305-1306,1477,1484:
+//     xyz  = ((u - cx)/fx * Z, (v - cy)/fy * Z, Z)        u in [0, W-1], v in [0, H-1]   (depth_to_3d)
+//     grad = cross-correlation of the REPLICATE-padded xyz with sobel_x / 8 and sobel_y / 8
+//     n    = cross(d xyz/du, d xyz/dv);  n / max(||n||, 1e-12)
+// Replicate padding acts on xyz, so a border neighbour contributes the xyz of the CLAMPED pixel
+// (clamped u and v as well as clamped depth).
+//
+// Roofline: HBM, 4 B read + 12 B written per pixel.  A CTA stages a (TH+2) x (TW+2) depth tile with
+// its halo in shared memory (each depth value is fetched from DRAM once and re-used 9 times from
+// shared memory); a thread produces four consecutive pixels and writes one 16-byte vector per plane.
+#include "polcue_device.cuh"
+#include "polcue_host.h"
+
+namespace polcue {
+namespace {
+
+constexpr int kTW = 128, kTH = 8, kStencilThreads = (kTW / 4) * kTH;  // 256
+constexpr int kPitch = kTW + 4;  // [halo | TW | halo | pad], keeps rows 16-byte multiples
+
+struct StencilParams {
+    const float* depth;
+    const float* K;
+    float* normals;
+    int H, W;
+    bool vec4;  // W % 4 == 0 and 16-byte aligned output
+};
+
+__global__ void __launch_bounds__(kStencilThreads) depth_to_normals_kernel(const StencilParams p) {
+    __shared__ float tile[(kTH + 2) * kPitch];
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const size_t hw = (size_t)p.H * p.W;
+    const float* z = p.depth + (size_t)b * hw;
+
+    // stage tile + halo with clamped (replicate) coordinates
+    for (int i = threadIdx.x; i < (kTH + 2) * (kTW + 2); i += kStencilThreads) {
+        const int r = i / (kTW + 2), c = i - r * (kTW + 2);
+        const int yy = min(max(y0 + r - 1, 0), p.H - 1);
+        const int xx = min(max(x0 + c - 1, 0), p.W - 1);
+        tile[r * kPitch + c] = __ldg(z + (size_t)yy * p.W + xx);
+    }
+    const float* k = p.K + (size_t)b * 9;
+    const float inv_fx = 1.0f / __ldg(k + 0), cx = __ldg(k + 2);
+    const float inv_fy = 1.0f / __ldg(k + 4), cy = __ldg(k + 5);
+    __syncthreads();
+
+    const int ty = threadIdx.x / (kTW / 4), tx = threadIdx.x - ty * (kTW / 4);
+    const int y = y0 + ty, xb = x0 + 4 * tx;
+    if (y >= p.H || xb >= p.W) return;
+
+    // ray factors of the three rows (clamped rows repeat the border row's factor)
+    float fy3[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) fy3[r] = ((float)min(max(y + r - 1, 0), p.H - 1) - cy) * inv_fy;
+    float fx6[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) fx6[c] = ((float)min(max(xb + c - 1, 0), p.W - 1) - cx) * inv_fx;
+
+    float zz[3][6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) zz[r][c] = tile[(ty + r) * kPitch + 4 * tx + c];
+
+    float out[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float gu[3], gv[3];  // d/du, d/dv of (X, Y, Z)
+#pragma unroll
+        for (int comp = 0; comp < 3; ++comp) {
+            float v[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float d = zz[r][j + c];
+                    v[r][c] = comp == 0 ? fx6[j + c] * d : (comp == 1 ? fy3[r] * d : d);
+                }
+            gu[comp] = 0.125f * ((v[0][2] - v[0][0]) + 2.0f * (v[1][2] - v[1][0]) + (v[2][2] - v[2][0]));
+            gv[comp] = 0.125f * ((v[2][0] - v[0][0]) + 2.0f * (v[2][1] - v[0][1]) + (v[2][2] - v[0][2]));
+        }
+        const float nx = gu[1] * gv[2] - gu[2] * gv[1];
+        const float ny = gu[2] * gv[0] - gu[0] * gv[2];
+        const float nz = gu[0] * gv[1] - gu[1] * gv[0];
+        const float len = sqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+        const float inv = 1.0f / fmaxf(len, 1e-12f);
+        out[0][j] = nx * inv;
+        out[1][j] = ny * inv;
+        out[2][j] = nz * inv;
+    }
+
+    float* o = p.normals + (size_t)b * 3 * hw + (size_t)y * p.W + xb;
+    if (p.vec4 && xb + 3 < p.W) {
+#pragma unroll
+        for (int comp = 0; comp < 3; ++comp) st_stream_vec<4>(o + comp * hw, out[comp]);
+    } else {
+#pragma unroll
+        for (int comp = 0; comp < 3; ++comp)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (xb + j < p.W) st_stream_f32(o + comp * hw + j, out[comp][j]);
+    }
+}
+
+}  // namespace
+}  // namespace polcue
+
+using namespace polcue;
+
+extern "C" int polcue_depth_to_normals_f32(const float* depth, const float* K, int B, int H, int W, float* normals,
+                                           polcue_stream_t stream) {
+    if (!depth || !K || !normals || B < 0 || H <= 0 || W <= 0 || B > 65535) return POLCUE_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(depth) | reinterpret_cast<uintptr_t>(normals) | reinterpret_cast<uintptr_t>(K)) & 3)
+        return POLCUE_EINVAL;
+    if (B == 0) return POLCUE_OK;
+    StencilParams p;
+    p.depth = depth;
+    p.K = K;
+    p.normals = normals;
+    p.H = H;
+    p.W = W;
+    p.vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(normals) & 15) == 0);
+    const dim3 grid((W + kTW - 1) / kTW, (H + kTH - 1) / kTH, B);
+    if (grid.y > 65535) return POLCUE_E2BIG;
+    depth_to_normals_kernel<<<grid, kStencilThreads, 0, (cudaStream_t)stream>>>(p);
+    return launch_status();
+}

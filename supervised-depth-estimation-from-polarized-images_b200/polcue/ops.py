@@ -1,0 +1,368 @@
+"""Tensor-level operators: torch CUDA tensors in, torch CUDA tensors out, through the C ABI.
+
+PyTorch is plumbing here (device memory, streams); every arithmetic step runs in libpolcue.so.
+Each function validates dtype / contiguity / device, allocates its outputs on the input's device,
+enqueues on the current CUDA stream and raises on a non-zero return code.  No fallbacks.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+
+CANONICAL_ANGLES = np.array([0.0, 45.0, 90.0, 135.0]) * np.pi / 180.0
+METRIC_NAMES = ("abs_rel", "sq_rel", "rmse", "rmse_log", "a1", "a2", "a3")
+
+_lut_cache = {}
+_lut_lock = threading.Lock()
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (polcue has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def lut_for(n, device):
+    """Zenith-angle tables for refractive index `n` on `device` (cached; built once per pair)."""
+    device = torch.device(device)
+    key = (float(n), device.index if device.index is not None else torch.cuda.current_device())
+    with _lut_lock:
+        h = _lut_cache.get(key)
+        if h is None:
+            with torch.cuda.device(key[1]):
+                out = C.c_void_p()
+                _lib.check(_lib.lib().polcue_lut_create(float(n), C.byref(out)), f"polcue_lut_create(n={n})")
+            h = _lut_cache[key] = out
+    return h
+
+
+# ------------------------------------------------------------------------------------------
+# quadrant split
+# ------------------------------------------------------------------------------------------
+def _split(img, b, h, w, tail):
+    if h % 2 or w % 2:
+        raise ValueError("array split does not result in an equal division")   # numpy's message (np.split)
+    px_bytes = img.element_size()
+    for t in tail:
+        px_bytes *= t
+    lead = (b,) if img.dim() == 2 + len(tail) + 1 else ()
+    outs = [torch.empty(lead + (h // 2, w // 2) + tuple(tail), dtype=img.dtype, device=img.device) for _ in range(4)]
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.lib().polcue_split_pol(_ptr(img), b, h, w, px_bytes, *(_ptr(o) for o in outs), _stream(img)),
+                   "polcue_split_pol")
+    return tuple(outs)
+
+
+def split_pol(img):
+    """One image H x W (x C...) -> (im00, im10, im01, im11), as pol_split_and_save.py:10-27 (axes 0 and 1)."""
+    img = _need_cuda(img, "img")
+    if img.dim() < 2:
+        raise ValueError("img must have at least two dimensions")
+    return _split(img, 1, img.shape[0], img.shape[1], tuple(img.shape[2:]))
+
+
+def split_pol_batch(imgs):
+    """B x H x W (x C...) -> four B x H/2 x W/2 (x C...) tensors in the order of `split_pol`."""
+    imgs = _need_cuda(imgs, "imgs")
+    if imgs.dim() < 3:
+        raise ValueError("imgs must be B x H x W (x C)")
+    return _split(imgs, imgs.shape[0], imgs.shape[1], imgs.shape[2], tuple(imgs.shape[3:]))
+
+
+# ------------------------------------------------------------------------------------------
+# fused pipeline
+# ------------------------------------------------------------------------------------------
+def fused_mosaic(mosaic, n=1.5, want_iun=False, want_planes=False, want_normals=True, out=None):
+    """B x H x W uint8 mosaics -> dict(xolp [B,2,Hs,Ws], normals [B,9,Hs,Ws], iun, planes).
+
+    `out` may hold preallocated tensors under the same keys (steady-state loops reuse them).
+    """
+    mosaic = _need_cuda(mosaic, "mosaic", torch.uint8)
+    if mosaic.dim() == 2:
+        mosaic = mosaic[None]
+    b, h, w = mosaic.shape
+    if h % 2 or w % 2:
+        raise ValueError("mosaic height and width must be even")
+    hs, ws = h // 2, w // 2
+    out = dict(out or {})
+    dev = mosaic.device
+
+    def buf(key, shape, dtype):
+        t = out.get(key)
+        if t is None:
+            t = out[key] = torch.empty(shape, dtype=dtype, device=dev)
+        elif tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_contiguous() or t.device != dev:
+            raise ValueError(f"preallocated `{key}` has the wrong shape/dtype/device")
+        return t
+
+    xolp = buf("xolp", (b, 2, hs, ws), torch.float32)
+    normals = buf("normals", (b, 9, hs, ws), torch.float32) if want_normals else None
+    iun = buf("iun", (b, hs, ws), torch.float32) if want_iun else None
+    planes = buf("planes", (b, 4, hs, ws), torch.uint8) if want_planes else None
+    lut = lut_for(n, dev) if want_normals else C.c_void_p(0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().polcue_fused_mosaic_u8(_ptr(mosaic), b, h, w, lut, _ptr(planes), _ptr(iun), _ptr(xolp),
+                                                     _ptr(normals), _stream(mosaic)), "polcue_fused_mosaic_u8")
+    return out
+
+
+def fused_mosaic_host(mosaic, n=1.5, want_iun=False, want_normals=True, out=None, chunk_frames=0, device=None):
+    """Host (ideally pinned) uint8 mosaics -> host float32 outputs; copies are pipelined inside the library."""
+    if not isinstance(mosaic, torch.Tensor) or mosaic.is_cuda or mosaic.dtype != torch.uint8:
+        raise TypeError("mosaic must be a CPU uint8 tensor")
+    mosaic = mosaic.contiguous()
+    if mosaic.dim() == 2:
+        mosaic = mosaic[None]
+    b, h, w = mosaic.shape
+    hs, ws = h // 2, w // 2
+    out = dict(out or {})
+
+    def buf(key, shape):
+        t = out.get(key)
+        if t is None:
+            t = out[key] = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        return t
+
+    xolp = buf("xolp", (b, 2, hs, ws))
+    normals = buf("normals", (b, 9, hs, ws)) if want_normals else None
+    iun = buf("iun", (b, hs, ws)) if want_iun else None
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lut = lut_for(n, dev) if want_normals else C.c_void_p(0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().polcue_fused_mosaic_u8_host(_ptr(mosaic), b, h, w, lut, _ptr(iun), _ptr(xolp), _ptr(normals),
+                                                          int(chunk_frames)), "polcue_fused_mosaic_u8_host")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# XOLP
+# ------------------------------------------------------------------------------------------
+def pinv_for_angles(angles):
+    """None for the canonical angles, else the 3x4 pseudo-inverse lstsq applies (xolp.py:15-21)."""
+    angles = np.asarray(angles, dtype=np.float64).reshape(4)
+    if np.allclose(angles, CANONICAL_ANGLES, rtol=0, atol=1e-12):
+        return None
+    design = np.stack((np.ones(4), np.cos(2 * angles), np.sin(2 * angles)), axis=1)
+    return np.linalg.pinv(design)
+
+
+def xolp_from_stack(stack, angles=None, want_iun=True):
+    """(B x) H x W x 4 uint8 / float32 stack -> (iun [B,H,W] or None, xolp [B,2,H,W]); xolp.py:8-34."""
+    stack = _need_cuda(stack, "stack")
+    if stack.dtype not in (torch.uint8, torch.float32):
+        stack = stack.float()
+    if stack.dim() == 3:
+        stack = stack[None]
+    if stack.dim() != 4 or stack.shape[-1] != 4:
+        raise ValueError("stack must be (B x) H x W x 4")
+    b, h, w, _ = stack.shape
+    pinv = None if angles is None else pinv_for_angles(angles)
+    pinv_arg = None if pinv is None else (C.c_float * 12)(*[float(v) for v in pinv.reshape(-1)])
+    iun = torch.empty((b, h, w), dtype=torch.float32, device=stack.device) if want_iun else None
+    xolp = torch.empty((b, 2, h, w), dtype=torch.float32, device=stack.device)
+    fn = _lib.lib().polcue_xolp_stack_u8 if stack.dtype == torch.uint8 else _lib.lib().polcue_xolp_stack_f32
+    with torch.cuda.device(stack.device):
+        _lib.check(fn(_ptr(stack), b, h, w, pinv_arg, _ptr(iun), _ptr(xolp), _stream(stack)), "polcue_xolp_stack")
+    return iun, xolp
+
+
+def xolp_from_planes(i0, i45, i90, i135, want_iun=False):
+    """Four B x H x W uint8 planes (indoor_dataset.py:435-438) -> (iun or None, xolp [B,2,H,W])."""
+    planes = [_need_cuda(p, "plane", torch.uint8) for p in (i0, i45, i90, i135)]
+    shape = planes[0].shape
+    if any(p.shape != shape for p in planes) or len(shape) not in (2, 3):
+        raise ValueError("planes must share one (B x) H x W shape")
+    b = shape[0] if len(shape) == 3 else 1
+    h, w = shape[-2:]
+    dev = planes[0].device
+    iun = torch.empty((b, h, w), dtype=torch.float32, device=dev) if want_iun else None
+    xolp = torch.empty((b, 2, h, w), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().polcue_xolp_planes_u8(*(_ptr(p) for p in planes), b, h, w, _ptr(iun), _ptr(xolp),
+                                                    _stream(planes[0])), "polcue_xolp_planes_u8")
+    return iun, xolp
+
+
+# ------------------------------------------------------------------------------------------
+# physics normals
+# ------------------------------------------------------------------------------------------
+def get_normals(x, n=1.5):
+    """B x 2 x H x W (rho, phi) -> B x 9 x H x W float32; pre_encoders.py:99-113."""
+    x = _need_cuda(x, "x")
+    if x.dim() != 4 or x.shape[1] != 2:
+        raise ValueError("x must be B x 2 x H x W")
+    x = x.float().contiguous()
+    b, _, h, w = x.shape
+    out = torch.empty((b, 9, h, w), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().polcue_normals_from_xolp_f32(_ptr(x), b, h, w, lut_for(n, x.device), _ptr(out), _stream(x)),
+                   "polcue_normals_from_xolp_f32")
+    return out
+
+
+def rho_diffuse(rho, n):
+    rho = _need_cuda(rho, "rho").float().contiguous()
+    theta = torch.empty_like(rho)
+    with torch.cuda.device(rho.device):
+        _lib.check(_lib.lib().polcue_rho_diffuse_f32(_ptr(rho), rho.numel(), lut_for(n, rho.device), _ptr(theta), _stream(rho)),
+                   "polcue_rho_diffuse_f32")
+    return theta
+
+
+def rho_spec(rho, n):
+    rho = _need_cuda(rho, "rho").float().contiguous()
+    t1, t2 = torch.empty_like(rho), torch.empty_like(rho)
+    with torch.cuda.device(rho.device):
+        _lib.check(_lib.lib().polcue_rho_spec_f32(_ptr(rho), rho.numel(), lut_for(n, rho.device), _ptr(t1), _ptr(t2),
+                                                  _stream(rho)), "polcue_rho_spec_f32")
+    return t1, t2
+
+
+def calc_normals(phi, theta):
+    """(phi, theta) B x H x W -> B x 3 x H x W; normals_vec.py:53-60."""
+    phi = _need_cuda(phi, "phi").float().contiguous()
+    theta = _need_cuda(theta, "theta").float().contiguous()
+    if phi.shape != theta.shape or phi.dim() < 2:
+        raise ValueError("phi and theta must share a B x ... shape")
+    b = phi.shape[0]
+    hw = phi.numel() // b if b else 0
+    out = torch.empty((b, 3) + tuple(phi.shape[1:]), dtype=torch.float32, device=phi.device)
+    with torch.cuda.device(phi.device):
+        _lib.check(_lib.lib().polcue_calc_normals_f32(_ptr(phi), _ptr(theta), b, hw, _ptr(out), _stream(phi)),
+                   "polcue_calc_normals_f32")
+    return out
+
+
+def stokes_channel(stack, mask):
+    """H x W x 4 float stack + H x W mask -> (rho, phi, iun); physical_normals_channels.py:15-36."""
+    stack = _need_cuda(stack, "stack").float().contiguous()
+    mask = _need_cuda(mask, "mask").to(torch.uint8).contiguous()
+    h, w, _ = stack.shape
+    rho, phi, iun = (torch.empty((h, w), dtype=torch.float32, device=stack.device) for _ in range(3))
+    with torch.cuda.device(stack.device):
+        _lib.check(_lib.lib().polcue_stokes_channel_f32(_ptr(stack), _ptr(mask), h, w, _ptr(rho), _ptr(phi), _ptr(iun),
+                                                        _stream(stack)), "polcue_stokes_channel_f32")
+    return rho, phi, iun
+
+
+def calc_normals_channel(phi, theta, mask, phi_offset=0.0):
+    """H x W x 3, zero outside mask; physical_normals_channels.py:75-83 (phi_offset: the caller's phi + pi/2)."""
+    phi = _need_cuda(phi, "phi").float().contiguous()
+    theta = _need_cuda(theta, "theta").float().contiguous()
+    mask = _need_cuda(mask, "mask").to(torch.uint8).contiguous()
+    out = torch.empty(tuple(phi.shape) + (3,), dtype=torch.float32, device=phi.device)
+    with torch.cuda.device(phi.device):
+        _lib.check(_lib.lib().polcue_calc_normals_channel_f32(_ptr(phi), _ptr(theta), _ptr(mask), phi.numel(), float(phi_offset),
+                                                              _ptr(out), _stream(phi)), "polcue_calc_normals_channel_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# depth -> normals
+# ------------------------------------------------------------------------------------------
+def depth_to_normals(depth, camera_matrix):
+    """depth B x 1 x H x W, camera_matrix B x 3 x 3 -> B x 3 x H x W (kornia 0.5.11 semantics, forward only)."""
+    depth = _need_cuda(depth, "depth")
+    if depth.requires_grad:
+        raise NotImplementedError(
+            "polcue.depth_to_normals is forward-only (the GT branch of trainer.py:1305); the predicted-depth branch "
+            "needs autograd and is listed as the next step in DESIGN.md")
+    if depth.dim() != 4 or depth.shape[1] != 1:
+        raise ValueError("depth must be B x 1 x H x W")
+    camera_matrix = _need_cuda(camera_matrix, "camera_matrix")
+    if camera_matrix.shape != (depth.shape[0], 3, 3):
+        raise ValueError("camera_matrix must be B x 3 x 3")
+    depth = depth.float().contiguous()
+    k = camera_matrix.float().contiguous()
+    b, _, h, w = depth.shape
+    out = torch.empty((b, 3, h, w), dtype=torch.float32, device=depth.device)
+    with torch.cuda.device(depth.device):
+        _lib.check(_lib.lib().polcue_depth_to_normals_f32(_ptr(depth), _ptr(k), b, h, w, _ptr(out), _stream(depth)),
+                   "polcue_depth_to_normals_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# depth metrics
+# ------------------------------------------------------------------------------------------
+_workspaces = {}
+
+
+def _workspace(device):
+    """Per-(device, stream) scratch for the flat reduction (ticket word + per-CTA partials)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = int(_lib.lib().polcue_depth_errors_workspace_bytes())
+        ws = _workspaces[key] = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    return ws
+
+
+def depth_error_sums(gt, pred, want_metrics=True):
+    """Flat (already masked) gt / pred -> (sums8 float64 [8], metrics float32 [7] or None), on device."""
+    gt = _need_cuda(gt, "gt").float().contiguous().reshape(-1)
+    pred = _need_cuda(pred, "pred").float().contiguous().reshape(-1)
+    if gt.numel() != pred.numel():
+        raise ValueError("gt and pred must have the same number of elements")
+    sums = torch.empty(8, dtype=torch.float64, device=gt.device)
+    metrics = torch.empty(7, dtype=torch.float32, device=gt.device) if want_metrics else None
+    with torch.cuda.device(gt.device):
+        _lib.check(_lib.lib().polcue_depth_errors_f32(_ptr(gt), _ptr(pred), gt.numel(), _ptr(_workspace(gt.device)), _ptr(sums),
+                                                      _ptr(metrics), _stream(gt)), "polcue_depth_errors_f32")
+    return sums, metrics
+
+
+def compute_depth_errors(gt, pred):
+    """manydepth/layers.py:539-557: 7 zero-dim float32 tensors (abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3)."""
+    _, metrics = depth_error_sums(gt, pred)
+    return tuple(metrics.unbind(0))
+
+
+def depth_errors_per_image(gt, pred, min_depth, max_depth, inst=None, inst_id=None):
+    """Per-image masked metrics (trainer.py:1376-1428): gt/pred B x H x W (or B x 1 x H x W), inst uint8 or None.
+
+    Returns (sums [B,8] float64, metrics [B,7] float32) on device.
+    """
+    gt = _need_cuda(gt, "gt").float().contiguous()
+    pred = _need_cuda(pred, "pred").float().contiguous()
+    b = gt.shape[0]
+    px = gt.numel() // b if b else 0
+    if pred.numel() != gt.numel():
+        raise ValueError("gt and pred must have the same shape")
+    use_inst = inst is not None and inst_id is not None
+    if use_inst:
+        inst = _need_cuda(inst, "inst", torch.uint8)
+        if inst.numel() != gt.numel():
+            raise ValueError("inst must have the same shape as gt")
+    sums = torch.empty((b, 8), dtype=torch.float64, device=gt.device)
+    metrics = torch.empty((b, 7), dtype=torch.float32, device=gt.device)
+    with torch.cuda.device(gt.device):
+        _lib.check(_lib.lib().polcue_depth_errors_images_f32(_ptr(gt), _ptr(pred), _ptr(inst) if use_inst else C.c_void_p(0), b,
+                                                             px, float(min_depth), float(max_depth),
+                                                             int(inst_id) if use_inst else 0, _ptr(sums), _ptr(metrics),
+                                                             _stream(gt)), "polcue_depth_errors_images_f32")
+    return sums, metrics
+
+
+def metrics_from_sums(sums):
+    """8 additive accumulators (any leading shape) -> 7 metrics in the reference order (float64 tensor/array)."""
+    n = sums[..., 0]
+    sqrt = torch.sqrt if isinstance(sums, torch.Tensor) else np.sqrt
+    stack = torch.stack if isinstance(sums, torch.Tensor) else np.stack
+    return stack((sums[..., 6] / n, sums[..., 7] / n, sqrt(sums[..., 4] / n), sqrt(sums[..., 5] / n),
+                  sums[..., 1] / n, sums[..., 2] / n, sums[..., 3] / n), -1)

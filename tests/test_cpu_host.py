@@ -1,0 +1,204 @@
+"""CPU-only checks: the C ABI surface, the host-side table construction, argument validation that needs no GPU,
+and the world_size-2 sharding / reduction logic over gloo."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import polcue_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from polcue import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return _lib.lib()
+
+
+def test_library_exports_every_declared_symbol(L):
+    header = open(os.path.join(ROOT, "include", "polcue.h")).read()
+    declared = set(re.findall(r"POLCUE_API[^;(]*?\b(polcue_\w+)\s*\(", header))
+    assert len(declared) >= 28
+    from polcue import _lib
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.polcue_version()
+    assert L.polcue_error_string(-22).startswith(b"invalid argument")
+
+
+def test_library_is_built_for_sm_100a_only():
+    from polcue import _lib
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def _host_lut(L, n):
+    h = C.c_void_p()
+    rc = L.polcue_lut_host_build(float(n), C.byref(h))
+    return rc, h
+
+
+@pytest.mark.parametrize("n", [1.3, 1.33, 1.5, 1.8, 2.5])
+def test_cell_tables_reproduce_the_reference_interpolant(L, n):
+    rc, h = _host_lut(L, n)
+    assert rc == 0
+    knots = O.sorted_knots(n)
+    rng = np.random.default_rng(int(n * 100))
+    queries = np.concatenate((rng.uniform(0, 1, 200_000) ** 2, rng.uniform(0, 2.2, 50_000), rng.uniform(-0.2, 0, 1000),
+                              [0.0, 1.0, 0.5, 0.49999997, 2.0])).astype(np.float32)
+    for t, name in enumerate(("diffuse", "spec1", "spec2")):
+        xk, yk = knots[name]
+        # same knots as the oracle / scipy hold (libm vs numpy sin/cos: 1 ulp)
+        count = L.polcue_lut_knots(h, t, None, None, 0)
+        assert count == len(xk)
+        x, y = np.empty(count), np.empty(count)
+        assert L.polcue_lut_knots(h, t, x.ctypes.data, y.ctypes.data, count) == count
+        assert np.allclose(x, xk, rtol=1e-12, atol=1e-30) and np.allclose(y, yk, rtol=1e-15)
+        # knot positions themselves (float32-rounded) and random queries
+        q = np.concatenate((queries, xk.astype(np.float32), (0.5 * (xk[1:] + xk[:-1])).astype(np.float32)))
+        theta = np.empty(q.size, np.float32)
+        assert L.polcue_lut_eval_host(h, t, q.ctypes.data, q.size, theta.ctypes.data) == 0
+        q64 = q.astype(np.float64)
+        ref = O.interp_linear_extrap(xk, yk, q64)
+        hi = np.clip(np.searchsorted(xk, q64), 1, len(xk) - 1)
+        slope = np.abs((yk[hi] - yk[hi - 1]) / (xk[hi] - xk[hi - 1]))
+        tol = 4e-7 * (1 + np.abs(ref)) + slope * 1.3e-7 * np.maximum(np.abs(q64), np.abs(1 - q64))
+        bad = np.abs(theta - ref) > tol
+        assert not bad.any(), (name, q[bad][:5], theta[bad][:5], ref[bad][:5])
+    cells = [L.polcue_lut_cells(h, t) for t in range(3)]
+    assert all(c > 0 for c in cells) and sum(cells) * 16 <= 200 * 1024
+    L.polcue_lut_destroy(h)
+
+
+def test_table_anchor_values(L):
+    rc, h = _host_lut(L, 1.5)
+    anchors = {0.0: (0.0, 0.0, 1.570796327), 0.01: (0.410434783, 0.086477641, 1.566324189), 0.3: (1.472298774, 0.460030611, 1.436485518),
+               0.5: (1.692111847, 0.590509261, 1.345596980), 1.0: (2.217812434, 0.981710534, 0.982727665),
+               1.2: (2.428092719, 9.416327864, -27.260250003), 2.0: (3.269213607, 43.154787130, -140.232127007)}
+    q = np.array(list(anchors), np.float32)
+    for t in range(3):
+        theta = np.empty(q.size, np.float32)
+        L.polcue_lut_eval_host(h, t, q.ctypes.data, q.size, theta.ctypes.data)
+        ref = np.array([anchors[k][t] for k in anchors])
+        assert np.allclose(theta, ref, rtol=3e-6, atol=1e-6), (t, theta, ref)
+    L.polcue_lut_destroy(h)
+
+
+def test_unrepresentable_refractive_indices_are_rejected(L):
+    for n in (1.0, 0.5, float("nan"), 1.0001):
+        rc, h = _host_lut(L, n)
+        assert rc == -34 and not h.value
+    assert L.polcue_lut_host_build(1.5, None) == -22
+
+
+def test_argument_validation_needs_no_gpu(L):
+    assert L.polcue_split_pol(None, 1, 4, 4, 1, None, None, None, None, None) == -22
+    assert L.polcue_fused_mosaic_u8(None, 1, 4, 4, None, None, None, None, None, None) == -22
+    assert L.polcue_depth_to_normals_f32(None, None, 1, 4, 4, None, None) == -22
+    assert L.polcue_depth_errors_f32(None, None, 4, None, None, None, None) == -22
+    assert L.polcue_depth_errors_workspace_bytes() >= 64 + 148 * 8 * 8 * 8
+
+
+def test_ops_refuse_cpu_tensors_and_missing_library():
+    from polcue import ops
+    with pytest.raises(TypeError):
+        ops.fused_mosaic(torch.zeros((1, 4, 4), dtype=torch.uint8))
+    with pytest.raises(TypeError):
+        ops.get_normals(torch.zeros((1, 2, 4, 4)))
+    code = ("import sys; sys.path.insert(0, %r); import polcue._lib as L; L.LIB_PATH = '/nonexistent/libpolcue.so'\n"
+            "try:\n    L.lib()\nexcept RuntimeError as e:\n    print('RAISED', 'no CPU fallback' in str(e))\n") % os.path.join(
+        ROOT, "supervised-depth-estimation-from-polarized-images_b200")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True).stdout
+    assert "RAISED True" in out
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert "polcue_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_synthetic_generators_are_seeded_per_frame():
+    from polcue import synth
+    a = synth.gen_batch("P", 3, 2, 32, 48)
+    assert np.array_equal(a[1], synth.gen_p_mosaic(4, 32, 48))
+    assert np.array_equal(synth.gen_u_mosaic(7, 32, 48), synth.gen_u_mosaic(7, 32, 48))
+    st = O.stack_quadrants(synth.gen_p_mosaic(0, 64, 96))
+    _, rho, _ = O.iun_and_xolp_closed(st)
+    assert 0.0 <= rho.min() and rho.max() < 0.8        # physically plausible DoLP
+    gt, pred, inst, k = synth.gen_depth_sample(0, 32, 48)
+    assert gt.dtype == np.float32 and set(np.unique(inst)) <= set(range(0, 201, 20)) and k.shape == (3, 3)
+    assert 0.05 < (gt == 0).mean() < 0.15
+
+
+def test_shard_ranges_partition_exactly():
+    from polcue.dist import shard_range
+    for total in (0, 1, 7, 120, 10_000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import numpy as np, torch
+from polcue import dist as D, synth
+from oracle import polcue_oracle as O
+rank, _, world = D.init("gloo")
+n_images = 7
+gt, pred, inst, _ = synth.gen_depth_batch(0, n_images, 32, 48)
+lo, hi = D.shard_range(n_images, rank, world)
+# each rank finalises its own images (here with the oracle standing in for the kernel: host logic only)
+rows, _ = O.depth_errors_per_image(gt[lo:hi], pred[lo:hi], 0.1, 2.0)
+mean = D.mean_over_images(torch.from_numpy(rows))
+pooled = torch.zeros(8, dtype=torch.float64)
+for b in range(lo, hi):
+    m = (gt[b] > 0.1) & (gt[b] < 2.0)
+    pooled += torch.from_numpy(O.depth_error_sums(gt[b][m], np.clip(pred[b][m], 0.1, 2.0)))
+D.all_reduce_sums(pooled)
+t = D.max_over_ranks(float(rank + 1), "cpu")
+if rank == 0:
+    np.save(sys.argv[3], np.concatenate((mean.numpy(), pooled.numpy(), [t])))
+D.barrier()
+"""
+
+
+def test_two_rank_gloo_reduction_matches_single_process(tmp_path):
+    from polcue import synth
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    out = tmp_path / "out.npy"
+    pkg = os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", str(script), pkg, ROOT, str(out)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    got = np.load(out)
+    gt, pred, _, _ = synth.gen_depth_batch(0, 7, 32, 48)
+    rows, mean = O.depth_errors_per_image(gt, pred, 0.1, 2.0)
+    assert np.allclose(got[:7], mean, rtol=1e-12)
+    pooled = np.zeros(8)
+    for b in range(7):
+        m = (gt[b] > 0.1) & (gt[b] < 2.0)
+        pooled += O.depth_error_sums(gt[b][m], np.clip(pred[b][m], 0.1, 2.0))
+    assert np.allclose(got[7:15], pooled, rtol=1e-12)
+    assert got[15] == 2.0

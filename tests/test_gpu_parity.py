@@ -1,0 +1,409 @@
+"""GPU parity tests: every CUDA entry point (through the C ABI) against the CPU oracle and the golden
+reference outputs, with BASELINE.json's tolerances (tests/parity.py)."""
+import numpy as np
+import pytest
+import torch
+
+import parity as P
+from oracle import polcue_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+from polcue import ops, synth  # noqa: E402
+from polcue import _lib  # noqa: E402
+from polcue.compat import (depth as c_depth, layers as c_layers, normals_vec as c_nv,  # noqa: E402
+                           physical_normals_channels as c_ppp, pol_split_and_save as c_split, pre_encoders as c_pre,
+                           xolp as c_xolp, xolp_and_normals as c_xn)
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def check_fused(mosaics, n=1.5, mufu=False):
+    """mosaics: B x H x W uint8 numpy.  Full protocol of SURVEY 8c against the closed-form oracle."""
+    _lib.lib().polcue_debug_set_trig(1 if mufu else 0)
+    try:
+        out = ops.fused_mosaic(dev(mosaics), n, want_iun=True, want_planes=True)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().polcue_debug_set_trig(0)
+    worst = 0.0
+    for b in range(mosaics.shape[0]):
+        stack = O.stack_quadrants(mosaics[b])
+        hs, ws = stack.shape[:2]
+        assert np.array_equal(out["planes"][b].cpu().numpy(), stack.transpose(2, 0, 1)), "split not bit-exact"
+        iun, rho, phi = O.iun_and_xolp_closed(stack)
+        _, degenerate = O.xolp_tie_masks(stack)
+        g_rho = out["xolp"][b, 0].cpu().numpy()
+        g_phi = out["xolp"][b, 1].cpu().numpy()
+        P.assert_dolp_close(out["iun"][b].cpu().numpy(), iun, "Iun")
+        P.assert_dolp_close(g_rho, rho, "rho")
+        P.assert_aolp_close(g_phi, phi)   # closed form vs closed form: no exclusions needed
+        ref = O.get_normals(np.stack((rho, phi))[None], n).reshape(3, 3, hs, ws)
+        got = out["normals"][b].cpu().numpy().reshape(3, 3, hs, ws)
+        worst = max(worst, P.assert_normals_close(got, ref, axis=1))
+        assert np.abs(np.linalg.norm(got, axis=1) - 1.0).max() < 3e-6
+    return worst
+
+
+@pytest.mark.parametrize("mufu", [False, True])
+@pytest.mark.parametrize("kind", ["P", "U"])
+def test_fused_small_batches(kind, mufu):
+    check_fused(synth.gen_batch(kind, 0, 3, 128, 192), mufu=mufu)
+
+
+@pytest.mark.parametrize("shape", [(2, 2), (2, 6), (6, 2), (10, 14), (12, 20), (34, 66), (130, 250)])
+def test_fused_ragged_shapes_exercise_every_vector_width(shape):
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    check_fused(rng.integers(0, 256, (2, h, w), dtype=np.uint8))
+
+
+def test_fused_edge_values():
+    # flat, black, saturated, ties, single-channel pixels
+    vals = np.array([[0, 0, 0, 0], [255, 255, 255, 255], [255, 0, 0, 0], [0, 255, 0, 0], [0, 0, 255, 0], [0, 0, 0, 255],
+                     [1, 0, 0, 0], [0, 0, 1, 1], [10, 20, 30, 40], [200, 100, 0, 100], [100, 100, 0, 0], [5, 5, 9, 5]],
+                    dtype=np.uint8)
+    hs, ws = 4, vals.shape[0]
+    planes = [np.tile(vals[:, k], (hs, 1)) for k in range(4)]
+    check_fused(synth.tile_mosaic(planes)[None])
+
+
+def test_fused_vs_golden_reference_outputs(golden):
+    """Kernel vs the REFERENCE's own outputs (lstsq + scipy), tie pixels handled per SURVEY 8c."""
+    for tag in ("u", "p"):
+        st = golden[f"xolp_{tag}_in"]
+        mosaic = synth.tile_mosaic([st[..., k] for k in range(4)])
+        out = ops.fused_mosaic(dev(mosaic)[None], 1.5, want_iun=True)
+        torch.cuda.synchronize()
+        sign_tie, degenerate = O.xolp_tie_masks(st)
+        P.assert_dolp_close(out["iun"][0].cpu().numpy(), golden[f"xolp_{tag}_iun"], "Iun")
+        P.assert_dolp_close(out["xolp"][0, 0].cpu().numpy(), golden[f"xolp_{tag}_rho"], "rho")
+        P.assert_aolp_close(out["xolp"][0, 1].cpu().numpy(), golden[f"xolp_{tag}_phi"], exclude=degenerate)
+        got = out["normals"][0].cpu().numpy().reshape(3, 3, *st.shape[:2])
+        for k, key in enumerate(("nd", "n1", "n2")):
+            ref = golden[f"chain_{tag}_{key}"].transpose(2, 0, 1)
+            skip = degenerate if key == "n2" else (degenerate & False)
+            P.assert_normals_close(got[k], ref, axis=0, twin_ok=sign_tie | degenerate if key != "n2" else sign_tie, skip=skip,
+                                   what=f"{tag}/{key}")
+        ref_n2z = np.abs(golden[f"chain_{tag}_n2"][..., 2])
+        assert np.abs(np.abs(got[2, 2]) - ref_n2z)[degenerate].max(initial=0) < 1e-3
+
+
+def test_fused_full_frame_properties():
+    """BASELINE full size (2448 x 2048): oracle on a strip + size-independent properties on the whole frame."""
+    mosaic = synth.gen_batch("P", 5, 2)
+    out = ops.fused_mosaic(dev(mosaic), 1.5, want_iun=True, want_planes=True)
+    torch.cuda.synchronize()
+    hs, ws = mosaic.shape[1] // 2, mosaic.shape[2] // 2
+    # re-tiling the planes reproduces the mosaic bit-exactly
+    pl = out["planes"].cpu().numpy()
+    for b in range(2):
+        assert np.array_equal(synth.tile_mosaic(list(pl[b])), mosaic[b])
+    nrm = out["normals"]
+    norms = nrm.view(2, 3, 3, hs, ws).norm(dim=2)
+    assert float((norms - 1).abs().max()) < 3e-6
+    phi = out["xolp"][:, 1]
+    assert float(phi.abs().max()) <= np.pi / 2 + 1e-6
+    # frames are independent: batch result == per-frame result, bit for bit
+    single = ops.fused_mosaic(dev(mosaic[1:2]), 1.5)
+    assert torch.equal(single["normals"][0], nrm[1]) and torch.equal(single["xolp"][0], out["xolp"][1])
+    # oracle on a 64-row strip of frame 0 (rows 480..543 of each quadrant)
+    stack = O.stack_quadrants(mosaic[0])[480:544]
+    iun, rho, phi_ref = O.iun_and_xolp_closed(stack)
+    P.assert_dolp_close(out["xolp"][0, 0, 480:544].cpu().numpy(), rho)
+    P.assert_aolp_close(out["xolp"][0, 1, 480:544].cpu().numpy(), phi_ref)
+    ref = O.get_normals(np.stack((rho, phi_ref))[None], 1.5).reshape(3, 3, 64, ws)
+    P.assert_normals_close(nrm[0, :, 480:544].cpu().numpy().reshape(3, 3, 64, ws), ref, axis=1)
+
+
+def test_fused_without_optional_outputs_and_bad_args():
+    mosaic = dev(synth.gen_u_mosaic(1, 64, 96))[None]
+    full = ops.fused_mosaic(mosaic, 1.5, want_iun=True)
+    lean = ops.fused_mosaic(mosaic, 1.5, want_normals=False)
+    assert set(lean) == {"xolp"} and torch.equal(lean["xolp"], full["xolp"])
+    with pytest.raises(ValueError):
+        ops.fused_mosaic(mosaic[:, :63], 1.5)
+    with pytest.raises(TypeError):
+        ops.fused_mosaic(mosaic.cpu(), 1.5)
+    L = _lib.lib()
+    assert L.polcue_fused_mosaic_u8(None, 1, 64, 96, None, None, None, None, None, None) == _lib.EINVAL
+    assert L.polcue_fused_mosaic_u8(mosaic.data_ptr(), 1, 63, 96, None, None, None, full["xolp"].data_ptr(), None, None) == _lib.EINVAL
+    assert L.polcue_fused_mosaic_u8(mosaic.data_ptr(), 0, 64, 96, None, None, None, full["xolp"].data_ptr(), None, None) == 0
+
+
+def test_fused_host_entry_point_matches_device_entry_point():
+    mosaic = torch.from_numpy(synth.gen_batch("P", 9, 5, 128, 192)).pin_memory()
+    host = ops.fused_mosaic_host(mosaic, 1.5, want_iun=True, chunk_frames=2)   # 3 chunks, ragged tail
+    devo = ops.fused_mosaic(mosaic.cuda(), 1.5, want_iun=True)
+    torch.cuda.synchronize()
+    for key in ("xolp", "normals", "iun"):
+        assert torch.equal(host[key], devo[key].cpu()), key
+    host2 = ops.fused_mosaic_host(mosaic, 1.5, want_iun=True)                  # default chunking
+    assert torch.equal(host2["normals"], host["normals"])
+
+
+# ------------------------------------------------------------------------------------------------
+def test_xolp_stack_u8_and_f32_vs_golden(golden):
+    for tag in ("u", "p"):
+        st = golden[f"xolp_{tag}_in"]
+        iun, rho, phi = c_xolp.Iun_and_xolp(st, O.CANONICAL_ANGLES)
+        assert iun.dtype == np.float64 and iun.shape == st.shape[:2]
+        _, degenerate = O.xolp_tie_masks(st)
+        P.assert_dolp_close(iun, golden[f"xolp_{tag}_iun"], "Iun")
+        P.assert_dolp_close(rho, golden[f"xolp_{tag}_rho"], "rho")
+        P.assert_aolp_close(phi, golden[f"xolp_{tag}_phi"], exclude=degenerate)
+    fl = golden["xolp_f32_in"]
+    iun, rho, phi = c_xolp.Iun_and_xolp(fl, O.CANONICAL_ANGLES)
+    s1, s2 = fl[..., 0] - fl[..., 2], fl[..., 1] - fl[..., 3]
+    P.assert_dolp_close(iun, golden["xolp_f32_iun"], "Iun")
+    P.assert_dolp_close(rho, golden["xolp_f32_rho"], "rho")
+    P.assert_aolp_close(phi, golden["xolp_f32_phi"], exclude=(s1 == 0) & (s2 == 0))
+
+
+def test_xolp_known_answers(golden):
+    iun, rho, phi = c_xolp.Iun_and_xolp(golden["kat_in"][None], O.CANONICAL_ANGLES)
+    _, degenerate = O.xolp_tie_masks(golden["kat_in"][None])
+    P.assert_dolp_close(iun[0], golden["kat_iun"])
+    P.assert_dolp_close(rho[0], golden["kat_rho"])
+    P.assert_aolp_close(phi[0], golden["kat_phi"], exclude=degenerate[0])
+    assert rho[0, 0] == 0.0 and phi[0, 0] == 0.0          # all-zero pixel: the inf/nan scrub of xolp.py:26-29
+
+
+def test_xolp_noncanonical_angles(golden):
+    iun, rho, phi = c_xolp.Iun_and_xolp(golden["xolp_p_in"], golden["xolp_ang2"])
+    P.assert_dolp_close(iun, golden["xolp_ang2_iun"], "Iun")
+    P.assert_dolp_close(rho, golden["xolp_ang2_rho"], "rho")
+    P.assert_aolp_close(phi, golden["xolp_ang2_phi"])
+
+
+def test_xolp_planes_matches_stack_path():
+    planes = synth.gen_p_planes(2, 96, 128)
+    _, x1 = ops.xolp_from_planes(*(dev(p)[None] for p in planes), want_iun=False)
+    iun2, x2 = ops.xolp_from_stack(dev(np.stack(planes, axis=2)), None)
+    iun1, _ = ops.xolp_from_planes(*(dev(p) for p in planes), want_iun=True)
+    assert torch.equal(x1, x2) and torch.equal(iun1, iun2)
+    with pytest.raises(ValueError):
+        c_xolp.Iun_and_xolp(np.zeros((4, 4, 3), np.uint8), O.CANONICAL_ANGLES)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1.3, 1.5, 1.8])
+def test_table_inversions_vs_golden(golden, n):
+    rq = golden["tab_rho"]
+    rho = dev(rq, torch.float32)[None, None]
+    rq32 = rho.cpu().numpy().astype(np.float64).ravel()      # what the kernel actually saw
+    knots = O.sorted_knots(n)
+
+    def slope_at(name, q):
+        xk, yk = knots[name]
+        hi = np.clip(np.searchsorted(xk, q), 1, len(xk) - 1)
+        return np.abs((yk[hi] - yk[hi - 1]) / (xk[hi] - xk[hi - 1]))
+
+    td = c_nv.rho_diffuse(rho, n).cpu().numpy().ravel()
+    t1, t2 = (t.cpu().numpy().ravel() for t in c_nv.rho_spec(rho, n))
+    for name, got, key in (("diffuse", td, "tab_d"), ("spec1", t1, "tab_s1"), ("spec2", t2, "tab_s2")):
+        ref = O.interp_linear_extrap(*knots[name], rq32)
+        # float32 evaluation: 2 ulp of theta plus the float32 spacing of rho times the local slope
+        tol = 4e-7 * (1 + np.abs(ref)) + slope_at(name, rq32) * 1.3e-7 * np.maximum(np.abs(rq32), np.abs(1 - rq32))
+        assert (np.abs(got - ref) <= tol).all(), (name, np.abs(got - ref).max())
+        # and against the reference's own float64 outputs for the float64 queries, where the table is not steep
+        tame = slope_at(name, rq) < 20
+        assert np.abs(got - golden[f"{key}_{n}"])[tame].max() < 5e-6
+
+
+def test_get_normals_vs_golden(golden):
+    for tag in ("u", "p"):
+        x = dev(golden[f"getn_{tag}_x32"])
+        got = c_pre.get_normals(x, 1.5)
+        assert got.shape == (1, 9, 64, 96) and got.dtype == torch.float32
+        ref = golden[f"getn_{tag}_n"]
+        P.assert_normals_close(got.cpu().numpy().reshape(3, 3, 64, 96), ref.reshape(3, 3, 64, 96), axis=1)
+        # composition of the three fine-grained mirrors gives the same normals
+        rho, phi = x[:, 0], x[:, 1]
+        parts = torch.cat((c_nv.calc_normals(phi, c_nv.rho_diffuse(rho, 1.5)),
+                           c_nv.calc_normals(phi + np.pi / 2, c_nv.rho_spec(rho, 1.5)[0]),
+                           c_nv.calc_normals(phi + np.pi / 2, c_nv.rho_spec(rho, 1.5)[1])), dim=1)
+        P.assert_normals_close(parts.cpu().numpy().reshape(3, 3, 64, 96), ref.reshape(3, 3, 64, 96), axis=1)
+
+
+def test_get_normals_odd_sizes_and_extreme_rho():
+    rng = np.random.default_rng(3)
+    x = np.stack((rng.uniform(-0.05, 2.0, (2, 7, 13)), rng.uniform(-np.pi / 2, np.pi / 2, (2, 7, 13))), axis=1).astype(np.float32)
+    got = ops.get_normals(dev(x), 1.5).cpu().numpy()
+    ref = O.get_normals(x, 1.5)
+    P.assert_normals_close(got.reshape(2, 3, 3, 7, 13), ref.reshape(2, 3, 3, 7, 13), axis=2)
+
+
+def test_numpy_chain_mirror(golden):
+    st = golden["xolp_p_in"]
+    mosaic = synth.tile_mosaic([st[..., k] for k in range(4)])
+    iun, rho, phi, nd, n1, n2 = c_xn.process_frame(mosaic, 1.5)
+    sign_tie, degenerate = O.xolp_tie_masks(st)
+    P.assert_dolp_close(rho, golden["xolp_p_rho"])
+    P.assert_normals_close(nd, golden["chain_p_nd"], axis=2, twin_ok=sign_tie | degenerate)
+    P.assert_normals_close(n1, golden["chain_p_n1"], axis=2, twin_ok=sign_tie | degenerate)
+    P.assert_normals_close(n2, golden["chain_p_n2"], axis=2, twin_ok=sign_tie, skip=degenerate)
+    th = c_xn.rho_diffuse(golden["xolp_p_rho"], 1.5)
+    assert th.dtype == np.float64 and np.abs(th - O.rho_diffuse(golden["xolp_p_rho"], 1.5)).max() < 5e-6
+    nn = c_xn.calc_normals(golden["xolp_p_phi"], th)
+    assert nn.shape == st.shape[:2] + (3,)
+    P.assert_normals_close(nn, O.calc_normals_hw3(golden["xolp_p_phi"], th), axis=2)
+
+
+def test_ppp_channel_variant_vs_golden(golden):
+    rho, phi, iun = c_ppp.PolarisationImage_channel(golden["ppp_images"], O.CANONICAL_ANGLES, golden["ppp_mask"])
+    assert np.array_equal(np.isnan(rho), np.isnan(golden["ppp_rho"]))
+    ok = ~np.isnan(golden["ppp_rho"])
+    P.assert_dolp_close(rho[ok], golden["ppp_rho"][ok])
+    P.assert_dolp_close(iun, golden["ppp_iun"])
+    s1 = golden["ppp_images"][..., 0] - golden["ppp_images"][..., 2]
+    s2 = golden["ppp_images"][..., 1] - golden["ppp_images"][..., 3]
+    P.assert_aolp_close(phi, golden["ppp_phi"], exclude=(s1 == 0) & (s2 == 0))
+    mask = golden["ppp_mask"]
+    th_d = c_ppp.rho_diffuse_channel(np.nan_to_num(golden["ppp_rho"]), 1.5)
+    got = c_ppp.calc_normals_channel(golden["ppp_phi"], th_d, mask)
+    ref = O.calc_normals_channel(golden["ppp_phi"], O.rho_diffuse(np.nan_to_num(golden["ppp_rho"]), 1.5), mask)
+    assert np.array_equal(got[~mask], np.zeros_like(got[~mask]))
+    P.assert_normals_close(got[mask], ref[mask], axis=1)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_split_pol_bit_exact(golden):
+    for tag in ("gray", "bgr"):
+        q = c_split.split_pol(golden[f"split_{tag}_in"])
+        for name, arr in zip(("im00", "im10", "im01", "im11"), q):
+            assert np.array_equal(arr, golden[f"split_{tag}_{name}"]), (tag, name)
+    with pytest.raises(ValueError):
+        c_split.split_pol(np.zeros((5, 4), np.uint8))
+    # full-size frame, every copy width (uint8 gray: 1224 % 8 == 0; BGR; float32; odd half-width)
+    rng = np.random.default_rng(0)
+    for shape, dtype in (((2048, 2448), np.uint8), ((64, 96, 3), np.uint8), ((32, 40), np.float32), ((6, 10), np.uint8),
+                         ((6, 14), np.uint16)):
+        img = rng.integers(0, 200, shape).astype(dtype)
+        for got, ref in zip(c_split.split_pol(img), O.split_pol(img)):
+            assert np.array_equal(got, ref)
+    batch = rng.integers(0, 256, (3, 16, 24), dtype=np.uint8)
+    for k, got in enumerate(ops.split_pol_batch(dev(batch))):
+        for b in range(3):
+            assert np.array_equal(got[b].cpu().numpy(), O.split_pol(batch[b])[k])
+
+
+# ------------------------------------------------------------------------------------------------
+def torch_sobel_restatement(depth, K):
+    """float32 torch restatement of kornia's op sequence (pad replicate + conv with sobel/8), for cross-checking."""
+    import torch.nn.functional as F
+    b, _, h, w = depth.shape
+    u = torch.arange(w, device=depth.device, dtype=depth.dtype)[None, None, :].expand(b, h, w)
+    v = torch.arange(h, device=depth.device, dtype=depth.dtype)[None, :, None].expand(b, h, w)
+    fx, fy, cx, cy = K[:, 0, 0, None, None], K[:, 1, 1, None, None], K[:, 0, 2, None, None], K[:, 1, 2, None, None]
+    z = depth[:, 0]
+    xyz = torch.stack(((u - cx) / fx * z, (v - cy) / fy * z, z), 1)
+    kx = torch.tensor([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]], device=depth.device, dtype=depth.dtype) / 8
+    ker = torch.stack((kx, kx.t()))[:, None]
+    g = F.conv2d(F.pad(xyz.reshape(b * 3, 1, h, w), (1, 1, 1, 1), mode="replicate"), ker).view(b, 3, 2, h, w)
+    return F.normalize(torch.cross(g[:, :, 0], g[:, :, 1], dim=1), dim=1, p=2, eps=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(320, 480), (64, 96), (37, 131), (5, 3), (1, 1), (9, 260)])
+def test_depth_to_normals(shape):
+    h, w = shape
+    gt, _, _, k = synth.gen_depth_batch(3, 3, h, w)
+    valid_only = np.where(gt > 0, gt, 0.7).astype(np.float32)          # smooth surface, no invalid holes
+    for depth, tol in ((valid_only, 1e-3), (gt, None)):
+        got = c_depth.depth_to_normals(dev(depth)[:, None], dev(k)).cpu().numpy()
+        ref64 = O.depth_to_normals(depth[:, None], k)
+        if tol is not None:
+            P.assert_normals_close(got, ref64, axis=1, tol=tol)
+        else:
+            # with zero-depth holes the cross product cancels catastrophically at a few pixels in float32:
+            # compare where the float64 normal is well conditioned, and require finite unit-or-zero output everywhere
+            err = P.angular_error(got, ref64, axis=1)
+            assert np.isfinite(got).all()
+            assert np.quantile(err, 0.999) < 2e-3
+        ref32 = torch_sobel_restatement(dev(depth)[:, None], dev(k)).cpu().numpy()
+        err32 = P.angular_error(got, ref32, axis=1)
+        assert np.quantile(err32, 0.999) < 2e-3
+    nrm = np.linalg.norm(got, axis=1)
+    assert ((np.abs(nrm - 1) < 1e-5) | (nrm == 0)).all()
+
+
+def test_depth_to_normals_properties():
+    k = dev(synth.scaled_intrinsics(64, 96)[None].astype(np.float32))
+    flat = torch.full((1, 1, 64, 96), 0.8, device="cuda")
+    n = ops.depth_to_normals(flat, k)
+    assert torch.allclose(n[:, 2], torch.ones_like(n[:, 2]), atol=1e-6) and float(n[:, :2].abs().max()) < 1e-5
+    # invariance to depth scale
+    gt = dev(np.where(synth.gen_depth_batch(0, 1, 64, 96)[0] > 0, 0.9, 0.9).astype(np.float32))[:, None]
+    v = torch.arange(64, device="cuda", dtype=torch.float32)[None, None, :, None]
+    ramp = gt + 0.002 * v
+    a, b2 = ops.depth_to_normals(ramp, k), ops.depth_to_normals(3.0 * ramp, k)
+    assert P.angular_error(a.cpu().numpy(), b2.cpu().numpy(), axis=1).max() < 2e-4
+    with pytest.raises(NotImplementedError):
+        ops.depth_to_normals(ramp.requires_grad_(True), k)
+    with pytest.raises(ValueError):
+        ops.depth_to_normals(ramp.detach()[0], k)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_depth_errors_vs_golden(golden):
+    gt, pred = dev(golden["met_gt"]), dev(golden["met_pred"])
+    got = np.array([float(v) for v in c_layers.compute_depth_errors(gt, pred)])
+    assert np.allclose(got, golden["met_torch"], rtol=2e-5)
+    assert got[4] == golden["met_torch"][4] and got[5] == golden["met_torch"][5] and got[6] == golden["met_torch"][6]
+    got_np = np.array(c_layers.compute_depth_errors_numpy(golden["met_gt"], golden["met_pred"]), dtype=np.float64)
+    assert np.allclose(got_np, golden["met_numpy"], rtol=2e-5)
+
+
+@pytest.mark.parametrize("count", [1, 3, 31, 257, 4099, 1_843_200, 5_000_003])
+def test_depth_error_sums_sizes(count):
+    rng = np.random.default_rng(count)
+    gt = (rng.random(count) * 1.9 + 0.1).astype(np.float32)
+    pred = np.clip(gt * (1 + 0.3 * (rng.random(count) - 0.5)), 0.1, 2.0).astype(np.float32)
+    sums, metrics = ops.depth_error_sums(dev(gt), dev(pred))
+    ref = O.depth_error_sums(gt, pred)
+    s = sums.cpu().numpy()
+    assert np.array_equal(s[:4], ref[:4])                      # integer counts: bit-exact
+    assert np.allclose(s[4:], ref[4:], rtol=3e-6)
+    assert np.allclose(metrics.cpu().numpy(), O.compute_depth_errors(gt, pred), rtol=3e-6)
+    # deterministic: same bits on a second launch (fixed reduction order), also from an unaligned view
+    sums2, _ = ops.depth_error_sums(dev(gt), dev(pred))
+    assert torch.equal(sums, sums2)
+    if count > 8:
+        s3, _ = ops.depth_error_sums(dev(np.concatenate(([1.0], gt)).astype(np.float32))[1:], dev(np.concatenate(([1.0], pred)).astype(np.float32))[1:])
+        assert np.array_equal(s3.cpu().numpy()[:4], ref[:4]) and np.allclose(s3.cpu().numpy()[4:], ref[4:], rtol=3e-6)
+
+
+def test_depth_errors_empty_is_nan():
+    sums, metrics = ops.depth_error_sums(torch.empty(0, device="cuda"), torch.empty(0, device="cuda"))
+    assert float(sums[0]) == 0.0 and torch.isnan(metrics).all()
+
+
+@pytest.mark.parametrize("shape", [(320, 480), (64, 96), (33, 47)])
+def test_depth_errors_per_image(golden, shape):
+    h, w = shape
+    gt, pred, inst, _ = synth.gen_depth_batch(0, 5, h, w)
+    for inst_id in (None, 40, 180, 7):
+        sums, metrics = ops.depth_errors_per_image(dev(gt), dev(pred), 0.1, 2.0, dev(inst) if inst_id is not None else None, inst_id)
+        rows, _ = O.depth_errors_per_image(gt, pred, np.float32(0.1), np.float32(2.0), inst, inst_id)
+        got = metrics.cpu().numpy().astype(np.float64)
+        assert np.array_equal(np.isnan(got), np.isnan(rows))
+        assert np.allclose(got, rows, rtol=5e-6, equal_nan=True)
+        for b in range(5):
+            m = (gt[b] > np.float32(0.1)) & (gt[b] < np.float32(2.0))
+            if inst_id is not None:
+                m &= inst[b] == inst_id
+            assert float(sums[b, 0]) == m.sum()
+    if shape == (64, 96):
+        _, metrics = ops.depth_errors_per_image(dev(gt[:3]), dev(pred[:3]), 0.1, 2.0)
+        assert np.allclose(metrics.cpu().numpy(), golden["met_img_rows"], rtol=2e-5)
+
+
+def test_launch_counter_counts_kernels():
+    before = _lib.launch_count()
+    ops.fused_mosaic(dev(synth.gen_u_mosaic(0, 32, 48))[None], 1.5)
+    assert _lib.launch_count() == before + 1
