@@ -63,44 +63,61 @@ def recorded_traffic():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and clock-event (throttle) reasons of one GPU through NVML while kernels run.
 
-    def __init__(self, index):
-        self.rows, self.proc, self.thread = [], None, None
+    NVML is polled from a thread every ~2 ms (the timed region is only tens of milliseconds long, too short for
+    `nvidia-smi -lms`); `mark()` / `stop()` bracket the timed region so its samples can be told from warm-up ones.
+    """
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+
+    def __init__(self, torch_index):
+        self.samples, self.t_mark, self.running, self.err = [], None, False, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.running = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:      # NVML missing: say so instead of inventing numbers
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.running:
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(get_reasons(self.h))))
+            except Exception as e:
+                self.err = repr(e)
+                return
+            time.sleep(0.002)
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        t_end = time.perf_counter()
+        self.running = False
+        if self.err and not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + self.err]}
+        timed = [s for s in self.samples if self.t_mark is not None and self.t_mark <= s[0] <= t_end]
+        use = timed if len(timed) >= 3 else self.samples      # warm-up samples run the same kernel back to back
+        bits = 0
+        for s in use:
+            bits |= s[2]
+        return {"sm_mhz": statistics.median(s[1] for s in use) if use else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(name for bit, name in self.REASONS.items() if bits & bit),
+                "samples": len(use), "samples_in_timed_region": len(timed)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -194,11 +211,18 @@ def run_polcue_arm(args, rank, local_rank, world):
     def step():
         ops.fused_mosaic(mosaic, 1.5, out=out)
 
-    for _ in range(max(args.warmup, 3)):
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_warm = time.perf_counter()
+    done = 0
+    while done < max(args.warmup, 3) or time.perf_counter() - t_warm < args.warmup_seconds:   # clocks settle under load
         step()
+        done += 1
+        if done % 16 == 0:
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
     D.barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     launches0 = _lib.launch_count()
     events = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize()
@@ -213,6 +237,31 @@ def run_polcue_arm(args, rank, local_rank, world):
     per_launch_ms = [events[i].elapsed_time(events[i + 1]) for i in range(args.steps)]
     ms_per_step = D.max_over_ranks(total_ms / args.steps, dev)
     clocks = sampler.stop() if sampler else None
+
+    # ---- the same step after `--sustained-seconds` of continuous load (clocks under the 1 kW power cap) ----
+    sustained = None
+    if args.sustained_seconds > 0:
+        s_sampler = ClockSampler(local_rank) if rank == 0 else None
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < args.sustained_seconds:
+            step()
+            n += 1
+            if n % 16 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        D.barrier()
+        if s_sampler:
+            s_sampler.mark()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(args.steps):
+            step()
+        ev[1].record()
+        torch.cuda.synchronize()
+        s_ms = D.max_over_ranks(ev[0].elapsed_time(ev[1]) / args.steps, dev)
+        sustained = {"ms_per_step": s_ms, "value": world * B * MPIX_PER_FRAME / (s_ms * 1e-3), "unit": "Mpix/s",
+                     "after_seconds_of_load": args.sustained_seconds, "clocks": s_sampler.stop() if s_sampler else None}
 
     # output checksum: the one collective of the sequence benchmark
     chk = torch.stack((out["xolp"].double().sum(), out["normals"].double().sum()))
@@ -258,6 +307,7 @@ def run_polcue_arm(args, rank, local_rank, world):
                 "matches_device_path": same},
         "gpu_launches": launches,
         "clocks": clocks,
+        "sustained": sustained,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -277,8 +327,12 @@ def main():
     ap.add_argument("--impl", choices=("polcue", "reference"), default="polcue")
     ap.add_argument("--frames", type=int, default=64, help="frames per GPU per step (BASELINE configs[1]: 64)")
     ap.add_argument("--gen", choices=("P", "U"), default="P", help="synthetic generator: physical (P) or uniform stress (U)")
-    ap.add_argument("--trig", choices=("poly", "mufu"), default="poly")
+    ap.add_argument("--trig", choices=("poly", "mufu"), default="mufu")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--warmup-seconds", type=float, default=0.0,
+                    help="extra warm-up time before the timed region (0: exactly --warmup steps, like the peak measurement)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0,
+                    help="also report ms/step after this long under continuous load (power-capped clocks); 0 disables")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -44,7 +44,7 @@ typedef struct polcue_lut polcue_lut; /* opaque: zenith-angle lookup tables for 
 
 POLCUE_API const char* polcue_version(void);
 POLCUE_API const char* polcue_error_string(int code);
-/* Tuning knob: 0 = polynomial sincos (1.4e-7 abs, default), 1 = MUFU sin/cos (3.6e-7 abs). */
+/* Tuning knob for the zenith-angle sincos: 1 = MUFU sin/cos (3.6e-7 abs, default), 0 = polynomial (1.4e-7 abs). */
 POLCUE_API int polcue_debug_set_trig(int mufu);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 POLCUE_API unsigned long long polcue_launch_count(void);

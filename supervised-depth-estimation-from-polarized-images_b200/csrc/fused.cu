@@ -45,7 +45,6 @@ struct LutArgs {
     uint32_t bytes;
     int offset[3];
     float scale[3];
-    int last[3];
 };
 
 LutArgs lut_args(const polcue_lut* lut) {
@@ -55,9 +54,19 @@ LutArgs lut_args(const polcue_lut* lut) {
     for (int t = 0; t < 3; ++t) {
         a.offset[t] = lut->offset[t];
         a.scale[t] = lut->scale[t];
-        a.last[t] = lut->cells[t] - 1;
     }
     return a;
+}
+
+__device__ __forceinline__ LutShared lut_shared(const void* smem_base, const LutArgs& a) {
+    LutShared v;
+    for (int t = 0; t < 3; ++t) {
+        uint32_t addr = smem_u32(smem_base) + 16u * (uint32_t)a.offset[t];
+        asm volatile("" : "+r"(addr));   // keep the three table bases as values: lookup = one LEA, not add + LEA
+        v.addr[t] = addr;
+        v.scale[t] = a.scale[t];
+    }
+    return v;
 }
 
 __device__ __forceinline__ LutView lut_view(const float4* base, const LutArgs& a) {
@@ -65,7 +74,6 @@ __device__ __forceinline__ LutView lut_view(const float4* base, const LutArgs& a
     for (int t = 0; t < 3; ++t) {
         v.cells[t] = base + a.offset[t];
         v.scale[t] = a.scale[t];
-        v.last[t] = a.last[t];
     }
     return v;
 }
@@ -83,9 +91,10 @@ struct FusedParams {
     uint32_t groups_total;   // B * Hs * (Ws / VEC)
     FastDiv groups_per_frame, groups_per_row;
     uint32_t W, Ws;
-    size_t frame_bytes;      // H * W
-    size_t quad_down;        // Hs * W : byte offset from a top quadrant to the one below it
-    size_t plane;            // Hs * Ws
+    uint32_t frame_bytes;    // H * W                                   (all strides < 2^32, checked on the host)
+    uint32_t quad_down;      // Hs * W : byte offset from a top quadrant to the one below it
+    uint32_t plane;          // Hs * Ws
+    uint32_t plane_bytes;    // 4 * Hs * Ws
 };
 
 template <int VEC>
@@ -110,29 +119,33 @@ template <int VEC, bool MUFU>
 __global__ void __launch_bounds__(kFusedThreads, 2) fused_mosaic_kernel(const FusedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
-    const float4* s_lut = reinterpret_cast<const float4*>(smem_raw);
+    __shared__ __align__(16) uint4 clc_resp;
+    __shared__ uint64_t clc_bar;
     const bool want_normals = p.normals != nullptr;
-    if (want_normals) {
-        lut_stage_begin(smem_raw, p.lut.blob, p.lut.bytes, &bar);
-        lut_stage_wait(&bar);
-    }
-    const LutView lut = lut_view(s_lut, p.lut);
+    if (want_normals) lut_stage_begin(smem_raw, p.lut.blob, p.lut.bytes, &bar);
+    ClcTiles clc;
+    clc.init(&clc_resp, &clc_bar);
+    if (want_normals) lut_stage_wait(&bar);
+    const LutShared lut = lut_shared(smem_raw, p.lut);
     using PK = Packed<VEC>;
 
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < p.groups_total; gid += stride) {
+    // one tile = one group of VEC pixels per thread; tiles arrive in order through cluster launch control
+    for (uint32_t tile = blockIdx.x;;) {
+        clc.prefetch();
+        const uint32_t gid = tile * kFusedThreads + threadIdx.x;
+        if (gid < p.groups_total) {
         const uint32_t b = fastdiv(gid, p.groups_per_frame);
         const uint32_t rem = gid - b * p.groups_per_frame.div;   // group index inside the frame
         const uint32_t y = fastdiv(rem, p.groups_per_row);
         const uint32_t xg = rem - y * p.groups_per_row.div;
 
-        const uint8_t* src = p.mosaic + (size_t)b * p.frame_bytes + (size_t)y * p.W + (size_t)xg * VEC;
+        const uint8_t* src = p.mosaic + ((size_t)b * p.frame_bytes + (y * p.W + xg * VEC));
         const typename PK::type w0 = PK::load(src);                     // TL:   0 deg
         const typename PK::type w45 = PK::load(src + p.Ws);             // TR:  45 deg
         const typename PK::type w90 = PK::load(src + p.quad_down);      // BL:  90 deg
         const typename PK::type w135 = PK::load(src + p.quad_down + p.Ws);  // BR: 135 deg
 
-        const size_t pix = (size_t)rem * VEC;   // first pixel inside the Hs x Ws plane (Ws = groups_per_row * VEC)
+        const uint32_t pix = rem * VEC;   // first pixel inside the Hs x Ws plane (Ws = groups_per_row * VEC)
 
         if (p.planes) {
             typename PK::type* dst = reinterpret_cast<typename PK::type*>(p.planes + (size_t)b * 4 * p.plane + pix);
@@ -143,37 +156,47 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_mosaic_kernel(const Fu
             dst[3 * ps] = w135;
         }
 
-        float rho[VEC], phi[VEC], iun[VEC];
+        float rho[VEC], phi[VEC], iun[VEC], sp[VEC], cp[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            const Cues q = cues_from_u8((w0 >> (8 * j)) & 0xff, (w45 >> (8 * j)) & 0xff, (w90 >> (8 * j)) & 0xff,
-                                        (w135 >> (8 * j)) & 0xff);
+            const Cues q = cues_from_u8(byte_to_float(w0, j), byte_to_float(w45, j), byte_to_float(w90, j), byte_to_float(w135, j));
             rho[j] = q.rho;
             phi[j] = q.phi;
             iun[j] = q.iun;
+            sp[j] = q.sin_phi;
+            cp[j] = q.cos_phi;
         }
-        float* xo = p.xolp + (size_t)b * 2 * p.plane + pix;
+        // plane pointers advance by a 32-bit stride: one IMAD.WIDE.U32 (fma pipe) per store address
+        float* xo = p.xolp + ((size_t)(2 * b) * p.plane + pix);
+        asm volatile("" : "+l"(xo));   // a pointer VALUE (not base + 64-bit index): the stride add stays one IMAD.WIDE
         st_stream_vec<VEC>(xo, rho);
-        st_stream_vec<VEC>(xo + p.plane, phi);
-        if (p.iun) st_stream_vec<VEC>(p.iun + (size_t)b * p.plane + pix, iun);
+        xo += p.plane;
+        st_stream_vec<VEC>(xo, phi);
+        if (p.iun) st_stream_vec<VEC>(p.iun + ((size_t)b * p.plane + pix), iun);
 
         if (want_normals) {
             float nrm[9][VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 float n9[9];
-                normals_from_cues<MUFU>(lut, rho[j], phi[j], n9);
+                normals_from_trig<MUFU>(lut, rho[j], sp[j], cp[j], n9);
 #pragma unroll
                 for (int c = 0; c < 9; ++c) nrm[c][j] = n9[c];
             }
-            float* no = p.normals + (size_t)b * 9 * p.plane + pix;
+            float* no = p.normals + ((size_t)(9 * b) * p.plane + pix);
+            asm volatile("" : "+l"(no));
 #pragma unroll
-            for (int c = 0; c < 9; ++c) st_stream_vec<VEC>(no + (size_t)c * p.plane, nrm[c]);
+            for (int c = 0; c < 9; ++c) {
+                st_stream_vec<VEC>(no, nrm[c]);
+                no += p.plane;
+            }
         }
+        }
+        if (!clc.next(tile)) break;
     }
 }
 
-int g_trig_mufu = 0;  // 0: polynomial sincos (1.4e-7), 1: MUFU sin/cos (3.6e-7).  Tuning knob, see DESIGN.md.
+int g_trig_mufu = 1;  // zenith-angle sincos: 1 = MUFU sin/cos (3.6e-7 abs, default), 0 = polynomial (1.4e-7).  DESIGN.md 5.
 
 template <int VEC>
 int launch_fused(const FusedParams& p, size_t smem, cudaStream_t stream) {
@@ -184,10 +207,8 @@ int launch_fused(const FusedParams& p, size_t smem, cudaStream_t stream) {
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) return POLCUE_ERANGE;
-    const uint32_t want = (p.groups_total + kFusedThreads - 1) / kFusedThreads;
-    const uint32_t resident = (uint32_t)(per_sm * device_info().sms);
-    const uint32_t grid = want < resident ? want : resident;
-    kern<<<grid, kFusedThreads, smem, stream>>>(p);
+    const uint32_t tiles = (p.groups_total + kFusedThreads - 1) / kFusedThreads;   // one CTA per tile (see ClcTiles)
+    kern<<<tiles, kFusedThreads, smem, stream>>>(p);
     return launch_status();
 }
 
@@ -258,7 +279,7 @@ __global__ void __launch_bounds__(256) xolp_stack_kernel(const T* __restrict__ s
         load_stack_px<T>(stack, i, v, iv);
         Cues q;
         if constexpr (GENERAL) q = cues_general(v, pv);
-        else if constexpr (sizeof(T) == 1) q = cues_from_u8(iv[0], iv[1], iv[2], iv[3]);
+        else if constexpr (sizeof(T) == 1) q = cues_from_u8(v[0], v[1], v[2], v[3]);
         else q = cues_canonical_f32(v);
         const size_t b = i / hw, r = i - b * hw;
         float* xo = xolp + b * 2 * hw + r;
@@ -274,7 +295,8 @@ __global__ void __launch_bounds__(256) xolp_planes_kernel(const uint8_t* __restr
                                                            float* __restrict__ xolp) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const Cues q = cues_from_u8(ld_stream_u8(i0 + i), ld_stream_u8(i45 + i), ld_stream_u8(i90 + i), ld_stream_u8(i135 + i));
+        const Cues q = cues_from_u8((float)ld_stream_u8(i0 + i), (float)ld_stream_u8(i45 + i), (float)ld_stream_u8(i90 + i),
+                                    (float)ld_stream_u8(i135 + i));
         const size_t b = i / hw, r = i - b * hw;
         float* xo = xolp + b * 2 * hw + r;
         st_stream_f32(xo, q.rho);
@@ -299,11 +321,17 @@ template <int VEC, bool MUFU>
 __global__ void __launch_bounds__(kFusedThreads, 2) normals_from_xolp_kernel(const NormalsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
+    __shared__ __align__(16) uint4 clc_resp;
+    __shared__ uint64_t clc_bar;
     lut_stage_begin(smem_raw, p.lut.blob, p.lut.bytes, &bar);
+    ClcTiles clc;
+    clc.init(&clc_resp, &clc_bar);
     lut_stage_wait(&bar);
-    const LutView lut = lut_view(reinterpret_cast<const float4*>(smem_raw), p.lut);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < p.groups_total; gid += stride) {
+    const LutShared lut = lut_shared(smem_raw, p.lut);
+    for (uint32_t tile = blockIdx.x;;) {
+        clc.prefetch();
+        const uint32_t gid = tile * kFusedThreads + threadIdx.x;
+        if (gid < p.groups_total) {
         const uint32_t b = fastdiv(gid, p.groups_per_image);
         const size_t pix = (size_t)(gid - b * p.groups_per_image.div) * VEC;
         const float* xi = p.xolp + (size_t)b * 2 * p.hw + pix;
@@ -330,6 +358,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) normals_from_xolp_kernel(con
         float* no = p.normals + (size_t)b * 9 * p.hw + pix;
 #pragma unroll
         for (int c = 0; c < 9; ++c) st_stream_vec<VEC>(no + (size_t)c * p.hw, nrm[c]);
+        }
+        if (!clc.next(tile)) break;
     }
 }
 
@@ -343,10 +373,10 @@ __global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ rh
         const float r = ld_stream_f32(rho + i);
         const float g = lut_coord(r);
         if constexpr (WHICH == 0) {
-            st_stream_f32(out0 + i, lut_eval(lut.cells[0], lut.scale[0], lut.last[0], r, g));
+            st_stream_f32(out0 + i, lut_eval(lut.cells[0], lut.scale[0], r, g));
         } else {
-            st_stream_f32(out0 + i, lut_eval(lut.cells[1], lut.scale[1], lut.last[1], r, g));
-            st_stream_f32(out1 + i, lut_eval(lut.cells[2], lut.scale[2], lut.last[2], r, g));
+            st_stream_f32(out0 + i, lut_eval(lut.cells[1], lut.scale[1], r, g));
+            st_stream_f32(out1 + i, lut_eval(lut.cells[2], lut.scale[2], r, g));
         }
     }
 }
@@ -449,9 +479,11 @@ int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W, const pol
     make_fastdiv(p.groups_per_row.div, p.groups_per_row.mul, p.groups_per_row.shift);
     p.W = (uint32_t)W;
     p.Ws = (uint32_t)Ws;
-    p.frame_bytes = (size_t)H * W;
-    p.quad_down = (size_t)Hs * W;
-    p.plane = (size_t)Hs * Ws;
+    if ((unsigned long long)H * W >= (1ull << 30)) return POLCUE_E2BIG;   // 32-bit strides inside the kernel
+    p.frame_bytes = (uint32_t)H * (uint32_t)W;
+    p.quad_down = (uint32_t)Hs * (uint32_t)W;
+    p.plane = (uint32_t)Hs * (uint32_t)Ws;
+    p.plane_bytes = 4u * p.plane;
     const size_t smem = normals ? lut->bytes() : 0;
     cudaStream_t s = (cudaStream_t)stream;
     switch (vec) {
@@ -527,9 +559,8 @@ int polcue_normals_from_xolp_f32(const float* xolp, int B, int H, int W, const p
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFusedThreads, smem);
         if (e != cudaSuccess) return (int)e;
         if (per_sm < 1) return POLCUE_ERANGE;
-        const uint32_t want = (p.groups_total + kFusedThreads - 1) / kFusedThreads;
-        const uint32_t resident = (uint32_t)(per_sm * device_info().sms);
-        kern<<<want < resident ? want : resident, kFusedThreads, smem, (cudaStream_t)stream>>>(p);
+        const uint32_t tiles = (p.groups_total + kFusedThreads - 1) / kFusedThreads;
+        kern<<<tiles, kFusedThreads, smem, (cudaStream_t)stream>>>(p);
         return launch_status();
     };
     if (vec == 4) return g_trig_mufu ? launch(normals_from_xolp_kernel<4, true>) : launch(normals_from_xolp_kernel<4, false>);

@@ -182,11 +182,13 @@ int build_host(double n, polcue_lut** out) {
         lut->cells[t] = chosen;
         lut->offset[t] = total;
         lut->scale[t] = (float)(chosen / kSqrt2);
-        total += chosen;
+        total += chosen + 1;   // + guard cell: float32 g * scale can land exactly on `chosen`
         lut->blob.resize(total);
-        for (int c = 0; c < chosen; ++c)
-            lut->blob[lut->offset[t] + c] =
-                make_float4((float)cells[c].x, (float)cells[c].y, (float)cells[c].sl, (float)cells[c].sr);
+        for (int c = 0; c <= chosen; ++c) {
+            const CellD& e = cells[c < chosen ? c : chosen - 1];
+            // device form: theta = y + d * sl + max(d, 0) * (sr - sl),  d = rho - x
+            lut->blob[lut->offset[t] + c] = make_float4((float)e.x, (float)e.y, (float)e.sl, (float)(e.sr - e.sl));
+        }
         lut->kx[t] = tab[t].x;
         lut->ky[t] = tab[t].y;
     }
@@ -247,17 +249,15 @@ int polcue_lut_eval_host(const polcue_lut* lut, int table, const float* rho, siz
     if (!lut || table < 0 || table > 2 || (!rho && count) || (!theta && count)) return POLCUE_EINVAL;
     const float4* cells = lut->blob.data() + lut->offset[table];
     const float scale = lut->scale[table];
-    const int last = lut->cells[table] - 1;
     for (size_t i = 0; i < count; ++i) {  // float32 arithmetic mirroring polcue::lut_coord / lut_eval
         const float r = rho[i];
         const bool low = r < 0.5f;
         const float t = fmaxf(low ? r : 1.0f - r, 0.0f);
         float g = sqrtf(t);
         g = low ? g : 1.41421356237309504880f - g;
-        const int c = std::min((int)(g * scale), last);
-        const float4 e = cells[c];
+        const float4 e = cells[(int)(g * scale)];
         const float d = r - e.x;
-        theta[i] = fmaf(d, (d <= 0.0f) ? e.z : e.w, e.y);
+        theta[i] = fmaf(fmaxf(d, 0.0f), e.w, fmaf(d, e.z, e.y));
     }
     return POLCUE_OK;
 }

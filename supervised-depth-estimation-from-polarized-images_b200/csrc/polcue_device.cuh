@@ -21,6 +21,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -64,6 +69,24 @@ __device__ __forceinline__ void st_stream_f32x2(float* p, float a, float b) {
 }
 __device__ __forceinline__ void st_stream_f32x4(float* p, float a, float b, float c, float d) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// base + a * b with a 32x32 -> 64-bit multiply-add: ONE fma-pipe instruction (IMAD.WIDE.U32) instead of the
+// IADD3 / IADD3.X pairs (two alu-pipe instructions, the busier pipe here) a 64-bit pointer add compiles to.
+__device__ __forceinline__ float* ptr_mad(float* base, uint32_t a, uint32_t b) {
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<float*>(r);
+}
+__device__ __forceinline__ const uint8_t* ptr_mad(const uint8_t* base, uint32_t a, uint32_t b) {
+    uint64_t r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(reinterpret_cast<uint64_t>(base)));
+    return reinterpret_cast<const uint8_t*>(r);
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t shared_addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(shared_addr));
+    return v;
 }
 
 // Vector store of V consecutive floats (V in {1,2,4}); p is V*4-byte aligned.
@@ -120,17 +143,17 @@ __device__ __forceinline__ void sincos_core(float r, float& s, float& c) {
 }
 
 __device__ __forceinline__ void sincos_poly(float x, float& s, float& c) {
-    float r = x;
-    int q = 0;
-    if (fabsf(x) > 1.6f) {  // rare: only extrapolated zenith angles
-        const float k = rintf(x * 0.636619772367581343f);
-        r = fmaf(k, -1.57079601e+00f, x);
-        r = fmaf(k, -3.13916473e-07f, r);
-        r = fmaf(k, -5.39030253e-15f, r);
-        q = (int)k;
+    if (fabsf(x) <= 1.6f) {  // every in-table zenith angle and every AoLP: no reduction, no quadrant fix-up
+        sincos_core(x, s, c);
+        return;
     }
+    const float k = rintf(x * 0.636619772367581343f);  // rare: extrapolated zenith angles only
+    float r = fmaf(k, -1.57079601e+00f, x);
+    r = fmaf(k, -3.13916473e-07f, r);
+    r = fmaf(k, -5.39030253e-15f, r);
     float ss, cc;
     sincos_core(r, ss, cc);
+    const int q = (int)k;
     const float s1 = (q & 1) ? cc : ss;
     const float c1 = (q & 1) ? ss : cc;
     s = (q & 2) ? -s1 : s1;
@@ -167,7 +190,6 @@ __device__ __forceinline__ void sincos_sel(float x, float& s, float& c) {
 struct LutView {
     const float4* cells[3];  // diffuse, spec1, spec2 (shared memory in the hot kernels)
     float scale[3];          // cells per unit g
-    int last[3];             // cell count - 1
 };
 
 __device__ __forceinline__ float lut_coord(float rho) {
@@ -177,11 +199,22 @@ __device__ __forceinline__ float lut_coord(float rho) {
     return low ? g : kSqrt2 - g;
 }
 
-__device__ __forceinline__ float lut_eval(const float4* __restrict__ cells, float scale, int last, float rho, float g) {
-    const int c = min((int)(g * scale), last);
-    const float4 e = cells[c];
+// cell = (x_k, y_k, slope_left, slope_right - slope_left); a guard cell past the end absorbs g * scale == cells.
+__device__ __forceinline__ float lut_line(const float4 e, float rho) {
     const float d = rho - e.x;
-    return fmaf(d, (d <= 0.0f) ? e.z : e.w, e.y);
+    return fmaf(fmaxf(d, 0.0f), e.w, fmaf(d, e.z, e.y));
+}
+__device__ __forceinline__ float lut_eval(const float4* __restrict__ cells, float scale, float rho, float g) {
+    return lut_line(cells[(int)(g * scale)], rho);
+}
+
+// Shared-memory tables addressed by 32-bit shared-window addresses (one IMAD per lookup).
+struct LutShared {
+    uint32_t addr[3];
+    float scale[3];
+};
+__device__ __forceinline__ float lut_eval_shared(const LutShared& lut, int t, float rho, float g) {
+    return lut_line(lds_f32x4(lut.addr[t] + 16u * (uint32_t)(int)(g * lut.scale[t])), rho);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -189,19 +222,44 @@ __device__ __forceinline__ float lut_eval(const float4* __restrict__ cells, floa
 // ------------------------------------------------------------------------------------------
 struct Cues {
     float iun, rho, phi;
+    float sin_phi, cos_phi;  // filled by cues_from_u8 only
 };
 
-// Canonical angles, integer samples: polarisation/xolp.py:8-34 in closed form.
+// atan on [0,1]: a + a s P7(s), s = a^2; max abs error 1.2e-7.
+__device__ __forceinline__ float atan_unit(float a, float s) {
+    float p = 0.004059889819473028f;
+    p = fmaf(p, s, -0.020706569775938988f);
+    p = fmaf(p, s, 0.049855392426252365f);
+    p = fmaf(p, s, -0.08074377477169037f);
+    p = fmaf(p, s, 0.10888639092445374f);
+    p = fmaf(p, s, -0.142609104514122f);
+    p = fmaf(p, s, 0.19998927414417267f);
+    p = fmaf(p, s, -0.33333325386047363f);
+    return fmaf(a * s, p, a);
+}
+
+// Canonical angles, 8-bit samples already widened to float (exact): polarisation/xolp.py:8-34 in closed form.
 //   x0 = (I0+I45+I90+I135)/4, x1 = (I0-I90)/2, x2 = (I45-I135)/2
 //   rho = sqrt(x1^2+x2^2)/x0 (x0 == 0 -> 0, the inf/nan scrub of xolp.py:26-29), phi = atan2(x2,x1)/2
-__device__ __forceinline__ Cues cues_from_u8(int i0, int i45, int i90, int i135) {
-    const int s1 = i0 - i90, s2 = i45 - i135, sum = i0 + i45 + i90 + i135;
-    const float fs1 = (float)s1, fs2 = (float)s2, fsum = (float)sum;
-    const float amp = sqrt_approx((float)(s1 * s1 + s2 * s2));  // exact integer under the root
+// The half angle is taken algebraically: with r = |(s1,s2)|, u = |s2| / (r + |s1|) = tan(phi'), phi' in
+// [0, pi/4], so atan needs no octant swap and cos/sin(phi) come from one rsqrt:
+//   s1 >= 0: |phi| = phi'           (cos, sin) = (c', s')        c' = rsqrt(1+u^2), s' = u c'
+//   s1 <  0: |phi| = pi/2 - phi'    (cos, sin) = (s', c')        sign(phi) = sign(s2), s2 = +0 -> +
+// Ties resolve as exact arithmetic does: s1 = s2 = 0 -> phi = 0; s2 = 0, s1 < 0 -> phi = +pi/2.
+__device__ __forceinline__ Cues cues_from_u8(float i0, float i45, float i90, float i135) {
+    const float s1 = i0 - i90, s2 = i45 - i135, sum = (i0 + i90) + (i45 + i135);
+    const float amp = sqrt_approx(fmaf(s1, s1, s2 * s2));   // integer < 2^24 under the root: exact
     Cues q;
-    q.iun = 0.25f * fsum;
-    q.rho = (sum == 0) ? 0.0f : (2.0f * amp) * rcp_approx(fsum);
-    q.phi = 0.5f * atan2_poly(fs2, fs1);
+    q.iun = 0.25f * sum;
+    q.rho = (2.0f * amp) * rcp_approx(sum + 1e-30f);        // sum >= 1 unless every sample is 0 (then amp = 0)
+    const float u = fabsf(s2) * rcp_approx((amp + fabsf(s1)) + 1e-30f);
+    const float t = u * u;
+    const float half = atan_unit(u, t);
+    const float cq = rsqrt_approx(1.0f + t), sq = u * cq;
+    const bool flip = s1 < 0.0f;
+    q.phi = copysignf(flip ? kHalfPi - half : half, s2);
+    q.cos_phi = flip ? sq : cq;
+    q.sin_phi = copysignf(flip ? cq : sq, s2);
     return q;
 }
 
@@ -209,13 +267,11 @@ __device__ __forceinline__ Cues cues_from_u8(int i0, int i45, int i90, int i135)
 //   N_diff = (cos phi sin td, sin phi sin td, cos td)
 //   N_spec = (cos(phi+pi/2) sin ts, sin(phi+pi/2) sin ts, cos ts) = (-sin phi sin ts, cos phi sin ts, cos ts)
 template <bool kMufu>
-__device__ __forceinline__ void normals_from_cues(const LutView& lut, float rho, float phi, float (&n)[9]) {
-    float sp, cp;
-    sincos_sel<kMufu>(phi, sp, cp);
+__device__ __forceinline__ void normals_from_trig(const LutShared& lut, float rho, float sp, float cp, float (&n)[9]) {
     const float g = lut_coord(rho);
-    const float td = lut_eval(lut.cells[0], lut.scale[0], lut.last[0], rho, g);
-    const float t1 = lut_eval(lut.cells[1], lut.scale[1], lut.last[1], rho, g);
-    const float t2 = lut_eval(lut.cells[2], lut.scale[2], lut.last[2], rho, g);
+    const float td = lut_eval_shared(lut, 0, rho, g);
+    const float t1 = lut_eval_shared(lut, 1, rho, g);
+    const float t2 = lut_eval_shared(lut, 2, rho, g);
     float s, c;
     sincos_sel<kMufu>(td, s, c);
     n[0] = cp * s; n[1] = sp * s; n[2] = c;
@@ -223,6 +279,18 @@ __device__ __forceinline__ void normals_from_cues(const LutView& lut, float rho,
     n[3] = -sp * s; n[4] = cp * s; n[5] = c;
     sincos_sel<kMufu>(t2, s, c);
     n[6] = -sp * s; n[7] = cp * s; n[8] = c;
+}
+
+template <bool kMufu>
+__device__ __forceinline__ void normals_from_cues(const LutShared& lut, float rho, float phi, float (&n)[9]) {
+    float sp, cp;
+    sincos_sel<kMufu>(phi, sp, cp);
+    normals_from_trig<kMufu>(lut, rho, sp, cp, n);
+}
+
+// byte k of a packed word as float, exactly: PRMT builds 0x4B0000bb = 2^23 + bb, one FADD removes 2^23.
+__device__ __forceinline__ float byte_to_float(uint32_t w, int k) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + k)) - 8388608.0f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -255,6 +323,72 @@ __device__ __forceinline__ void lut_stage_wait(uint64_t* bar) {
             : "memory");
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// Dynamic tile scheduling with Cluster Launch Control (sm_100).  The grid has one CTA per tile; only as many
+// CTAs as fit are resident.  A resident CTA that finishes a tile asks the hardware work distributor to CANCEL a
+// still-pending CTA of the same grid and takes over its blockIdx, so tiles are handed out in order to
+// whichever SM is free: no global counter, no host-side reset, table staging paid once per resident CTA.
+// On the two-die B200 this matters: under HBM saturation SMs do not all get the same bandwidth, and a static
+// grid-stride split finishes with its slowest SM (measured 0.73 ms static vs 0.60 ms dynamic for this kernel's
+// access pattern, tools/hbm_probe.cu).
+// Usage (all threads):  ClcTiles clc; clc.init();  for (tile = blockIdx.x;;) { clc.prefetch(); work(tile);
+//                        if (!clc.next(tile)) break; }
+// ------------------------------------------------------------------------------------------
+struct ClcTiles {
+    uint4* resp;       // 16-byte response slot (shared)
+    uint64_t* bar;     // mbarrier (shared)
+    uint32_t phase;
+
+    __device__ __forceinline__ void init(uint4* resp_slot, uint64_t* barrier) {
+        resp = resp_slot;
+        bar = barrier;
+        phase = 0;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    // ask for the next tile while the current one is being processed
+    __device__ __forceinline__ void prefetch() {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 16;" ::"r"(smem_u32(bar)) : "memory");
+            asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
+                             smem_u32(resp)),
+                         "r"(smem_u32(bar))
+                         : "memory");
+        }
+    }
+    // false when no pending CTA was left to cancel (this CTA is done)
+    __device__ __forceinline__ bool next(uint32_t& tile) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(smem_u32(bar)), "r"(phase)
+                : "memory");
+        }
+        phase ^= 1;
+        uint32_t valid, first;
+        asm volatile(
+            "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+            "ld.shared.b128 r, [%2];\n\t"
+            "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+            "selp.u32 %1, 1, 0, p1;\n\t"
+            "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t}"
+            : "=r"(first), "=r"(valid)
+            : "r"(smem_u32(resp))
+            : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();  // every thread has read the response before thread 0 re-arms the slot
+        tile = first;
+        return valid != 0;
+    }
+};
 
 // Exact unsigned division by a runtime constant (d >= 1, n < 2^31): q = (n * mul) >> 32 >> shift.
 struct FastDiv {

@@ -82,9 +82,11 @@ __global__ void __launch_bounds__(kStencilThreads) depth_to_normals_kernel(const
             gu[comp] = 0.125f * ((v[0][2] - v[0][0]) + 2.0f * (v[1][2] - v[1][0]) + (v[2][2] - v[2][0]));
             gv[comp] = 0.125f * ((v[2][0] - v[0][0]) + 2.0f * (v[2][1] - v[0][1]) + (v[2][2] - v[0][2]));
         }
-        const float nx = gu[1] * gv[2] - gu[2] * gv[1];
-        const float ny = gu[2] * gv[0] - gu[0] * gv[2];
-        const float nz = gu[0] * gv[1] - gu[1] * gv[0];
+        // products rounded separately (no FMA contraction): parallel gradients next to zero-depth holes then cancel
+        // to an exact zero vector, as they do in the reference's torch.cross, instead of leaving round-off
+        const float nx = __fsub_rn(__fmul_rn(gu[1], gv[2]), __fmul_rn(gu[2], gv[1]));
+        const float ny = __fsub_rn(__fmul_rn(gu[2], gv[0]), __fmul_rn(gu[0], gv[2]));
+        const float nz = __fsub_rn(__fmul_rn(gu[0], gv[1]), __fmul_rn(gu[1], gv[0]));
         const float len = sqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
         const float inv = 1.0f / fmaxf(len, 1e-12f);
         out[0][j] = nx * inv;

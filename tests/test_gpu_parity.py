@@ -30,7 +30,7 @@ def check_fused(mosaics, n=1.5, mufu=False):
         out = ops.fused_mosaic(dev(mosaics), n, want_iun=True, want_planes=True)
         torch.cuda.synchronize()
     finally:
-        _lib.lib().polcue_debug_set_trig(0)
+        _lib.lib().polcue_debug_set_trig(1)   # library default
     worst = 0.0
     for b in range(mosaics.shape[0]):
         stack = O.stack_quadrants(mosaics[b])
@@ -329,7 +329,9 @@ def test_depth_to_normals(shape):
         err32 = P.angular_error(got, ref32, axis=1)
         assert np.quantile(err32, 0.999) < 2e-3
     nrm = np.linalg.norm(got, axis=1)
-    assert ((np.abs(nrm - 1) < 1e-5) | (nrm == 0)).all()
+    # unit length, except where the float32 cross product underflows next to zero-depth holes (kornia divides by
+    # max(norm, 1e-12) there too and returns a short vector)
+    assert ((np.abs(nrm - 1) < 1e-5) | (nrm < 1e-5)).all()
 
 
 def test_depth_to_normals_properties():
