@@ -296,17 +296,28 @@ def depth_to_normals(depth, camera_matrix, dtype=np.float64):
 METRIC_NAMES = ("abs_rel", "sq_rel", "rmse", "rmse_log", "a1", "a2", "a3")
 
 
-def compute_depth_errors(gt, pred):
-    """manydepth/layers.py:539-577 in float64; order (abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3).
+def _threshold_ratio(gt, pred):
+    """max(gt/pred, pred/gt) evaluated in the inputs' OWN dtype, as layers.py:542 / :562 do: for float32 inputs the
+    quotients are float32-rounded before they are compared with 1.25**k, which decides borderline pixels."""
+    gt, pred = np.asarray(gt).ravel(), np.asarray(pred).ravel()
+    if gt.dtype != np.float32 or pred.dtype != np.float32:
+        gt, pred = gt.astype(np.float64), pred.astype(np.float64)
+    with np.errstate(all="ignore"):
+        return np.maximum(gt / pred, pred / gt)
 
+
+def compute_depth_errors(gt, pred):
+    """manydepth/layers.py:539-577; order (abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3).
+
+    The threshold ratio keeps the inputs' dtype (see `_threshold_ratio`); every mean is accumulated in float64.
     Empty inputs give NaN for every entry, like numpy/torch means of empty arrays.
     """
+    ratio = _threshold_ratio(gt, pred)
     gt = np.asarray(gt, dtype=np.float64).ravel()
     pred = np.asarray(pred, dtype=np.float64).ravel()
     with np.errstate(all="ignore"):
         if gt.size == 0:
             return (np.nan,) * 7
-        ratio = np.maximum(gt / pred, pred / gt)
         a1 = (ratio < 1.25).mean()
         a2 = (ratio < 1.25 ** 2).mean()
         a3 = (ratio < 1.25 ** 3).mean()
@@ -321,10 +332,10 @@ def compute_depth_errors(gt, pred):
 def depth_error_sums(gt, pred):
     """The eight additive accumulators behind `compute_depth_errors`:
     (count, n[t<1.25], n[t<1.25^2], n[t<1.25^3], sum d^2, sum dlog^2, sum |d|/gt, sum d^2/gt)."""
+    ratio = _threshold_ratio(gt, pred)
     gt = np.asarray(gt, dtype=np.float64).ravel()
     pred = np.asarray(pred, dtype=np.float64).ravel()
     with np.errstate(all="ignore"):
-        ratio = np.maximum(gt / pred, pred / gt)
         diff = gt - pred
         return np.array([gt.size, (ratio < 1.25).sum(), (ratio < 1.25 ** 2).sum(), (ratio < 1.25 ** 3).sum(),
                          (diff ** 2).sum(), ((np.log(gt) - np.log(pred)) ** 2).sum(),
@@ -341,8 +352,9 @@ def depth_errors_per_image(gt, pred, min_depth, max_depth, inst=None, inst_id=No
     image.  Returns (B x 7 per-image metrics, mean over images).  The reference's try/except
     quirk (re-appending the previous image's errors) is not reproduced: an empty mask yields NaN.
     """
-    gt = np.asarray(gt, dtype=np.float64)
-    pred = np.asarray(pred, dtype=np.float64)
+    gt, pred = np.asarray(gt), np.asarray(pred)       # dtype preserved: see `_threshold_ratio`
+    if gt.dtype == np.float32:
+        min_depth, max_depth = np.float32(min_depth), np.float32(max_depth)
     rows = []
     for b in range(gt.shape[0]):
         m = (gt[b] > min_depth) & (gt[b] < max_depth)

@@ -115,84 +115,119 @@ struct Packed<1> {
     static __device__ __forceinline__ type load(const uint8_t* p) { return ld_stream_u8(p); }
 };
 
-template <int VEC, bool MUFU>
+// The four quadrant words of one pixel group, plus where the group lives.
+template <int VEC>
+struct GroupIn {
+    typename Packed<VEC>::type w0, w45, w90, w135;
+    uint32_t b, rem;   // frame, group index inside the frame
+    bool valid;
+};
+
+template <int VEC>
+__device__ __forceinline__ GroupIn<VEC> load_group(const FusedParams& p, uint32_t tile) {
+    using PK = Packed<VEC>;
+    GroupIn<VEC> g;
+    const uint32_t gid = tile * kFusedThreads + threadIdx.x;
+    g.valid = gid < p.groups_total;
+    g.b = 0; g.rem = 0;
+    g.w0 = g.w45 = g.w90 = g.w135 = 0;
+    if (g.valid) {
+        g.b = fastdiv(gid, p.groups_per_frame);
+        g.rem = gid - g.b * p.groups_per_frame.div;
+        const uint32_t y = fastdiv(g.rem, p.groups_per_row);
+        const uint32_t xg = g.rem - y * p.groups_per_row.div;
+        const uint8_t* src = p.mosaic + ((size_t)g.b * p.frame_bytes + (y * p.W + xg * VEC));
+        g.w0 = PK::load(src);                          // TL:   0 deg
+        g.w45 = PK::load(src + p.Ws);                  // TR:  45 deg
+        g.w90 = PK::load(src + p.quad_down);           // BL:  90 deg
+        g.w135 = PK::load(src + p.quad_down + p.Ws);   // BR: 135 deg
+    }
+    return g;
+}
+
+template <int VEC, bool MUFU, bool NORMALS>
+__device__ __forceinline__ void process_group(const FusedParams& p, const LutShared& lut, const GroupIn<VEC>& g) {
+    using PK = Packed<VEC>;
+    const uint32_t b = g.b;
+    const uint32_t pix = g.rem * VEC;   // first pixel inside the Hs x Ws plane (Ws = groups_per_row * VEC)
+
+    if (p.planes) {
+        typename PK::type* dst = reinterpret_cast<typename PK::type*>(p.planes + (size_t)b * 4 * p.plane + pix);
+        const size_t ps = p.plane / VEC;    // plane stride in packed words
+        dst[0] = g.w0;
+        dst[ps] = g.w45;
+        dst[2 * ps] = g.w90;
+        dst[3 * ps] = g.w135;
+    }
+
+    float rho[VEC], phi[VEC], iun[VEC], sp[VEC], cp[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const Cues q = cues_from_u8<NORMALS>(byte_to_float(g.w0, j), byte_to_float(g.w45, j), byte_to_float(g.w90, j),
+                                             byte_to_float(g.w135, j));
+        rho[j] = q.rho;
+        phi[j] = q.phi;
+        iun[j] = q.iun;
+        sp[j] = q.sin_phi;
+        cp[j] = q.cos_phi;
+    }
+    // plane pointers advance by a 32-bit stride
+    float* xo = p.xolp + ((size_t)(2 * b) * p.plane + pix);
+    asm volatile("" : "+l"(xo));   // keep a pointer VALUE (not base + 64-bit index) across the plane steps
+    st_stream_vec<VEC>(xo, rho);
+    xo += p.plane;
+    st_stream_vec<VEC>(xo, phi);
+    if (p.iun) st_stream_vec<VEC>(p.iun + ((size_t)b * p.plane + pix), iun);
+
+    if constexpr (NORMALS) {
+        float nrm[9][VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float n9[9];
+            normals_from_trig<MUFU>(lut, rho[j], sp[j], cp[j], n9);
+#pragma unroll
+            for (int c = 0; c < 9; ++c) nrm[c][j] = n9[c];
+        }
+        float* no = p.normals + ((size_t)(9 * b) * p.plane + pix);
+        asm volatile("" : "+l"(no));
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            st_stream_vec<VEC>(no, nrm[c]);
+            no += p.plane;
+        }
+    }
+}
+
+// One tile = one group of VEC pixels per thread (512 groups per CTA).  Tiles arrive in order through cluster launch
+// control; the loop is software-pipelined two deep: while tile k is computed and stored, the quadrant words of tile
+// k+1 are already in flight and the query for tile k+2 is outstanding, so no warp waits on DRAM latency.
+template <int VEC, bool MUFU, bool NORMALS>
 __global__ void __launch_bounds__(kFusedThreads, 2) fused_mosaic_kernel(const FusedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ __align__(16) uint4 clc_resp;
     __shared__ uint64_t clc_bar;
-    const bool want_normals = p.normals != nullptr;
-    if (want_normals) lut_stage_begin(smem_raw, p.lut.blob, p.lut.bytes, &bar);
+    if constexpr (NORMALS) lut_stage_begin(smem_raw, p.lut.blob, p.lut.bytes, &bar);
     ClcTiles clc;
     clc.init(&clc_resp, &clc_bar);
-    if (want_normals) lut_stage_wait(&bar);
+    clc.prefetch();                                      // query for the tile after blockIdx.x
+    GroupIn<VEC> cur = load_group<VEC>(p, blockIdx.x);
+    if constexpr (NORMALS) lut_stage_wait(&bar);
     const LutShared lut = lut_shared(smem_raw, p.lut);
-    using PK = Packed<VEC>;
 
-    // one tile = one group of VEC pixels per thread; tiles arrive in order through cluster launch control
-    for (uint32_t tile = blockIdx.x;;) {
-        clc.prefetch();
-        const uint32_t gid = tile * kFusedThreads + threadIdx.x;
-        if (gid < p.groups_total) {
-        const uint32_t b = fastdiv(gid, p.groups_per_frame);
-        const uint32_t rem = gid - b * p.groups_per_frame.div;   // group index inside the frame
-        const uint32_t y = fastdiv(rem, p.groups_per_row);
-        const uint32_t xg = rem - y * p.groups_per_row.div;
-
-        const uint8_t* src = p.mosaic + ((size_t)b * p.frame_bytes + (y * p.W + xg * VEC));
-        const typename PK::type w0 = PK::load(src);                     // TL:   0 deg
-        const typename PK::type w45 = PK::load(src + p.Ws);             // TR:  45 deg
-        const typename PK::type w90 = PK::load(src + p.quad_down);      // BL:  90 deg
-        const typename PK::type w135 = PK::load(src + p.quad_down + p.Ws);  // BR: 135 deg
-
-        const uint32_t pix = rem * VEC;   // first pixel inside the Hs x Ws plane (Ws = groups_per_row * VEC)
-
-        if (p.planes) {
-            typename PK::type* dst = reinterpret_cast<typename PK::type*>(p.planes + (size_t)b * 4 * p.plane + pix);
-            const size_t ps = p.plane / VEC;    // plane stride in packed words
-            dst[0] = w0;
-            dst[ps] = w45;
-            dst[2 * ps] = w90;
-            dst[3 * ps] = w135;
+    for (;;) {
+        uint32_t next_tile;
+        const bool more = clc.next(next_tile);           // response to the query issued one tile ago
+        __syncthreads();                                 // every thread has read it: the slot may be re-armed
+        GroupIn<VEC> nxt;
+        nxt.valid = false;
+        if (more) {
+            clc.prefetch();
+            nxt = load_group<VEC>(p, next_tile);         // in flight while `cur` is processed
         }
-
-        float rho[VEC], phi[VEC], iun[VEC], sp[VEC], cp[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const Cues q = cues_from_u8(byte_to_float(w0, j), byte_to_float(w45, j), byte_to_float(w90, j), byte_to_float(w135, j));
-            rho[j] = q.rho;
-            phi[j] = q.phi;
-            iun[j] = q.iun;
-            sp[j] = q.sin_phi;
-            cp[j] = q.cos_phi;
-        }
-        // plane pointers advance by a 32-bit stride: one IMAD.WIDE.U32 (fma pipe) per store address
-        float* xo = p.xolp + ((size_t)(2 * b) * p.plane + pix);
-        asm volatile("" : "+l"(xo));   // a pointer VALUE (not base + 64-bit index): the stride add stays one IMAD.WIDE
-        st_stream_vec<VEC>(xo, rho);
-        xo += p.plane;
-        st_stream_vec<VEC>(xo, phi);
-        if (p.iun) st_stream_vec<VEC>(p.iun + ((size_t)b * p.plane + pix), iun);
-
-        if (want_normals) {
-            float nrm[9][VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                float n9[9];
-                normals_from_trig<MUFU>(lut, rho[j], sp[j], cp[j], n9);
-#pragma unroll
-                for (int c = 0; c < 9; ++c) nrm[c][j] = n9[c];
-            }
-            float* no = p.normals + ((size_t)(9 * b) * p.plane + pix);
-            asm volatile("" : "+l"(no));
-#pragma unroll
-            for (int c = 0; c < 9; ++c) {
-                st_stream_vec<VEC>(no, nrm[c]);
-                no += p.plane;
-            }
-        }
-        }
-        if (!clc.next(tile)) break;
+        if (cur.valid) process_group<VEC, MUFU, NORMALS>(p, lut, cur);
+        if (!more) break;
+        cur = nxt;
     }
 }
 
@@ -200,7 +235,8 @@ int g_trig_mufu = 1;  // zenith-angle sincos: 1 = MUFU sin/cos (3.6e-7 abs, defa
 
 template <int VEC>
 int launch_fused(const FusedParams& p, size_t smem, cudaStream_t stream) {
-    auto kern = g_trig_mufu ? fused_mosaic_kernel<VEC, true> : fused_mosaic_kernel<VEC, false>;
+    auto kern = !p.normals ? fused_mosaic_kernel<VEC, true, false>
+                           : (g_trig_mufu ? fused_mosaic_kernel<VEC, true, true> : fused_mosaic_kernel<VEC, false, true>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
@@ -268,41 +304,69 @@ __device__ __forceinline__ void load_stack_px<float>(const float* stack, size_t 
     iv[0] = iv[1] = iv[2] = iv[3] = 0;
 }
 
-// One thread per pixel: a warp reads 128 (u8) or 512 (f32) contiguous bytes and writes 128 per plane.
-template <typename T, bool GENERAL>
+// XOLP-only kernels.  A thread owns V consecutive pixels (V = 4 when the image size allows: one 16-byte load of
+// four interleaved u8 pixels, one 16-byte store per output plane); one CTA per tile of 256 * V pixels, launched
+// plainly (no per-CTA setup to amortise, so the hardware's own CTA queue is the dynamic scheduler).
+template <typename T, bool GENERAL, int V>
 __global__ void __launch_bounds__(256) xolp_stack_kernel(const T* __restrict__ stack, size_t hw, size_t total, Pinv pv,
                                                           float* __restrict__ iun, float* __restrict__ xolp) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        float v[4];
-        int iv[4];
-        load_stack_px<T>(stack, i, v, iv);
-        Cues q;
-        if constexpr (GENERAL) q = cues_general(v, pv);
-        else if constexpr (sizeof(T) == 1) q = cues_from_u8(v[0], v[1], v[2], v[3]);
-        else q = cues_canonical_f32(v);
-        const size_t b = i / hw, r = i - b * hw;
-        float* xo = xolp + b * 2 * hw + r;
-        st_stream_f32(xo, q.rho);
-        st_stream_f32(xo + hw, q.phi);
-        if (iun) st_stream_f32(iun + i, q.iun);
+    const size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * V;
+    if (i >= total) return;
+    float rho[V], phi[V], un[V];
+    if constexpr (sizeof(T) == 1 && V == 4) {
+        const uint4 w = *reinterpret_cast<const uint4*>(stack + 4 * i);   // 4 pixels x 4 samples
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v[4] = {byte_to_float(ws[j], 0), byte_to_float(ws[j], 1), byte_to_float(ws[j], 2), byte_to_float(ws[j], 3)};
+            const Cues q = GENERAL ? cues_general(v, pv) : cues_from_u8<false>(v[0], v[1], v[2], v[3]);
+            rho[j] = q.rho; phi[j] = q.phi; un[j] = q.iun;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float v[4];
+            int iv[4];
+            load_stack_px<T>(stack, i + j, v, iv);
+            Cues q;
+            if constexpr (GENERAL) q = cues_general(v, pv);
+            else if constexpr (sizeof(T) == 1) q = cues_from_u8<false>(v[0], v[1], v[2], v[3]);
+            else q = cues_canonical_f32(v);
+            rho[j] = q.rho; phi[j] = q.phi; un[j] = q.iun;
+        }
     }
+    const size_t b = i / hw, r = i - b * hw;      // V divides hw when V > 1: a group never straddles two images
+    float* xo = xolp + b * 2 * hw + r;
+    st_stream_vec<V>(xo, rho);
+    st_stream_vec<V>(xo + hw, phi);
+    if (iun) st_stream_vec<V>(iun + i, un);
 }
 
+template <int V>
 __global__ void __launch_bounds__(256) xolp_planes_kernel(const uint8_t* __restrict__ i0, const uint8_t* __restrict__ i45,
                                                            const uint8_t* __restrict__ i90, const uint8_t* __restrict__ i135,
                                                            size_t hw, size_t total, float* __restrict__ iun,
                                                            float* __restrict__ xolp) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const Cues q = cues_from_u8((float)ld_stream_u8(i0 + i), (float)ld_stream_u8(i45 + i), (float)ld_stream_u8(i90 + i),
-                                    (float)ld_stream_u8(i135 + i));
-        const size_t b = i / hw, r = i - b * hw;
-        float* xo = xolp + b * 2 * hw + r;
-        st_stream_f32(xo, q.rho);
-        st_stream_f32(xo + hw, q.phi);
-        if (iun) st_stream_f32(iun + i, q.iun);
+    const size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * V;
+    if (i >= total) return;
+    float rho[V], phi[V], un[V];
+    if constexpr (V == 4) {
+        const uint32_t a = ld_stream_u32(i0 + i), b45 = ld_stream_u32(i45 + i), c = ld_stream_u32(i90 + i), d = ld_stream_u32(i135 + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const Cues q = cues_from_u8<false>(byte_to_float(a, j), byte_to_float(b45, j), byte_to_float(c, j), byte_to_float(d, j));
+            rho[j] = q.rho; phi[j] = q.phi; un[j] = q.iun;
+        }
+    } else {
+        const Cues q = cues_from_u8<false>((float)ld_stream_u8(i0 + i), (float)ld_stream_u8(i45 + i), (float)ld_stream_u8(i90 + i),
+                                           (float)ld_stream_u8(i135 + i));
+        rho[0] = q.rho; phi[0] = q.phi; un[0] = q.iun;
     }
+    const size_t b = i / hw, r = i - b * hw;
+    float* xo = xolp + b * 2 * hw + r;
+    st_stream_vec<V>(xo, rho);
+    st_stream_vec<V>(xo + hw, phi);
+    if (iun) st_stream_vec<V>(iun + i, un);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -317,6 +381,41 @@ struct NormalsParams {
     size_t hw;
 };
 
+template <int VEC>
+struct XolpIn {
+    float rho[VEC], phi[VEC];
+    uint32_t b, rem;
+    bool valid;
+};
+
+template <int VEC>
+__device__ __forceinline__ XolpIn<VEC> load_xolp(const NormalsParams& p, uint32_t tile) {
+    XolpIn<VEC> g;
+    const uint32_t gid = tile * kFusedThreads + threadIdx.x;
+    g.valid = gid < p.groups_total;
+    g.b = 0; g.rem = 0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) g.rho[j] = g.phi[j] = 0.0f;
+    if (g.valid) {
+        g.b = fastdiv(gid, p.groups_per_image);
+        g.rem = gid - g.b * p.groups_per_image.div;
+        const float* xi = p.xolp + ((size_t)g.b * 2 * p.hw + (size_t)g.rem * VEC);
+        if constexpr (VEC == 4) {
+            const float4 r = ld_stream_f32x4(xi), f = ld_stream_f32x4(xi + p.hw);
+            g.rho[0] = r.x; g.rho[1] = r.y; g.rho[2] = r.z; g.rho[3] = r.w;
+            g.phi[0] = f.x; g.phi[1] = f.y; g.phi[2] = f.z; g.phi[3] = f.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                g.rho[j] = ld_stream_f32(xi + j);
+                g.phi[j] = ld_stream_f32(xi + p.hw + j);
+            }
+        }
+    }
+    return g;
+}
+
+// get_normals: same tile scheduling and two-deep software pipeline as the fused kernel.
 template <int VEC, bool MUFU>
 __global__ void __launch_bounds__(kFusedThreads, 2) normals_from_xolp_kernel(const NormalsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -326,40 +425,39 @@ __global__ void __launch_bounds__(kFusedThreads, 2) normals_from_xolp_kernel(con
     lut_stage_begin(smem_raw, p.lut.blob, p.lut.bytes, &bar);
     ClcTiles clc;
     clc.init(&clc_resp, &clc_bar);
+    clc.prefetch();
+    XolpIn<VEC> cur = load_xolp<VEC>(p, blockIdx.x);
     lut_stage_wait(&bar);
     const LutShared lut = lut_shared(smem_raw, p.lut);
-    for (uint32_t tile = blockIdx.x;;) {
-        clc.prefetch();
-        const uint32_t gid = tile * kFusedThreads + threadIdx.x;
-        if (gid < p.groups_total) {
-        const uint32_t b = fastdiv(gid, p.groups_per_image);
-        const size_t pix = (size_t)(gid - b * p.groups_per_image.div) * VEC;
-        const float* xi = p.xolp + (size_t)b * 2 * p.hw + pix;
-        float rho[VEC], phi[VEC];
-        if constexpr (VEC == 4) {
-            const float4 r = ld_stream_f32x4(xi), f = ld_stream_f32x4(xi + p.hw);
-            rho[0] = r.x; rho[1] = r.y; rho[2] = r.z; rho[3] = r.w;
-            phi[0] = f.x; phi[1] = f.y; phi[2] = f.z; phi[3] = f.w;
-        } else {
+    for (;;) {
+        uint32_t next_tile;
+        const bool more = clc.next(next_tile);
+        __syncthreads();
+        XolpIn<VEC> nxt;
+        nxt.valid = false;
+        if (more) {
+            clc.prefetch();
+            nxt = load_xolp<VEC>(p, next_tile);
+        }
+        if (cur.valid) {
+            float nrm[9][VEC];
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                rho[j] = ld_stream_f32(xi + j);
-                phi[j] = ld_stream_f32(xi + p.hw + j);
+                float n9[9];
+                normals_from_cues<MUFU>(lut, cur.rho[j], cur.phi[j], n9);
+#pragma unroll
+                for (int c = 0; c < 9; ++c) nrm[c][j] = n9[c];
+            }
+            float* no = p.normals + ((size_t)cur.b * 9 * p.hw + (size_t)cur.rem * VEC);
+            asm volatile("" : "+l"(no));
+#pragma unroll
+            for (int c = 0; c < 9; ++c) {
+                st_stream_vec<VEC>(no, nrm[c]);
+                no += p.hw;
             }
         }
-        float nrm[9][VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            float n9[9];
-            normals_from_cues<MUFU>(lut, rho[j], phi[j], n9);
-#pragma unroll
-            for (int c = 0; c < 9; ++c) nrm[c][j] = n9[c];
-        }
-        float* no = p.normals + (size_t)b * 9 * p.hw + pix;
-#pragma unroll
-        for (int c = 0; c < 9; ++c) st_stream_vec<VEC>(no + (size_t)c * p.hw, nrm[c]);
-        }
-        if (!clc.next(tile)) break;
+        if (!more) break;
+        cur = nxt;
     }
 }
 
@@ -502,15 +600,25 @@ static int xolp_stack_common(const void* stack, bool is_u8, int B, int H, int W,
     Pinv pv{};
     if (pinv)
         for (int k = 0; k < 12; ++k) pv.m[k] = pinv[k];
-    const unsigned grid = grid_for(total, 256);
+    const bool v4 = hw % 4 == 0 && aligned(stack, 16) && aligned(xolp, 16) && aligned(iun, 16);
+    const size_t per_cta = 256 * (v4 ? 4 : 1);
+    const size_t ctas = (total + per_cta - 1) / per_cta;
+    if (ctas >= (1ull << 31)) return POLCUE_E2BIG;
+    const unsigned grid = (unsigned)ctas;
     cudaStream_t s = (cudaStream_t)stream;
+#define POLCUE_LAUNCH_STACK(T, G)                                                                              \
+    do {                                                                                                       \
+        if (v4) xolp_stack_kernel<T, G, 4><<<grid, 256, 0, s>>>((const T*)stack, hw, total, pv, iun, xolp);    \
+        else xolp_stack_kernel<T, G, 1><<<grid, 256, 0, s>>>((const T*)stack, hw, total, pv, iun, xolp);       \
+    } while (0)
     if (is_u8) {
-        if (pinv) xolp_stack_kernel<uint8_t, true><<<grid, 256, 0, s>>>((const uint8_t*)stack, hw, total, pv, iun, xolp);
-        else xolp_stack_kernel<uint8_t, false><<<grid, 256, 0, s>>>((const uint8_t*)stack, hw, total, pv, iun, xolp);
+        if (pinv) POLCUE_LAUNCH_STACK(uint8_t, true);
+        else POLCUE_LAUNCH_STACK(uint8_t, false);
     } else {
-        if (pinv) xolp_stack_kernel<float, true><<<grid, 256, 0, s>>>((const float*)stack, hw, total, pv, iun, xolp);
-        else xolp_stack_kernel<float, false><<<grid, 256, 0, s>>>((const float*)stack, hw, total, pv, iun, xolp);
+        if (pinv) POLCUE_LAUNCH_STACK(float, true);
+        else POLCUE_LAUNCH_STACK(float, false);
     }
+#undef POLCUE_LAUNCH_STACK
     return launch_status();
 }
 
@@ -530,7 +638,13 @@ int polcue_xolp_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t* 
     if (!aligned(xolp, 4) || !aligned(iun, 4)) return POLCUE_EINVAL;
     if (B == 0) return POLCUE_OK;
     const size_t hw = (size_t)H * W, total = hw * B;
-    xolp_planes_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(i0, i45, i90, i135, hw, total, iun, xolp);
+    const bool v4 = hw % 4 == 0 && aligned(i0, 4) && aligned(i45, 4) && aligned(i90, 4) && aligned(i135, 4) && aligned(xolp, 16) &&
+                    aligned(iun, 16);
+    const size_t per_cta = 256 * (v4 ? 4 : 1);
+    const size_t ctas = (total + per_cta - 1) / per_cta;
+    if (ctas >= (1ull << 31)) return POLCUE_E2BIG;
+    if (v4) xolp_planes_kernel<4><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(i0, i45, i90, i135, hw, total, iun, xolp);
+    else xolp_planes_kernel<1><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(i0, i45, i90, i135, hw, total, iun, xolp);
     return launch_status();
 }
 

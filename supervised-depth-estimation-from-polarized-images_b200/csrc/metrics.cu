@@ -25,33 +25,44 @@ namespace polcue {
 namespace {
 
 constexpr int kMetricThreads = 256;
-constexpr int kMaxMetricBlocks = 148 * 8;
+constexpr int kMaxMetricBlocks = 148 * 16;
 constexpr int kCluster = 8;  // CTAs per image in the per-image kernel (portable cluster size)
 
 struct Acc {
-    float f[5];  // d^2, dlog^2, |d|/gt, d^2/gt, (unused pad keeps the loop simple)
+    float f[4];  // d^2, (log2 hi - log2 lo)^2, |d|/gt, d^2/gt
     int n, c1, c2, c3;
 };
 
 __device__ __forceinline__ void acc_clear(Acc& a) {
-    a.f[0] = a.f[1] = a.f[2] = a.f[3] = a.f[4] = 0.0f;
+    a.f[0] = a.f[1] = a.f[2] = a.f[3] = 0.0f;
     a.n = a.c1 = a.c2 = a.c3 = 0;
 }
 
-__device__ __forceinline__ void acc_add(Acc& a, float gt, float pred) {
+// fl(hi / lo) < c, decided WITHOUT the division, exactly as IEEE round-to-nearest-even would decide it.
+// For c in [1, 2) with an even significand (1.25, 1.5625 and 1.953125 all are), fl(x) < c  <=>  x < c - 2^-24
+// (the midpoint below c rounds up to c).  So the test is hi - c lo < -2^-24 lo; near the threshold hi - c lo is
+// a small multiple of ulp(lo)/8 and the FMA returns it exactly, far from it the sign is unambiguous.
+__device__ __forceinline__ bool ratio_below(float hi, float lo, float c, float neg_half_ulp_lo) {
+    return fmaf(-c, lo, hi) < neg_half_ulp_lo;
+}
+
+// One element.  `keep` (0 or 1) gates every contribution so masked kernels stay branch-free.
+__device__ __forceinline__ void acc_add(Acc& a, float gt, float pred, bool keep = true) {
     const float hi = fmaxf(gt, pred), lo = fminf(gt, pred);
-    const float t = __fdiv_rn(hi, lo);                   // == max(gt/pred, pred/gt) of layers.py:542
-    a.c1 += t < 1.25f;
-    a.c2 += t < 1.5625f;                                 // 1.25 ** 2, exact in float32
-    a.c3 += t < 1.953125f;                               // 1.25 ** 3, exact in float32
-    const float d = gt - pred, d2 = d * d;
+    const float thr = -5.9604644775390625e-08f * lo;     // -2^-24 lo
+    // == (max(gt/pred, pred/gt) < 1.25 ** k) of layers.py:542-545, bit for bit, for positive inputs
+    a.c1 += keep && ratio_below(hi, lo, 1.25f, thr);
+    a.c2 += keep && ratio_below(hi, lo, 1.5625f, thr);
+    a.c3 += keep && ratio_below(hi, lo, 1.953125f, thr);
+    const float k = keep ? 1.0f : 0.0f;
+    const float d = gt - pred, d2 = k * d * d;
     const float inv_gt = rcp_approx(gt);
-    const float dl = 0.693147180559945f * (__log2f(gt) - __log2f(pred));
+    const float dl = keep ? __log2f(hi) - __log2f(lo) : 0.0f;   // |log gt - log pred| / ln 2; ln^2 2 is applied at the flush
     a.f[0] += d2;
     a.f[1] = fmaf(dl, dl, a.f[1]);
-    a.f[2] = fmaf(fabsf(d), inv_gt, a.f[2]);
+    a.f[2] = fmaf(k * fabsf(d), inv_gt, a.f[2]);
     a.f[3] = fmaf(d2, inv_gt, a.f[3]);
-    a.n += 1;
+    a.n += keep;
 }
 
 struct Acc64 {
@@ -64,7 +75,7 @@ __device__ __forceinline__ void flush(Acc64& s, Acc& a) {
     s.v[2] += a.c2;
     s.v[3] += a.c3;
     s.v[4] += a.f[0];
-    s.v[5] += a.f[1];
+    s.v[5] += 0.4804530139182014 * (double)a.f[1];   // ln(2)^2
     s.v[6] += a.f[2];
     s.v[7] += a.f[3];
     acc_clear(a);
@@ -151,11 +162,19 @@ __global__ void __launch_bounds__(kMetricThreads) depth_errors_kernel(const floa
     __syncthreads();
     if (!last) return;
     __threadfence();
-    if (threadIdx.x < 8) {  // fixed summation order over CTAs: bitwise reproducible
+    {   // fixed summation order over CTAs (bitwise reproducible): 32 lanes x 8 accumulators, then lanes in order
+        __shared__ double lane_rows[32][8];
+        const unsigned k = threadIdx.x & 7, lane = threadIdx.x >> 3;
         double v = 0.0;
-        for (unsigned blk = 0; blk < gridDim.x; ++blk) v += __ldcg(partials + (size_t)blk * 8 + threadIdx.x);
-        warp_rows[0][threadIdx.x] = v;
-        sums8[threadIdx.x] = v;
+        for (unsigned blk = lane; blk < gridDim.x; blk += 32) v += __ldcg(partials + (size_t)blk * 8 + k);
+        lane_rows[lane][k] = v;
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            double t = 0.0;
+            for (int l = 0; l < 32; ++l) t += lane_rows[l][threadIdx.x];
+            warp_rows[0][threadIdx.x] = t;
+            sums8[threadIdx.x] = t;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -182,7 +201,8 @@ struct ImageParams {
 __device__ __forceinline__ void acc_masked(Acc& a, const ImageParams& p, float g, float q, int id) {
     // trainer.py:1380 mask, :1410-1411 material filter, :1417-1418 clamp of the prediction
     const bool keep = (g > p.min_d) && (g < p.max_d) && (p.inst == nullptr || id == p.inst_id);
-    if (keep) acc_add(a, g, fminf(fmaxf(q, p.min_d), p.max_d));
+    // rejected pixels (gt = 0 holes included) are evaluated on harmless stand-in values and gated out
+    acc_add(a, keep ? g : 1.0f, fminf(fmaxf(q, p.min_d), p.max_d), keep);
 }
 
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThreads)
@@ -257,7 +277,7 @@ int polcue_depth_errors_f32(const float* gt, const float* pred, size_t count, vo
     const bool vec4 = ((reinterpret_cast<uintptr_t>(gt) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0;
     const size_t items = vec4 ? (count + 3) / 4 : count;
     size_t blocks = (items + kMetricThreads - 1) / kMetricThreads;
-    const size_t cap = (size_t)device_info().sms * 8;
+    const size_t cap = (size_t)device_info().sms * 16;   // two waves of 8 resident CTAs: evens out per-SM bandwidth
     blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
     if (blocks > (size_t)kMaxMetricBlocks) blocks = kMaxMetricBlocks;
     auto* ticket = static_cast<unsigned long long*>(workspace);

@@ -246,6 +246,7 @@ __device__ __forceinline__ float atan_unit(float a, float s) {
 //   s1 >= 0: |phi| = phi'           (cos, sin) = (c', s')        c' = rsqrt(1+u^2), s' = u c'
 //   s1 <  0: |phi| = pi/2 - phi'    (cos, sin) = (s', c')        sign(phi) = sign(s2), s2 = +0 -> +
 // Ties resolve as exact arithmetic does: s1 = s2 = 0 -> phi = 0; s2 = 0, s1 < 0 -> phi = +pi/2.
+template <bool kTrig = true>   // kTrig = false: XOLP only, skip cos/sin(phi)
 __device__ __forceinline__ Cues cues_from_u8(float i0, float i45, float i90, float i135) {
     const float s1 = i0 - i90, s2 = i45 - i135, sum = (i0 + i90) + (i45 + i135);
     const float amp = sqrt_approx(fmaf(s1, s1, s2 * s2));   // integer < 2^24 under the root: exact
@@ -255,11 +256,15 @@ __device__ __forceinline__ Cues cues_from_u8(float i0, float i45, float i90, flo
     const float u = fabsf(s2) * rcp_approx((amp + fabsf(s1)) + 1e-30f);
     const float t = u * u;
     const float half = atan_unit(u, t);
-    const float cq = rsqrt_approx(1.0f + t), sq = u * cq;
     const bool flip = s1 < 0.0f;
     q.phi = copysignf(flip ? kHalfPi - half : half, s2);
-    q.cos_phi = flip ? sq : cq;
-    q.sin_phi = copysignf(flip ? cq : sq, s2);
+    if constexpr (kTrig) {
+        const float cq = rsqrt_approx(1.0f + t), sq = u * cq;
+        q.cos_phi = flip ? sq : cq;
+        q.sin_phi = copysignf(flip ? cq : sq, s2);
+    } else {
+        q.cos_phi = q.sin_phi = 0.0f;
+    }
     return q;
 }
 
@@ -332,8 +337,9 @@ __device__ __forceinline__ void lut_stage_wait(uint64_t* bar) {
 // On the two-die B200 this matters: under HBM saturation SMs do not all get the same bandwidth, and a static
 // grid-stride split finishes with its slowest SM (measured 0.73 ms static vs 0.60 ms dynamic for this kernel's
 // access pattern, tools/hbm_probe.cu).
-// Usage (all threads):  ClcTiles clc; clc.init();  for (tile = blockIdx.x;;) { clc.prefetch(); work(tile);
-//                        if (!clc.next(tile)) break; }
+// Usage (all threads):  clc.init(..); clc.prefetch(); tile = blockIdx.x;
+//                        for (;;) { more = clc.next(nxt); __syncthreads(); if (more) clc.prefetch();
+//                                   work(tile); if (!more) break; tile = nxt; }
 // ------------------------------------------------------------------------------------------
 struct ClcTiles {
     uint4* resp;       // 16-byte response slot (shared)
@@ -384,9 +390,8 @@ struct ClcTiles {
             : "r"(smem_u32(resp))
             : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();  // every thread has read the response before thread 0 re-arms the slot
         tile = first;
-        return valid != 0;
+        return valid != 0;   // caller: __syncthreads() before the next prefetch() re-arms the slot
     }
 };
 

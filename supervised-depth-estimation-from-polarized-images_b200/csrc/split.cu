@@ -15,40 +15,58 @@ namespace {
 struct SplitParams {
     const unsigned char* img;
     unsigned char* out[4];   // im00, im10, im01, im11
-    unsigned long long units_total;  // B * 4 * Hs * units_per_row
-    unsigned units_per_row;  // (Ws * px_bytes) / sizeof(T)
-    unsigned Hs;
+    uint32_t units_total;    // B * 4 * Hs * units_per_row  (< 2^31)
+    FastDiv units_per_row;   // (Ws * px_bytes) / sizeof(T)
+    FastDiv rows_per_quad;   // Hs
+    uint32_t Hs;
     size_t row_bytes;        // W * px_bytes
     size_t half_row_bytes;   // Ws * px_bytes
     size_t frame_bytes;      // H * W * px_bytes
     size_t quad_bytes;       // Hs * Ws * px_bytes
 };
 
+constexpr int kSplitThreads = 256, kSplitItems = 4;   // four independent copies in flight per thread
+
+// One CTA per tile of 256 x 4 units, plain launch: the hardware CTA queue balances the two dies' SMs.
 template <typename T>
-__global__ void __launch_bounds__(256) split_pol_kernel(const SplitParams p) {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.units_total; i += stride) {
-        const unsigned u = (unsigned)(i % p.units_per_row);
-        unsigned long long r = i / p.units_per_row;
-        const unsigned y = (unsigned)(r % p.Hs);
-        r /= p.Hs;
-        const unsigned q = (unsigned)(r & 3);        // 0: im00, 1: im10, 2: im01, 3: im11
-        const unsigned long long b = r >> 2;
-        const size_t src_row = (size_t)y + ((q & 1) ? p.Hs : 0);           // im10 / im11: bottom half
-        const size_t src_col = (q & 2) ? p.half_row_bytes : 0;             // im01 / im11: right half
-        const T* src = reinterpret_cast<const T*>(p.img + b * p.frame_bytes + src_row * p.row_bytes + src_col) + u;
-        T* dst = reinterpret_cast<T*>(p.out[q] + b * p.quad_bytes + (size_t)y * p.half_row_bytes) + u;
-        *dst = *src;
+__global__ void __launch_bounds__(kSplitThreads) split_pol_kernel(const SplitParams p) {
+    const uint32_t base = blockIdx.x * (kSplitThreads * kSplitItems) + threadIdx.x;
+    T v[kSplitItems];
+    T* dst[kSplitItems];
+#pragma unroll
+    for (int k = 0; k < kSplitItems; ++k) {
+        const uint32_t i = base + k * kSplitThreads;
+        dst[k] = nullptr;
+        if (i < p.units_total) {
+            uint32_t r = fastdiv(i, p.units_per_row);
+            const uint32_t u = i - r * p.units_per_row.div;
+            const uint32_t r2 = fastdiv(r, p.rows_per_quad);
+            const uint32_t y = r - r2 * p.Hs;
+            const uint32_t q = r2 & 3;        // 0: im00, 1: im10, 2: im01, 3: im11
+            const uint32_t b = r2 >> 2;
+            const size_t src_row = (size_t)y + ((q & 1) ? p.Hs : 0);           // im10 / im11: bottom half
+            const size_t src_col = (q & 2) ? p.half_row_bytes : 0;             // im01 / im11: right half
+            v[k] = *(reinterpret_cast<const T*>(p.img + (size_t)b * p.frame_bytes + src_row * p.row_bytes + src_col) + u);
+            dst[k] = reinterpret_cast<T*>(p.out[q] + (size_t)b * p.quad_bytes + (size_t)y * p.half_row_bytes) + u;
+        }
     }
+#pragma unroll
+    for (int k = 0; k < kSplitItems; ++k)
+        if (dst[k]) *dst[k] = v[k];
 }
 
 template <typename T>
-int launch_split(SplitParams p, cudaStream_t s) {
-    p.units_per_row = (unsigned)(p.half_row_bytes / sizeof(T));
-    p.units_total = p.units_total * p.units_per_row;
-    const unsigned long long want = (p.units_total + 255) / 256;
-    const unsigned long long cap = (unsigned long long)device_info().sms * 32;
-    split_pol_kernel<T><<<(unsigned)(want < cap ? want : cap), 256, 0, s>>>(p);
+int launch_split(SplitParams p, unsigned long long rows, cudaStream_t s) {
+    const unsigned long long upr = p.half_row_bytes / sizeof(T);
+    const unsigned long long units = rows * upr;
+    if (units >= (1ull << 31)) return POLCUE_E2BIG;
+    p.units_total = (uint32_t)units;
+    p.units_per_row.div = (uint32_t)upr;
+    make_fastdiv(p.units_per_row.div, p.units_per_row.mul, p.units_per_row.shift);
+    p.rows_per_quad.div = p.Hs;
+    make_fastdiv(p.rows_per_quad.div, p.rows_per_quad.mul, p.rows_per_quad.shift);
+    const unsigned per_cta = kSplitThreads * kSplitItems;
+    split_pol_kernel<T><<<(unsigned)((units + per_cta - 1) / per_cta), kSplitThreads, 0, s>>>(p);
     return launch_status();
 }
 
@@ -73,13 +91,13 @@ extern "C" int polcue_split_pol(const void* img, int B, int H, int W, int px_byt
     p.half_row_bytes = p.row_bytes / 2;
     p.frame_bytes = (size_t)H * p.row_bytes;
     p.quad_bytes = (size_t)p.Hs * p.half_row_bytes;
-    p.units_total = (unsigned long long)B * 4 * p.Hs;   // rows; launch_split multiplies by units per row
+    const unsigned long long rows = (unsigned long long)B * 4 * p.Hs;   // output rows
     uintptr_t bits = reinterpret_cast<uintptr_t>(img) | p.half_row_bytes;
     for (int q = 0; q < 4; ++q) bits |= reinterpret_cast<uintptr_t>(p.out[q]);
     cudaStream_t s = (cudaStream_t)stream;
-    if ((bits & 15) == 0) return launch_split<uint4>(p, s);
-    if ((bits & 7) == 0) return launch_split<uint2>(p, s);
-    if ((bits & 3) == 0) return launch_split<uint32_t>(p, s);
-    if ((bits & 1) == 0) return launch_split<uint16_t>(p, s);
-    return launch_split<uint8_t>(p, s);
+    if ((bits & 15) == 0) return launch_split<uint4>(p, rows, s);
+    if ((bits & 7) == 0) return launch_split<uint2>(p, rows, s);
+    if ((bits & 3) == 0) return launch_split<uint32_t>(p, rows, s);
+    if ((bits & 1) == 0) return launch_split<uint16_t>(p, rows, s);
+    return launch_split<uint8_t>(p, rows, s);
 }

@@ -59,36 +59,47 @@ __global__ void __launch_bounds__(kStencilThreads) depth_to_normals_kernel(const
 #pragma unroll
     for (int c = 0; c < 6; ++c) fx6[c] = ((float)min(max(xb + c - 1, 0), p.W - 1) - cx) * inv_fx;
 
-    float zz[3][6];
+    // xyz of the 3 x 6 window, shared by the thread's four pixels
+    float X[3][6], Y[3][6], Z[3][6];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 6; ++c) zz[r][c] = tile[(ty + r) * kPitch + 4 * tx + c];
+        for (int c = 0; c < 6; ++c) {
+            const float d = tile[(ty + r) * kPitch + 4 * tx + c];
+            Z[r][c] = d;
+            X[r][c] = fx6[c] * d;
+            Y[r][c] = fy3[r] * d;
+        }
+    // separable Sobel: per column the vertical smoothing S = top + 2 mid + bottom and the vertical difference
+    // D = bottom - top; then d/du = S[c+2] - S[c], d/dv = D[c] + 2 D[c+1] + D[c+2].  The common factor 1/8 of
+    // both gradients only scales the cross product by 1/64, so it is folded into the normalisation guard below.
+    float Su[3][6], Dv[3][6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        Su[0][c] = fmaf(2.0f, X[1][c], X[0][c] + X[2][c]);
+        Su[1][c] = fmaf(2.0f, Y[1][c], Y[0][c] + Y[2][c]);
+        Su[2][c] = fmaf(2.0f, Z[1][c], Z[0][c] + Z[2][c]);
+        Dv[0][c] = X[2][c] - X[0][c];
+        Dv[1][c] = Y[2][c] - Y[0][c];
+        Dv[2][c] = Z[2][c] - Z[0][c];
+    }
 
     float out[3][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float gu[3], gv[3];  // d/du, d/dv of (X, Y, Z)
+        float gu[3], gv[3];  // 8 * d/du, 8 * d/dv of (X, Y, Z)
 #pragma unroll
         for (int comp = 0; comp < 3; ++comp) {
-            float v[3][3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float d = zz[r][j + c];
-                    v[r][c] = comp == 0 ? fx6[j + c] * d : (comp == 1 ? fy3[r] * d : d);
-                }
-            gu[comp] = 0.125f * ((v[0][2] - v[0][0]) + 2.0f * (v[1][2] - v[1][0]) + (v[2][2] - v[2][0]));
-            gv[comp] = 0.125f * ((v[2][0] - v[0][0]) + 2.0f * (v[2][1] - v[0][1]) + (v[2][2] - v[0][2]));
+            gu[comp] = Su[comp][j + 2] - Su[comp][j];
+            gv[comp] = fmaf(2.0f, Dv[comp][j + 1], Dv[comp][j] + Dv[comp][j + 2]);
         }
         // products rounded separately (no FMA contraction): parallel gradients next to zero-depth holes then cancel
         // to an exact zero vector, as they do in the reference's torch.cross, instead of leaving round-off
         const float nx = __fsub_rn(__fmul_rn(gu[1], gv[2]), __fmul_rn(gu[2], gv[1]));
         const float ny = __fsub_rn(__fmul_rn(gu[2], gv[0]), __fmul_rn(gu[0], gv[2]));
         const float nz = __fsub_rn(__fmul_rn(gu[0], gv[1]), __fmul_rn(gu[1], gv[0]));
-        const float len = sqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
-        const float inv = 1.0f / fmaxf(len, 1e-12f);
+        // n / max(|n|, eps) with n = 64 x the reference's cross product: 1 / max(|n|, 64 eps) = min(rsqrt(|n|^2), 1 / (64 eps))
+        const float inv = fminf(rsqrt_approx(fmaf(nx, nx, fmaf(ny, ny, nz * nz))), 1.0f / (64.0f * 1e-12f));
         out[0][j] = nx * inv;
         out[1][j] = ny * inv;
         out[2][j] = nz * inv;

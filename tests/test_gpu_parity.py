@@ -380,6 +380,24 @@ def test_depth_error_sums_sizes(count):
         assert np.array_equal(s3.cpu().numpy()[:4], ref[:4]) and np.allclose(s3.cpu().numpy()[4:], ref[4:], rtol=3e-6)
 
 
+def test_threshold_counts_follow_float32_division_semantics():
+    """a1/a2/a3 decide borderline pixels exactly like the reference's float32 quotients (layers.py:542-545)."""
+    rng = np.random.default_rng(1)
+    n = 2_000_000
+    lo = (rng.random(n) * 1.9 + 0.1).astype(np.float32)
+    thr = rng.choice(np.array([1.25, 1.5625, 1.953125]), n)
+    hi = (lo.astype(np.float64) * thr).astype(np.float32)
+    hi = (hi.view(np.int32) + rng.integers(-3, 4, n).astype(np.int32)).view(np.float32)   # within 3 ulp of a threshold
+    swap = rng.random(n) < 0.5
+    gt, pred = np.where(swap, hi, lo), np.where(swap, lo, hi)
+    ratio = np.maximum(gt / pred, pred / gt)                    # float32, as numpy/torch evaluate it
+    want = [(ratio < np.float32(1.25 ** k)).sum() for k in (1, 2, 3)]
+    sums, _ = ops.depth_error_sums(dev(gt), dev(pred))
+    assert [int(v) for v in sums[1:4].cpu().numpy()] == [int(v) for v in want]
+    bsums, _ = ops.depth_errors_per_image(dev(gt.reshape(4, -1)), dev(pred.reshape(4, -1)), 0.05, 5.0)
+    assert [int(v) for v in bsums[:, 1:4].sum(0).cpu().numpy()] == [int(v) for v in want]
+
+
 def test_depth_errors_empty_is_nan():
     sums, metrics = ops.depth_error_sums(torch.empty(0, device="cuda"), torch.empty(0, device="cuda"))
     assert float(sums[0]) == 0.0 and torch.isnan(metrics).all()

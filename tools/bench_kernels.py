@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Per-kernel roofline readings for every CUDA entry point of libpolcue.so other than the headline fused kernel
+(bench.py covers that one).  For each kernel: algorithmic bytes per launch / mean launch time (CUDA
+events on the launching stream) against the measured HBM copy peak.  Working sets smaller than ~2x the L2 are
+preceded by an L2 flush (a 512 MB write) inside the loop but outside the timed events.
+
+  python tools/bench_kernels.py [--reps 10] [--only stencil,metrics] > profiles/kernels_rNN.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200"))
+from polcue import _lib, ops, synth  # noqa: E402
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def timeit(fn, reps, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    return float(np.mean(times)), float(np.min(times))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    only = set(filter(None, args.only.split(",")))
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peak, peak_src = hbm_peak()
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    rng = np.random.default_rng(0)
+
+    def emit(name, config, alg_bytes, fn, small=False):
+        if only and name.split("/")[0] not in only:
+            return
+        l0 = _lib.launch_count()
+        fn()
+        launches = _lib.launch_count() - l0
+        mean_ms, min_ms = timeit(fn, args.reps, flush_buf if small else None)
+        achieved = alg_bytes / (mean_ms * 1e-3) / 1e9
+        print(json.dumps({"kernel": name, "config": config, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": mean_ms,
+                          "best_ms": min_ms, "achieved_gbs": achieved, "peak_gbs": peak, "peak_source": peak_src,
+                          "frac": achieved / peak, "l2_flushed": bool(small), "kernels_per_call": launches}), flush=True)
+
+    # ---- XOLP-only and normals-only members of the fused family (cfg2 geometry) ----
+    B, hs, ws = 64, 1024, 1224
+    px = B * hs * ws
+    planes = [torch.from_numpy(rng.integers(0, 256, (B, hs, ws), dtype=np.uint8)).to(dev) for _ in range(4)]
+    stack = torch.stack(planes, dim=3).contiguous()
+    emit("xolp_stack_u8", f"stack u8 [{B},{hs},{ws},4] -> xolp f32", 12 * px, lambda: ops.xolp_from_stack(stack, None, want_iun=False))
+    emit("xolp_planes_u8", f"4 planes u8 [{B},{hs},{ws}] -> xolp f32", 12 * px, lambda: ops.xolp_from_planes(*planes))
+    _, xolp = ops.xolp_from_stack(stack, None, want_iun=False)
+    del stack, planes
+    emit("normals_from_xolp", f"xolp f32 [{B},2,{hs},{ws}] -> normals f32 [{B},9,..]", 44 * px, lambda: ops.get_normals(xolp, 1.5))
+    mosaic = torch.from_numpy(rng.integers(0, 256, (B, 2 * hs, 2 * ws), dtype=np.uint8)).to(dev)
+    emit("split_pol", f"mosaic u8 [{B},{2 * hs},{2 * ws}] -> 4 quadrants", 2 * mosaic.numel(), lambda: ops.split_pol_batch(mosaic))
+    emit("fused_xolp_only", f"mosaic u8 [{B},{2 * hs},{2 * ws}] -> xolp f32 (no normals)", 12 * px,
+         lambda: ops.fused_mosaic(mosaic, 1.5, want_normals=False))
+    del xolp, mosaic
+    torch.cuda.empty_cache()
+
+    # ---- depth -> normals stencil and metrics (cfg5 geometry and a 16x scaled split) ----
+    for n_img in (120, 1920):
+        h, w = 320, 480
+        base = synth.gen_depth_batch(0, 8, h, w)
+        reps_ = n_img // 8
+        gt = torch.from_numpy(base[0]).to(dev).repeat(reps_, 1, 1)
+        pred = torch.from_numpy(base[1]).to(dev).repeat(reps_, 1, 1)
+        inst = torch.from_numpy(base[2]).to(dev).repeat(reps_, 1, 1)
+        k = torch.from_numpy(base[3]).to(dev).repeat(reps_, 1, 1)
+        npx = gt.numel()
+        small = npx * 16 < 300e6
+        depth = gt[:, None].contiguous()
+        emit("stencil/depth_to_normals", f"depth f32 [{n_img},1,{h},{w}] -> normals f32 [{n_img},3,{h},{w}]", 16 * npx,
+             lambda: ops.depth_to_normals(depth, k), small)
+        emit("metrics/per_image", f"gt,pred f32 [{n_img},{h},{w}], range mask", 8 * npx,
+             lambda: ops.depth_errors_per_image(gt, pred, 0.1, 2.0), small)
+        emit("metrics/per_image_inst", f"gt,pred f32 + inst u8 [{n_img},{h},{w}], material filter", 9 * npx,
+             lambda: ops.depth_errors_per_image(gt, pred, 0.1, 2.0, inst, 40), small)
+        m = gt > 0
+        gflat, pflat = gt[m].contiguous(), pred[m].contiguous()
+        emit("metrics/flat", f"gt,pred f32 [{gflat.numel()}] (compacted)", 8 * gflat.numel(),
+             lambda: ops.depth_error_sums(gflat, pflat), small)
+        del gt, pred, inst, depth, gflat, pflat
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(T, 2) dyn_kernel(const unsigned* __restrict__ 
 // Cluster Launch Control (sm_100): one CTA per tile in the grid; a resident CTA cancels a pending CTA and takes
 // over its tile, so tiles are handed out dynamically by the hardware work distributor (no global counter).
 __device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__global__ void __launch_bounds__(T, 2) clc_kernel(const unsigned* __restrict__ in, float* __restrict__ out, size_t groups, size_t plane,
+template <int TT, int MINB>
+__global__ void __launch_bounds__(TT, MINB) clc_kernel(const unsigned* __restrict__ in, float* __restrict__ out, size_t groups, size_t plane,
                                                    unsigned* tiles_done) {
     __shared__ __align__(16) uint4 resp;
     __shared__ __align__(8) unsigned long long bar;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(T, 2) clc_kernel(const unsigned* __restrict__ 
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 16;" ::"r"(s32(&bar)) : "memory");
             asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(s32(&resp)), "r"(s32(&bar)) : "memory");
         }
-        const size_t g = (size_t)tile * T + threadIdx.x;
+        const size_t g = (size_t)tile * TT + threadIdx.x;
         if (g < groups) store_planes(out, plane, g, load_quads(in, groups, g));
         if (threadIdx.x == 0 && tiles_done) atomicAdd(tiles_done, 1u);
         unsigned done = 0;
@@ -170,11 +171,16 @@ int main(int argc, char** argv) {
     report("tile = 16 x 512 groups, batched reads", RW, dyn(dyn_kernel<16, true>));
     {
         const unsigned tiles = (unsigned)((groups + T - 1) / T);
-        report("CLC (cluster launch control), tile = 512 groups", RW, time_ms([&] { clc_kernel<<<tiles, T>>>(in, out, groups, plane, nullptr); }, reps));
+        report("CLC (cluster launch control), tile = 512 groups", RW, time_ms([&] { clc_kernel<512, 2><<<tiles, 512>>>(in, out, groups, plane, nullptr); }, reps));
+        report("CLC, tile = 128 groups (128 thr, 8 CTA/SM)", RW, time_ms([&] { clc_kernel<128, 8><<<(unsigned)((groups + 127) / 128), 128>>>(in, out, groups, plane, nullptr); }, reps));
+        report("CLC, tile = 256 groups (256 thr, 4 CTA/SM)", RW, time_ms([&] { clc_kernel<256, 4><<<(unsigned)((groups + 255) / 256), 256>>>(in, out, groups, plane, nullptr); }, reps));
+        report("CLC, tile = 1024 groups (1024 thr, 1 CTA/SM)", RW, time_ms([&] { clc_kernel<1024, 1><<<(unsigned)((groups + 1023) / 1024), 1024>>>(in, out, groups, plane, nullptr); }, reps));
+        report("CLC, tile = 512 groups, 4 CTA/SM", RW, time_ms([&] { clc_kernel<512, 4><<<tiles, 512>>>(in, out, groups, plane, nullptr); }, reps));
+        report("plain launch, one CTA per 512-group tile", RW, time_ms([&] { stat_kernel<1><<<tiles, T>>>(in, out, groups, plane, counter); }, reps));
         // every tile must be processed exactly once
         CK(cudaMemset(counter, 0, 4));
         CK(cudaMemset(out, 0, plane * PLANES * sizeof(float)));
-        clc_kernel<<<tiles, T>>>(in, out, groups, plane, counter);
+        clc_kernel<512, 2><<<tiles, T>>>(in, out, groups, plane, counter);
         CK(cudaDeviceSynchronize());
         unsigned done = 0; CK(cudaMemcpy(&done, counter, 4, cudaMemcpyDeviceToHost));
         float probe[4] = {0, 0, 0, 0};
