@@ -304,13 +304,17 @@ __device__ __forceinline__ void load_stack_px<float>(const float* stack, size_t 
     iv[0] = iv[1] = iv[2] = iv[3] = 0;
 }
 
+constexpr int kXolpItems = 4;   // pixel groups per thread: a CTA moves ~48 KB, long enough to amortise its launch
+
 // XOLP-only kernels.  A thread owns V consecutive pixels (V = 4 when the image size allows: one 16-byte load of
 // four interleaved u8 pixels, one 16-byte store per output plane); one CTA per tile of 256 * V pixels, launched
 // plainly (no per-CTA setup to amortise, so the hardware's own CTA queue is the dynamic scheduler).
 template <typename T, bool GENERAL, int V>
 __global__ void __launch_bounds__(256) xolp_stack_kernel(const T* __restrict__ stack, size_t hw, size_t total, Pinv pv,
                                                           float* __restrict__ iun, float* __restrict__ xolp) {
-    const size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * V;
+#pragma unroll 2
+    for (int item = 0; item < kXolpItems; ++item) {
+    const size_t i = (((size_t)blockIdx.x * kXolpItems + item) * 256 + threadIdx.x) * V;
     if (i >= total) return;
     float rho[V], phi[V], un[V];
     if constexpr (sizeof(T) == 1 && V == 4) {
@@ -340,6 +344,7 @@ __global__ void __launch_bounds__(256) xolp_stack_kernel(const T* __restrict__ s
     st_stream_vec<V>(xo, rho);
     st_stream_vec<V>(xo + hw, phi);
     if (iun) st_stream_vec<V>(iun + i, un);
+    }
 }
 
 template <int V>
@@ -347,7 +352,9 @@ __global__ void __launch_bounds__(256) xolp_planes_kernel(const uint8_t* __restr
                                                            const uint8_t* __restrict__ i90, const uint8_t* __restrict__ i135,
                                                            size_t hw, size_t total, float* __restrict__ iun,
                                                            float* __restrict__ xolp) {
-    const size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * V;
+#pragma unroll 2
+    for (int item = 0; item < kXolpItems; ++item) {
+    const size_t i = (((size_t)blockIdx.x * kXolpItems + item) * 256 + threadIdx.x) * V;
     if (i >= total) return;
     float rho[V], phi[V], un[V];
     if constexpr (V == 4) {
@@ -367,6 +374,7 @@ __global__ void __launch_bounds__(256) xolp_planes_kernel(const uint8_t* __restr
     st_stream_vec<V>(xo, rho);
     st_stream_vec<V>(xo + hw, phi);
     if (iun) st_stream_vec<V>(iun + i, un);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -601,7 +609,7 @@ static int xolp_stack_common(const void* stack, bool is_u8, int B, int H, int W,
     if (pinv)
         for (int k = 0; k < 12; ++k) pv.m[k] = pinv[k];
     const bool v4 = hw % 4 == 0 && aligned(stack, 16) && aligned(xolp, 16) && aligned(iun, 16);
-    const size_t per_cta = 256 * (v4 ? 4 : 1);
+    const size_t per_cta = 256 * kXolpItems * (v4 ? 4 : 1);
     const size_t ctas = (total + per_cta - 1) / per_cta;
     if (ctas >= (1ull << 31)) return POLCUE_E2BIG;
     const unsigned grid = (unsigned)ctas;
@@ -640,7 +648,7 @@ int polcue_xolp_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t* 
     const size_t hw = (size_t)H * W, total = hw * B;
     const bool v4 = hw % 4 == 0 && aligned(i0, 4) && aligned(i45, 4) && aligned(i90, 4) && aligned(i135, 4) && aligned(xolp, 16) &&
                     aligned(iun, 16);
-    const size_t per_cta = 256 * (v4 ? 4 : 1);
+    const size_t per_cta = 256 * kXolpItems * (v4 ? 4 : 1);
     const size_t ctas = (total + per_cta - 1) / per_cta;
     if (ctas >= (1ull << 31)) return POLCUE_E2BIG;
     if (v4) xolp_planes_kernel<4><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(i0, i45, i90, i135, hw, total, iun, xolp);

@@ -51,18 +51,18 @@ __device__ __forceinline__ void acc_add(Acc& a, float gt, float pred, bool keep 
     const float hi = fmaxf(gt, pred), lo = fminf(gt, pred);
     const float thr = -5.9604644775390625e-08f * lo;     // -2^-24 lo
     // == (max(gt/pred, pred/gt) < 1.25 ** k) of layers.py:542-545, bit for bit, for positive inputs
-    a.c1 += keep && ratio_below(hi, lo, 1.25f, thr);
-    a.c2 += keep && ratio_below(hi, lo, 1.5625f, thr);
-    a.c3 += keep && ratio_below(hi, lo, 1.953125f, thr);
+    a.c1 += (int)keep & (int)ratio_below(hi, lo, 1.25f, thr);
+    a.c2 += (int)keep & (int)ratio_below(hi, lo, 1.5625f, thr);
+    a.c3 += (int)keep & (int)ratio_below(hi, lo, 1.953125f, thr);
     const float k = keep ? 1.0f : 0.0f;
-    const float d = gt - pred, d2 = k * d * d;
+    const float d = gt - pred, kd = k * d, d2 = kd * d;
     const float inv_gt = rcp_approx(gt);
-    const float dl = keep ? __log2f(hi) - __log2f(lo) : 0.0f;   // |log gt - log pred| / ln 2; ln^2 2 is applied at the flush
+    const float dl = k * (lg2_approx(hi) - lg2_approx(lo));    // |log gt - log pred| / ln 2; ln^2 2 is applied at the flush
     a.f[0] += d2;
     a.f[1] = fmaf(dl, dl, a.f[1]);
-    a.f[2] = fmaf(k * fabsf(d), inv_gt, a.f[2]);
+    a.f[2] = fmaf(fabsf(kd), inv_gt, a.f[2]);
     a.f[3] = fmaf(d2, inv_gt, a.f[3]);
-    a.n += keep;
+    a.n += (int)keep;
 }
 
 struct Acc64 {
@@ -200,7 +200,7 @@ struct ImageParams {
 
 __device__ __forceinline__ void acc_masked(Acc& a, const ImageParams& p, float g, float q, int id) {
     // trainer.py:1380 mask, :1410-1411 material filter, :1417-1418 clamp of the prediction
-    const bool keep = (g > p.min_d) && (g < p.max_d) && (p.inst == nullptr || id == p.inst_id);
+    const bool keep = (g > p.min_d) & (g < p.max_d) & ((p.inst == nullptr) | (id == p.inst_id));
     // rejected pixels (gt = 0 holes included) are evaluated on harmless stand-in values and gated out
     acc_add(a, keep ? g : 1.0f, fminf(fmaxf(q, p.min_d), p.max_d), keep);
 }

@@ -26,6 +26,11 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float lg2_approx(float x) {   // abs error 2^-22 on [0.5, 2]; denormals flush (never depths)
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

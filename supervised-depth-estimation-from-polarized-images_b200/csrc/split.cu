@@ -25,11 +25,12 @@ struct SplitParams {
     size_t quad_bytes;       // Hs * Ws * px_bytes
 };
 
-constexpr int kSplitThreads = 256, kSplitItems = 4;   // four independent copies in flight per thread
+constexpr int kSplitThreads = 256;   // each thread keeps ITEMS independent copies in flight (64 bytes)
 
 // One CTA per tile of 256 x 4 units, plain launch: the hardware CTA queue balances the two dies' SMs.
 template <typename T>
 __global__ void __launch_bounds__(kSplitThreads) split_pol_kernel(const SplitParams p) {
+    constexpr int kSplitItems = sizeof(T) >= 16 ? 4 : (sizeof(T) >= 8 ? 8 : 16);
     const uint32_t base = blockIdx.x * (kSplitThreads * kSplitItems) + threadIdx.x;
     T v[kSplitItems];
     T* dst[kSplitItems];
@@ -65,7 +66,7 @@ int launch_split(SplitParams p, unsigned long long rows, cudaStream_t s) {
     make_fastdiv(p.units_per_row.div, p.units_per_row.mul, p.units_per_row.shift);
     p.rows_per_quad.div = p.Hs;
     make_fastdiv(p.rows_per_quad.div, p.rows_per_quad.mul, p.rows_per_quad.shift);
-    const unsigned per_cta = kSplitThreads * kSplitItems;
+    const unsigned per_cta = kSplitThreads * (sizeof(T) >= 16 ? 4 : (sizeof(T) >= 8 ? 8 : 16));
     split_pol_kernel<T><<<(unsigned)((units + per_cta - 1) / per_cta), kSplitThreads, 0, s>>>(p);
     return launch_status();
 }

@@ -17,7 +17,7 @@
 namespace polcue {
 namespace {
 
-constexpr int kTW = 128, kTH = 8, kStencilThreads = (kTW / 4) * kTH;  // 256
+constexpr int kTW = 128, kTH = 32, kRowGroups = 4, kStencilThreads = (kTW / 4) * (kTH / kRowGroups);  // 256 threads, 4 rows each
 constexpr int kPitch = kTW + 4;  // [halo | TW | halo | pad], keeps rows 16-byte multiples
 
 struct StencilParams {
@@ -47,18 +47,23 @@ __global__ void __launch_bounds__(kStencilThreads) depth_to_normals_kernel(const
     const float inv_fy = 1.0f / __ldg(k + 4), cy = __ldg(k + 5);
     __syncthreads();
 
-    const int ty = threadIdx.x / (kTW / 4), tx = threadIdx.x - ty * (kTW / 4);
-    const int y = y0 + ty, xb = x0 + 4 * tx;
-    if (y >= p.H || xb >= p.W) return;
+    const int ty0 = threadIdx.x / (kTW / 4), tx = threadIdx.x - ty0 * (kTW / 4);
+    const int xb = x0 + 4 * tx;
+    if (xb >= p.W) return;
+    float fx6[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) fx6[c] = ((float)min(max(xb + c - 1, 0), p.W - 1) - cx) * inv_fx;
+
+#pragma unroll 1
+    for (int rg = 0; rg < kRowGroups; ++rg) {
+    const int ty = ty0 + rg * (kTH / kRowGroups);
+    const int y = y0 + ty;
+    if (y >= p.H) break;
 
     // ray factors of the three rows (clamped rows repeat the border row's factor)
     float fy3[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) fy3[r] = ((float)min(max(y + r - 1, 0), p.H - 1) - cy) * inv_fy;
-    float fx6[6];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) fx6[c] = ((float)min(max(xb + c - 1, 0), p.W - 1) - cx) * inv_fx;
-
     // xyz of the 3 x 6 window, shared by the thread's four pixels
     float X[3][6], Y[3][6], Z[3][6];
 #pragma unroll
@@ -115,6 +120,7 @@ __global__ void __launch_bounds__(kStencilThreads) depth_to_normals_kernel(const
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (xb + j < p.W) st_stream_f32(o + comp * hw + j, out[comp][j]);
+    }
     }
 }
 
