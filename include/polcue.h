@@ -46,6 +46,8 @@ POLCUE_API const char* polcue_version(void);
 POLCUE_API const char* polcue_error_string(int code);
 /* Tuning knob for the zenith-angle sincos: 1 = MUFU sin/cos (3.6e-7 abs, default), 0 = polynomial (1.4e-7 abs). */
 POLCUE_API int polcue_debug_set_trig(int mufu);
+/* How many depth->normals launches took the TMA-staged kernel (the rest used the manually staged one). */
+POLCUE_API unsigned long long polcue_debug_stencil_tma_launches(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 POLCUE_API unsigned long long polcue_launch_count(void);
 

@@ -30,12 +30,13 @@ constexpr int kCluster = 8;  // CTAs per image in the per-image kernel (portable
 
 struct Acc {
     float f[4];  // d^2, (log2 hi - log2 lo)^2, |d|/gt, d^2/gt
-    int n, c1, c2, c3;
+    int n, c1, c2, c3;   // kept elements; raw threshold counts (kept + rejected, see acc_add)
+    int seen;            // elements passed to acc_add since the last flush
 };
 
 __device__ __forceinline__ void acc_clear(Acc& a) {
     a.f[0] = a.f[1] = a.f[2] = a.f[3] = 0.0f;
-    a.n = a.c1 = a.c2 = a.c3 = 0;
+    a.n = a.c1 = a.c2 = a.c3 = a.seen = 0;
 }
 
 // fl(hi / lo) < c, decided WITHOUT the division, exactly as IEEE round-to-nearest-even would decide it.
@@ -46,23 +47,23 @@ __device__ __forceinline__ bool ratio_below(float hi, float lo, float c, float n
     return fmaf(-c, lo, hi) < neg_half_ulp_lo;
 }
 
-// One element.  `keep` (0 or 1) gates every contribution so masked kernels stay branch-free.
-__device__ __forceinline__ void acc_add(Acc& a, float gt, float pred, bool keep = true) {
+// One element.  The masked kernels stay branch-free: a rejected element is replaced by the pair (1, 1), which adds
+// exactly zero to the four float sums (d = 0, log ratio = 0) and exactly one to each threshold count; `flush`
+// removes those spurious counts again (they equal the number of rejected elements).
+__device__ __forceinline__ void acc_add(Acc& a, float gt, float pred) {
     const float hi = fmaxf(gt, pred), lo = fminf(gt, pred);
     const float thr = -5.9604644775390625e-08f * lo;     // -2^-24 lo
     // == (max(gt/pred, pred/gt) < 1.25 ** k) of layers.py:542-545, bit for bit, for positive inputs
-    a.c1 += (int)keep & (int)ratio_below(hi, lo, 1.25f, thr);
-    a.c2 += (int)keep & (int)ratio_below(hi, lo, 1.5625f, thr);
-    a.c3 += (int)keep & (int)ratio_below(hi, lo, 1.953125f, thr);
-    const float k = keep ? 1.0f : 0.0f;
-    const float d = gt - pred, kd = k * d, d2 = kd * d;
+    a.c1 += ratio_below(hi, lo, 1.25f, thr);
+    a.c2 += ratio_below(hi, lo, 1.5625f, thr);
+    a.c3 += ratio_below(hi, lo, 1.953125f, thr);
+    const float d = gt - pred, d2 = d * d;
     const float inv_gt = rcp_approx(gt);
-    const float dl = k * (lg2_approx(hi) - lg2_approx(lo));    // |log gt - log pred| / ln 2; ln^2 2 is applied at the flush
+    const float dl = lg2_approx(hi) - lg2_approx(lo);    // |log gt - log pred| / ln 2; ln^2 2 is applied at the flush
     a.f[0] += d2;
     a.f[1] = fmaf(dl, dl, a.f[1]);
-    a.f[2] = fmaf(fabsf(kd), inv_gt, a.f[2]);
+    a.f[2] = fmaf(fabsf(d), inv_gt, a.f[2]);
     a.f[3] = fmaf(d2, inv_gt, a.f[3]);
-    a.n += (int)keep;
 }
 
 struct Acc64 {
@@ -70,10 +71,11 @@ struct Acc64 {
 };
 
 __device__ __forceinline__ void flush(Acc64& s, Acc& a) {
+    const int rejected = a.seen - a.n;
     s.v[0] += a.n;
-    s.v[1] += a.c1;
-    s.v[2] += a.c2;
-    s.v[3] += a.c3;
+    s.v[1] += a.c1 - rejected;
+    s.v[2] += a.c2 - rejected;
+    s.v[3] += a.c3 - rejected;
     s.v[4] += a.f[0];
     s.v[5] += 0.4804530139182014 * (double)a.f[1];   // ln(2)^2
     s.v[6] += a.f[2];
@@ -137,16 +139,24 @@ __global__ void __launch_bounds__(kMetricThreads) depth_errors_kernel(const floa
             acc_add(a, g.y, q.y);
             acc_add(a, g.z, q.z);
             acc_add(a, g.w, q.w);
+            a.n += 4;
+            a.seen += 4;
             if (++since == 16) {
                 flush(s, a);
                 since = 0;
             }
         }
-        for (size_t i = (n4 << 2) + tid; i < count; i += stride) acc_add(a, gt[i], pred[i]);
+        for (size_t i = (n4 << 2) + tid; i < count; i += stride) {
+            acc_add(a, gt[i], pred[i]);
+            a.n += 1;
+            a.seen += 1;
+        }
     } else {
         int since = 0;
         for (size_t i = tid; i < count; i += stride) {
             acc_add(a, ld_stream_f32(gt + i), ld_stream_f32(pred + i));
+            a.n += 1;
+            a.seen += 1;
             if (++since == 64) {
                 flush(s, a);
                 since = 0;
@@ -201,8 +211,9 @@ struct ImageParams {
 __device__ __forceinline__ void acc_masked(Acc& a, const ImageParams& p, float g, float q, int id) {
     // trainer.py:1380 mask, :1410-1411 material filter, :1417-1418 clamp of the prediction
     const bool keep = (g > p.min_d) & (g < p.max_d) & ((p.inst == nullptr) | (id == p.inst_id));
-    // rejected pixels (gt = 0 holes included) are evaluated on harmless stand-in values and gated out
-    acc_add(a, keep ? g : 1.0f, fminf(fmaxf(q, p.min_d), p.max_d), keep);
+    acc_add(a, keep ? g : 1.0f, keep ? fminf(fmaxf(q, p.min_d), p.max_d) : 1.0f);   // rejected -> the neutral pair (1, 1)
+    a.n += keep;
+    a.seen += 1;
 }
 
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThreads)

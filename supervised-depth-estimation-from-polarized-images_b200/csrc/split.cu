@@ -15,8 +15,8 @@ namespace {
 struct SplitParams {
     const unsigned char* img;
     unsigned char* out[4];   // im00, im10, im01, im11
-    uint32_t units_total;    // B * 4 * Hs * units_per_row  (< 2^31)
-    FastDiv units_per_row;   // (Ws * px_bytes) / sizeof(T)
+    uint32_t rows_total;     // B * 4 * Hs output rows
+    uint32_t units_per_row;  // (Ws * px_bytes) / sizeof(T)
     FastDiv rows_per_quad;   // Hs
     uint32_t Hs;
     size_t row_bytes;        // W * px_bytes
@@ -25,49 +25,49 @@ struct SplitParams {
     size_t quad_bytes;       // Hs * Ws * px_bytes
 };
 
-constexpr int kSplitThreads = 256;   // each thread keeps ITEMS independent copies in flight (64 bytes)
+constexpr int kSplitThreads = 256, kSplitRowsPerWarp = 4, kSplitUnroll = 4;
+constexpr int kSplitRowsPerCta = (kSplitThreads / 32) * kSplitRowsPerWarp;
 
-// One CTA per tile of 256 x 4 units, plain launch: the hardware CTA queue balances the two dies' SMs.
+// A warp copies whole output rows: the (frame, quadrant, row) decode is done once per row (warp-uniform), the
+// lanes then stream the row's units with kSplitUnroll independent copies in flight.  One CTA per 32 rows,
+// launched plainly so the hardware CTA queue balances the SMs.
 template <typename T>
 __global__ void __launch_bounds__(kSplitThreads) split_pol_kernel(const SplitParams p) {
-    constexpr int kSplitItems = sizeof(T) >= 16 ? 4 : (sizeof(T) >= 8 ? 8 : 16);
-    const uint32_t base = blockIdx.x * (kSplitThreads * kSplitItems) + threadIdx.x;
-    T v[kSplitItems];
-    T* dst[kSplitItems];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t row0 = (blockIdx.x * (kSplitThreads / 32) + warp) * kSplitRowsPerWarp;
+#pragma unroll 1
+    for (uint32_t k = 0; k < kSplitRowsPerWarp; ++k) {
+        const uint32_t r = row0 + k;
+        if (r >= p.rows_total) return;
+        const uint32_t r2 = fastdiv(r, p.rows_per_quad);
+        const uint32_t y = r - r2 * p.Hs;
+        const uint32_t q = r2 & 3;        // 0: im00, 1: im10, 2: im01, 3: im11
+        const uint32_t b = r2 >> 2;
+        const size_t src_row = (size_t)y + ((q & 1) ? p.Hs : 0);           // im10 / im11: bottom half
+        const size_t src_col = (q & 2) ? p.half_row_bytes : 0;             // im01 / im11: right half
+        const T* src = reinterpret_cast<const T*>(p.img + (size_t)b * p.frame_bytes + src_row * p.row_bytes + src_col);
+        T* dst = reinterpret_cast<T*>(p.out[q] + (size_t)b * p.quad_bytes + (size_t)y * p.half_row_bytes);
+        for (uint32_t u0 = lane; u0 < p.units_per_row; u0 += 32 * kSplitUnroll) {
+            T v[kSplitUnroll];
 #pragma unroll
-    for (int k = 0; k < kSplitItems; ++k) {
-        const uint32_t i = base + k * kSplitThreads;
-        dst[k] = nullptr;
-        if (i < p.units_total) {
-            uint32_t r = fastdiv(i, p.units_per_row);
-            const uint32_t u = i - r * p.units_per_row.div;
-            const uint32_t r2 = fastdiv(r, p.rows_per_quad);
-            const uint32_t y = r - r2 * p.Hs;
-            const uint32_t q = r2 & 3;        // 0: im00, 1: im10, 2: im01, 3: im11
-            const uint32_t b = r2 >> 2;
-            const size_t src_row = (size_t)y + ((q & 1) ? p.Hs : 0);           // im10 / im11: bottom half
-            const size_t src_col = (q & 2) ? p.half_row_bytes : 0;             // im01 / im11: right half
-            v[k] = *(reinterpret_cast<const T*>(p.img + (size_t)b * p.frame_bytes + src_row * p.row_bytes + src_col) + u);
-            dst[k] = reinterpret_cast<T*>(p.out[q] + (size_t)b * p.quad_bytes + (size_t)y * p.half_row_bytes) + u;
+            for (int j = 0; j < kSplitUnroll; ++j)
+                if (u0 + 32 * j < p.units_per_row) v[j] = src[u0 + 32 * j];
+#pragma unroll
+            for (int j = 0; j < kSplitUnroll; ++j)
+                if (u0 + 32 * j < p.units_per_row) dst[u0 + 32 * j] = v[j];
         }
     }
-#pragma unroll
-    for (int k = 0; k < kSplitItems; ++k)
-        if (dst[k]) *dst[k] = v[k];
 }
 
 template <typename T>
 int launch_split(SplitParams p, unsigned long long rows, cudaStream_t s) {
     const unsigned long long upr = p.half_row_bytes / sizeof(T);
-    const unsigned long long units = rows * upr;
-    if (units >= (1ull << 31)) return POLCUE_E2BIG;
-    p.units_total = (uint32_t)units;
-    p.units_per_row.div = (uint32_t)upr;
-    make_fastdiv(p.units_per_row.div, p.units_per_row.mul, p.units_per_row.shift);
+    if (rows >= (1ull << 31) || upr >= (1ull << 31)) return POLCUE_E2BIG;
+    p.rows_total = (uint32_t)rows;
+    p.units_per_row = (uint32_t)upr;
     p.rows_per_quad.div = p.Hs;
     make_fastdiv(p.rows_per_quad.div, p.rows_per_quad.mul, p.rows_per_quad.shift);
-    const unsigned per_cta = kSplitThreads * (sizeof(T) >= 16 ? 4 : (sizeof(T) >= 8 ? 8 : 16));
-    split_pol_kernel<T><<<(unsigned)((units + per_cta - 1) / per_cta), kSplitThreads, 0, s>>>(p);
+    split_pol_kernel<T><<<(unsigned)((rows + kSplitRowsPerCta - 1) / kSplitRowsPerCta), kSplitThreads, 0, s>>>(p);
     return launch_status();
 }
 

@@ -29,6 +29,7 @@ _SIGNATURES = {
     "polcue_error_string": (C.c_char_p, [C.c_int]),
     "polcue_debug_set_trig": (C.c_int, [C.c_int]),
     "polcue_launch_count": (C.c_ulonglong, []),
+    "polcue_debug_stencil_tma_launches": (C.c_ulonglong, []),
     "polcue_lut_create": (C.c_int, [C.c_double, C.POINTER(C.c_void_p)]),
     "polcue_lut_destroy": (None, [C.c_void_p]),
     "polcue_lut_host_build": (C.c_int, [C.c_double, C.POINTER(C.c_void_p)]),

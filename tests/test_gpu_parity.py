@@ -334,6 +334,17 @@ def test_depth_to_normals(shape):
     assert ((np.abs(nrm - 1) < 1e-5) | (nrm < 1e-5)).all()
 
 
+def test_depth_to_normals_uses_tma_staging_when_rows_are_16_byte_multiples():
+    L = _lib.lib()
+    gt, _, _, k = synth.gen_depth_batch(0, 2, 64, 96)
+    before = L.polcue_debug_stencil_tma_launches()
+    ops.depth_to_normals(dev(gt)[:, None], dev(k))
+    assert L.polcue_debug_stencil_tma_launches() == before + 1
+    gt, _, _, k = synth.gen_depth_batch(0, 2, 37, 131)
+    ops.depth_to_normals(dev(gt)[:, None], dev(k))              # odd width: manually staged tile
+    assert L.polcue_debug_stencil_tma_launches() == before + 1
+
+
 def test_depth_to_normals_properties():
     k = dev(synth.scaled_intrinsics(64, 96)[None].astype(np.float32))
     flat = torch.full((1, 1, 64, 96), 0.8, device="cuda")

@@ -28,20 +28,32 @@ def hbm_peak():
 
 
 def timeit(fn, reps, flush):
+    """Mean launch time with the GPU kept busy: `reps` calls are enqueued back to back between two events, so host
+    launch overhead overlaps with the previous kernel (as it does in a real pipeline).  With `flush`, an L2-sized
+    write precedes every call inside the loop and the separately measured cost of those writes is subtracted."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    times = []
-    for _ in range(reps):
-        if flush is not None:
-            flush.fill_(1)
+
+    def run(body):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(reps):
+            body()
         b.record()
         torch.cuda.synchronize()
-        times.append(a.elapsed_time(b))
-    return float(np.mean(times)), float(np.min(times))
+        return a.elapsed_time(b) / reps
+
+    if flush is None:
+        return run(fn), run(fn)
+
+    def both():
+        flush.fill_(1)
+        fn()
+
+    t_flush = min(run(lambda: flush.fill_(1)) for _ in range(2))
+    t_both = min(run(both) for _ in range(2))
+    return t_both - t_flush, t_both - t_flush
 
 
 def main():
