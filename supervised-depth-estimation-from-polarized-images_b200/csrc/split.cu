@@ -15,59 +15,62 @@ namespace {
 struct SplitParams {
     const unsigned char* img;
     unsigned char* out[4];   // im00, im10, im01, im11
-    uint32_t rows_total;     // B * 4 * Hs output rows
-    uint32_t units_per_row;  // (Ws * px_bytes) / sizeof(T)
-    FastDiv rows_per_quad;   // Hs
+    uint32_t units_total;    // B * H * 2 * units_per_half_row  (< 2^31)
+    FastDiv units_per_row;   // 2 * units_per_half_row : units in one full input row
+    FastDiv rows_per_frame;  // H
+    uint32_t upr_half;       // (Ws * px_bytes) / sizeof(T)
     uint32_t Hs;
-    size_t row_bytes;        // W * px_bytes
     size_t half_row_bytes;   // Ws * px_bytes
-    size_t frame_bytes;      // H * W * px_bytes
     size_t quad_bytes;       // Hs * Ws * px_bytes
 };
 
-constexpr int kSplitThreads = 256, kSplitRowsPerWarp = 4, kSplitUnroll = 4;
-constexpr int kSplitRowsPerCta = (kSplitThreads / 32) * kSplitRowsPerWarp;
+constexpr int kSplitThreads = 256;
 
-// A warp copies whole output rows: the (frame, quadrant, row) decode is done once per row (warp-uniform), the
-// lanes then stream the row's units with kSplitUnroll independent copies in flight.  One CTA per 32 rows,
-// launched plainly so the hardware CTA queue balances the SMs.
+// The input is read strictly linearly (unit i is bytes [i, i+1) * sizeof(T) of the batch), so DRAM sees one
+// sequential read stream; each unit is scattered to its quadrant, whose rows are contiguous runs of half a row.
+// A thread keeps ITEMS independent copies (64 bytes) in flight; one CTA per tile, launched plainly.
 template <typename T>
 __global__ void __launch_bounds__(kSplitThreads) split_pol_kernel(const SplitParams p) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t row0 = (blockIdx.x * (kSplitThreads / 32) + warp) * kSplitRowsPerWarp;
-#pragma unroll 1
-    for (uint32_t k = 0; k < kSplitRowsPerWarp; ++k) {
-        const uint32_t r = row0 + k;
-        if (r >= p.rows_total) return;
-        const uint32_t r2 = fastdiv(r, p.rows_per_quad);
-        const uint32_t y = r - r2 * p.Hs;
-        const uint32_t q = r2 & 3;        // 0: im00, 1: im10, 2: im01, 3: im11
-        const uint32_t b = r2 >> 2;
-        const size_t src_row = (size_t)y + ((q & 1) ? p.Hs : 0);           // im10 / im11: bottom half
-        const size_t src_col = (q & 2) ? p.half_row_bytes : 0;             // im01 / im11: right half
-        const T* src = reinterpret_cast<const T*>(p.img + (size_t)b * p.frame_bytes + src_row * p.row_bytes + src_col);
-        T* dst = reinterpret_cast<T*>(p.out[q] + (size_t)b * p.quad_bytes + (size_t)y * p.half_row_bytes);
-        for (uint32_t u0 = lane; u0 < p.units_per_row; u0 += 32 * kSplitUnroll) {
-            T v[kSplitUnroll];
+    constexpr int kItems = sizeof(T) >= 16 ? 4 : (sizeof(T) >= 8 ? 8 : 16);
+    const uint32_t base = blockIdx.x * (kSplitThreads * kItems) + threadIdx.x;
+    const T* src = reinterpret_cast<const T*>(p.img);
+    T v[kItems];
 #pragma unroll
-            for (int j = 0; j < kSplitUnroll; ++j)
-                if (u0 + 32 * j < p.units_per_row) v[j] = src[u0 + 32 * j];
+    for (int k = 0; k < kItems; ++k) {
+        const uint32_t i = base + k * kSplitThreads;
+        if (i < p.units_total) v[k] = src[i];
+    }
 #pragma unroll
-            for (int j = 0; j < kSplitUnroll; ++j)
-                if (u0 + 32 * j < p.units_per_row) dst[u0 + 32 * j] = v[j];
+    for (int k = 0; k < kItems; ++k) {
+        const uint32_t i = base + k * kSplitThreads;
+        if (i < p.units_total) {
+            const uint32_t row = fastdiv(i, p.units_per_row);
+            uint32_t u = i - row * p.units_per_row.div;
+            const uint32_t b = fastdiv(row, p.rows_per_frame);
+            uint32_t y = row - b * p.rows_per_frame.div;
+            const bool right = u >= p.upr_half, bottom = y >= p.Hs;
+            u -= right ? p.upr_half : 0;
+            y -= bottom ? p.Hs : 0;
+            // return order of split_pol: im00 (top-left), im10 (bottom-left), im01 (top-right), im11 (bottom-right)
+            unsigned char* q = right ? (bottom ? p.out[3] : p.out[2]) : (bottom ? p.out[1] : p.out[0]);
+            reinterpret_cast<T*>(q + (size_t)b * p.quad_bytes + (size_t)y * p.half_row_bytes)[u] = v[k];
         }
     }
 }
 
 template <typename T>
 int launch_split(SplitParams p, unsigned long long rows, cudaStream_t s) {
-    const unsigned long long upr = p.half_row_bytes / sizeof(T);
-    if (rows >= (1ull << 31) || upr >= (1ull << 31)) return POLCUE_E2BIG;
-    p.rows_total = (uint32_t)rows;
-    p.units_per_row = (uint32_t)upr;
-    p.rows_per_quad.div = p.Hs;
-    make_fastdiv(p.rows_per_quad.div, p.rows_per_quad.mul, p.rows_per_quad.shift);
-    split_pol_kernel<T><<<(unsigned)((rows + kSplitRowsPerCta - 1) / kSplitRowsPerCta), kSplitThreads, 0, s>>>(p);
+    const unsigned long long upr_half = p.half_row_bytes / sizeof(T);
+    const unsigned long long units = rows * 2 * upr_half;      // rows = B * H input rows
+    if (units >= (1ull << 31)) return POLCUE_E2BIG;
+    p.units_total = (uint32_t)units;
+    p.upr_half = (uint32_t)upr_half;
+    p.units_per_row.div = (uint32_t)(2 * upr_half);
+    make_fastdiv(p.units_per_row.div, p.units_per_row.mul, p.units_per_row.shift);
+    p.rows_per_frame.div = 2 * p.Hs;
+    make_fastdiv(p.rows_per_frame.div, p.rows_per_frame.mul, p.rows_per_frame.shift);
+    const unsigned per_cta = kSplitThreads * (sizeof(T) >= 16 ? 4 : (sizeof(T) >= 8 ? 8 : 16));
+    split_pol_kernel<T><<<(unsigned)((units + per_cta - 1) / per_cta), kSplitThreads, 0, s>>>(p);
     return launch_status();
 }
 
@@ -88,11 +91,9 @@ extern "C" int polcue_split_pol(const void* img, int B, int H, int W, int px_byt
     p.out[2] = static_cast<unsigned char*>(im01);
     p.out[3] = static_cast<unsigned char*>(im11);
     p.Hs = (unsigned)(H / 2);
-    p.row_bytes = (size_t)W * px_bytes;
-    p.half_row_bytes = p.row_bytes / 2;
-    p.frame_bytes = (size_t)H * p.row_bytes;
+    p.half_row_bytes = (size_t)W * px_bytes / 2;
     p.quad_bytes = (size_t)p.Hs * p.half_row_bytes;
-    const unsigned long long rows = (unsigned long long)B * 4 * p.Hs;   // output rows
+    const unsigned long long rows = (unsigned long long)B * H;          // input rows
     uintptr_t bits = reinterpret_cast<uintptr_t>(img) | p.half_row_bytes;
     for (int q = 0; q < 4; ++q) bits |= reinterpret_cast<uintptr_t>(p.out[q]);
     cudaStream_t s = (cudaStream_t)stream;
