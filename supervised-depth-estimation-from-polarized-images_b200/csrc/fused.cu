@@ -38,13 +38,18 @@ const DeviceInfo& device_info() {
 
 namespace {
 
-constexpr int kFusedThreads = 512;
+#ifndef POLCUE_FUSED_THREADS
+#define POLCUE_FUSED_THREADS 256
+#endif
+constexpr int kFusedThreads = POLCUE_FUSED_THREADS;            // pixel groups per tile = threads per CTA
+constexpr int kFusedMinBlocks = 1024 / kFusedThreads;           // 1024 resident threads per SM at <= 64 registers
 
 struct LutArgs {
     const float4* blob;
     uint32_t bytes;
     int offset[3];
     float scale[3];
+    float last[3];
 };
 
 LutArgs lut_args(const polcue_lut* lut) {
@@ -54,6 +59,7 @@ LutArgs lut_args(const polcue_lut* lut) {
     for (int t = 0; t < 3; ++t) {
         a.offset[t] = lut->offset[t];
         a.scale[t] = lut->scale[t];
+        a.last[t] = (float)lut->cells[t] - 0.5f;
     }
     return a;
 }
@@ -65,6 +71,7 @@ __device__ __forceinline__ LutShared lut_shared(const void* smem_base, const Lut
         asm volatile("" : "+r"(addr));   // keep the three table bases as values: lookup = one LEA, not add + LEA
         v.addr[t] = addr;
         v.scale[t] = a.scale[t];
+        v.last[t] = a.last[t];
     }
     return v;
 }
@@ -74,6 +81,7 @@ __device__ __forceinline__ LutView lut_view(const float4* base, const LutArgs& a
     for (int t = 0; t < 3; ++t) {
         v.cells[t] = base + a.offset[t];
         v.scale[t] = a.scale[t];
+        v.last[t] = a.last[t];
     }
     return v;
 }
@@ -202,7 +210,7 @@ __device__ __forceinline__ void process_group(const FusedParams& p, const LutSha
 // control; the loop is software-pipelined two deep: while tile k is computed and stored, the quadrant words of tile
 // k+1 are already in flight and the query for tile k+2 is outstanding, so no warp waits on DRAM latency.
 template <int VEC, bool MUFU, bool NORMALS>
-__global__ void __launch_bounds__(kFusedThreads, 2) fused_mosaic_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) fused_mosaic_kernel(const FusedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ __align__(16) uint4 clc_resp;
@@ -425,7 +433,7 @@ __device__ __forceinline__ XolpIn<VEC> load_xolp(const NormalsParams& p, uint32_
 
 // get_normals: same tile scheduling and two-deep software pipeline as the fused kernel.
 template <int VEC, bool MUFU>
-__global__ void __launch_bounds__(kFusedThreads, 2) normals_from_xolp_kernel(const NormalsParams p) {
+__global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) normals_from_xolp_kernel(const NormalsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ __align__(16) uint4 clc_resp;
@@ -479,10 +487,10 @@ __global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ rh
         const float r = ld_stream_f32(rho + i);
         const float g = lut_coord(r);
         if constexpr (WHICH == 0) {
-            st_stream_f32(out0 + i, lut_eval(lut.cells[0], lut.scale[0], r, g));
+            st_stream_f32(out0 + i, lut_eval(lut.cells[0], lut.scale[0], lut.last[0], r, g));
         } else {
-            st_stream_f32(out0 + i, lut_eval(lut.cells[1], lut.scale[1], r, g));
-            st_stream_f32(out1 + i, lut_eval(lut.cells[2], lut.scale[2], r, g));
+            st_stream_f32(out0 + i, lut_eval(lut.cells[1], lut.scale[1], lut.last[1], r, g));
+            st_stream_f32(out1 + i, lut_eval(lut.cells[2], lut.scale[2], lut.last[2], r, g));
         }
     }
 }

@@ -9,7 +9,8 @@
 // device finds the segment with one multiply instead of a search:
 //   * g(rho) = sqrt(rho) below 0.5 and sqrt2 - sqrt(1-rho) above spreads the knots (which crowd
 //     quadratically at rho -> 0 and at the specular peak rho -> 1) almost evenly;
-//   * a uniform grid over g in [0, sqrt2] is chosen fine enough that a cell holds at most one knot;
+//   * a uniform grid over g in [0, g(last knot)] is chosen fine enough that a cell holds at most one knot
+//     (queries beyond the last knot clamp to the last cell = the extrapolation segment);
 //   * a cell stores that knot (or the next one to its right) and the slopes on either side of it.
 // The grid size is found by verification against the exact interpolant, not assumed.
 #include <algorithm>
@@ -90,6 +91,10 @@ struct CellD {
     double x, y, sl, sr;
 };
 
+// Span of the cell grid in g: just past the last knot.  Queries beyond it clamp to the last cell, which holds the
+// last knot and the extrapolation slope, so no cells are spent on the (often long) extrapolation range.
+double grid_span(const Knots& k) { return std::min(kSqrt2, g_of(k.x.back()) * (1.0 + 1e-6) + 1e-9); }
+
 void build_cells(const Knots& k, int cells, std::vector<CellD>& out) {
     const int n = k.n();
     std::vector<double> gk(n);
@@ -97,7 +102,7 @@ void build_cells(const Knots& k, int cells, std::vector<CellD>& out) {
     out.resize(cells);
     int j = 0;
     for (int c = 0; c < cells; ++c) {
-        const double g_start = kSqrt2 * c / cells;
+        const double g_start = grid_span(k) * c / cells;
         while (j < n && gk[j] < g_start) ++j;      // first knot at or right of the cell start
         const int kn = std::min(j, n - 1);
         const int left = std::min(std::max(kn - 1, 0), n - 2);
@@ -116,7 +121,8 @@ double eval_cell(const CellD& e, double q) {
 // and the extrapolation ranges.
 double verify(const Knots& k, const std::vector<CellD>& cells) {
     const int m = (int)cells.size();
-    auto cell_of = [&](double q) { return std::min((int)(g_of(q) * m / kSqrt2), m - 1); };
+    const double span = grid_span(k);
+    auto cell_of = [&](double q) { return std::min((int)(g_of(q) * m / span), m - 1); };
     double worst = 0;
     auto probe = [&](double q, int c) {
         c = std::min(std::max(c, 0), m - 1);
@@ -131,7 +137,7 @@ double verify(const Knots& k, const std::vector<CellD>& cells) {
         }
     }
     for (int c = 1; c < m; ++c) {
-        const double b = rho_of(kSqrt2 * c / m);
+        const double b = rho_of(span * c / m);
         for (double rel : {-4e-7, -1e-9, 1e-9, 4e-7}) {
             const double q = b + rel * (b < 0.5 ? b : 1.0 - b);  // relative to what the device rounds
             probe(q, c - 1 + (rel > 0));
@@ -181,8 +187,8 @@ int build_host(double n, polcue_lut** out) {
         }
         lut->cells[t] = chosen;
         lut->offset[t] = total;
-        lut->scale[t] = (float)(chosen / kSqrt2);
-        total += chosen + 1;   // + guard cell: float32 g * scale can land exactly on `chosen`
+        lut->scale[t] = (float)(chosen / grid_span(tab[t]));
+        total += chosen + 1;   // + one spare cell (copy of the last) so a 16-byte read one past the end stays in bounds
         lut->blob.resize(total);
         for (int c = 0; c <= chosen; ++c) {
             const CellD& e = cells[c < chosen ? c : chosen - 1];
@@ -255,7 +261,7 @@ int polcue_lut_eval_host(const polcue_lut* lut, int table, const float* rho, siz
         const float t = fmaxf(low ? r : 1.0f - r, 0.0f);
         float g = sqrtf(t);
         g = low ? g : 1.41421356237309504880f - g;
-        const float4 e = cells[(int)(g * scale)];
+        const float4 e = cells[std::min((int)(g * scale), lut->cells[table] - 1)];
         const float d = r - e.x;
         theta[i] = fmaf(fmaxf(d, 0.0f), e.w, fmaf(d, e.z, e.y));
     }

@@ -193,8 +193,9 @@ __device__ __forceinline__ void sincos_sel(float x, float& s, float& c) {
 // same line scipy's interp1d(linear, extrapolate) evaluates on that segment.  Built in lut.cu.
 // ------------------------------------------------------------------------------------------
 struct LutView {
-    const float4* cells[3];  // diffuse, spec1, spec2 (shared memory in the hot kernels)
+    const float4* cells[3];  // diffuse, spec1, spec2 (global memory, L1-resident)
     float scale[3];          // cells per unit g
+    float last[3];           // cells - 0.5
 };
 
 __device__ __forceinline__ float lut_coord(float rho) {
@@ -204,22 +205,23 @@ __device__ __forceinline__ float lut_coord(float rho) {
     return low ? g : kSqrt2 - g;
 }
 
-// cell = (x_k, y_k, slope_left, slope_right - slope_left); a guard cell past the end absorbs g * scale == cells.
+// cell = (x_k, y_k, slope_left, slope_right - slope_left); the cell coordinate is clamped to the last cell.
 __device__ __forceinline__ float lut_line(const float4 e, float rho) {
     const float d = rho - e.x;
     return fmaf(fmaxf(d, 0.0f), e.w, fmaf(d, e.z, e.y));
 }
-__device__ __forceinline__ float lut_eval(const float4* __restrict__ cells, float scale, float rho, float g) {
-    return lut_line(cells[(int)(g * scale)], rho);
+__device__ __forceinline__ float lut_eval(const float4* __restrict__ cells, float scale, float last, float rho, float g) {
+    return lut_line(cells[(int)fminf(g * scale, last)], rho);
 }
 
 // Shared-memory tables addressed by 32-bit shared-window addresses (one IMAD per lookup).
 struct LutShared {
     uint32_t addr[3];
     float scale[3];
+    float last[3];    // cells - 0.5: clamp of the cell coordinate (beyond the last knot = extrapolation cell)
 };
 __device__ __forceinline__ float lut_eval_shared(const LutShared& lut, int t, float rho, float g) {
-    return lut_line(lds_f32x4(lut.addr[t] + 16u * (uint32_t)(int)(g * lut.scale[t])), rho);
+    return lut_line(lds_f32x4(lut.addr[t] + 16u * (uint32_t)(int)fminf(g * lut.scale[t], lut.last[t])), rho);
 }
 
 // ------------------------------------------------------------------------------------------

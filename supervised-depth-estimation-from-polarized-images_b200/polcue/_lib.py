@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpolcue.so")
+LIB_PATH = os.environ.get("POLCUE_LIB") or os.path.join(_HERE, "libpolcue.so")   # POLCUE_LIB: tuning builds only
 
 OK, EINVAL, ENOMEM, ERANGE, E2BIG = 0, -22, -12, -34, -7
 
