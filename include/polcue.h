@@ -176,6 +176,17 @@ POLCUE_API int polcue_depth_errors_images_f32(const float* gt, const float* pred
                                    float min_d, float max_d, int inst_id, double* sums, float* metrics,
                                    polcue_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Per-channel sum and sum of squares (float64) of a planar float32 tensor x[B, C, hw].
+ *   polarisation/xolp_mean_and_std_dev.py:26-32 (mean / std of DoLP and AoLP over a set of frames; the constants
+ *   of manydepth/networks/pre_encoders.py:79); also the output checksum of the sequence benchmark.
+ * stats: C x 2 doubles (device): sum, sum of squares per channel; additive across frames and ranks.
+ * workspace: polcue_channel_stats_workspace_bytes(B, C, hw) bytes, first 8 bytes zero before the first use.
+ * ------------------------------------------------------------------------------------------- */
+POLCUE_API size_t polcue_channel_stats_workspace_bytes(int B, int C, size_t hw);
+POLCUE_API int polcue_channel_stats_f32(const float* x, int B, int C, size_t hw, void* workspace, double* stats,
+                             polcue_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -366,6 +366,19 @@ def depth_errors_per_image(gt, pred, min_depth, max_depth, inst=None, inst_id=No
 
 
 # --------------------------------------------------------------------------------------
+# XOLP dataset statistics
+# --------------------------------------------------------------------------------------
+def xolp_statistics(dolp, aolp):
+    """polarisation/xolp_mean_and_std_dev.py:26-32: mean and population std of all DoLP / AoLP values of a set of
+    frames, and the two 'XOLP' averages the script prints.  dolp, aolp: N x H x W."""
+    dolp, aolp = np.asarray(dolp, dtype=np.float64), np.asarray(aolp, dtype=np.float64)
+    dm, ds = dolp.mean(axis=(0, 1, 2)), dolp.std(axis=(0, 1, 2))
+    am, asd = aolp.mean(axis=(0, 1, 2)), aolp.std(axis=(0, 1, 2))
+    return {"dolp_mean": dm, "dolp_std": ds, "aolp_mean": am, "aolp_std": asd,
+            "xolp_mean": 0.5 * (dm + am), "xolp_std": 0.5 * (ds + asd)}
+
+
+# --------------------------------------------------------------------------------------
 # whole chain (polarisation/xolp_and_normals.py:101-129) -- used for the CPU baseline timing
 # --------------------------------------------------------------------------------------
 def frame_chain_reference(mosaic, n=1.5, angles=CANONICAL_ANGLES):

@@ -366,3 +366,44 @@ def metrics_from_sums(sums):
     stack = torch.stack if isinstance(sums, torch.Tensor) else np.stack
     return stack((sums[..., 6] / n, sums[..., 7] / n, sqrt(sums[..., 4] / n), sqrt(sums[..., 5] / n),
                   sums[..., 1] / n, sums[..., 2] / n, sums[..., 3] / n), -1)
+
+
+# ------------------------------------------------------------------------------------------
+# per-channel statistics (XOLP dataset statistics, output checksums)
+# ------------------------------------------------------------------------------------------
+_stat_workspaces = {}
+
+
+def channel_stats(x):
+    """x: B x C x ... float32 CUDA tensor -> float64 tensor [C, 2] on device: per-channel (sum, sum of squares)."""
+    x = _need_cuda(x, "x", torch.float32)
+    if x.dim() < 3:
+        raise ValueError("x must be B x C x ...")
+    b, c = x.shape[0], x.shape[1]
+    hw = x.numel() // (b * c) if b * c else 0
+    nbytes = int(_lib.lib().polcue_channel_stats_workspace_bytes(b, c, hw))
+    key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+    ws = _stat_workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _stat_workspaces[key] = torch.zeros(nbytes, dtype=torch.uint8, device=x.device)
+    stats = torch.empty((c, 2), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().polcue_channel_stats_f32(_ptr(x), b, c, hw, _ptr(ws), _ptr(stats), _stream(x)),
+                   "polcue_channel_stats_f32")
+    return stats
+
+
+def xolp_statistics(xolp, reduce_over_ranks=True):
+    """DoLP / AoLP mean and (population) std over a set of frames, as polarisation/xolp_mean_and_std_dev.py:26-32 prints
+    them.  xolp: B x 2 x H x W.  With torch.distributed initialised the sums are all-reduced first."""
+    from . import dist as D
+    b = xolp.shape[0]
+    acc = torch.cat((channel_stats(xolp).reshape(-1),
+                     torch.tensor([float(xolp.numel() // 2)], dtype=torch.float64, device=xolp.device)))
+    if reduce_over_ranks:
+        D.all_reduce_sums(acc)
+    n = acc[4]
+    mean = acc[[0, 2]] / n
+    std = torch.sqrt(torch.clamp(acc[[1, 3]] / n - mean * mean, min=0.0))
+    return {"dolp_mean": float(mean[0]), "dolp_std": float(std[0]), "aolp_mean": float(mean[1]), "aolp_std": float(std[1]),
+            "xolp_mean": float(0.5 * (mean[0] + mean[1])), "xolp_std": float(0.5 * (std[0] + std[1])), "frames": b}

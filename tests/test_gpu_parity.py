@@ -434,6 +434,36 @@ def test_depth_errors_per_image(golden, shape):
         assert np.allclose(metrics.cpu().numpy(), golden["met_img_rows"], rtol=2e-5)
 
 
+@pytest.mark.parametrize("shape", [(3, 2, 64, 96), (2, 9, 33, 47), (5, 11, 320, 480), (1, 1, 1, 1)])
+def test_channel_stats_and_xolp_statistics(shape):
+    rng = np.random.default_rng(sum(shape))
+    x = (rng.normal(0.3, 0.8, shape)).astype(np.float32)
+    got = ops.channel_stats(dev(x)).cpu().numpy()
+    x64 = x.astype(np.float64)
+    assert np.allclose(got[:, 0], x64.sum(axis=(0, 2, 3)), rtol=1e-7, atol=1e-6)
+    assert np.allclose(got[:, 1], (x64 ** 2).sum(axis=(0, 2, 3)), rtol=1e-7)
+    assert torch.equal(ops.channel_stats(dev(x)), ops.channel_stats(dev(x)))          # fixed reduction order
+    if shape[1] == 2:
+        st = ops.xolp_statistics(dev(x))
+        ref = O.xolp_statistics(x[:, 0], x[:, 1])
+        for key, val in ref.items():
+            assert abs(st[key] - val) < 1e-6 * max(1.0, abs(val)), key
+
+
+def test_xolp_statistics_of_fused_output_match_the_reference_script():
+    mosaic = synth.gen_batch("P", 0, 3, 128, 192)
+    out = ops.fused_mosaic(dev(mosaic), 1.5)
+    st = ops.xolp_statistics(out["xolp"])
+    rho, phi = [], []
+    for b in range(3):
+        _, r, p = O.iun_and_xolp_closed(O.stack_quadrants(mosaic[b]))
+        rho.append(r)
+        phi.append(p)
+    ref = O.xolp_statistics(np.stack(rho), np.stack(phi))
+    for key, val in ref.items():
+        assert abs(st[key] - val) < 2e-6, (key, st[key], val)
+
+
 def test_launch_counter_counts_kernels():
     before = _lib.launch_count()
     ops.fused_mosaic(dev(synth.gen_u_mosaic(0, 32, 48))[None], 1.5)
