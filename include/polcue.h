@@ -157,6 +157,23 @@ POLCUE_API int polcue_depth_to_normals_f32(const float* depth, const float* K, i
                                 polcue_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Supervised normals loss, forward and backward (the consumer of the stencil in training).
+ *   manydepth/trainer.py:1298-1309  Trainer.compute_supervised_normals_losses(depth_gt, depth_pred, intrinsics, mask)
+ *     loss = sum((2 - cos(n_gt, n_pred)) * mask) / sum(mask),  n = depth_to_normals(depth, K)
+ * depth_gt, depth_pred, mask: B x 1 x H x W float32; K: B x 3 x 3.
+ * fwd: sums2 (device, 2 doubles) receives {sum((2-cos) m), sum(m)}; loss (device float, may be NULL) = their ratio.
+ *      workspace: polcue_normals_loss_workspace_bytes() bytes, first 8 bytes zero before the first use.
+ * bwd: grad_pred (B x 1 x H x W) = d(loss)/d(depth_pred) * grad_out, with sums2 from the forward call and grad_out a
+ *      DEVICE float scalar.  depth_gt and mask receive no gradient (they are data).
+ * ------------------------------------------------------------------------------------------- */
+POLCUE_API size_t polcue_normals_loss_workspace_bytes(void);
+POLCUE_API int polcue_normals_loss_fwd_f32(const float* depth_gt, const float* depth_pred, const float* K, const float* mask,
+                                int B, int H, int W, void* workspace, double* sums2, float* loss, polcue_stream_t stream);
+POLCUE_API int polcue_normals_loss_bwd_f32(const float* depth_gt, const float* depth_pred, const float* K, const float* mask,
+                                int B, int H, int W, const double* sums2, const float* grad_out, float* grad_pred,
+                                polcue_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Depth error metrics.
  *   manydepth/layers.py:539-557 compute_depth_errors / :559-577 compute_depth_errors_numpy
  * sums8   : 8 doubles (device): count, n[t<1.25], n[t<1.25^2], n[t<1.25^3], S d^2, S dlog^2, S |d|/gt, S d^2/gt

@@ -290,6 +290,39 @@ def depth_to_normals(depth, camera_matrix, dtype=np.float64):
     return nrm / np.maximum(length, dtype(1e-12))
 
 
+def normals_loss_torch(depth_gt, depth_pred, camera_matrix, mask):
+    """Trainer.compute_supervised_normals_losses, manydepth/trainer.py:1298-1309, as a float64 torch graph (CPU) so that
+    autograd supplies the reference gradient w.r.t. depth_pred.
+
+    depth_to_normals follows kornia 0.5.11 (pad replicate + cross-correlation with sobel/8, cross, F.normalize);
+    the similarity follows torch 1.7.1's F.cosine_similarity, w12 * rsqrt(clamp_min(w1 * w2, eps^2)) with eps = 1e-8
+    (environment.yml pins torch 1.7.1).  PARITY UNPINNED for the kornia part, see the module docstring.
+    Inputs: torch tensors B x 1 x H x W (camera_matrix B x 3 x 3).  Returns the zero-dim loss tensor.
+    """
+    import torch
+    import torch.nn.functional as F
+
+    def d2n(depth):
+        b, _, h, w = depth.shape
+        u = torch.arange(w, dtype=depth.dtype)[None, None, :].expand(b, h, w)
+        v = torch.arange(h, dtype=depth.dtype)[None, :, None].expand(b, h, w)
+        km = camera_matrix.to(depth.dtype)
+        fx, fy = km[:, 0, 0, None, None], km[:, 1, 1, None, None]
+        cx, cy = km[:, 0, 2, None, None], km[:, 1, 2, None, None]
+        z = depth[:, 0]
+        xyz = torch.stack(((u - cx) / fx * z, (v - cy) / fy * z, z), 1)
+        kx = torch.tensor([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]], dtype=depth.dtype) / 8
+        ker = torch.stack((kx, kx.t()))[:, None]
+        g = F.conv2d(F.pad(xyz.reshape(b * 3, 1, h, w), (1, 1, 1, 1), mode="replicate"), ker).view(b, 3, 2, h, w)
+        return F.normalize(torch.cross(g[:, :, 0], g[:, :, 1], dim=1), dim=1, p=2, eps=1e-12)
+
+    n_gt, n_pred = d2n(depth_gt), d2n(depth_pred)
+    w12 = (n_gt * n_pred).sum(1)
+    w1, w2 = (n_gt * n_gt).sum(1), (n_pred * n_pred).sum(1)
+    cos = (w12 * torch.rsqrt(torch.clamp_min(w1 * w2, 1e-16))).unsqueeze(1)
+    return ((2.0 - cos) * mask).sum() / mask.sum()
+
+
 # --------------------------------------------------------------------------------------
 # a9 -- depth error metrics
 # --------------------------------------------------------------------------------------

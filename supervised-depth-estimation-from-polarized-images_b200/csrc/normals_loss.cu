@@ -1,0 +1,476 @@
+// Supervised normals loss, forward and backward.
+//
+// Replaces Trainer.compute_supervised_normals_losses, manydepth/trainer.py:1298-1309 (called once per scale at :1248):
+//     n_gt = depth_to_normals(depth_gt, K); n_pred = depth_to_normals(depth_pred, K)        (kornia 0.5.11)
+//     cos  = F.cosine_similarity(n_gt, n_pred, dim=1)      = <a,b> / max(|a| |b|, 1e-8)      (torch 1.7.1)
+//     loss = sum((2 - cos) * mask) / sum(mask)
+// The reference runs ~25 launches per scale (two pads, two conv3d, crosses, normalisations, the similarity, the
+// masked mean) and autograd stores every intermediate.  Here the forward is ONE kernel (both stencils, the cosine
+// and the masked sums; 12 B read per pixel) and the backward is ONE kernel that recomputes the window quantities
+// instead of storing them (12 B read + 4 B written per pixel).
+//
+// Backward, per image (depth_to_normals as in stencil.cu, with the unnormalised Sobel taps s = (1,2,1), d = (-1,0,1):
+// gu = sum_ab s[a] d[b] P(p+(a,b)), gv = sum_ab d[a] s[b] P(p+(a,b)), P = (fx(u) Z, fy(v) Z, Z), n = gu x gv, b = n/|n|):
+//     k_p   = -grad_out * m_p / sum(m)
+//     n_bar = k_p (g - <g,b> b) / |n|,   g = dcos/db = a/D - <a,b> b / (D |b|^2),  D = max(|a||b|, 1e-8)
+//     gu_bar = gv x n_bar,  gv_bar = n_bar x gu
+//     Zbar(q) = fx(q) A_0(q) + fy(q) A_1(q) + A_2(q),
+//     A_c(q)  = sum_{i,j in {-1,0,1}} Sv[i] Du[j] gu_bar_c(q+(i,j)) + Dv[i] Su[j] gv_bar_c(q+(i,j))
+// where the per-axis weights fold the replicate padding back onto border pixels:
+//     S[-1] = S[+1] = 1, D[-1] = +1, D[+1] = -1, S[0] = 2 + [q == 0] + [q == last], D[0] = [q == last] - [q == 0].
+// Phase 1 of the backward kernel writes gu_bar, gv_bar of the tile + 1-pixel ring to shared memory, phase 2 gathers.
+// Depth tiles (halo 2) are staged by TMA tensor copies when rows are 16-byte multiples, else by hand.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "polcue_device.cuh"
+#include "polcue_host.h"
+
+namespace polcue {
+namespace {
+
+constexpr int kLW = 128, kLH = 16, kLossThreads = 256;
+constexpr int kHalo = 2;
+constexpr int kLBoxW = kLW + 8, kLBoxH = kLH + 2 * kHalo;   // interior at column 4, row 2
+constexpr int kLCol = 4, kLRow = kHalo;
+constexpr uint32_t kLTileBytes = kLBoxW * kLBoxH * sizeof(float);
+constexpr int kGW = kLW + 2, kGH = kLH + 2, kGPitch = kGW + 2;   // ring-1 region of the adjoint fields
+constexpr int kMaxLossBlocks = 1 << 16;
+constexpr uint32_t kLTilePad = (kLTileBytes + 127) / 128 * 128;                 // TMA destinations are 128-byte aligned
+constexpr size_t kBwdSmem = 2 * kLTilePad + 6 * kGH * kGPitch * sizeof(float);
+
+struct LossParams {
+    const float* gt;
+    const float* pred;
+    const float* K;
+    const float* mask;
+    int H, W;
+    // forward
+    unsigned long long* ticket;
+    double* partials;      // [ctas][2]
+    double* sums2;         // S = sum (2 - cos) m, M = sum m
+    float* loss;           // S / M
+    // backward
+    const float* grad_out; // device scalar
+    float* grad_pred;
+};
+
+// Stage a halo'd depth tile: TMA (zero-filled outside the image) or manual with clamped coordinates.
+template <bool TMA>
+__device__ __forceinline__ void stage_begin(float (*tile)[kLBoxW], const CUtensorMap* tmap, const float* plane, int H, int W, int x0,
+                                            int y0, int b, uint64_t* bar) {
+    if constexpr (TMA) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(kLTileBytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                    smem_u32(&tile[0][0])),
+                "l"(tmap), "r"(x0 - kLCol), "r"(y0 - kLRow), "r"(b), "r"(smem_u32(bar))
+                : "memory");
+        }
+    } else {
+        for (int i = threadIdx.x; i < kLBoxH * (kLW + 2 * kHalo); i += kLossThreads) {
+            const int r = i / (kLW + 2 * kHalo), c = i - r * (kLW + 2 * kHalo);
+            const int yy = min(max(y0 + r - kLRow, 0), H - 1);
+            const int xx = min(max(x0 + c - kHalo, 0), W - 1);
+            tile[r][kLCol - kHalo + c] = __ldg(plane + (size_t)yy * W + xx);
+        }
+    }
+}
+
+// After a TMA load: replicate the image border into the first ring outside the image (the only out-of-image cells
+// any in-image pixel's window touches).
+__device__ __forceinline__ void patch_replicate(float (*tile)[kLBoxW], int H, int W, int x0, int y0) {
+    const int last_x = W - 1 - x0, last_y = H - 1 - y0;
+    const bool left = x0 == 0, right = last_x < kLW + 1, top = y0 == 0, bottom = last_y < kLH + 1;
+    if (left | right) {
+        for (int r = threadIdx.x; r < kLBoxH; r += kLossThreads) {
+            if (left) tile[r][kLCol - 1] = tile[r][kLCol];
+            if (right && last_x >= -1) tile[r][kLCol + last_x + 1] = tile[r][kLCol + last_x];
+        }
+    }
+    __syncthreads();
+    if (top | bottom) {
+        for (int c = threadIdx.x; c < kLBoxW; c += kLossThreads) {
+            if (top) tile[kLRow - 1][c] = tile[kLRow][c];
+            if (bottom && last_y >= -1) tile[kLRow + last_y + 1][c] = tile[kLRow + last_y][c];
+        }
+    }
+    __syncthreads();
+}
+
+struct Cam {
+    float inv_fx, cx, inv_fy, cy;
+};
+__device__ __forceinline__ Cam load_cam(const float* K, int b) {
+    const float* k = K + (size_t)b * 9;
+    Cam c;
+    c.inv_fx = 1.0f / __ldg(k + 0);
+    c.cx = __ldg(k + 2);
+    c.inv_fy = 1.0f / __ldg(k + 4);
+    c.cy = __ldg(k + 5);
+    return c;
+}
+
+// 8 x gradients of xyz at tile-local pixel (ty, tx) (image pixel (y0+ty, x0+tx)), same arithmetic as stencil.cu.
+__device__ __forceinline__ void gradients(const float (*tile)[kLBoxW], int ty, int tx, int x, int y, int H, int W, const Cam& cam,
+                                          float (&gu)[3], float (&gv)[3]) {
+    float fx3[3], fy3[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        fx3[k] = ((float)min(max(x + k - 1, 0), W - 1) - cam.cx) * cam.inv_fx;
+        fy3[k] = ((float)min(max(y + k - 1, 0), H - 1) - cam.cy) * cam.inv_fy;
+    }
+    float Z[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Z[r][c] = tile[kLRow + ty + r - 1][kLCol + tx + c - 1];
+    float Su[3][3], Dv[3][3];
+    const float fy1x2 = 2.0f * fy3[1];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Su[2][c] = fmaf(2.0f, Z[1][c], Z[0][c] + Z[2][c]);
+        Dv[2][c] = Z[2][c] - Z[0][c];
+        Su[0][c] = fx3[c] * Su[2][c];
+        Dv[0][c] = fx3[c] * Dv[2][c];
+        Su[1][c] = fmaf(fy3[2], Z[2][c], fmaf(fy1x2, Z[1][c], fy3[0] * Z[0][c]));
+        Dv[1][c] = __fsub_rn(__fmul_rn(fy3[2], Z[2][c]), __fmul_rn(fy3[0], Z[0][c]));
+    }
+#pragma unroll
+    for (int comp = 0; comp < 3; ++comp) {
+        gu[comp] = Su[comp][2] - Su[comp][0];
+        gv[comp] = fmaf(2.0f, Dv[comp][1], Dv[comp][0] + Dv[comp][2]);
+    }
+}
+
+__device__ __forceinline__ void cross_rn(const float (&a)[3], const float (&b)[3], float (&n)[3]) {
+    n[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
+    n[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
+    n[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
+}
+
+constexpr float kInvCap = 1.0f / (64.0f * 1e-12f);   // n here is 64 x the reference's cross product (see stencil.cu)
+
+// unit (or capped) normal and the factor it was scaled by
+__device__ __forceinline__ float normalize3(const float (&n)[3], float (&u)[3]) {
+    const float inv = fminf(rsqrt_approx(fmaf(n[0], n[0], fmaf(n[1], n[1], n[2] * n[2]))), kInvCap);
+    u[0] = n[0] * inv;
+    u[1] = n[1] * inv;
+    u[2] = n[2] * inv;
+    return inv;
+}
+
+// cos = <a,b> / max(|a||b|, 1e-8)   (torch 1.7.1 F.cosine_similarity: w12 * rsqrt(clamp_min(w1 w2, eps^2)))
+__device__ __forceinline__ float cosine(const float (&a)[3], const float (&b)[3], float& inv_den, float& ab, float& bb,
+                                        bool& clamped) {
+    ab = fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2]));
+    const float aa = fmaf(a[0], a[0], fmaf(a[1], a[1], a[2] * a[2]));
+    bb = fmaf(b[0], b[0], fmaf(b[1], b[1], b[2] * b[2]));
+    clamped = aa * bb <= 1e-16f;
+    inv_den = clamped ? 1e8f : rsqrtf(aa * bb);
+    return ab * inv_den;
+}
+
+template <bool TMA>
+__global__ void __launch_bounds__(kLossThreads) normals_loss_fwd_kernel(const __grid_constant__ CUtensorMap tm_gt,
+                                                                        const __grid_constant__ CUtensorMap tm_pred, const LossParams p) {
+    __shared__ __align__(128) float tg[kLBoxH][kLBoxW];
+    __shared__ __align__(128) float tp[kLBoxH][kLBoxW];
+    __shared__ uint64_t bar;
+    __shared__ double red[kLossThreads / 32][2];
+    __shared__ bool last;
+    const int b = blockIdx.z, x0 = blockIdx.x * kLW, y0 = blockIdx.y * kLH;
+    const size_t hw = (size_t)p.H * p.W;
+    if (TMA && threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (TMA) __syncthreads();
+    stage_begin<TMA>(tg, &tm_gt, p.gt + b * hw, p.H, p.W, x0, y0, b, &bar);
+    stage_begin<TMA>(tp, &tm_pred, p.pred + b * hw, p.H, p.W, x0, y0, b, &bar);
+    if constexpr (TMA) {
+        lut_stage_wait(&bar);
+        patch_replicate(tg, p.H, p.W, x0, y0);
+        patch_replicate(tp, p.H, p.W, x0, y0);
+    } else {
+        __syncthreads();
+    }
+    const Cam cam = load_cam(p.K, b);
+    double s = 0.0, m = 0.0;
+    for (int i = threadIdx.x; i < kLW * kLH; i += kLossThreads) {
+        const int ty = i / kLW, tx = i - ty * kLW;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= p.W || y >= p.H) continue;
+        const float mk = __ldg(p.mask + b * hw + (size_t)y * p.W + x);
+        float gu[3], gv[3], n[3], a[3], bb3[3];
+        gradients(tg, ty, tx, x, y, p.H, p.W, cam, gu, gv);
+        cross_rn(gu, gv, n);
+        normalize3(n, a);
+        gradients(tp, ty, tx, x, y, p.H, p.W, cam, gu, gv);
+        cross_rn(gu, gv, n);
+        normalize3(n, bb3);
+        float inv_den, ab, bb;
+        bool clamped;
+        const float c = cosine(a, bb3, inv_den, ab, bb, clamped);
+        s += (double)((2.0f - c) * mk);
+        m += (double)mk;
+    }
+    // deterministic reduction: warp shuffle -> shared -> per-CTA partial -> last CTA folds in fixed order
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, off);
+        m += __shfl_down_sync(0xffffffffu, m, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5][0] = s;
+        red[threadIdx.x >> 5][1] = m;
+    }
+    __syncthreads();
+    const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const unsigned ctas = gridDim.x * gridDim.y * gridDim.z;
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tmk = 0.0;
+        for (int w = 0; w < kLossThreads / 32; ++w) {
+            ts += red[w][0];
+            tmk += red[w][1];
+        }
+        p.partials[2 * (size_t)cta] = ts;
+        p.partials[2 * (size_t)cta + 1] = tmk;
+        __threadfence();
+        last = atomicAdd(p.ticket, 1ull) == ctas - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double fs = 0.0, fm = 0.0;
+    for (unsigned j = threadIdx.x; j < ctas; j += kLossThreads) {
+        fs += __ldcg(p.partials + 2 * (size_t)j);
+        fm += __ldcg(p.partials + 2 * (size_t)j + 1);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        fs += __shfl_down_sync(0xffffffffu, fs, off);
+        fm += __shfl_down_sync(0xffffffffu, fm, off);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5][0] = fs;
+        red[threadIdx.x >> 5][1] = fm;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tmk = 0.0;
+        for (int w = 0; w < kLossThreads / 32; ++w) {
+            ts += red[w][0];
+            tmk += red[w][1];
+        }
+        p.sums2[0] = ts;
+        p.sums2[1] = tmk;
+        if (p.loss) *p.loss = (float)(ts / tmk);
+        *p.ticket = 0ull;
+    }
+}
+
+template <bool TMA>
+__global__ void __launch_bounds__(kLossThreads) normals_loss_bwd_kernel(const __grid_constant__ CUtensorMap tm_gt,
+                                                                        const __grid_constant__ CUtensorMap tm_pred, const LossParams p) {
+    // 79 KB of dynamic shared memory: two halo'd depth tiles and the six adjoint fields of the tile + 1-pixel ring
+    extern __shared__ __align__(128) unsigned char bwd_smem[];
+    float (*tg)[kLBoxW] = reinterpret_cast<float (*)[kLBoxW]>(bwd_smem);
+    float (*tp)[kLBoxW] = reinterpret_cast<float (*)[kLBoxW]>(bwd_smem + kLTilePad);
+    float (*G)[kGH][kGPitch] = reinterpret_cast<float (*)[kGH][kGPitch]>(bwd_smem + 2 * kLTilePad);   // gu_bar xyz, gv_bar xyz
+    __shared__ uint64_t bar;
+    const int b = blockIdx.z, x0 = blockIdx.x * kLW, y0 = blockIdx.y * kLH;
+    const size_t hw = (size_t)p.H * p.W;
+    if (TMA && threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (TMA) __syncthreads();
+    stage_begin<TMA>(tg, &tm_gt, p.gt + b * hw, p.H, p.W, x0, y0, b, &bar);
+    stage_begin<TMA>(tp, &tm_pred, p.pred + b * hw, p.H, p.W, x0, y0, b, &bar);
+    if constexpr (TMA) {
+        lut_stage_wait(&bar);
+        patch_replicate(tg, p.H, p.W, x0, y0);
+        patch_replicate(tp, p.H, p.W, x0, y0);
+    } else {
+        __syncthreads();
+    }
+    const Cam cam = load_cam(p.K, b);
+    const float scale = -__ldg(p.grad_out) / (float)p.sums2[1];    // -grad_out / sum(mask)
+
+    // phase 1: adjoint of the two gradients at every pixel of the tile and its 1-pixel ring
+    for (int i = threadIdx.x; i < kGW * kGH; i += kLossThreads) {
+        const int gy = i / kGW, gx = i - gy * kGW;
+        const int ty = gy - 1, tx = gx - 1;
+        const int x = x0 + tx, y = y0 + ty;
+        float gub[3] = {0.f, 0.f, 0.f}, gvb[3] = {0.f, 0.f, 0.f};
+        if (x >= 0 && x < p.W && y >= 0 && y < p.H) {
+            const float k = scale * __ldg(p.mask + b * hw + (size_t)y * p.W + x);
+            if (k != 0.0f) {
+                float gu[3], gv[3], n[3], a[3], bn[3];
+                gradients(tg, ty, tx, x, y, p.H, p.W, cam, gu, gv);
+                cross_rn(gu, gv, n);
+                normalize3(n, a);
+                gradients(tp, ty, tx, x, y, p.H, p.W, cam, gu, gv);
+                cross_rn(gu, gv, n);
+                const float inv = normalize3(n, bn);
+                float inv_den, ab, bb;
+                bool clamped;
+                cosine(a, bn, inv_den, ab, bb, clamped);
+                // g = dcos/db: above the eps clamp a/D - <a,b> b / (D |b|^2), inside it a / eps
+                const float w_b = clamped ? 0.0f : ab * inv_den / fmaxf(bb, 1e-30f);
+                float g[3], nb[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) g[c] = a[c] * inv_den - w_b * bn[c];
+                // b = n * inv: capped normalisation is linear, otherwise project out b and divide by |n| (= multiply by inv)
+                const float gb = (inv >= kInvCap) ? 0.0f : fmaf(g[0], bn[0], fmaf(g[1], bn[1], g[2] * bn[2]));
+#pragma unroll
+                for (int c = 0; c < 3; ++c) nb[c] = k * inv * (g[c] - gb * bn[c]);
+                // n = gu x gv  =>  gu_bar = gv x n_bar, gv_bar = n_bar x gu
+                gub[0] = gv[1] * nb[2] - gv[2] * nb[1];
+                gub[1] = gv[2] * nb[0] - gv[0] * nb[2];
+                gub[2] = gv[0] * nb[1] - gv[1] * nb[0];
+                gvb[0] = nb[1] * gu[2] - nb[2] * gu[1];
+                gvb[1] = nb[2] * gu[0] - nb[0] * gu[2];
+                gvb[2] = nb[0] * gu[1] - nb[1] * gu[0];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            G[c][gy][gx] = gub[c];
+            G[3 + c][gy][gx] = gvb[c];
+        }
+    }
+    __syncthreads();
+
+    // phase 2: gather the adjoint stencil, fold replicate padding onto border pixels
+    for (int i = threadIdx.x; i < kLW * kLH; i += kLossThreads) {
+        const int ty = i / kLW, tx = i - ty * kLW;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= p.W || y >= p.H) continue;
+        const float Sv[3] = {1.0f, 2.0f + (y == 0) + (y == p.H - 1), 1.0f};
+        const float Dv[3] = {1.0f, (float)(y == p.H - 1) - (float)(y == 0), -1.0f};
+        const float Sh[3] = {1.0f, 2.0f + (x == 0) + (x == p.W - 1), 1.0f};
+        const float Dh[3] = {1.0f, (float)(x == p.W - 1) - (float)(x == 0), -1.0f};
+        float A[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int di = 0; di < 3; ++di)
+#pragma unroll
+            for (int dj = 0; dj < 3; ++dj) {
+                const float wu = Sv[di] * Dh[dj], wv = Dv[di] * Sh[dj];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    A[c] = fmaf(wu, G[c][ty + di][tx + dj], fmaf(wv, G[3 + c][ty + di][tx + dj], A[c]));
+            }
+        const float fxq = ((float)x - cam.cx) * cam.inv_fx, fyq = ((float)y - cam.cy) * cam.inv_fy;
+        p.grad_pred[b * hw + (size_t)y * p.W + x] = fmaf(fxq, A[0], fmaf(fyq, A[1], A[2]));
+    }
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn loss_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+bool make_map(CUtensorMap* tmap, const float* base, int B, int H, int W) {
+    EncodeTiledFn encode = loss_encode_tiled();
+    if (!encode || W % 4 != 0 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
+    const cuuint32_t box[3] = {kLBoxW, kLBoxH, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int check_common(const float* gt, const float* pred, const float* K, const float* mask, int B, int H, int W, dim3& grid) {
+    if (!gt || !pred || !K || !mask || B < 0 || H <= 0 || W <= 0 || B > 65535) return POLCUE_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(gt) | reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(K) |
+         reinterpret_cast<uintptr_t>(mask)) & 3)
+        return POLCUE_EINVAL;
+    grid = dim3((W + kLW - 1) / kLW, (H + kLH - 1) / kLH, B);
+    if (grid.y > 65535 || (unsigned long long)grid.x * grid.y * grid.z > (unsigned long long)kMaxLossBlocks) return POLCUE_E2BIG;
+    return POLCUE_OK;
+}
+
+}  // namespace
+}  // namespace polcue
+
+using namespace polcue;
+
+extern "C" {
+
+size_t polcue_normals_loss_workspace_bytes(void) { return 64 + (size_t)kMaxLossBlocks * 2 * sizeof(double); }
+
+int polcue_normals_loss_fwd_f32(const float* depth_gt, const float* depth_pred, const float* K, const float* mask, int B, int H,
+                                int W, void* workspace, double* sums2, float* loss, polcue_stream_t stream) {
+    dim3 grid;
+    const int rc = check_common(depth_gt, depth_pred, K, mask, B, H, W, grid);
+    if (rc != POLCUE_OK) return rc;
+    if (!workspace || !sums2 || (reinterpret_cast<uintptr_t>(workspace) & 63) || (reinterpret_cast<uintptr_t>(sums2) & 7))
+        return POLCUE_EINVAL;
+    if (B == 0) return POLCUE_EINVAL;   // the loss of an empty batch is 0/0; let the caller decide
+    LossParams p{};
+    p.gt = depth_gt;
+    p.pred = depth_pred;
+    p.K = K;
+    p.mask = mask;
+    p.H = H;
+    p.W = W;
+    p.ticket = static_cast<unsigned long long*>(workspace);
+    p.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 64);
+    p.sums2 = sums2;
+    p.loss = loss;
+    CUtensorMap mg, mp;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (make_map(&mg, depth_gt, B, H, W) && make_map(&mp, depth_pred, B, H, W))
+        normals_loss_fwd_kernel<true><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
+    else
+        normals_loss_fwd_kernel<false><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
+    return launch_status();
+}
+
+int polcue_normals_loss_bwd_f32(const float* depth_gt, const float* depth_pred, const float* K, const float* mask, int B, int H,
+                                int W, const double* sums2, const float* grad_out, float* grad_pred, polcue_stream_t stream) {
+    dim3 grid;
+    const int rc = check_common(depth_gt, depth_pred, K, mask, B, H, W, grid);
+    if (rc != POLCUE_OK) return rc;
+    if (!sums2 || !grad_out || !grad_pred || (reinterpret_cast<uintptr_t>(grad_pred) & 3)) return POLCUE_EINVAL;
+    if (B == 0) return POLCUE_OK;
+    LossParams p{};
+    p.gt = depth_gt;
+    p.pred = depth_pred;
+    p.K = K;
+    p.mask = mask;
+    p.H = H;
+    p.W = W;
+    p.sums2 = const_cast<double*>(sums2);
+    p.grad_out = grad_out;
+    p.grad_pred = grad_pred;
+    CUtensorMap mg, mp;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool tma = make_map(&mg, depth_gt, B, H, W) && make_map(&mp, depth_pred, B, H, W);
+    auto kern = tma ? normals_loss_bwd_kernel<true> : normals_loss_bwd_kernel<false>;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, kLossThreads, kBwdSmem, s>>>(mg, mp, p);
+    return launch_status();
+}
+
+}  // extern "C"

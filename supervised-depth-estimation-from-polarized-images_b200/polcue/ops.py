@@ -407,3 +407,60 @@ def xolp_statistics(xolp, reduce_over_ranks=True):
     std = torch.sqrt(torch.clamp(acc[[1, 3]] / n - mean * mean, min=0.0))
     return {"dolp_mean": float(mean[0]), "dolp_std": float(std[0]), "aolp_mean": float(mean[1]), "aolp_std": float(std[1]),
             "xolp_mean": float(0.5 * (mean[0] + mean[1])), "xolp_std": float(0.5 * (std[0] + std[1])), "frames": b}
+
+
+# ------------------------------------------------------------------------------------------
+# supervised normals loss (forward + backward)
+# ------------------------------------------------------------------------------------------
+_loss_workspaces = {}
+
+
+def _loss_workspace(device):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _loss_workspaces.get(key)
+    if ws is None:
+        ws = _loss_workspaces[key] = torch.zeros(int(_lib.lib().polcue_normals_loss_workspace_bytes()), dtype=torch.uint8,
+                                                 device=device)
+    return ws
+
+
+class _NormalsLoss(torch.autograd.Function):
+    """loss = sum((2 - cos(n_gt, n_pred)) * mask) / sum(mask); gradient flows to depth_pred only."""
+
+    @staticmethod
+    def forward(ctx, depth_gt, depth_pred, camera_matrix, mask):
+        b, _, h, w = depth_pred.shape
+        sums = torch.empty(2, dtype=torch.float64, device=depth_pred.device)
+        loss = torch.empty((), dtype=torch.float32, device=depth_pred.device)
+        with torch.cuda.device(depth_pred.device):
+            _lib.check(_lib.lib().polcue_normals_loss_fwd_f32(_ptr(depth_gt), _ptr(depth_pred), _ptr(camera_matrix), _ptr(mask), b, h, w,
+                                                              _ptr(_loss_workspace(depth_pred.device)), _ptr(sums), _ptr(loss),
+                                                              _stream(depth_pred)), "polcue_normals_loss_fwd_f32")
+        ctx.save_for_backward(depth_gt, depth_pred, camera_matrix, mask, sums)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        depth_gt, depth_pred, camera_matrix, mask, sums = ctx.saved_tensors
+        b, _, h, w = depth_pred.shape
+        grad_out = grad_out.to(torch.float32).contiguous()
+        grad_pred = torch.empty_like(depth_pred)
+        with torch.cuda.device(depth_pred.device):
+            _lib.check(_lib.lib().polcue_normals_loss_bwd_f32(_ptr(depth_gt), _ptr(depth_pred), _ptr(camera_matrix), _ptr(mask), b, h, w,
+                                                              _ptr(sums), _ptr(grad_out), _ptr(grad_pred), _stream(depth_pred)),
+                       "polcue_normals_loss_bwd_f32")
+        return None, grad_pred, None, None
+
+
+def normals_loss(depth_gt, depth_pred, camera_matrix, mask):
+    """Trainer.compute_supervised_normals_losses (manydepth/trainer.py:1298-1309): zero-dim float32 loss, differentiable
+    w.r.t. depth_pred.  depth_gt / depth_pred / mask: B x 1 x H x W, camera_matrix: B x 3 x 3 (CUDA)."""
+    depth_gt = _need_cuda(depth_gt, "depth_gt").detach().float().contiguous()
+    depth_pred = _need_cuda(depth_pred, "depth_pred").float().contiguous()
+    camera_matrix = _need_cuda(camera_matrix, "camera_matrix").detach().float().contiguous()
+    mask = _need_cuda(mask, "mask").detach().float().contiguous()
+    if depth_pred.dim() != 4 or depth_pred.shape[1] != 1 or depth_gt.shape != depth_pred.shape or mask.shape != depth_pred.shape:
+        raise ValueError("depth_gt, depth_pred and mask must share one B x 1 x H x W shape")
+    if camera_matrix.shape != (depth_pred.shape[0], 3, 3):
+        raise ValueError("camera_matrix must be B x 3 x 3")
+    return _NormalsLoss.apply(depth_gt, depth_pred, camera_matrix, mask)

@@ -345,6 +345,71 @@ def test_depth_to_normals_uses_tma_staging_when_rows_are_16_byte_multiples():
     assert L.polcue_debug_stencil_tma_launches() == before + 1
 
 
+def _loss_case(shape, batch=3, first=0):
+    h, w = shape
+    gt, pred, _, k = synth.gen_depth_batch(first, batch, h, w)
+    smooth = np.where(gt > 0, gt, 0.7).astype(np.float32)
+    # a smooth prediction: noise-free surface with a different low-frequency error per image (what a network outputs)
+    vv, uu = np.mgrid[0:h, 0:w].astype(np.float32)
+    pred_s = (smooth * (1.0 + 0.05 * np.sin(uu / 23.0 + np.arange(batch)[:, None, None]) * np.cos(vv / 17.0))).astype(np.float32)
+    mask = ((gt >= 0.1) & (gt <= 2.0)).astype(np.float32)          # trainer.py:1242-1243
+    return smooth, pred_s, mask, k
+
+
+@pytest.mark.parametrize("shape", [(320, 480), (64, 96), (37, 131), (16, 128), (17, 129), (5, 3), (1, 1), (2, 260)])
+def test_normals_loss_forward_and_backward_vs_autograd_oracle(shape):
+    gt, pred, mask, k = _loss_case(shape)
+    if mask.sum() == 0:
+        mask[:] = 1.0
+    t64 = lambda a: torch.from_numpy(a.astype(np.float64))
+    p64 = t64(pred)[:, None].requires_grad_(True)
+    ref = O.normals_loss_torch(t64(gt)[:, None], p64, t64(k), t64(mask)[:, None])
+    ref.backward()
+    ref_grad = p64.grad[:, 0].numpy()
+
+    d_pred = dev(pred)[:, None].requires_grad_(True)
+    loss = ops.normals_loss(dev(gt)[:, None], d_pred, dev(k), dev(mask)[:, None])
+    assert loss.dim() == 0 and loss.dtype == torch.float32
+    assert abs(float(loss) - float(ref)) < 2e-5 * max(1.0, abs(float(ref)))
+    (3.0 * loss).backward()                                           # upstream gradient 3
+    got = d_pred.grad[:, 0].cpu().numpy() / 3.0
+    scale = np.abs(ref_grad).max() + 1e-30
+    err = np.abs(got - ref_grad)
+    # float32 kernel vs float64 autograd: gradients of normalised cross products cancel heavily where the surface is flat
+    assert err.max() < 2e-3 * scale, (err.max(), scale)
+    assert np.sqrt((err ** 2).mean()) < 2e-4 * scale
+
+
+def test_normals_loss_matches_composition_of_public_ops_and_is_deterministic():
+    gt, pred, mask, k = _loss_case((64, 96))
+    args = (dev(gt)[:, None], dev(pred)[:, None], dev(k), dev(mask)[:, None])
+    loss = ops.normals_loss(*args)
+    n_gt, n_pred = ops.depth_to_normals(args[0], args[2]), ops.depth_to_normals(args[1], args[2])
+    cos = torch.nn.functional.cosine_similarity(n_gt.double(), n_pred.double(), dim=1).unsqueeze(1)
+    ref = ((2 - cos) * args[3]).sum() / args[3].sum()
+    assert abs(float(loss) - float(ref)) < 1e-6
+    assert torch.equal(loss, ops.normals_loss(*args))
+    from polcue.compat import trainer as c_trainer
+    k44 = torch.eye(4, device="cuda")[None].repeat(3, 1, 1)
+    k44[:, :3, :3] = args[2]
+    assert torch.equal(c_trainer.compute_supervised_normals_losses(args[0], args[1], k44, args[3]), loss)
+
+
+def test_normals_loss_gradient_by_finite_differences():
+    gt, pred, mask, k = _loss_case((24, 40), batch=1)
+    args = (dev(gt)[:, None], dev(k), dev(mask)[:, None])
+    d_pred = dev(pred)[:, None].requires_grad_(True)
+    ops.normals_loss(args[0], d_pred, args[1], args[2]).backward()
+    grad = d_pred.grad[0, 0].cpu().numpy()
+    t64 = lambda a: torch.from_numpy(a.astype(np.float64))
+    base = lambda p: float(O.normals_loss_torch(t64(gt)[:, None], t64(p)[:, None], t64(k), t64(mask)[:, None]))
+    for (y, x) in ((0, 0), (0, 17), (23, 39), (12, 20), (11, 0), (23, 5)):      # corners, borders, interior
+        e = np.zeros_like(pred, dtype=np.float64)
+        e[0, y, x] = 1e-5
+        fd = (base(pred.astype(np.float64) + e) - base(pred.astype(np.float64) - e)) / 2e-5
+        assert abs(grad[y, x] - fd) < 2e-3 * np.abs(grad).max() + 1e-7, ((y, x), grad[y, x], fd)
+
+
 def test_depth_to_normals_properties():
     k = dev(synth.scaled_intrinsics(64, 96)[None].astype(np.float32))
     flat = torch.full((1, 1, 64, 96), 0.8, device="cuda")
