@@ -204,6 +204,14 @@ POLCUE_API size_t polcue_channel_stats_workspace_bytes(int B, int C, size_t hw);
 POLCUE_API int polcue_channel_stats_f32(const float* x, int B, int C, size_t hw, void* workspace, double* stats,
                              polcue_stream_t stream);
 
+/* All mask groups of the evaluation loop in ONE launch (the reference makes 11-12 CPU passes, manydepth/trainer.py:920-980,
+ * evaluation.py:169-213): group_ids[g] = instance id of group g (20, 40, ... 200, trainer.py:1389-1411) or -1 for
+ * object == "all"; n_groups <= 16 HOST ints.  sums: B x n_groups x 8 doubles, metrics: B x n_groups x 7 floats or NULL.
+ * One pass: each pixel's contributions are computed once and routed to "all" and to its material group. */
+POLCUE_API int polcue_depth_errors_groups_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px,
+                                   float min_d, float max_d, const int* group_ids, int n_groups, double* sums,
+                                   float* metrics, polcue_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

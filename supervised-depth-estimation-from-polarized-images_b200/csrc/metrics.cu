@@ -202,15 +202,16 @@ struct ImageParams {
     const uint8_t* inst;  // may be null
     size_t px;
     float min_d, max_d;
-    int inst_id;
+    int n_groups;         // mask groups evaluated in this launch (grid.y); outputs are [B][n_groups][...]
+    int group_ids[16];    // instance id of each group, or -1 for "all" (range mask only)
     double* sums;
     float* metrics;  // may be null
     bool vec4;
 };
 
-__device__ __forceinline__ void acc_masked(Acc& a, const ImageParams& p, float g, float q, int id) {
+__device__ __forceinline__ void acc_masked(Acc& a, const ImageParams& p, int want_id, float g, float q, int id) {
     // trainer.py:1380 mask, :1410-1411 material filter, :1417-1418 clamp of the prediction
-    const bool keep = (g > p.min_d) & (g < p.max_d) & ((p.inst == nullptr) | (id == p.inst_id));
+    const bool keep = (g > p.min_d) & (g < p.max_d) & ((want_id < 0) | (id == want_id));
     acc_add(a, keep ? g : 1.0f, keep ? fminf(fmaxf(q, p.min_d), p.max_d) : 1.0f);   // rejected -> the neutral pair (1, 1)
     a.n += keep;
     a.seen += 1;
@@ -222,9 +223,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
     const size_t b = blockIdx.y;
+    const int want_id = p.inst ? p.group_ids[0] : -1;
     const float* gt = p.gt + b * p.px;
     const float* pred = p.pred + b * p.px;
-    const uint8_t* inst = p.inst ? p.inst + b * p.px : nullptr;
+    const uint8_t* inst = (p.inst && want_id >= 0) ? p.inst + b * p.px : nullptr;
 
     Acc a;
     acc_clear(a);
@@ -237,10 +239,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
             const float4 g = ld_stream_f32x4(gt + 4 * i), q = ld_stream_f32x4(pred + 4 * i);
             uint32_t ids = 0;
             if (inst) ids = ld_stream_u32(inst + 4 * i);
-            acc_masked(a, p, g.x, q.x, ids & 0xff);
-            acc_masked(a, p, g.y, q.y, (ids >> 8) & 0xff);
-            acc_masked(a, p, g.z, q.z, (ids >> 16) & 0xff);
-            acc_masked(a, p, g.w, q.w, ids >> 24);
+            acc_masked(a, p, want_id, g.x, q.x, ids & 0xff);
+            acc_masked(a, p, want_id, g.y, q.y, (ids >> 8) & 0xff);
+            acc_masked(a, p, want_id, g.z, q.z, (ids >> 16) & 0xff);
+            acc_masked(a, p, want_id, g.w, q.w, ids >> 24);
             if (++since == 16) {
                 flush(s, a);
                 since = 0;
@@ -248,7 +250,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
         }
     } else {
         for (size_t i = tid; i < p.px; i += stride) {
-            acc_masked(a, p, gt[i], pred[i], inst ? inst[i] : 0);
+            acc_masked(a, p, want_id, gt[i], pred[i], inst ? inst[i] : 0);
             if (++since == 64) {
                 flush(s, a);
                 since = 0;
@@ -269,6 +271,148 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     }
     cluster.sync();  // keep remote shared memory alive until rank 0 has read it
     if (rank == 0 && threadIdx.x == 0 && p.metrics) finalize(warp_rows[1], p.metrics + b * 7);
+}
+
+// ------------------------------------------------------------------------------------------
+// every mask group of the evaluation loop in ONE pass over (gt, pred, inst)
+// ------------------------------------------------------------------------------------------
+// Each pixel's eight contributions are computed once.  A thread keeps the "all" group and the current material
+// run in registers; when the material under its pixels changes it adds the finished run into its PRIVATE column of
+// a shared-memory table [group][accumulator][thread] (no atomics, so the result is bitwise reproducible), then the
+// CTA folds the table over threads in a fixed order and the cluster folds the CTAs through distributed shared memory.
+struct Contrib {
+    float f[4];
+    int n, c1, c2, c3;
+};
+
+__device__ __forceinline__ Contrib make_contrib(float gt, float pred, bool keep) {
+    gt = keep ? gt : 1.0f;          // rejected -> the neutral pair (1, 1): every float term is exactly 0
+    pred = keep ? pred : 1.0f;
+    const float hi = fmaxf(gt, pred), lo = fminf(gt, pred);
+    const float thr = -5.9604644775390625e-08f * lo;
+    Contrib c;
+    c.n = keep;
+    c.c1 = (int)keep & (int)ratio_below(hi, lo, 1.25f, thr);
+    c.c2 = (int)keep & (int)ratio_below(hi, lo, 1.5625f, thr);
+    c.c3 = (int)keep & (int)ratio_below(hi, lo, 1.953125f, thr);
+    const float d = gt - pred, d2 = d * d, inv_gt = rcp_approx(gt);
+    const float dl = lg2_approx(hi) - lg2_approx(lo);
+    c.f[0] = d2;
+    c.f[1] = dl * dl;
+    c.f[2] = fabsf(d) * inv_gt;
+    c.f[3] = d2 * inv_gt;
+    return c;
+}
+
+struct Run {
+    float f[4];
+    int n, c1, c2, c3;
+};
+__device__ __forceinline__ void run_clear(Run& r) {
+    r.f[0] = r.f[1] = r.f[2] = r.f[3] = 0.0f;
+    r.n = r.c1 = r.c2 = r.c3 = 0;
+}
+__device__ __forceinline__ void run_add(Run& r, const Contrib& c, bool on) {
+    const float k = on ? 1.0f : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r.f[j] = fmaf(k, c.f[j], r.f[j]);
+    r.n += on ? c.n : 0;
+    r.c1 += on ? c.c1 : 0;
+    r.c2 += on ? c.c2 : 0;
+    r.c3 += on ? c.c3 : 0;
+}
+// table layout: [slot][8][kMetricThreads] floats; counts are exact in float32 below 2^24 pixels per thread
+__device__ __forceinline__ void run_flush(float* table, int slot, Run& r) {
+    float* col = table + (size_t)slot * 8 * kMetricThreads + threadIdx.x;
+    col[0 * kMetricThreads] += (float)r.n;
+    col[1 * kMetricThreads] += (float)r.c1;
+    col[2 * kMetricThreads] += (float)r.c2;
+    col[3 * kMetricThreads] += (float)r.c3;
+    col[4 * kMetricThreads] += r.f[0];
+    col[5 * kMetricThreads] += r.f[1];
+    col[6 * kMetricThreads] += r.f[2];
+    col[7 * kMetricThreads] += r.f[3];
+    run_clear(r);
+}
+
+struct GroupParams {
+    const float* gt;
+    const float* pred;
+    const uint8_t* inst;   // may be null when no material group is requested
+    size_t px;
+    float min_d, max_d;
+    int n_groups;
+    int all_slot;          // slot of the "all" group or -1
+    uint8_t slot_of[256];  // instance id -> slot, 0xFF = not requested
+    double* sums;          // [B][n_groups][8]
+    float* metrics;        // [B][n_groups][7] or null
+    bool vec4;
+};
+
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThreads)
+    depth_errors_groups_kernel(const __grid_constant__ GroupParams p) {
+    extern __shared__ __align__(16) float table[];          // [n_groups][8][kMetricThreads]
+    __shared__ double cta_tot[16][8];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    const size_t b = blockIdx.y;
+    const float* gt = p.gt + b * p.px;
+    const float* pred = p.pred + b * p.px;
+    const uint8_t* inst = p.inst ? p.inst + b * p.px : nullptr;
+    for (int i = threadIdx.x; i < p.n_groups * 8 * kMetricThreads; i += kMetricThreads) table[i] = 0.0f;
+    // (each thread only ever touches its own column, no barrier needed before use)
+
+    Run all, mat;
+    run_clear(all);
+    run_clear(mat);
+    int cur = 0xFF;
+    auto pixel = [&](float g, float q, int id) {
+        const bool keep = (g > p.min_d) & (g < p.max_d);
+        const Contrib c = make_contrib(g, fminf(fmaxf(q, p.min_d), p.max_d), keep);
+        run_add(all, c, true);
+        const int slot = inst ? p.slot_of[id] : 0xFF;
+        if (slot != cur) {                                   // the material under this thread's pixels changed
+            if (cur != 0xFF) run_flush(table, cur, mat);
+            cur = slot;
+        }
+        run_add(mat, c, slot != 0xFF);
+    };
+    const size_t tid = (size_t)rank * kMetricThreads + threadIdx.x, stride = (size_t)kCluster * kMetricThreads;
+    if (p.vec4) {
+        const size_t n4 = p.px >> 2;
+        for (size_t i = tid; i < n4; i += stride) {
+            const float4 g = ld_stream_f32x4(gt + 4 * i), q = ld_stream_f32x4(pred + 4 * i);
+            uint32_t ids = 0;
+            if (inst) ids = ld_stream_u32(inst + 4 * i);
+            pixel(g.x, q.x, ids & 0xff);
+            pixel(g.y, q.y, (ids >> 8) & 0xff);
+            pixel(g.z, q.z, (ids >> 16) & 0xff);
+            pixel(g.w, q.w, ids >> 24);
+        }
+    } else {
+        for (size_t i = tid; i < p.px; i += stride) pixel(gt[i], pred[i], inst ? inst[i] : 0);
+    }
+    if (cur != 0xFF) run_flush(table, cur, mat);
+    if (p.all_slot >= 0) run_flush(table, p.all_slot, all);
+    __syncthreads();
+    // CTA fold over threads, fixed order: thread t owns (slot, accumulator) pair t
+    if (threadIdx.x < p.n_groups * 8) {
+        const float* col = table + (size_t)threadIdx.x * kMetricThreads;
+        double v = 0.0;
+        for (int t = 0; t < kMetricThreads; ++t) v += (double)col[t];
+        if ((threadIdx.x & 7) == 5) v *= 0.4804530139182014;   // ln(2)^2 on the squared log2 differences
+        cta_tot[threadIdx.x >> 3][threadIdx.x & 7] = v;
+    }
+    cluster.sync();
+    if (rank == 0 && threadIdx.x < p.n_groups * 8) {
+        const int slot = threadIdx.x >> 3, k = threadIdx.x & 7;
+        double v = 0.0;
+        for (unsigned r = 0; r < kCluster; ++r) v += cluster.map_shared_rank(&cta_tot[0][0], r)[slot * 8 + k];
+        p.sums[(b * p.n_groups + slot) * 8 + k] = v;
+        cta_tot[slot][k] = v;       // rank 0's own copy has been read by this same thread already
+    }
+    cluster.sync();
+    if (rank == 0 && p.metrics && threadIdx.x < p.n_groups) finalize(cta_tot[threadIdx.x], p.metrics + (b * p.n_groups + threadIdx.x) * 7);
 }
 
 }  // namespace
@@ -298,9 +442,9 @@ int polcue_depth_errors_f32(const float* gt, const float* pred, size_t count, vo
     return launch_status();
 }
 
-int polcue_depth_errors_images_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px, float min_d,
-                                   float max_d, int inst_id, double* sums, float* metrics, polcue_stream_t stream) {
-    if (!gt || !pred || !sums || B < 0 || B > 65535) return POLCUE_EINVAL;
+static int launch_images(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px, float min_d, float max_d,
+                         const int* group_ids, int n_groups, double* sums, float* metrics, polcue_stream_t stream) {
+    if (!gt || !pred || !sums || B < 0 || B > 65535 || n_groups < 1 || n_groups > 16) return POLCUE_EINVAL;
     if (reinterpret_cast<uintptr_t>(sums) & 7) return POLCUE_EINVAL;
     if (B == 0) return POLCUE_OK;
     ImageParams p;
@@ -310,12 +454,58 @@ int polcue_depth_errors_images_f32(const float* gt, const float* pred, const uin
     p.px = px;
     p.min_d = min_d;
     p.max_d = max_d;
-    p.inst_id = inst_id;
+    p.n_groups = n_groups;
+    for (int g = 0; g < 16; ++g) p.group_ids[g] = (g < n_groups && inst) ? group_ids[g] : -1;
     p.sums = sums;
     p.metrics = metrics;
     p.vec4 = (px % 4 == 0) && (((reinterpret_cast<uintptr_t>(gt) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(inst) & 3) == 0);
     depth_errors_images_kernel<<<dim3(kCluster, B, 1), kMetricThreads, 0, (cudaStream_t)stream>>>(p);
+    return launch_status();
+}
+
+int polcue_depth_errors_images_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px, float min_d,
+                                   float max_d, int inst_id, double* sums, float* metrics, polcue_stream_t stream) {
+    const int id = inst ? inst_id : -1;
+    return launch_images(gt, pred, inst, B, px, min_d, max_d, &id, 1, sums, metrics, stream);
+}
+
+int polcue_depth_errors_groups_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px, float min_d,
+                                   float max_d, const int* group_ids, int n_groups, double* sums, float* metrics,
+                                   polcue_stream_t stream) {
+    if (!gt || !pred || !sums || !group_ids || B < 0 || B > 65535 || n_groups < 1 || n_groups > 16) return POLCUE_EINVAL;
+    if (reinterpret_cast<uintptr_t>(sums) & 7) return POLCUE_EINVAL;
+    GroupParams p;
+    p.all_slot = -1;
+    for (int i = 0; i < 256; ++i) p.slot_of[i] = 0xFF;
+    bool any_material = false;
+    for (int g = 0; g < n_groups; ++g) {
+        const int id = group_ids[g];
+        if (id < 0) {
+            if (p.all_slot >= 0) return POLCUE_EINVAL;            // "all" listed twice
+            p.all_slot = g;
+        } else {
+            if (id > 255 || p.slot_of[id] != 0xFF || !inst) return POLCUE_EINVAL;   // out of range, duplicate, or no map
+            p.slot_of[id] = (uint8_t)g;
+            any_material = true;
+        }
+    }
+    if (B == 0) return POLCUE_OK;
+    p.gt = gt;
+    p.pred = pred;
+    p.inst = any_material ? inst : nullptr;
+    p.px = px;
+    p.min_d = min_d;
+    p.max_d = max_d;
+    p.n_groups = n_groups;
+    p.sums = sums;
+    p.metrics = metrics;
+    p.vec4 = (px % 4 == 0) && (((reinterpret_cast<uintptr_t>(gt) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0) &&
+             ((reinterpret_cast<uintptr_t>(inst) & 3) == 0);
+    const size_t smem = (size_t)n_groups * 8 * kMetricThreads * sizeof(float);
+    const cudaError_t e = cudaFuncSetAttribute(depth_errors_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    depth_errors_groups_kernel<<<dim3(kCluster, B, 1), kMetricThreads, smem, (cudaStream_t)stream>>>(p);
     return launch_status();
 }
 

@@ -359,6 +359,35 @@ def depth_errors_per_image(gt, pred, min_depth, max_depth, inst=None, inst_id=No
     return sums, metrics
 
 
+def depth_errors_groups(gt, pred, inst, min_depth, max_depth, group_ids):
+    """Every mask group of the reference's evaluation loop in one launch.  group_ids: iterable of instance ids
+    (20 ... 200, trainer.py:1389-1411) with None / -1 meaning object == "all".
+    Returns (sums [B, G, 8] float64, metrics [B, G, 7] float32) on device."""
+    gt = _need_cuda(gt, "gt").float().contiguous()
+    pred = _need_cuda(pred, "pred").float().contiguous()
+    ids = [(-1 if g is None else int(g)) for g in group_ids]
+    if not 1 <= len(ids) <= 16:
+        raise ValueError("between 1 and 16 groups per launch")
+    if any(g >= 0 for g in ids):
+        inst = _need_cuda(inst, "inst", torch.uint8)
+        if inst.numel() != gt.numel():
+            raise ValueError("inst must have the same shape as gt")
+    else:
+        inst = None
+    if pred.numel() != gt.numel():
+        raise ValueError("gt and pred must have the same shape")
+    b = gt.shape[0]
+    px = gt.numel() // b if b else 0
+    sums = torch.empty((b, len(ids), 8), dtype=torch.float64, device=gt.device)
+    metrics = torch.empty((b, len(ids), 7), dtype=torch.float32, device=gt.device)
+    arr = (C.c_int * len(ids))(*ids)
+    with torch.cuda.device(gt.device):
+        _lib.check(_lib.lib().polcue_depth_errors_groups_f32(_ptr(gt), _ptr(pred), _ptr(inst), b, px, float(min_depth), float(max_depth),
+                                                             arr, len(ids), _ptr(sums), _ptr(metrics), _stream(gt)),
+                   "polcue_depth_errors_groups_f32")
+    return sums, metrics
+
+
 def metrics_from_sums(sums):
     """8 additive accumulators (any leading shape) -> 7 metrics in the reference order (float64 tensor/array)."""
     n = sums[..., 0]

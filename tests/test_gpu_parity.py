@@ -529,6 +529,30 @@ def test_xolp_statistics_of_fused_output_match_the_reference_script():
         assert abs(st[key] - val) < 2e-6, (key, st[key], val)
 
 
+def test_all_mask_groups_in_one_launch_match_separate_launches_and_oracle():
+    gt, pred, inst, _ = synth.gen_depth_batch(0, 6, 96, 128)
+    groups = [None] + list(synth.MATERIAL_LEVELS)
+    before = _lib.launch_count()
+    sums, metrics = ops.depth_errors_groups(dev(gt), dev(pred), dev(inst), 0.1, 2.0, groups)
+    assert _lib.launch_count() == before + 1 and sums.shape == (6, 11, 8) and metrics.shape == (6, 11, 7)
+    for gi, level in enumerate(groups):
+        s1, m1 = ops.depth_errors_per_image(dev(gt), dev(pred), 0.1, 2.0, dev(inst) if level is not None else None, level)
+        assert torch.equal(s1[:, :4], sums[:, gi, :4])                                   # pixel counts: exact
+        assert torch.allclose(s1[:, 4:], sums[:, gi, 4:], rtol=1e-6, atol=1e-12)         # float sums: other summation order
+        assert torch.allclose(m1, metrics[:, gi], rtol=2e-6, equal_nan=True)
+        rows, _ = O.depth_errors_per_image(gt, pred, 0.1, 2.0, inst if level is not None else None, level)
+        assert np.allclose(metrics[:, gi].cpu().numpy(), rows, rtol=5e-6, equal_nan=True)
+    only_all, _ = ops.depth_errors_groups(dev(gt), dev(pred), None, 0.1, 2.0, [None])
+    assert torch.equal(only_all[:, 0], sums[:, 0])                                       # bitwise reproducible
+    again, _ = ops.depth_errors_groups(dev(gt), dev(pred), dev(inst), 0.1, 2.0, groups)
+    assert torch.equal(again, sums)
+    odd = ops.depth_errors_groups(dev(gt[:, :95, :127].copy()), dev(pred[:, :95, :127].copy()), dev(inst[:, :95, :127].copy()), 0.1, 2.0,
+                                  [40, None, 200])[1].cpu().numpy()                     # scalar path, other group order
+    for gi, level in enumerate([40, None, 200]):
+        rows, _ = O.depth_errors_per_image(gt[:, :95, :127], pred[:, :95, :127], 0.1, 2.0, inst[:, :95, :127] if level else None, level)
+        assert np.allclose(odd[:, gi], rows, rtol=5e-6, equal_nan=True)
+
+
 def test_launch_counter_counts_kernels():
     before = _lib.launch_count()
     ops.fused_mosaic(dev(synth.gen_u_mosaic(0, 32, 48))[None], 1.5)

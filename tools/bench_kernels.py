@@ -115,6 +115,19 @@ def main():
              lambda: ops.depth_errors_per_image(gt, pred, 0.1, 2.0), small)
         emit("metrics/per_image_inst", f"gt,pred f32 + inst u8 [{n_img},{h},{w}], material filter", 9 * npx,
              lambda: ops.depth_errors_per_image(gt, pred, 0.1, 2.0, inst, 40), small)
+        emit("metrics/groups11", f"gt,pred f32 + inst u8 [{n_img},{h},{w}], 11 mask groups in one launch (bytes counted once)", 9 * npx,
+             lambda: ops.depth_errors_groups(gt, pred, inst, 0.1, 2.0, [None] + list(synth.MATERIAL_LEVELS)), small)
+        smooth = torch.where(gt > 0, gt, torch.full_like(gt, 0.7))[:, None].contiguous()
+        predd = pred[:, None].contiguous().requires_grad_(True)
+        maskf = ((gt >= 0.1) & (gt <= 2.0)).float()[:, None].contiguous()
+        if n_img * ((h + 15) // 16) * ((w + 127) // 128) <= 65536:
+            emit("loss/normals_fwd", f"depth_gt, depth_pred, mask f32 [{n_img},1,{h},{w}] -> loss", 12 * npx,
+                 lambda: ops.normals_loss(smooth, predd.detach(), k, maskf), small)
+
+            def fwd_bwd():
+                predd.grad = None
+                ops.normals_loss(smooth, predd, k, maskf).backward()
+            emit("loss/normals_fwd_bwd", "forward + backward (12 + 16 B/px)", 28 * npx, fwd_bwd, small)
         m = gt > 0
         gflat, pflat = gt[m].contiguous(), pred[m].contiguous()
         emit("metrics/flat", f"gt,pred f32 [{gflat.numel()}] (compacted)", 8 * gflat.numel(),
