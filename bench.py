@@ -30,6 +30,8 @@ for _p in (PKG_DIR, ROOT):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+print_result = print   # replaced in main() by a writer bound to the real stdout
+
 FRAME_H, FRAME_W = 2048, 2448
 MPIX_PER_FRAME = FRAME_H * FRAME_W / 1e6
 BYTES_PER_OUT_PX = 48            # 4 B read + 8 B XOLP + 36 B normals (SURVEY 8d / BASELINE.md 3)
@@ -178,7 +180,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print_result(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -316,10 +318,22 @@ def run_polcue_arm(args, rank, local_rank, world):
         line["cpu_baseline"] = {"value": v, "unit": "Mpix/s", "cores": workers, "kind": "port",
                                 "sample": f"{frames} Gen-P frames per pass x 2 passes ({sec:.1f} s per pass), one process per core, "
                                           "BLAS threads=1; oracle/polcue_oracle.frame_chain_reference"}
-    print(json.dumps(line), flush=True)
+    print_result(json.dumps(line))
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else written to fd 1 during the run (NCCL's version banner,
+    library chatter) is sent to stderr.  Returns a file object on the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    real_stdout = claim_stdout()
+    global print_result
+    print_result = lambda line: (real_stdout.write(line + "\n"), real_stdout.flush())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
