@@ -553,6 +553,67 @@ def test_all_mask_groups_in_one_launch_match_separate_launches_and_oracle():
         assert np.allclose(odd[:, gi], rows, rtol=5e-6, equal_nan=True)
 
 
+def _guarded(shape, dtype, fill):
+    """A tensor view with 4 KB canary bands on both sides (compute-sanitizer is closed on this pool)."""
+    n = int(np.prod(shape))
+    item = torch.empty((), dtype=dtype).element_size()
+    pad = 4096 // item
+    buf = torch.full((n + 2 * pad,), fill, dtype=dtype, device="cuda")
+    return buf, buf[pad:pad + n].view(shape), pad
+
+
+def _bands_intact(buf, pad, fill):
+    return bool((buf[:pad] == fill).all()) and bool((buf[-pad:] == fill).all())
+
+
+@pytest.mark.parametrize("shape", [(2, 2), (6, 10), (34, 66), (66, 128), (130, 250), (128, 192)])
+def test_kernels_never_write_outside_their_outputs(shape):
+    import ctypes as C
+    h, w = shape
+    hs, ws = h // 2, w // 2
+    L = _lib.lib()
+    b = 3
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    mosaic = dev(np.random.default_rng(1).integers(0, 256, (b, h, w), dtype=np.uint8))
+    lut = ops.lut_for(1.5, mosaic.device)
+    xb, xolp, xp = _guarded((b, 2, hs, ws), torch.float32, -7.0)
+    nb, nrm, npad = _guarded((b, 9, hs, ws), torch.float32, -7.0)
+    ib, iun, ipad = _guarded((b, hs, ws), torch.float32, -7.0)
+    pb, planes, ppad = _guarded((b, 4, hs, ws), torch.uint8, 201)
+    assert L.polcue_fused_mosaic_u8(mosaic.data_ptr(), b, h, w, lut, planes.data_ptr(), iun.data_ptr(), xolp.data_ptr(),
+                                    nrm.data_ptr(), stream) == 0
+    torch.cuda.synchronize()
+    assert _bands_intact(xb, xp, -7.0) and _bands_intact(nb, npad, -7.0) and _bands_intact(ib, ipad, -7.0) and _bands_intact(pb, ppad, 201)
+    assert not bool((nrm == -7.0).any()) and not bool((xolp == -7.0).any())          # and every element was written
+    # get_normals, XOLP from planes, split, stencil and the loss gradient through the same guard
+    nb2, nrm2, npad2 = _guarded((b, 9, hs, ws), torch.float32, -7.0)
+    assert L.polcue_normals_from_xolp_f32(xolp.data_ptr(), b, hs, ws, lut, nrm2.data_ptr(), stream) == 0
+    xb2, xolp2, xp2 = _guarded((b, 2, hs, ws), torch.float32, -7.0)
+    pl = [planes[:, k].contiguous() for k in range(4)]
+    assert L.polcue_xolp_planes_u8(*(q.data_ptr() for q in pl), b, hs, ws, None, xolp2.data_ptr(), stream) == 0
+    quads = [_guarded((b, hs, ws), torch.uint8, 201) for _ in range(4)]
+    assert L.polcue_split_pol(mosaic.data_ptr(), b, h, w, 1, *(q[1].data_ptr() for q in quads), stream) == 0
+    gt, pred, _, k = synth.gen_depth_batch(0, b, hs, ws)
+    d_gt, d_pred, d_k = dev(np.where(gt > 0, gt, 0.7).astype(np.float32)), dev(pred), dev(k)
+    sb, sn, spad = _guarded((b, 3, hs, ws), torch.float32, -7.0)
+    assert L.polcue_depth_to_normals_f32(d_gt.data_ptr(), d_k.data_ptr(), b, hs, ws, sn.data_ptr(), stream) == 0
+    gb, grad, gpad = _guarded((b, 1, hs, ws), torch.float32, -7.0)
+    mask = torch.ones_like(d_gt)
+    ws_buf = torch.zeros(int(L.polcue_normals_loss_workspace_bytes()), dtype=torch.uint8, device="cuda")
+    sums, one = torch.empty(2, dtype=torch.float64, device="cuda"), torch.ones((), device="cuda")
+    assert L.polcue_normals_loss_fwd_f32(d_gt.data_ptr(), d_pred.data_ptr(), d_k.data_ptr(), mask.data_ptr(), b, hs, ws,
+                                         ws_buf.data_ptr(), sums.data_ptr(), None, stream) == 0
+    assert L.polcue_normals_loss_bwd_f32(d_gt.data_ptr(), d_pred.data_ptr(), d_k.data_ptr(), mask.data_ptr(), b, hs, ws,
+                                         sums.data_ptr(), one.data_ptr(), grad.data_ptr(), stream) == 0
+    torch.cuda.synchronize()
+    assert _bands_intact(nb2, npad2, -7.0) and _bands_intact(xb2, xp2, -7.0) and _bands_intact(sb, spad, -7.0)
+    assert _bands_intact(gb, gpad, -7.0) and all(_bands_intact(q[0], q[2], 201) for q in quads)
+    assert torch.allclose(nrm2, nrm, atol=3e-6) and torch.equal(xolp2, xolp)   # sincos(phi) vs the algebraic half angle
+    for got, ref in zip((q[1] for q in quads), O.split_pol(mosaic[0].cpu().numpy())):
+        assert np.array_equal(got[0].cpu().numpy(), ref)
+    assert not bool((sn == -7.0).any()) and not bool((grad == -7.0).any())
+
+
 def test_launch_counter_counts_kernels():
     before = _lib.launch_count()
     ops.fused_mosaic(dev(synth.gen_u_mosaic(0, 32, 48))[None], 1.5)

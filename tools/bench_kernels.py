@@ -60,6 +60,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--only", default="")
+    ap.add_argument("--once", action="store_true", help="call every kernel exactly once (for ncu captures), no timing")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     dev = torch.device("cuda", 0)
@@ -70,6 +71,10 @@ def main():
 
     def emit(name, config, alg_bytes, fn, small=False):
         if only and name.split("/")[0] not in only:
+            return
+        if args.once:
+            fn()
+            torch.cuda.synchronize()
             return
         l0 = _lib.launch_count()
         fn()
@@ -89,6 +94,8 @@ def main():
     emit("xolp_planes_u8", f"4 planes u8 [{B},{hs},{ws}] -> xolp f32", 12 * px, lambda: ops.xolp_from_planes(*planes))
     _, xolp = ops.xolp_from_stack(stack, None, want_iun=False)
     del stack, planes
+    emit("stats/channel_stats", f"xolp f32 [{B},2,{hs},{ws}] -> per-channel sum, sum of squares (float64)", 8 * px,
+         lambda: ops.channel_stats(xolp))
     emit("normals_from_xolp", f"xolp f32 [{B},2,{hs},{ws}] -> normals f32 [{B},9,..]", 44 * px, lambda: ops.get_normals(xolp, 1.5))
     mosaic = torch.from_numpy(rng.integers(0, 256, (B, 2 * hs, 2 * ws), dtype=np.uint8)).to(dev)
     emit("split_pol", f"mosaic u8 [{B},{2 * hs},{2 * ws}] -> 4 quadrants", 2 * mosaic.numel(), lambda: ops.split_pol_batch(mosaic))
