@@ -36,6 +36,32 @@ def test_library_exports_every_declared_symbol(L):
     assert L.polcue_error_string(-22).startswith(b"invalid argument")
 
 
+def test_header_is_plain_c_and_a_c_program_can_bind_the_library(tmp_path):
+    """include/polcue.h must compile as C (no C++-isms, no CUDA or torch types) and a C program must link against it."""
+    from polcue import _lib
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "polcue.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  polcue_lut* lut = 0;\n"
+        "  int rc = polcue_lut_host_build(1.5, &lut);\n"
+        "  float rho[3] = {0.0f, 0.3f, 2.0f}, theta[3];\n"
+        "  if (rc != POLCUE_OK) return 1;\n"
+        "  if (polcue_lut_eval_host(lut, 0, rho, 3, theta) != POLCUE_OK) return 2;\n"
+        '  printf("%s %d %.6f %.6f\\n", polcue_version(), polcue_lut_cells(lut, 0), theta[1], theta[2]);\n'
+        "  if (polcue_fused_mosaic_u8(0, 1, 4, 4, lut, 0, 0, 0, 0, 0) != POLCUE_EINVAL) return 3;\n"
+        "  polcue_lut_destroy(lut);\n  return 0;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    build = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                            "-L", libdir, "-l:libpolcue.so", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    fields = run.stdout.split()
+    assert abs(float(fields[-2]) - 1.472298774) < 1e-5 and abs(float(fields[-1]) - 3.269213607) < 1e-5
+
+
 def test_library_is_built_for_sm_100a_only():
     from polcue import _lib
     out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout

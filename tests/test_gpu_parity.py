@@ -614,6 +614,35 @@ def test_kernels_never_write_outside_their_outputs(shape):
     assert not bool((sn == -7.0).any()) and not bool((grad == -7.0).any())
 
 
+def test_cuda_graph_capture_and_replay_of_the_loader_path():
+    """The launch-latency-bound training-resolution path (two kernels) captured in a CUDA graph and replayed."""
+    planes_a = [dev(p)[None].repeat(4, 1, 1) for p in synth.gen_p_planes(1, 64, 96)]
+    planes_b = [dev(p)[None].repeat(4, 1, 1) for p in synth.gen_p_planes(2, 64, 96)]
+    static = [p.clone() for p in planes_a]
+    mosaic_static = dev(synth.gen_batch("P", 0, 2, 64, 96))
+    out = {"xolp": torch.empty((2, 2, 32, 48), device="cuda"), "normals": torch.empty((2, 9, 32, 48), device="cuda")}
+    ops.lut_for(1.5, static[0].device)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):                         # warm-up on the side stream, as torch's graph recipe asks
+        ops.get_normals(ops.xolp_from_planes(*static)[1], 1.5)
+        ops.fused_mosaic(mosaic_static, 1.5, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        _, xolp = ops.xolp_from_planes(*static)
+        normals = ops.get_normals(xolp, 1.5)
+        ops.fused_mosaic(mosaic_static, 1.5, out=out)
+    for src in (planes_b, planes_a):
+        for dst, s_ in zip(static, src):
+            dst.copy_(s_)
+        mosaic_static.copy_(dev(synth.gen_batch("P", 5 if src is planes_b else 9, 2, 64, 96)))
+        graph.replay()
+        torch.cuda.synchronize()
+        ref = ops.get_normals(ops.xolp_from_planes(*src)[1], 1.5)
+        assert torch.equal(normals, ref)
+        assert torch.equal(out["normals"], ops.fused_mosaic(mosaic_static, 1.5)["normals"])
+
+
 def test_launch_counter_counts_kernels():
     before = _lib.launch_count()
     ops.fused_mosaic(dev(synth.gen_u_mosaic(0, 32, 48))[None], 1.5)

@@ -127,14 +127,32 @@ def main():
         smooth = torch.where(gt > 0, gt, torch.full_like(gt, 0.7))[:, None].contiguous()
         predd = pred[:, None].contiguous().requires_grad_(True)
         maskf = ((gt >= 0.1) & (gt <= 2.0)).float()[:, None].contiguous()
-        if n_img * ((h + 15) // 16) * ((w + 127) // 128) <= 65536:
-            emit("loss/normals_fwd", f"depth_gt, depth_pred, mask f32 [{n_img},1,{h},{w}] -> loss", 12 * npx,
-                 lambda: ops.normals_loss(smooth, predd.detach(), k, maskf), small)
+        if n_img * ((h + 15) // 16) * ((w + 127) // 128) <= (1 << 18):
+            # straight through the C ABI with preallocated buffers (the autograd wrapper costs more host time than the kernels)
+            import ctypes as C
+            L = _lib.lib()
+            wsb = torch.zeros(int(L.polcue_normals_loss_workspace_bytes()), dtype=torch.uint8, device=dev)
+            sums2 = torch.empty(2, dtype=torch.float64, device=dev)
+            lossv, one = torch.empty((), device=dev), torch.ones((), device=dev)
+            gradp = torch.empty_like(predd)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            pd = predd.detach()
+
+            def fwd():
+                assert L.polcue_normals_loss_fwd_f32(smooth.data_ptr(), pd.data_ptr(), k.data_ptr(), maskf.data_ptr(), n_img, h, w,
+                                                     wsb.data_ptr(), sums2.data_ptr(), lossv.data_ptr(), st) == 0
+
+            def bwd():
+                assert L.polcue_normals_loss_bwd_f32(smooth.data_ptr(), pd.data_ptr(), k.data_ptr(), maskf.data_ptr(), n_img, h, w,
+                                                     sums2.data_ptr(), one.data_ptr(), gradp.data_ptr(), st) == 0
+            emit("loss/normals_fwd", f"depth_gt, depth_pred, mask f32 [{n_img},1,{h},{w}] -> loss (C ABI)", 12 * npx, fwd, small)
+            emit("loss/normals_bwd", f"-> d loss / d depth_pred f32 [{n_img},1,{h},{w}] (C ABI)", 16 * npx, bwd, small)
 
             def fwd_bwd():
                 predd.grad = None
                 ops.normals_loss(smooth, predd, k, maskf).backward()
-            emit("loss/normals_fwd_bwd", "forward + backward (12 + 16 B/px)", 28 * npx, fwd_bwd, small)
+            emit("loss/normals_autograd", "ops.normals_loss(...).backward(): forward + backward through torch.autograd (12 + 16 B/px)",
+                 28 * npx, fwd_bwd, small)
         m = gt > 0
         gflat, pflat = gt[m].contiguous(), pred[m].contiguous()
         emit("metrics/flat", f"gt,pred f32 [{gflat.numel()}] (compacted)", 8 * gflat.numel(),
