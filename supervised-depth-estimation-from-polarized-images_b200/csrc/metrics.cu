@@ -395,13 +395,19 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     if (cur != 0xFF) run_flush(table, cur, mat);
     if (p.all_slot >= 0) run_flush(table, p.all_slot, all);
     __syncthreads();
-    // CTA fold over threads, fixed order: thread t owns (slot, accumulator) pair t
-    if (threadIdx.x < p.n_groups * 8) {
-        const float* col = table + (size_t)threadIdx.x * kMetricThreads;
-        double v = 0.0;
-        for (int t = 0; t < kMetricThreads; ++t) v += (double)col[t];
-        if ((threadIdx.x & 7) == 5) v *= 0.4804530139182014;   // ln(2)^2 on the squared log2 differences
-        cta_tot[threadIdx.x >> 3][threadIdx.x & 7] = v;
+    // CTA fold over threads in a fixed order: a warp takes (slot, accumulator) pairs warp, warp + 8, ...; each lane adds its
+    // eight columns (bank-conflict free), then a fixed shuffle tree
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int pair = warp; pair < p.n_groups * 8; pair += kMetricThreads / 32) {
+            const float* col = table + (size_t)pair * kMetricThreads;
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < kMetricThreads / 32; ++j) v += (double)col[lane + 32 * j];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0) cta_tot[pair >> 3][pair & 7] = ((pair & 7) == 5) ? v * 0.4804530139182014 : v;   // ln(2)^2 on the log2 term
+        }
     }
     cluster.sync();
     if (rank == 0 && threadIdx.x < p.n_groups * 8) {

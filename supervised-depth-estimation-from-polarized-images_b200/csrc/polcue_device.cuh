@@ -76,18 +76,6 @@ __device__ __forceinline__ void st_stream_f32x4(float* p, float a, float b, floa
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// base + a * b with a 32x32 -> 64-bit multiply-add: ONE fma-pipe instruction (IMAD.WIDE.U32) instead of the
-// IADD3 / IADD3.X pairs (two alu-pipe instructions, the busier pipe here) a 64-bit pointer add compiles to.
-__device__ __forceinline__ float* ptr_mad(float* base, uint32_t a, uint32_t b) {
-    uint64_t r;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(reinterpret_cast<uint64_t>(base)));
-    return reinterpret_cast<float*>(r);
-}
-__device__ __forceinline__ const uint8_t* ptr_mad(const uint8_t* base, uint32_t a, uint32_t b) {
-    uint64_t r;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(reinterpret_cast<uint64_t>(base)));
-    return reinterpret_cast<const uint8_t*>(r);
-}
 __device__ __forceinline__ float4 lds_f32x4(uint32_t shared_addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(shared_addr));

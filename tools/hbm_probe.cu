@@ -118,6 +118,53 @@ __global__ void __launch_bounds__(TT, MINB) clc_kernel(const unsigned* __restric
     }
 }
 
+// CLC tiles + bursty input prefetch: the CTA that owns tile t with t % BURST == 0 asks the L2 to fetch the input of the
+// next BURST tiles (one bulk prefetch per quadrant stream), so DRAM sees the reads in large clustered bursts instead
+// of a trickle interleaved with the writes.
+template <int TT, int MINB, int BURST, int AHEAD>
+__global__ void __launch_bounds__(TT, MINB) clc_prefetch_kernel(const unsigned* __restrict__ in, float* __restrict__ out, size_t groups,
+                                                                 size_t plane) {
+    __shared__ __align__(16) uint4 resp;
+    __shared__ __align__(8) unsigned long long bar;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned tile = blockIdx.x, phase = 0;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 16;" ::"r"(s32(&bar)) : "memory");
+            asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(s32(&resp)), "r"(s32(&bar)) : "memory");
+        }
+        if (tile % BURST == 0 && threadIdx.x < 4) {
+            const size_t g0 = ((size_t)tile + AHEAD) * TT;               // first group of the burst, AHEAD tiles ahead
+            if (g0 < groups) {
+                size_t n = (size_t)BURST * TT;
+                if (g0 + n > groups) n = groups - g0;
+                const unsigned* src = in + (size_t)threadIdx.x * groups + g0;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((unsigned)(n * 4)) : "memory");
+            }
+        }
+        const size_t g = (size_t)tile * TT + threadIdx.x;
+        if (g < groups) store_planes(out, plane, g, load_quads(in, groups, g));
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(s32(&bar)), "r"(phase) : "memory");
+        }
+        phase ^= 1;
+        unsigned valid, next;
+        asm volatile("{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\tld.shared.b128 r, [%2];\n\t"
+                     "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\tselp.u32 %1, 1, 0, p1;\n\t"
+                     "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t}"
+                     : "=r"(next), "=r"(valid) : "r"(s32(&resp)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (!valid) break;
+        tile = next;
+    }
+}
+
 __global__ void __launch_bounds__(T, 2) copy_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
@@ -176,6 +223,13 @@ int main(int argc, char** argv) {
         report("CLC, tile = 256 groups (256 thr, 4 CTA/SM)", RW, time_ms([&] { clc_kernel<256, 4><<<(unsigned)((groups + 255) / 256), 256>>>(in, out, groups, plane, nullptr); }, reps));
         report("CLC, tile = 1024 groups (1024 thr, 1 CTA/SM)", RW, time_ms([&] { clc_kernel<1024, 1><<<(unsigned)((groups + 1023) / 1024), 1024>>>(in, out, groups, plane, nullptr); }, reps));
         report("CLC, tile = 512 groups, 4 CTA/SM", RW, time_ms([&] { clc_kernel<512, 4><<<tiles, 512>>>(in, out, groups, plane, nullptr); }, reps));
+        {
+            const unsigned t256 = (unsigned)((groups + 255) / 256);
+            report("CLC 256 thr, prefetch burst 64 tiles, 64 ahead", RW, time_ms([&] { clc_prefetch_kernel<256, 4, 64, 64><<<t256, 256>>>(in, out, groups, plane); }, reps));
+            report("CLC 256 thr, prefetch burst 256 tiles, 256 ahead", RW, time_ms([&] { clc_prefetch_kernel<256, 4, 256, 256><<<t256, 256>>>(in, out, groups, plane); }, reps));
+            report("CLC 256 thr, prefetch burst 1024 tiles, 1024 ahead", RW, time_ms([&] { clc_prefetch_kernel<256, 4, 1024, 1024><<<t256, 256>>>(in, out, groups, plane); }, reps));
+            report("CLC 256 thr, prefetch burst 4096 tiles, 2048 ahead", RW, time_ms([&] { clc_prefetch_kernel<256, 4, 4096, 2048><<<t256, 256>>>(in, out, groups, plane); }, reps));
+        }
         report("plain launch, one CTA per 512-group tile", RW, time_ms([&] { stat_kernel<1><<<tiles, T>>>(in, out, groups, plane, counter); }, reps));
         // every tile must be processed exactly once
         CK(cudaMemset(counter, 0, 4));
