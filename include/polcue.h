@@ -94,6 +94,13 @@ POLCUE_API int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W
                            uint8_t* planes, float* iun, float* xolp, float* normals,
                            polcue_stream_t stream);
 
+/* The same fused kernel fed by four separate B x H x W uint8 planes (the loader's pol00 / pol01 / pol10 / pol11 images,
+ * manydepth/datasets/indoor_dataset.py:435-438) instead of a quadrant mosaic: XOLP (+ Iun) and the nine normal channels
+ * at the planes' resolution in one launch -- get_xolp (:430-442) + get_normals (pre_encoders.py:99-113). */
+POLCUE_API int polcue_fused_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t* i90, const uint8_t* i135,
+                           int B, int H, int W, const polcue_lut* lut, float* iun, float* xolp, float* normals,
+                           polcue_stream_t stream);
+
 /* Same pipeline with HOST buffers (pinned or pageable): chunks of frames are copied in, processed
  * and copied out on three streams so H2D, the kernel and D2H overlap.  Blocks until done.
  * `chunk_frames` <= 0 picks a default.  This is the call bench.py's `e2e` figure times. */

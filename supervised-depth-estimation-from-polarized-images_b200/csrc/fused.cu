@@ -90,7 +90,9 @@ __device__ __forceinline__ LutView lut_view(const float4* base, const LutArgs& a
 // Fused kernel
 // ---------------------------------------------------------------------------------------------
 struct FusedParams {
-    const uint8_t* mosaic;
+    const uint8_t* mosaic;   // address of the 0-degree sample of pixel (0,0) of frame 0
+    long long off45, off90, off135;   // byte offsets from a pixel's 0-degree sample to its 45 / 90 / 135-degree samples:
+                                      // quadrant mosaic: Ws, Hs*W, Hs*W + Ws;  four separate planes: pointer differences
     uint8_t* planes;   // may be null
     float* iun;        // may be null
     float* xolp;
@@ -98,9 +100,8 @@ struct FusedParams {
     LutArgs lut;
     uint32_t groups_total;   // B * Hs * (Ws / VEC)
     FastDiv groups_per_frame, groups_per_row;
-    uint32_t W, Ws;
-    uint32_t frame_bytes;    // H * W                                   (all strides < 2^32, checked on the host)
-    uint32_t quad_down;      // Hs * W : byte offset from a top quadrant to the one below it
+    uint32_t W;              // input row stride in bytes (mosaic width, or Ws for separate planes)
+    uint32_t frame_bytes;    // input frame stride in bytes                 (all strides < 2^32, checked on the host)
     uint32_t plane;          // Hs * Ws
     uint32_t plane_bytes;    // 4 * Hs * Ws
 };
@@ -145,10 +146,10 @@ __device__ __forceinline__ GroupIn<VEC> load_group(const FusedParams& p, uint32_
         const uint32_t y = fastdiv(g.rem, p.groups_per_row);
         const uint32_t xg = g.rem - y * p.groups_per_row.div;
         const uint8_t* src = p.mosaic + ((size_t)g.b * p.frame_bytes + (y * p.W + xg * VEC));
-        g.w0 = PK::load(src);                          // TL:   0 deg
-        g.w45 = PK::load(src + p.Ws);                  // TR:  45 deg
-        g.w90 = PK::load(src + p.quad_down);           // BL:  90 deg
-        g.w135 = PK::load(src + p.quad_down + p.Ws);   // BR: 135 deg
+        g.w0 = PK::load(src);                  // TL:   0 deg
+        g.w45 = PK::load(src + p.off45);       // TR:  45 deg
+        g.w90 = PK::load(src + p.off90);       // BL:  90 deg
+        g.w135 = PK::load(src + p.off135);     // BR: 135 deg
     }
     return g;
 }
@@ -592,11 +593,53 @@ int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W, const pol
     p.groups_per_row.div = (uint32_t)(Ws / vec);
     make_fastdiv(p.groups_per_row.div, p.groups_per_row.mul, p.groups_per_row.shift);
     p.W = (uint32_t)W;
-    p.Ws = (uint32_t)Ws;
     if ((unsigned long long)H * W >= (1ull << 30)) return POLCUE_E2BIG;   // 32-bit strides inside the kernel
     p.frame_bytes = (uint32_t)H * (uint32_t)W;
-    p.quad_down = (uint32_t)Hs * (uint32_t)W;
+    p.off45 = Ws;
+    p.off90 = (long long)Hs * W;
+    p.off135 = (long long)Hs * W + Ws;
     p.plane = (uint32_t)Hs * (uint32_t)Ws;
+    p.plane_bytes = 4u * p.plane;
+    const size_t smem = normals ? lut->bytes() : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (vec) {
+        case 4: return launch_fused<4>(p, smem, s);
+        case 2: return launch_fused<2>(p, smem, s);
+        default: return launch_fused<1>(p, smem, s);
+    }
+}
+
+int polcue_fused_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t* i90, const uint8_t* i135, int B, int H, int W,
+                           const polcue_lut* lut, float* iun, float* xolp, float* normals, polcue_stream_t stream) {
+    if (!i0 || !i45 || !i90 || !i135 || !xolp || B < 0 || H <= 0 || W <= 0) return POLCUE_EINVAL;
+    if (normals && (!lut || !lut->d_blob)) return POLCUE_EINVAL;
+    if (B == 0) return POLCUE_OK;
+    auto all4 = [&](size_t a) { return aligned(i0, a) && aligned(i45, a) && aligned(i90, a) && aligned(i135, a); };
+    int vec = 1;
+    if (W % 4 == 0 && all4(4) && aligned(xolp, 16) && aligned(normals, 16) && aligned(iun, 16)) vec = 4;
+    else if (W % 2 == 0 && all4(2) && aligned(xolp, 8) && aligned(normals, 8) && aligned(iun, 8)) vec = 2;
+    else if (!aligned(xolp, 4) || !aligned(normals, 4) || !aligned(iun, 4)) return POLCUE_EINVAL;
+    const unsigned long long groups = (unsigned long long)B * H * (W / vec);
+    if (groups >= (1ull << 31) || (unsigned long long)H * W >= (1ull << 30)) return POLCUE_E2BIG;
+    FusedParams p;
+    p.mosaic = i0;
+    p.off45 = i45 - i0;
+    p.off90 = i90 - i0;
+    p.off135 = i135 - i0;
+    p.planes = nullptr;
+    p.iun = iun;
+    p.xolp = xolp;
+    p.normals = normals;
+    if (normals) p.lut = lut_args(lut);
+    else p.lut = LutArgs{};
+    p.groups_total = (uint32_t)groups;
+    p.groups_per_frame.div = (uint32_t)H * (W / vec);
+    make_fastdiv(p.groups_per_frame.div, p.groups_per_frame.mul, p.groups_per_frame.shift);
+    p.groups_per_row.div = (uint32_t)(W / vec);
+    make_fastdiv(p.groups_per_row.div, p.groups_per_row.mul, p.groups_per_row.shift);
+    p.W = (uint32_t)W;
+    p.frame_bytes = (uint32_t)H * (uint32_t)W;
+    p.plane = (uint32_t)H * (uint32_t)W;
     p.plane_bytes = 4u * p.plane;
     const size_t smem = normals ? lut->bytes() : 0;
     cudaStream_t s = (cudaStream_t)stream;

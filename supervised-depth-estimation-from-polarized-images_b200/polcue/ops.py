@@ -121,6 +121,36 @@ def fused_mosaic(mosaic, n=1.5, want_iun=False, want_planes=False, want_normals=
     return out
 
 
+def fused_planes(i0, i45, i90, i135, n=1.5, want_iun=False, want_normals=True, out=None):
+    """Four (B x) H x W uint8 planes (indoor_dataset.py:435-438) -> dict(xolp [B,2,H,W], normals [B,9,H,W], iun) in one launch:
+    the loader's get_xolp plus the encoder's get_normals."""
+    planes = [_need_cuda(p, "plane", torch.uint8) for p in (i0, i45, i90, i135)]
+    shape = planes[0].shape
+    if any(p.shape != shape or p.device != planes[0].device for p in planes) or len(shape) not in (2, 3):
+        raise ValueError("planes must share one (B x) H x W shape and device")
+    b = shape[0] if len(shape) == 3 else 1
+    h, w = shape[-2:]
+    dev = planes[0].device
+    out = dict(out or {})
+
+    def buf(key, shp):
+        t = out.get(key)
+        if t is None:
+            t = out[key] = torch.empty(shp, dtype=torch.float32, device=dev)
+        elif tuple(t.shape) != tuple(shp) or t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+            raise ValueError(f"preallocated `{key}` has the wrong shape/dtype/device")
+        return t
+
+    xolp = buf("xolp", (b, 2, h, w))
+    normals = buf("normals", (b, 9, h, w)) if want_normals else None
+    iun = buf("iun", (b, h, w)) if want_iun else None
+    lut = lut_for(n, dev) if want_normals else C.c_void_p(0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().polcue_fused_planes_u8(*(_ptr(p) for p in planes), b, h, w, lut, _ptr(iun), _ptr(xolp), _ptr(normals),
+                                                     _stream(planes[0])), "polcue_fused_planes_u8")
+    return out
+
+
 def fused_mosaic_host(mosaic, n=1.5, want_iun=False, want_normals=True, out=None, chunk_frames=0, device=None):
     """Host (ideally pinned) uint8 mosaics -> host float32 outputs; copies are pipelined inside the library."""
     if not isinstance(mosaic, torch.Tensor) or mosaic.is_cuda or mosaic.dtype != torch.uint8:

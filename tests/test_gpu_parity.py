@@ -181,6 +181,23 @@ def test_xolp_noncanonical_angles(golden):
     P.assert_aolp_close(phi, golden["xolp_ang2_phi"])
 
 
+@pytest.mark.parametrize("shape", [(320, 480), (64, 96), (33, 47), (10, 14)])
+def test_fused_planes_matches_fused_mosaic(shape):
+    hs, ws = shape
+    planes = [np.stack([synth.gen_p_planes(f, hs, ws)[k] for f in range(3)]) for k in range(4)]
+    mosaic = np.stack([synth.tile_mosaic([planes[k][f] for k in range(4)]) for f in range(3)])
+    a = ops.fused_planes(*(dev(p) for p in planes), want_iun=True)
+    m = ops.fused_mosaic(dev(mosaic), 1.5, want_iun=True)
+    for key in ("xolp", "normals", "iun"):
+        assert torch.equal(a[key], m[key]), key
+    # views into one [B,4,H,W] tensor and single images work too
+    packed = dev(np.stack(planes, axis=1))
+    v = ops.fused_planes(*(packed[:, k].contiguous() for k in range(4)))
+    assert torch.equal(v["normals"], m["normals"])
+    one = ops.fused_planes(*(dev(p[0]) for p in planes), want_normals=False)
+    assert torch.equal(one["xolp"][0], m["xolp"][0])
+
+
 def test_xolp_planes_matches_stack_path():
     planes = synth.gen_p_planes(2, 96, 128)
     _, x1 = ops.xolp_from_planes(*(dev(p)[None] for p in planes), want_iun=False)
