@@ -32,3 +32,51 @@ def to_device(array, dtype=None):
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t.to(default_device(), non_blocking=False)
+
+
+def install(verbose=False):
+    """Replace, in place, the hot-path functions of the reference modules that are ALREADY imported (`sys.modules`).
+
+    For the `manydepth` package, of which only a few functions are on the path:
+      manydepth.normals_vec.{rho_diffuse, rho_spec, calc_normals}
+      manydepth.networks.pre_encoders.{rho_diffuse, rho_spec, calc_normals} and ShallowNormalsEncoder.get_normals
+      manydepth.layers.{compute_depth_errors, compute_depth_errors_numpy}
+      manydepth.trainer.{compute_depth_errors, compute_depth_errors_numpy, Iun_and_xolp} and
+          Trainer.compute_supervised_normals_losses (the GT + predicted stencils, cosine and masked mean, with backward)
+      manydepth.datasets.indoor_dataset.Iun_and_xolp, polarisation.* and ppp_code.physical_normals_channels.* if imported.
+    Returns the list of "module.attribute" names that were replaced.
+    """
+    import sys
+
+    from . import layers, normals_vec, physical_normals_channels, pol_split_and_save, pre_encoders, trainer, xolp, xolp_and_normals
+
+    done = []
+
+    def patch(mod_name, attr, value, owner=None):
+        mod = sys.modules.get(mod_name)
+        target = getattr(mod, owner, None) if (mod is not None and owner) else mod
+        if target is not None and hasattr(target, attr):
+            setattr(target, attr, value)
+            done.append(f"{mod_name}.{owner + '.' if owner else ''}{attr}")
+
+    for name in ("rho_diffuse", "rho_spec", "calc_normals"):
+        patch("manydepth.normals_vec", name, getattr(normals_vec, name))
+        patch("manydepth.networks.pre_encoders", name, getattr(normals_vec, name))
+    patch("manydepth.networks.pre_encoders", "get_normals", staticmethod(pre_encoders.get_normals), owner="ShallowNormalsEncoder")
+    for mod_name in ("manydepth.layers", "manydepth.trainer", "manydepth.evaluation"):
+        patch(mod_name, "compute_depth_errors", layers.compute_depth_errors)
+        patch(mod_name, "compute_depth_errors_numpy", layers.compute_depth_errors_numpy)
+    for mod_name in ("manydepth.trainer", "manydepth.datasets.indoor_dataset", "polarisation.xolp", "polarisation.xolp_and_normals"):
+        patch(mod_name, "Iun_and_xolp", xolp.Iun_and_xolp)
+    patch("manydepth.trainer", "compute_supervised_normals_losses",
+          lambda self, depth_gt, depth_pred, intrinsics, mask: trainer.compute_supervised_normals_losses(depth_gt, depth_pred, intrinsics, mask),
+          owner="Trainer")
+    for mod_name in ("polarisation.pol_split_and_save", "polarisation.xolp_and_normals"):
+        patch(mod_name, "split_pol", pol_split_and_save.split_pol)
+    for name in ("rho_diffuse", "rho_spec", "calc_normals"):
+        patch("polarisation.xolp_and_normals", name, getattr(xolp_and_normals, name))
+    for name in ("PolarisationImage_channel", "rho_diffuse_channel", "rho_spec_channel", "calc_normals_channel"):
+        patch("ppp_code.physical_normals_channels", name, getattr(physical_normals_channels, name))
+    if verbose:
+        print("polcue.compat.install: replaced", ", ".join(done) or "nothing (import the reference modules first)")
+    return done

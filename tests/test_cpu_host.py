@@ -158,6 +158,35 @@ def test_product_package_never_imports_the_oracle():
                 assert "polcue_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
 
 
+def test_dropin_packages_shadow_the_reference_module_names():
+    """`polcue/dropin` on sys.path serves `polarisation.*` and `ppp_code.physical_normals_channels` under the reference's names."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from polarisation.xolp import Iun_and_xolp\n"
+            "from polarisation.pol_split_and_save import split_pol\n"
+            "from polarisation.xolp_and_normals import rho_spec, rho_diffuse, calc_normals\n"
+            "from ppp_code.physical_normals_channels import PolarisationImage_channel, calc_normals_channel\n"
+            "import polcue.compat.xolp as c; print('OK', Iun_and_xolp is c.Iun_and_xolp, split_pol.__module__)\n") % (
+        os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200"),
+        os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200", "polcue", "dropin"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "OK True polcue.compat.pol_split_and_save" in out.stdout, out.stderr[-1500:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/manydepth"), reason="reference checkout not present on this box")
+def test_install_patches_the_imported_reference_modules():
+    """`polcue.compat.install()` swaps the hot-path functions of the real reference modules in place (no GPU needed)."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, '/root/reference')\n"
+            "import manydepth.normals_vec as nv, manydepth.layers as ly, manydepth.networks.pre_encoders as pe, polarisation.xolp as px\n"
+            "import polcue.compat as c, polcue.compat.normals_vec as cnv, polcue.compat.layers as cly\n"
+            "done = c.install()\n"
+            "assert nv.rho_diffuse is cnv.rho_diffuse and pe.rho_spec is cnv.rho_spec and ly.compute_depth_errors is cly.compute_depth_errors\n"
+            "assert pe.ShallowNormalsEncoder.get_normals.__module__ == 'polcue.compat.pre_encoders'\n"
+            "assert px.Iun_and_xolp.__module__ == 'polcue.compat.xolp'\n"
+            "print('PATCHED', len(done))\n") % os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "PATCHED" in out.stdout and int(out.stdout.split()[-1]) >= 10, out.stderr[-1500:]
+
+
 def test_synthetic_generators_are_seeded_per_frame():
     from polcue import synth
     a = synth.gen_batch("P", 3, 2, 32, 48)
