@@ -68,6 +68,11 @@ POLCUE_API int polcue_lut_cells(const polcue_lut* lut, int table);
 POLCUE_API int polcue_lut_knots(const polcue_lut* lut, int table, double* x, double* y, int capacity);
 /* Evaluates the float32 cell tables on the host exactly as the kernels do (float32 arithmetic). */
 POLCUE_API int polcue_lut_eval_host(const polcue_lut* lut, int table, const float* rho, size_t count, float* theta);
+/* Steep end segment of table t: where the last segment of the reference's table is steeper than 512 rad per unit rho
+ * (second specular branch at n = 1.8: slope -10797, theta -> -1e4 rad for rho -> 2) float32 holds neither rho nor
+ * theta to the parity bound, so every kernel evaluates queries beyond the second-to-last knot in float64.
+ * Returns 1 and fills xys = {x_lo, y_lo, slope} if table t has one, 0 if not. */
+POLCUE_API int polcue_lut_steep(const polcue_lut* lut, int table, double* xys);
 
 /* ---------------------------------------------------------------------------------------------
  * Quadrant split ("demosaic" of the stored 2x2-tiled polarizer image), bit-exact.
@@ -93,6 +98,13 @@ POLCUE_API int polcue_split_pol(const void* img, int B, int H, int W, int px_byt
 POLCUE_API int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W, const polcue_lut* lut,
                            uint8_t* planes, float* iun, float* xolp, float* normals,
                            polcue_stream_t stream);
+
+/* The same pipeline for the RAW sensor layout (not used by the reference, whose HAMMER images are stored pre-tiled):
+ * an interleaved 2x2 super-pixel mosaic, output pixel (y, x) owning mosaic pixels (2y, 2x), (2y, 2x+1), (2y+1, 2x),
+ * (2y+1, 2x+1).  angle_at: 4 HOST ints, the angle index (0, 1, 2, 3 = 0, 45, 90, 135 deg) found at those four
+ * positions, each exactly once -- e.g. {2, 1, 3, 0} for a 90/45 over 135/0 polarizer array. */
+POLCUE_API int polcue_fused_superpixel_u8(const uint8_t* mosaic, int B, int H, int W, const int* angle_at, const polcue_lut* lut,
+                               uint8_t* planes, float* iun, float* xolp, float* normals, polcue_stream_t stream);
 
 /* The same fused kernel fed by four separate B x H x W uint8 planes (the loader's pol00 / pol01 / pol10 / pol11 images,
  * manydepth/datasets/indoor_dataset.py:435-438) instead of a quadrant mosaic: XOLP (+ Iun) and the nine normal channels

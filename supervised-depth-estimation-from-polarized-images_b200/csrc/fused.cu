@@ -50,6 +50,7 @@ struct LutArgs {
     int offset[3];
     float scale[3];
     float last[3];
+    LutSteep steep;
 };
 
 LutArgs lut_args(const polcue_lut* lut) {
@@ -60,6 +61,18 @@ LutArgs lut_args(const polcue_lut* lut) {
         a.offset[t] = lut->offset[t];
         a.scale[t] = lut->scale[t];
         a.last[t] = (float)lut->cells[t] - 0.5f;
+    }
+    a.steep.mask = lut->steep_mask;
+    a.steep.from = INFINITY;
+    for (int t = 0; t < 3; ++t) {
+        a.steep.x[t] = lut->steep_x[t];
+        a.steep.y[t] = lut->steep_y[t];
+        a.steep.slope[t] = lut->steep_slope[t];
+        if ((lut->steep_mask >> t) & 1) {
+            float f = (float)lut->steep_x[t];
+            if ((double)f > lut->steep_x[t]) f = nextafterf(f, -INFINITY);   // round DOWN: never miss a query
+            a.steep.from = fminf(a.steep.from, f);
+        }
     }
     return a;
 }
@@ -100,7 +113,10 @@ struct FusedParams {
     LutArgs lut;
     uint32_t groups_total;   // B * Hs * (Ws / VEC)
     FastDiv groups_per_frame, groups_per_row;
+    int superpixel;          // 0: samples are `offXX` apart (quadrants / planes); 1: interleaved 2x2 super-pixels
+    int angle_at[4];         // superpixel only: angle index (0..3 = 0, 45, 90, 135 deg) at (0,0), (0,1), (1,0), (1,1)
     uint32_t W;              // input row stride in bytes (mosaic width, or Ws for separate planes)
+    uint32_t row_px;         // output pixels per row (Ws)
     uint32_t frame_bytes;    // input frame stride in bytes                 (all strides < 2^32, checked on the host)
     uint32_t plane;          // Hs * Ws
     uint32_t plane_bytes;    // 4 * Hs * Ws
@@ -145,13 +161,75 @@ __device__ __forceinline__ GroupIn<VEC> load_group(const FusedParams& p, uint32_
         g.rem = gid - g.b * p.groups_per_frame.div;
         const uint32_t y = fastdiv(g.rem, p.groups_per_row);
         const uint32_t xg = g.rem - y * p.groups_per_row.div;
-        const uint8_t* src = p.mosaic + ((size_t)g.b * p.frame_bytes + (y * p.W + xg * VEC));
-        g.w0 = PK::load(src);                  // TL:   0 deg
-        g.w45 = PK::load(src + p.off45);       // TR:  45 deg
-        g.w90 = PK::load(src + p.off90);       // BL:  90 deg
-        g.w135 = PK::load(src + p.off135);     // BR: 135 deg
+        if (!p.superpixel) {
+            const uint8_t* src = p.mosaic + ((size_t)g.b * p.frame_bytes + (y * p.W + xg * VEC));
+            g.w0 = PK::load(src);                  // TL:   0 deg
+            g.w45 = PK::load(src + p.off45);       // TR:  45 deg
+            g.w90 = PK::load(src + p.off90);       // BL:  90 deg
+            g.w135 = PK::load(src + p.off135);     // BR: 135 deg
+        } else {
+            // raw sensor layout: output pixel (y, x) owns mosaic bytes (2y, 2x), (2y, 2x+1), (2y+1, 2x), (2y+1, 2x+1)
+            const uint8_t* src = p.mosaic + ((size_t)g.b * p.frame_bytes + ((2 * y) * p.W + 2 * xg * VEC));
+            uint32_t pos[4] = {0, 0, 0, 0};        // VEC samples of each super-pixel position, packed like Packed<VEC>
+            if constexpr (VEC == 4) {
+                const uint2 r0 = *reinterpret_cast<const uint2*>(src), r1 = *reinterpret_cast<const uint2*>(src + p.W);
+                pos[0] = __byte_perm(r0.x, r0.y, 0x6420);   // even bytes of row 2y
+                pos[1] = __byte_perm(r0.x, r0.y, 0x7531);   // odd bytes
+                pos[2] = __byte_perm(r1.x, r1.y, 0x6420);
+                pos[3] = __byte_perm(r1.x, r1.y, 0x7531);
+            } else {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    pos[0] |= (uint32_t)ld_stream_u8(src + 2 * j) << (8 * j);
+                    pos[1] |= (uint32_t)ld_stream_u8(src + 2 * j + 1) << (8 * j);
+                    pos[2] |= (uint32_t)ld_stream_u8(src + p.W + 2 * j) << (8 * j);
+                    pos[3] |= (uint32_t)ld_stream_u8(src + p.W + 2 * j + 1) << (8 * j);
+                }
+            }
+            uint32_t ang[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                    if (p.angle_at[k] == a) ang[a] = pos[k];    // warp-uniform selects
+            g.w0 = (typename PK::type)ang[0];
+            g.w45 = (typename PK::type)ang[1];
+            g.w90 = (typename PK::type)ang[2];
+            g.w135 = (typename PK::type)ang[3];
+        }
     }
     return g;
+}
+
+// Pixels whose rho may lie on a steep end segment (LutSteep; bit j of `bits` = pixel pix + j of frame b): the samples are
+// read again, rho is formed in float64 and the candidates of the steep tables are stored over the float32 ones (same
+// thread, same addresses, program order).  Out of line so the hot loop carries one flag register for it.
+__device__ __noinline__ void steep_redo(const FusedParams& p, uint32_t b, uint32_t pix, uint32_t bits) {
+    for (int j = 0; j < 4; ++j) {
+        if (!((bits >> j) & 1)) continue;
+        const uint32_t px = pix + j;
+        const uint32_t ws = p.superpixel ? p.W / 2 : p.row_px;
+        const uint32_t y = px / ws, x = px - y * ws;
+        float i[4];
+        if (!p.superpixel) {
+            const uint8_t* src = p.mosaic + ((size_t)b * p.frame_bytes + (y * p.W + x));
+            i[0] = (float)src[0]; i[1] = (float)src[p.off45]; i[2] = (float)src[p.off90]; i[3] = (float)src[p.off135];
+        } else {
+            const uint8_t* src = p.mosaic + ((size_t)b * p.frame_bytes + ((2 * y) * p.W + 2 * x));
+            const float pos[4] = {(float)src[0], (float)src[1], (float)src[p.W], (float)src[p.W + 1]};
+            for (int k = 0; k < 4; ++k) i[p.angle_at[k]] = pos[k];
+        }
+        const Cues q = cues_from_u8<true>(i[0], i[1], i[2], i[3]);
+        const double rho = rho_exact_u8(i[0], i[1], i[2], i[3]);
+        float* no = p.normals + ((size_t)(9 * b) * p.plane + px);
+        for (int t = 0; t < 3; ++t) {
+            if (!((p.lut.steep.mask >> t) & 1) || !(rho > p.lut.steep.x[t])) continue;
+            const float2 sc = steep_sincos(steep_theta(p.lut.steep, t, rho));
+            no[(size_t)(3 * t + 0) * p.plane] = (t == 0 ? q.cos_phi : -q.sin_phi) * sc.x;
+            no[(size_t)(3 * t + 1) * p.plane] = (t == 0 ? q.sin_phi : q.cos_phi) * sc.x;
+            no[(size_t)(3 * t + 2) * p.plane] = sc.y;
+        }
+    }
 }
 
 template <int VEC, bool MUFU, bool NORMALS>
@@ -190,10 +268,12 @@ __device__ __forceinline__ void process_group(const FusedParams& p, const LutSha
 
     if constexpr (NORMALS) {
         float nrm[9][VEC];
+        uint32_t steep_bits = 0;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             float n9[9];
             normals_from_trig<MUFU>(lut, rho[j], sp[j], cp[j], n9);
+            steep_bits |= (rho[j] >= p.lut.steep.from ? 1u : 0u) << j;
 #pragma unroll
             for (int c = 0; c < 9; ++c) nrm[c][j] = n9[c];
         }
@@ -204,6 +284,7 @@ __device__ __forceinline__ void process_group(const FusedParams& p, const LutSha
             st_stream_vec<VEC>(no, nrm[c]);
             no += p.plane;
         }
+        if (steep_bits) steep_redo(p, b, pix, steep_bits);   // rare: float64 evaluation of a steep end segment
     }
 }
 
@@ -211,7 +292,7 @@ __device__ __forceinline__ void process_group(const FusedParams& p, const LutSha
 // control; the loop is software-pipelined two deep: while tile k is computed and stored, the quadrant words of tile
 // k+1 are already in flight and the query for tile k+2 is outstanding, so no warp waits on DRAM latency.
 template <int VEC, bool MUFU, bool NORMALS>
-__global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) fused_mosaic_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) fused_mosaic_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ __align__(16) uint4 clc_resp;
@@ -432,9 +513,28 @@ __device__ __forceinline__ XolpIn<VEC> load_xolp(const NormalsParams& p, uint32_
     return g;
 }
 
+// As steep_redo, for the XOLP-fed kernel: rho is the float32 input widened exactly, as scipy widens it.
+__device__ __noinline__ void steep_redo_xolp(const NormalsParams& p, uint32_t b, uint32_t pix, uint32_t bits) {
+    for (int j = 0; j < 4; ++j) {
+        if (!((bits >> j) & 1)) continue;
+        const float* xi = p.xolp + ((size_t)b * 2 * p.hw + pix + j);
+        const double rho = (double)xi[0];
+        float sp, cp;
+        sincos_poly(xi[p.hw], sp, cp);
+        float* no = p.normals + ((size_t)b * 9 * p.hw + pix + j);
+        for (int t = 0; t < 3; ++t) {
+            if (!((p.lut.steep.mask >> t) & 1) || !(rho > p.lut.steep.x[t])) continue;
+            const float2 sc = steep_sincos(steep_theta(p.lut.steep, t, rho));
+            no[(size_t)(3 * t + 0) * p.hw] = (t == 0 ? cp : -sp) * sc.x;
+            no[(size_t)(3 * t + 1) * p.hw] = (t == 0 ? sp : cp) * sc.x;
+            no[(size_t)(3 * t + 2) * p.hw] = sc.y;
+        }
+    }
+}
+
 // get_normals: same tile scheduling and two-deep software pipeline as the fused kernel.
 template <int VEC, bool MUFU>
-__global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) normals_from_xolp_kernel(const NormalsParams p) {
+__global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) normals_from_xolp_kernel(const __grid_constant__ NormalsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ __align__(16) uint4 clc_resp;
@@ -458,10 +558,12 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) normals_from_x
         }
         if (cur.valid) {
             float nrm[9][VEC];
+            uint32_t steep_bits = 0;
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 float n9[9];
                 normals_from_cues<MUFU>(lut, cur.rho[j], cur.phi[j], n9);
+                steep_bits |= (cur.rho[j] >= p.lut.steep.from ? 1u : 0u) << j;
 #pragma unroll
                 for (int c = 0; c < 9; ++c) nrm[c][j] = n9[c];
             }
@@ -472,6 +574,7 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) normals_from_x
                 st_stream_vec<VEC>(no, nrm[c]);
                 no += p.hw;
             }
+            if (steep_bits) steep_redo_xolp(p, cur.b, cur.rem * VEC, steep_bits);
         }
         if (!more) break;
         cur = nxt;
@@ -487,11 +590,18 @@ __global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ rh
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         const float r = ld_stream_f32(rho + i);
         const float g = lut_coord(r);
+        float th[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int t = (WHICH == 0 ? 0 : 1); t < (WHICH == 0 ? 1 : 3); ++t) {
+            th[t] = lut_eval(lut.cells[t], lut.scale[t], lut.last[t], r, g);
+            if (r >= a.steep.from && ((a.steep.mask >> t) & 1) && (double)r > a.steep.x[t])
+                th[t] = (float)steep_theta(a.steep, t, (double)r);    // float64 line, rounded once
+        }
         if constexpr (WHICH == 0) {
-            st_stream_f32(out0 + i, lut_eval(lut.cells[0], lut.scale[0], lut.last[0], r, g));
+            st_stream_f32(out0 + i, th[0]);
         } else {
-            st_stream_f32(out0 + i, lut_eval(lut.cells[1], lut.scale[1], lut.last[1], r, g));
-            st_stream_f32(out1 + i, lut_eval(lut.cells[2], lut.scale[2], lut.last[2], r, g));
+            st_stream_f32(out0 + i, th[1]);
+            st_stream_f32(out1 + i, th[2]);
         }
     }
 }
@@ -564,14 +674,25 @@ int polcue_debug_set_trig(int mufu) {
     return POLCUE_OK;
 }
 
-int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W, const polcue_lut* lut, uint8_t* planes,
-                           float* iun, float* xolp, float* normals, polcue_stream_t stream) {
+static int fused_mosaic_common(const uint8_t* mosaic, int B, int H, int W, bool layout_superpixel, const int* angle_at,
+                               const polcue_lut* lut, uint8_t* planes, float* iun, float* xolp, float* normals,
+                               polcue_stream_t stream) {
     if (!mosaic || !xolp || B < 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return POLCUE_EINVAL;
+    if (layout_superpixel) {
+        if (!angle_at) return POLCUE_EINVAL;
+        int seen = 0;
+        for (int k = 0; k < 4; ++k) {
+            if (angle_at[k] < 0 || angle_at[k] > 3) return POLCUE_EINVAL;
+            seen |= 1 << angle_at[k];
+        }
+        if (seen != 15) return POLCUE_EINVAL;          // every angle exactly once
+    }
     if (normals && (!lut || !lut->d_blob)) return POLCUE_EINVAL;
     if (B == 0) return POLCUE_OK;
     const int Hs = H / 2, Ws = W / 2;
     int vec = 1;
-    if (Ws % 4 == 0 && aligned(mosaic, 4) && aligned(xolp, 16) && aligned(normals, 16) && aligned(iun, 16) && aligned(planes, 4))
+    if (Ws % 4 == 0 && aligned(mosaic, layout_superpixel ? 8 : 4) && aligned(xolp, 16) && aligned(normals, 16) && aligned(iun, 16) &&
+        aligned(planes, 4))
         vec = 4;
     else if (Ws % 2 == 0 && aligned(mosaic, 2) && aligned(xolp, 8) && aligned(normals, 8) && aligned(iun, 8) && aligned(planes, 2))
         vec = 2;
@@ -593,11 +714,14 @@ int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W, const pol
     p.groups_per_row.div = (uint32_t)(Ws / vec);
     make_fastdiv(p.groups_per_row.div, p.groups_per_row.mul, p.groups_per_row.shift);
     p.W = (uint32_t)W;
+    p.row_px = (uint32_t)Ws;
     if ((unsigned long long)H * W >= (1ull << 30)) return POLCUE_E2BIG;   // 32-bit strides inside the kernel
     p.frame_bytes = (uint32_t)H * (uint32_t)W;
     p.off45 = Ws;
     p.off90 = (long long)Hs * W;
     p.off135 = (long long)Hs * W + Ws;
+    p.superpixel = layout_superpixel ? 1 : 0;
+    for (int k = 0; k < 4; ++k) p.angle_at[k] = layout_superpixel ? angle_at[k] : k;
     p.plane = (uint32_t)Hs * (uint32_t)Ws;
     p.plane_bytes = 4u * p.plane;
     const size_t smem = normals ? lut->bytes() : 0;
@@ -607,6 +731,16 @@ int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W, const pol
         case 2: return launch_fused<2>(p, smem, s);
         default: return launch_fused<1>(p, smem, s);
     }
+}
+
+int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W, const polcue_lut* lut, uint8_t* planes, float* iun,
+                           float* xolp, float* normals, polcue_stream_t stream) {
+    return fused_mosaic_common(mosaic, B, H, W, false, nullptr, lut, planes, iun, xolp, normals, stream);
+}
+
+int polcue_fused_superpixel_u8(const uint8_t* mosaic, int B, int H, int W, const int* angle_at, const polcue_lut* lut,
+                               uint8_t* planes, float* iun, float* xolp, float* normals, polcue_stream_t stream) {
+    return fused_mosaic_common(mosaic, B, H, W, true, angle_at, lut, planes, iun, xolp, normals, stream);
 }
 
 int polcue_fused_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t* i90, const uint8_t* i135, int B, int H, int W,
@@ -626,6 +760,8 @@ int polcue_fused_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t*
     p.off45 = i45 - i0;
     p.off90 = i90 - i0;
     p.off135 = i135 - i0;
+    p.superpixel = 0;
+    for (int k = 0; k < 4; ++k) p.angle_at[k] = k;
     p.planes = nullptr;
     p.iun = iun;
     p.xolp = xolp;
@@ -638,6 +774,7 @@ int polcue_fused_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t*
     p.groups_per_row.div = (uint32_t)(W / vec);
     make_fastdiv(p.groups_per_row.div, p.groups_per_row.mul, p.groups_per_row.shift);
     p.W = (uint32_t)W;
+    p.row_px = (uint32_t)W;
     p.frame_bytes = (uint32_t)H * (uint32_t)W;
     p.plane = (uint32_t)H * (uint32_t)W;
     p.plane_bytes = 4u * p.plane;

@@ -29,6 +29,7 @@ constexpr int kKnots = 1000;       // normals_vec.py:13,27
 constexpr double kSqrt2 = 1.41421356237309504880;
 constexpr int kMaxCells = 12288;   // per table; 3 tables must also fit the shared-memory budget
 constexpr size_t kMaxBlobBytes = 200 * 1024;
+constexpr double kSteepSlope = 512.0;  // end segments steeper than this are evaluated in float64 (polcue_host.h)
 
 double g_of(double rho) {
     return rho < 0.5 ? std::sqrt(std::max(rho, 0.0)) : kSqrt2 - std::sqrt(std::max(1.0 - rho, 0.0));
@@ -197,6 +198,13 @@ int build_host(double n, polcue_lut** out) {
         }
         lut->kx[t] = tab[t].x;
         lut->ky[t] = tab[t].y;
+        const int last_seg = tab[t].n() - 2;
+        if (std::fabs(tab[t].slope(last_seg)) > kSteepSlope) {
+            lut->steep_mask |= 1 << t;
+            lut->steep_x[t] = tab[t].x[last_seg];
+            lut->steep_y[t] = tab[t].y[last_seg];
+            lut->steep_slope[t] = tab[t].slope(last_seg);
+        }
     }
     if (lut->bytes() > kMaxBlobBytes) {
         delete lut;
@@ -251,6 +259,17 @@ int polcue_lut_knots(const polcue_lut* lut, int table, double* x, double* y, int
     return n;
 }
 
+int polcue_lut_steep(const polcue_lut* lut, int table, double* xys) {
+    if (!lut || table < 0 || table > 2) return POLCUE_EINVAL;
+    if (!((lut->steep_mask >> table) & 1)) return 0;
+    if (xys) {
+        xys[0] = lut->steep_x[table];
+        xys[1] = lut->steep_y[table];
+        xys[2] = lut->steep_slope[table];
+    }
+    return 1;
+}
+
 int polcue_lut_eval_host(const polcue_lut* lut, int table, const float* rho, size_t count, float* theta) {
     if (!lut || table < 0 || table > 2 || (!rho && count) || (!theta && count)) return POLCUE_EINVAL;
     const float4* cells = lut->blob.data() + lut->offset[table];
@@ -264,6 +283,8 @@ int polcue_lut_eval_host(const polcue_lut* lut, int table, const float* rho, siz
         const float4 e = cells[std::min((int)(g * scale), lut->cells[table] - 1)];
         const float d = r - e.x;
         theta[i] = fmaf(fmaxf(d, 0.0f), e.w, fmaf(d, e.z, e.y));
+        if (((lut->steep_mask >> table) & 1) && (double)r > lut->steep_x[table])   // as polcue::steep_theta
+            theta[i] = (float)(lut->steep_slope[table] * ((double)r - lut->steep_x[table]) + lut->steep_y[table]);
     }
     return POLCUE_OK;
 }

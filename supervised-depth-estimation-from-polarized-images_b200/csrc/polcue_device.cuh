@@ -213,6 +213,51 @@ __device__ __forceinline__ float lut_eval_shared(const LutShared& lut, int t, fl
 }
 
 // ------------------------------------------------------------------------------------------
+// Steep end segments.  Where a table's last segment is steeper than 512 rad per unit rho (second specular branch
+// at n = 1.8: -10797, the knot next to the peak lies 1.5e-7 below it) neither rho nor theta fit float32 to the
+// 1e-3 rad parity bound: theta reaches -1e4 rad for rho -> 2.  Queries beyond the second-to-last knot of such a
+// table (rare: rho > ~0.99999) are evaluated in float64 exactly as scipy's _call_linear does on that segment,
+// theta = slope (rho - x_lo) + y_lo, reduced by 2 pi in float64 before the float32 sin/cos.
+// ------------------------------------------------------------------------------------------
+struct LutSteep {
+    int mask;                      // bit t: table t has a steep end segment
+    float from;                    // rho >= from may lie on one (float32 rounded down); +inf when mask == 0
+    double x[3], y[3], slope[3];   // (x_lo, y_lo) = second-to-last knot
+};
+
+__device__ __forceinline__ double steep_theta(const LutSteep& st, int t, double rho) {
+    return fma(st.slope[t], rho - st.x[t], st.y[t]);
+}
+
+static __device__ __noinline__ float2 steep_sincos(double theta) {
+    const double k = rint(theta * 0.15915494309189535);
+    double r = fma(k, -6.283185307179586232, theta);      // 2 pi = hi + lo
+    r = fma(k, -2.4492935982947064e-16, r);
+    float s, c;
+    sincos_poly((float)r, s, c);
+    return make_float2(s, c);
+}
+
+// Overwrites the candidates of steep tables in n[9] (layout of normals_from_trig) for a float64 rho.
+__device__ __forceinline__ void steep_fix(const LutSteep& st, double rho, float sp, float cp, float (&n)[9]) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        if (((st.mask >> t) & 1) && rho > st.x[t]) {
+            const float2 sc = steep_sincos(steep_theta(st, t, rho));
+            n[3 * t + 0] = (t == 0 ? cp : -sp) * sc.x;
+            n[3 * t + 1] = (t == 0 ? sp : cp) * sc.x;
+            n[3 * t + 2] = sc.y;
+        }
+    }
+}
+
+// rho of cues_from_u8 in float64 (every intermediate is an exact integer)
+__device__ __forceinline__ double rho_exact_u8(float i0, float i45, float i90, float i135) {
+    const float s1 = i0 - i90, s2 = i45 - i135, sum = (i0 + i90) + (i45 + i135);
+    return 2.0 * sqrt((double)fmaf(s1, s1, s2 * s2)) / (double)sum;
+}
+
+// ------------------------------------------------------------------------------------------
 // Per-pixel pipeline pieces.
 // ------------------------------------------------------------------------------------------
 struct Cues {

@@ -14,6 +14,13 @@ struct polcue_lut {
     float scale[3] = {0, 0, 0};    // cells per unit g
     std::vector<float4> blob;      // host copy of the device blob
     std::vector<double> kx[3], ky[3];  // sorted knots as scipy's interp1d holds them
+    // Steep end segments (|slope| > 512, e.g. -10797 for the second specular branch at n = 1.8, where a knot lands
+    // within 1.5e-7 of the peak): float32 cannot hold rho or theta to 1e-3 rad there, so queries beyond the
+    // second-to-last knot are evaluated in float64 on the device (polcue::steep_sincos).
+    int steep_mask = 0;                 // bit t: table t has a steep end segment
+    double steep_x[3] = {0, 0, 0};      // second-to-last knot (the anchor scipy's _call_linear uses)
+    double steep_y[3] = {0, 0, 0};
+    double steep_slope[3] = {0, 0, 0};
     float4* d_blob = nullptr;      // device copy (null for host-only builds)
     int device = -1;
     size_t bytes() const { return blob.size() * sizeof(float4); }

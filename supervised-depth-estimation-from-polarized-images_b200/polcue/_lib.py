@@ -34,10 +34,12 @@ _SIGNATURES = {
     "polcue_lut_destroy": (None, [C.c_void_p]),
     "polcue_lut_host_build": (C.c_int, [C.c_double, C.POINTER(C.c_void_p)]),
     "polcue_lut_cells": (C.c_int, [C.c_void_p, C.c_int]),
+    "polcue_lut_steep": (C.c_int, [C.c_void_p, C.c_int, _f64p]),
     "polcue_lut_knots": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p, C.c_int]),
     "polcue_lut_eval_host": (C.c_int, [C.c_void_p, C.c_int, _f32p, C.c_size_t, _f32p]),
     "polcue_split_pol": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "polcue_fused_mosaic_u8": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _u8p, _f32p, _f32p, _f32p, _vp]),
+    "polcue_fused_superpixel_u8": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, _u8p, _f32p, _f32p, _f32p, _vp]),
     "polcue_fused_planes_u8": (C.c_int, [_u8p, _u8p, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _f32p, _f32p, _f32p, _vp]),
     "polcue_fused_mosaic_u8_host": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _f32p, _f32p, _f32p, C.c_int]),
     "polcue_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),

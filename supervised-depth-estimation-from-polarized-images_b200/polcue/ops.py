@@ -87,10 +87,12 @@ def split_pol_batch(imgs):
 # ------------------------------------------------------------------------------------------
 # fused pipeline
 # ------------------------------------------------------------------------------------------
-def fused_mosaic(mosaic, n=1.5, want_iun=False, want_planes=False, want_normals=True, out=None):
+def fused_mosaic(mosaic, n=1.5, want_iun=False, want_planes=False, want_normals=True, out=None, superpixel=None):
     """B x H x W uint8 mosaics -> dict(xolp [B,2,Hs,Ws], normals [B,9,Hs,Ws], iun, planes).
 
     `out` may hold preallocated tensors under the same keys (steady-state loops reuse them).
+    `superpixel`: None for the reference's quadrant-tiled images; for a raw interleaved 2x2 polarizer mosaic the four
+    angle indices (0..3 = 0/45/90/135 deg) at positions (0,0), (0,1), (1,0), (1,1), e.g. (2, 1, 3, 0).
     """
     mosaic = _need_cuda(mosaic, "mosaic", torch.uint8)
     if mosaic.dim() == 2:
@@ -116,8 +118,15 @@ def fused_mosaic(mosaic, n=1.5, want_iun=False, want_planes=False, want_normals=
     planes = buf("planes", (b, 4, hs, ws), torch.uint8) if want_planes else None
     lut = lut_for(n, dev) if want_normals else C.c_void_p(0)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().polcue_fused_mosaic_u8(_ptr(mosaic), b, h, w, lut, _ptr(planes), _ptr(iun), _ptr(xolp),
-                                                     _ptr(normals), _stream(mosaic)), "polcue_fused_mosaic_u8")
+        if superpixel is None:
+            _lib.check(_lib.lib().polcue_fused_mosaic_u8(_ptr(mosaic), b, h, w, lut, _ptr(planes), _ptr(iun), _ptr(xolp),
+                                                         _ptr(normals), _stream(mosaic)), "polcue_fused_mosaic_u8")
+        else:
+            if sorted(int(a) for a in superpixel) != [0, 1, 2, 3]:
+                raise ValueError("superpixel must list each angle index 0..3 exactly once")
+            arr = (C.c_int * 4)(*[int(a) for a in superpixel])
+            _lib.check(_lib.lib().polcue_fused_superpixel_u8(_ptr(mosaic), b, h, w, arr, lut, _ptr(planes), _ptr(iun), _ptr(xolp),
+                                                             _ptr(normals), _stream(mosaic)), "polcue_fused_superpixel_u8")
     return out
 
 

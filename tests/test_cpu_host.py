@@ -107,6 +107,29 @@ def test_cell_tables_reproduce_the_reference_interpolant(L, n):
     L.polcue_lut_destroy(h)
 
 
+def test_steep_end_segments_are_evaluated_in_float64(L):
+    """n = 1.8: the knot next to the specular peak lies 1.5e-7 below it, so the last segment of the second branch has
+    slope -10797 and theta reaches -1e4 rad at rho = 2; float32 arithmetic is 2e-3 rad off there (found by the
+    randomized GPU sweep).  The library flags such tables and evaluates them in float64."""
+    rc, h = _host_lut(L, 1.8)
+    xys = np.empty(3)
+    assert [L.polcue_lut_steep(h, t, xys.ctypes.data) for t in (0, 1)] == [0, 0]
+    assert L.polcue_lut_steep(h, 2, xys.ctypes.data) == 1
+    xk, yk = O.sorted_knots(1.8)["spec2"]
+    assert xys[0] == xk[-2] and xys[1] == yk[-2] and abs(xys[2] + 10796.578) < 1e-2
+    q = np.concatenate((np.linspace(0.99999, 1.00001, 401), np.linspace(1.0, 2.2, 1000))).astype(np.float32)
+    theta = np.empty(q.size, np.float32)
+    assert L.polcue_lut_eval_host(h, 2, q.ctypes.data, q.size, theta.ctypes.data) == 0
+    ref = O.interp_linear_extrap(xk, yk, q.astype(np.float64))
+    assert np.abs(ref).max() > 1e4
+    assert (np.abs(theta - ref) <= 6.0e-8 * np.abs(ref) + 7e-6).all()     # one float32 rounding of theta (+ 66 * ulp(rho) below the steep segment)
+    L.polcue_lut_destroy(h)
+    for n in (1.2, 1.33, 1.5, 2.4):
+        rc, h = _host_lut(L, n)
+        assert [L.polcue_lut_steep(h, t, None) for t in range(3)] == [0, 0, 0]
+        L.polcue_lut_destroy(h)
+
+
 def test_table_anchor_values(L):
     rc, h = _host_lut(L, 1.5)
     anchors = {0.0: (0.0, 0.0, 1.570796327), 0.01: (0.410434783, 0.086477641, 1.566324189), 0.3: (1.472298774, 0.460030611, 1.436485518),

@@ -63,6 +63,22 @@ def test_fused_ragged_shapes_exercise_every_vector_width(shape):
     check_fused(rng.integers(0, 256, (2, h, w), dtype=np.uint8))
 
 
+def test_fused_randomized_shapes_generators_and_refractive_indices():
+    """Differential sweep: 36 (shape, generator, n) combinations against the oracle, full protocol each."""
+    rng = np.random.default_rng(2026)
+    for case in range(36):
+        hs, ws = int(rng.integers(1, 90)), int(rng.integers(1, 150))
+        if case % 3 == 0:
+            ws = 4 * max(1, ws // 4)                              # exercise the 16-byte path as well
+        b = int(rng.integers(1, 4))
+        n = float(rng.choice([1.2, 1.33, 1.5, 1.5, 1.5, 1.8, 2.4]))
+        if case % 2:
+            mosaics = rng.integers(0, 256, (b, 2 * hs, 2 * ws), dtype=np.uint8)
+        else:
+            mosaics = np.stack([synth.tile_mosaic(synth.gen_p_planes(case * 10 + f, hs, ws)) for f in range(b)])
+        check_fused(mosaics, n=n, mufu=bool(case % 4 < 2))
+
+
 def test_fused_edge_values():
     # flat, black, saturated, ties, single-channel pixels
     vals = np.array([[0, 0, 0, 0], [255, 255, 255, 255], [255, 0, 0, 0], [0, 255, 0, 0], [0, 0, 255, 0], [0, 0, 0, 255],
@@ -198,6 +214,23 @@ def test_fused_planes_matches_fused_mosaic(shape):
     assert torch.equal(one["xolp"][0], m["xolp"][0])
 
 
+@pytest.mark.parametrize("pattern", [(0, 1, 2, 3), (2, 1, 3, 0), (3, 0, 1, 2)])
+@pytest.mark.parametrize("shape", [(64, 96), (33, 47), (10, 14), (1, 1)])
+def test_fused_superpixel_layout_matches_planes(shape, pattern):
+    hs, ws = shape
+    planes = [np.stack([synth.gen_p_planes(f, hs, ws)[k] for f in range(2)]) for k in range(4)]
+    raw = np.zeros((2, 2 * hs, 2 * ws), np.uint8)
+    for pos, angle in enumerate(pattern):
+        raw[:, pos // 2::2, pos % 2::2] = planes[angle]
+    a = ops.fused_mosaic(dev(raw), 1.5, want_iun=True, want_planes=True, superpixel=pattern)
+    ref = ops.fused_planes(*(dev(p) for p in planes), want_iun=True)
+    for key in ("xolp", "normals", "iun"):
+        assert torch.equal(a[key], ref[key]), key
+    assert np.array_equal(a["planes"].cpu().numpy(), np.stack(planes, axis=1))       # de-interleave is bit-exact
+    with pytest.raises(ValueError):
+        ops.fused_mosaic(dev(raw), 1.5, superpixel=(0, 0, 1, 2))
+
+
 def test_xolp_planes_matches_stack_path():
     planes = synth.gen_p_planes(2, 96, 128)
     _, x1 = ops.xolp_from_planes(*(dev(p)[None] for p in planes), want_iun=False)
@@ -254,6 +287,44 @@ def test_get_normals_odd_sizes_and_extreme_rho():
     got = ops.get_normals(dev(x), 1.5).cpu().numpy()
     ref = O.get_normals(x, 1.5)
     P.assert_normals_close(got.reshape(2, 3, 3, 7, 13), ref.reshape(2, 3, 3, 7, 13), axis=2)
+
+
+@pytest.mark.parametrize("mufu", [False, True])
+def test_steep_end_segment_is_evaluated_in_float64(mufu):
+    """n = 1.8: the second specular branch ends in a segment of slope -10797 (tests/test_cpu_host.py); beyond it theta
+    reaches -1e4 rad, which only float64 holds to 1e-3 rad.  Every kernel family, both vector widths."""
+    n = 1.8
+    xk, yk = O.sorted_knots(n)["spec2"]
+    rng = np.random.default_rng(18)
+    _lib.lib().polcue_debug_set_trig(1 if mufu else 0)
+    try:
+        for shape in ((2, 16, 64), (1, 7, 13)):
+            rho = np.concatenate((rng.uniform(0.99999, 1.00001, 500), rng.uniform(1.0, 2.5, 500), rng.uniform(0, 1, 1000),
+                                  np.float32(xk[-3:]).astype(np.float64), np.nextafter(np.float32(xk[-2:]), np.float32(2)).astype(np.float64)))
+            rho = rng.choice(rho, shape).astype(np.float32)
+            x = np.stack((rho, rng.uniform(-np.pi / 2, np.pi / 2, shape).astype(np.float32)), axis=1)
+            got = ops.get_normals(dev(x), n).cpu().numpy()
+            ref = O.get_normals(x, n)
+            b, h, w = shape
+            P.assert_normals_close(got.reshape(b, 3, 3, h, w), ref.reshape(b, 3, 3, h, w), axis=2)
+            # the fine-grained mirror returns float32 angles: the float64 line rounded once
+            t2 = c_nv.rho_spec(dev(rho), n)[1].cpu().numpy()
+            ref2 = O.interp_linear_extrap(xk, yk, rho.astype(np.float64))
+            assert np.abs(ref2).max() > 1e4
+            assert (np.abs(t2 - ref2) <= 6.0e-8 * np.abs(ref2) + 7e-6).all()
+        # fused kernel: uniform bytes put ~10 % of the pixels beyond rho = 1; flat-topped pixels sit exactly on rho = 1
+        mosaics = rng.integers(0, 256, (2, 60, 144), dtype=np.uint8)
+        mosaics[0, :4, :8] = 200          # I0 = 200 ...
+        mosaics[0, 30:34, :8] = 0         # ... I90 = 0, I45 = I135: rho = 1 exactly
+        mosaics[0, :4, 72:80] = 100
+        mosaics[0, 30:34, 72:80] = 100
+        check_fused(mosaics, n=n, mufu=mufu)
+        check_fused(mosaics[:, :, :142], n=n, mufu=mufu)       # Ws = 71: scalar path
+        planes = [np.ascontiguousarray(O.stack_quadrants(mosaics[0])[..., k]) for k in range(4)]
+        assert torch.equal(ops.fused_planes(*(dev(p)[None] for p in planes), n=n)["normals"],
+                           ops.fused_mosaic(dev(mosaics[:1]), n)["normals"])
+    finally:
+        _lib.lib().polcue_debug_set_trig(1)
 
 
 def test_numpy_chain_mirror(golden):
