@@ -113,6 +113,36 @@ POLCUE_API int polcue_fused_planes_u8(const uint8_t* i0, const uint8_t* i45, con
                            int B, int H, int W, const polcue_lut* lut, float* iun, float* xolp, float* normals,
                            polcue_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Loader front end.  The Lanczos resize of the 8-bit polarizer images, bit-exact with Pillow:
+ *   manydepth/datasets/indoor_dataset.py:77,115   Image.ANTIALIAS, transforms.Resize((height, width))
+ *   manydepth/datasets/indoor_dataset.py:335-349  resize_pol(get_gray(..)) of pol00 / pol10 / pol01 / pol11
+ *   manydepth/datasets/hammer_dataset.py:68-75    get_gray: 'L' image, optional FLIP_LEFT_RIGHT
+ * Arithmetic: Pillow (6.2.1 pinned, environment.yml:14) src/libImaging/Resample.c -- float64 Lanczos-3 weights,
+ * 22-bit fixed point, horizontal pass into an 8-bit intermediate, vertical pass.
+ * A plan holds the weights of one (in_h, in_w) -> (out_h, out_w) geometry on the CURRENT device.
+ * workspace: polcue_resize_workspace_bytes(plan, images) device bytes (the 8-bit intermediate, images x in_h x out_w).
+ * flip: NULL or one device byte per image (polcue_resize_lanczos_u8) / per sample (front end): non-zero mirrors the
+ *       image left-right before the resize, as hammer_dataset.py:72-73 does.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct polcue_resize_plan polcue_resize_plan;
+POLCUE_API int polcue_resize_plan_create(int in_h, int in_w, int out_h, int out_w, polcue_resize_plan** out);
+POLCUE_API int polcue_resize_plan_host_build(int in_h, int in_w, int out_h, int out_w, polcue_resize_plan** out); /* no device copy */
+POLCUE_API void polcue_resize_plan_destroy(polcue_resize_plan* plan);
+/* Host introspection: returns ksize of axis (0 horizontal, 1 vertical); bounds = out x (first, count), kk = out x ksize. */
+POLCUE_API int polcue_resize_plan_coeffs(const polcue_resize_plan* plan, int axis, int* bounds, int* kk, size_t kk_capacity);
+POLCUE_API size_t polcue_resize_workspace_bytes(const polcue_resize_plan* plan, int images);
+/* src: images x in_h x in_w uint8 -> dst: images x out_h x out_w uint8 (two launches). */
+POLCUE_API int polcue_resize_lanczos_u8(const polcue_resize_plan* plan, const uint8_t* src, int images, const uint8_t* flip,
+                             uint8_t* workspace, uint8_t* dst, polcue_stream_t stream);
+/* The polarization branch of __getitem__ + the encoder front end for a batch: the four full-resolution gray images
+ * (each B x in_h x in_w; i0 = pol00, i45 = pol01, i90 = pol10, i135 = pol11, indoor_dataset.py:435-438) are resized
+ * into planes (B x 4 x out_h x out_w, angle order, required), then get_xolp (:430-442) and get_normals
+ * (pre_encoders.py:99-113) run on them as in polcue_fused_planes_u8.  workspace: 4 * B images.  Three launches. */
+POLCUE_API int polcue_loader_front_end_u8(const polcue_resize_plan* plan, const uint8_t* i0, const uint8_t* i45, const uint8_t* i90,
+                               const uint8_t* i135, int B, const uint8_t* flip, const polcue_lut* lut, uint8_t* workspace,
+                               uint8_t* planes, float* iun, float* xolp, float* normals, polcue_stream_t stream);
+
 /* Same pipeline with HOST buffers (pinned or pageable): chunks of frames are copied in, processed
  * and copied out on three streams so H2D, the kernel and D2H overlap.  Blocks until done.
  * `chunk_frames` <= 0 picks a default.  This is the call bench.py's `e2e` figure times. */

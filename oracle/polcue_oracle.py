@@ -15,6 +15,10 @@ Pinning status
   container by ``tests/golden/make_golden.py`` and committed as ``tests/golden/*.npz``.
 * ``ppp_code/physical_normals_channels.py`` (needs matplotlib/TkAgg to import): the numpy
   bodies were executed with a stub ``matplotlib`` by the same script  ->  PINNED.
+* loader front end (``indoor_dataset.py:115,335-349``: ``transforms.Resize(..., Image.ANTIALIAS)`` of the four
+  8-bit polarizer images): the arithmetic lives in Pillow (pinned 6.2.1, ``environment.yml:14``; installed 12.2),
+  ``src/libImaging/Resample.c``.  PINNED by execution: ``tests/test_oracle_golden.py`` runs the installed Pillow on the
+  same inputs, and ``tests/golden/resize_golden.npz`` holds Pillow outputs made by ``tests/golden/make_golden.py``.
 * ``depth_to_normals``: the algorithm lives in kornia 0.5.11 (``environment.yml:41``), which is
   neither vendored in the reference nor installed here.  PARITY UNPINNED: the restatement
   follows kornia's published algorithm (depth_to_3d -> spatial_gradient(sobel, normalized,
@@ -409,6 +413,100 @@ def xolp_statistics(dolp, aolp):
     am, asd = aolp.mean(axis=(0, 1, 2)), aolp.std(axis=(0, 1, 2))
     return {"dolp_mean": dm, "dolp_std": ds, "aolp_mean": am, "aolp_std": asd,
             "xolp_mean": 0.5 * (dm + am), "xolp_std": 0.5 * (ds + asd)}
+
+
+# --------------------------------------------------------------------------------------
+# loader front end: PIL Lanczos resize of 8-bit images (manydepth/datasets/indoor_dataset.py:77,115,335-349)
+# --------------------------------------------------------------------------------------
+PIL_PRECISION_BITS = 32 - 8 - 2   # Resample.c: PRECISION_BITS
+
+
+def _lanczos(x):
+    """Resample.c lanczos_filter: sinc(x) sinc(x/3) on [-3, 3), 0 elsewhere."""
+    def sinc(v):
+        v = np.asarray(v, dtype=np.float64)
+        out = np.ones_like(v)
+        nz = v != 0.0
+        out[nz] = np.sin(v[nz] * np.pi) / (v[nz] * np.pi)
+        return out
+    x = np.asarray(x, dtype=np.float64)
+    return np.where((x >= -3.0) & (x < 3.0), sinc(x) * sinc(x / 3.0), 0.0)
+
+
+def lanczos_coeffs_8bpc(in_size, out_size):
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the whole-image box (0, in_size).
+    Returns (ksize, bounds[out_size, 2] = (xmin, count), kk[out_size, ksize] int32)."""
+    scale = float(np.float32(in_size) - np.float32(0)) / out_size       # box edges are C floats
+    filterscale = max(scale, 1.0)
+    support = 3.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = _lanczos((np.arange(xmax) + xmin - center + 0.5) * ss)
+        ww = 0.0
+        for v in w:                      # sequential sum, as the C loop
+            ww += v
+        if ww != 0.0:
+            w = w / ww
+        fixed = np.where(w < 0, -0.5 + w * (1 << PIL_PRECISION_BITS), 0.5 + w * (1 << PIL_PRECISION_BITS))
+        kk[xx, :xmax] = np.trunc(fixed).astype(np.int32)
+        bounds[xx] = (xmin, xmax)
+    return ksize, bounds, kk
+
+
+def _clip8(acc):
+    """Resample.c clip8: lookup of (acc >> PRECISION_BITS) clamped to [0, 255] (arithmetic shift = floor)."""
+    return np.clip(acc >> PIL_PRECISION_BITS, 0, 255).astype(np.uint8)
+
+
+def resize_lanczos_u8(img, out_hw):
+    """PIL ``Image.resize((W, H), Image.ANTIALIAS)`` of a single-band 8-bit image (ImagingResampleInner: horizontal
+    pass over the rows the vertical pass needs, 8-bit intermediate, then the vertical pass).  img: H x W uint8."""
+    img = np.asarray(img)
+    assert img.dtype == np.uint8 and img.ndim == 2
+    h_out, w_out = out_hw
+    h_in, w_in = img.shape
+    cur = img
+    half = 1 << (PIL_PRECISION_BITS - 1)
+    if w_out != w_in:
+        _, bounds, kk = lanczos_coeffs_8bpc(w_in, w_out)
+        tmp = np.empty((h_in, w_out), np.uint8)
+        for xx in range(w_out):
+            x0, cnt = bounds[xx]
+            acc = half + (cur[:, x0:x0 + cnt].astype(np.int64) * kk[xx, :cnt].astype(np.int64)).sum(axis=1)
+            tmp[:, xx] = _clip8(acc)
+        cur = tmp
+    if h_out != h_in:
+        _, bounds, kk = lanczos_coeffs_8bpc(h_in, h_out)
+        out = np.empty((h_out, cur.shape[1]), np.uint8)
+        for yy in range(h_out):
+            y0, cnt = bounds[yy]
+            acc = half + (cur[y0:y0 + cnt].astype(np.int64) * kk[yy, :cnt, None].astype(np.int64)).sum(axis=0)
+            out[yy] = _clip8(acc)
+        cur = out
+    return cur if cur is not img else img.copy()
+
+
+def loader_front_end(pol00, pol01, pol10, pol11, out_hw, n=1.5, flip=False):
+    """indoor_dataset.py:335-349 + get_xolp (:430-442) + get_normals (pre_encoders.py:99-113) for one sample:
+    optional left-right flip (hammer_dataset.py:72-73), Lanczos resize of the four gray images, stack in the order
+    (im00, im01, im10, im11) = (0, 45, 90, 135 deg), closed-form XOLP, three normal candidates.
+    Returns (planes u8 [4, H, W] in angle order, xolp f64 [2, H, W], normals f64 [9, H, W])."""
+    planes = []
+    for im in (pol00, pol01, pol10, pol11):
+        im = np.asarray(im)
+        if flip:
+            im = im[:, ::-1]
+        planes.append(resize_lanczos_u8(np.ascontiguousarray(im), out_hw))
+    stack = np.stack(planes, axis=2)
+    _, rho, phi = iun_and_xolp_closed(stack)
+    xolp = np.stack((rho, phi))
+    return np.stack(planes), xolp, get_normals(xolp[None], n)[0]
 
 
 # --------------------------------------------------------------------------------------

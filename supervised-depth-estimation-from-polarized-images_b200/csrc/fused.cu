@@ -743,23 +743,23 @@ int polcue_fused_superpixel_u8(const uint8_t* mosaic, int B, int H, int W, const
     return fused_mosaic_common(mosaic, B, H, W, true, angle_at, lut, planes, iun, xolp, normals, stream);
 }
 
-int polcue_fused_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t* i90, const uint8_t* i135, int B, int H, int W,
-                           const polcue_lut* lut, float* iun, float* xolp, float* normals, polcue_stream_t stream) {
-    if (!i0 || !i45 || !i90 || !i135 || !xolp || B < 0 || H <= 0 || W <= 0) return POLCUE_EINVAL;
+// Four sample planes at `i0 + {0, off45, off90, off135}`, consecutive frames `frame_stride` bytes apart.
+static int fused_planes_common(const uint8_t* i0, long long off45, long long off90, long long off135, unsigned long long frame_stride,
+                               bool aligned4, bool aligned2, int B, int H, int W, const polcue_lut* lut, float* iun, float* xolp,
+                               float* normals, polcue_stream_t stream) {
     if (normals && (!lut || !lut->d_blob)) return POLCUE_EINVAL;
     if (B == 0) return POLCUE_OK;
-    auto all4 = [&](size_t a) { return aligned(i0, a) && aligned(i45, a) && aligned(i90, a) && aligned(i135, a); };
     int vec = 1;
-    if (W % 4 == 0 && all4(4) && aligned(xolp, 16) && aligned(normals, 16) && aligned(iun, 16)) vec = 4;
-    else if (W % 2 == 0 && all4(2) && aligned(xolp, 8) && aligned(normals, 8) && aligned(iun, 8)) vec = 2;
+    if (W % 4 == 0 && aligned4 && aligned(xolp, 16) && aligned(normals, 16) && aligned(iun, 16)) vec = 4;
+    else if (W % 2 == 0 && aligned2 && aligned(xolp, 8) && aligned(normals, 8) && aligned(iun, 8)) vec = 2;
     else if (!aligned(xolp, 4) || !aligned(normals, 4) || !aligned(iun, 4)) return POLCUE_EINVAL;
     const unsigned long long groups = (unsigned long long)B * H * (W / vec);
-    if (groups >= (1ull << 31) || (unsigned long long)H * W >= (1ull << 30)) return POLCUE_E2BIG;
+    if (groups >= (1ull << 31) || frame_stride >= (1ull << 30)) return POLCUE_E2BIG;
     FusedParams p;
     p.mosaic = i0;
-    p.off45 = i45 - i0;
-    p.off90 = i90 - i0;
-    p.off135 = i135 - i0;
+    p.off45 = off45;
+    p.off90 = off90;
+    p.off135 = off135;
     p.superpixel = 0;
     for (int k = 0; k < 4; ++k) p.angle_at[k] = k;
     p.planes = nullptr;
@@ -775,7 +775,7 @@ int polcue_fused_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t*
     make_fastdiv(p.groups_per_row.div, p.groups_per_row.mul, p.groups_per_row.shift);
     p.W = (uint32_t)W;
     p.row_px = (uint32_t)W;
-    p.frame_bytes = (uint32_t)H * (uint32_t)W;
+    p.frame_bytes = (uint32_t)frame_stride;
     p.plane = (uint32_t)H * (uint32_t)W;
     p.plane_bytes = 4u * p.plane;
     const size_t smem = normals ? lut->bytes() : 0;
@@ -785,6 +785,14 @@ int polcue_fused_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t*
         case 2: return launch_fused<2>(p, smem, s);
         default: return launch_fused<1>(p, smem, s);
     }
+}
+
+int polcue_fused_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t* i90, const uint8_t* i135, int B, int H, int W,
+                           const polcue_lut* lut, float* iun, float* xolp, float* normals, polcue_stream_t stream) {
+    if (!i0 || !i45 || !i90 || !i135 || !xolp || B < 0 || H <= 0 || W <= 0) return POLCUE_EINVAL;
+    auto all4 = [&](size_t a) { return aligned(i0, a) && aligned(i45, a) && aligned(i90, a) && aligned(i135, a); };
+    return fused_planes_common(i0, i45 - i0, i90 - i0, i135 - i0, (unsigned long long)H * W, all4(4), all4(2), B, H, W, lut, iun,
+                               xolp, normals, stream);
 }
 
 static int xolp_stack_common(const void* stack, bool is_u8, int B, int H, int W, const float* pinv, float* iun, float* xolp,
@@ -919,3 +927,12 @@ int polcue_calc_normals_channel_f32(const float* phi, const float* theta, const 
 }
 
 }  // extern "C"
+
+// planes: B x 4 x H x W (angle order) -- the layout the loader front end produces (resize.cu)
+int polcue::fused_planes_strided(const uint8_t* planes, int B, int H, int W, const polcue_lut* lut, float* iun, float* xolp,
+                                 float* normals, cudaStream_t stream) {
+    if (!planes || !xolp || B < 0 || H <= 0 || W <= 0) return POLCUE_EINVAL;
+    const long long hw = (long long)H * W;
+    return fused_planes_common(planes, hw, 2 * hw, 3 * hw, 4ull * hw, aligned(planes, 4) && hw % 4 == 0,
+                               aligned(planes, 2) && hw % 2 == 0, B, H, W, lut, iun, xolp, normals, (polcue_stream_t)stream);
+}

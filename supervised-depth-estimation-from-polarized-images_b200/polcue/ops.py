@@ -160,6 +160,100 @@ def fused_planes(i0, i45, i90, i135, n=1.5, want_iun=False, want_normals=True, o
     return out
 
 
+# ------------------------------------------------------------------------------------------
+# loader front end: Pillow-exact Lanczos resize (+ XOLP + normals)
+# ------------------------------------------------------------------------------------------
+_plan_cache = {}
+
+
+def resize_plan(in_hw, out_hw, device):
+    """Lanczos weights for one (in_h, in_w) -> (out_h, out_w) geometry on `device` (cached)."""
+    device = torch.device(device)
+    key = (int(in_hw[0]), int(in_hw[1]), int(out_hw[0]), int(out_hw[1]),
+           device.index if device.index is not None else torch.cuda.current_device())
+    with _lut_lock:
+        h = _plan_cache.get(key)
+        if h is None:
+            with torch.cuda.device(key[4]):
+                out = C.c_void_p()
+                _lib.check(_lib.lib().polcue_resize_plan_create(*key[:4], C.byref(out)), f"polcue_resize_plan_create{key[:4]}")
+            h = _plan_cache[key] = out
+    return h
+
+
+def _flip_flags(flip, count, device):
+    if flip is None:
+        return None
+    if isinstance(flip, bool):
+        flip = [flip] * count
+    t = torch.as_tensor(flip).to(device=device, dtype=torch.uint8).contiguous()
+    if t.numel() != count:
+        raise ValueError(f"flip needs one flag per image ({count}), got {t.numel()}")
+    return t
+
+
+def lanczos_resize(images, out_hw, flip=None, workspace=None):
+    """uint8 (N x ... x) H x W -> same leading dims x out_h x out_w, bit-exact with PIL ``Image.resize(.., ANTIALIAS)`` of an
+    'L' image -- ``transforms.Resize((height, width), Image.ANTIALIAS)``, indoor_dataset.py:115.  `flip`: bool or one flag per
+    image, mirrors left-right first (hammer_dataset.py:72-73)."""
+    images = _need_cuda(images, "images", torch.uint8)
+    if images.dim() < 2:
+        raise ValueError("images must be (... x) H x W")
+    lead, (h, w) = tuple(images.shape[:-2]), images.shape[-2:]
+    count = 1
+    for d in lead:
+        count *= d
+    plan = resize_plan((h, w), out_hw, images.device)
+    flags = _flip_flags(flip, count, images.device)
+    need = _lib.lib().polcue_resize_workspace_bytes(plan, count)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 1), dtype=torch.uint8, device=images.device)
+    out = torch.empty(lead + (int(out_hw[0]), int(out_hw[1])), dtype=torch.uint8, device=images.device)
+    with torch.cuda.device(images.device):
+        _lib.check(_lib.lib().polcue_resize_lanczos_u8(plan, _ptr(images), count, _ptr(flags), _ptr(workspace), _ptr(out),
+                                                       _stream(images)), "polcue_resize_lanczos_u8")
+    return out
+
+
+def loader_front_end(i0, i45, i90, i135, out_hw, n=1.5, flip=None, want_iun=False, want_normals=True, out=None):
+    """The polarization branch of ``__getitem__`` for a batch, on the GPU: four full-resolution uint8 images (B x H x W each;
+    pol00, pol01, pol10, pol11 = 0, 45, 90, 135 deg) -> dict(planes u8 [B,4,h,w] (the resized images), xolp [B,2,h,w],
+    normals [B,9,h,w], iun).  indoor_dataset.py:335-349 + get_xolp (:430-442) + get_normals (pre_encoders.py:99-113)."""
+    planes = [_need_cuda(p, "image", torch.uint8) for p in (i0, i45, i90, i135)]
+    shape = planes[0].shape
+    if any(p.shape != shape or p.device != planes[0].device for p in planes) or len(shape) != 3:
+        raise ValueError("images must share one B x H x W shape and device")
+    b, h, w = shape
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    dev = planes[0].device
+    out = dict(out or {})
+
+    def buf(key, shp, dtype=torch.float32):
+        t = out.get(key)
+        if t is None:
+            t = out[key] = torch.empty(shp, dtype=dtype, device=dev)
+        elif tuple(t.shape) != tuple(shp) or t.dtype != dtype or not t.is_contiguous() or t.device != dev:
+            raise ValueError(f"preallocated `{key}` has the wrong shape/dtype/device")
+        return t
+
+    plan = resize_plan((h, w), (oh, ow), dev)
+    small = buf("planes", (b, 4, oh, ow), torch.uint8)
+    xolp = buf("xolp", (b, 2, oh, ow))
+    normals = buf("normals", (b, 9, oh, ow)) if want_normals else None
+    iun = buf("iun", (b, oh, ow)) if want_iun else None
+    need = _lib.lib().polcue_resize_workspace_bytes(plan, 4 * b)
+    ws = out.get("workspace")
+    if ws is None or ws.numel() < need or ws.device != dev:
+        ws = out["workspace"] = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    flags = _flip_flags(flip, b, dev)
+    lut = lut_for(n, dev) if want_normals else C.c_void_p(0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().polcue_loader_front_end_u8(plan, *(_ptr(p) for p in planes), b, _ptr(flags), lut, _ptr(ws), _ptr(small),
+                                                         _ptr(iun), _ptr(xolp), _ptr(normals), _stream(planes[0])),
+                   "polcue_loader_front_end_u8")
+    return out
+
+
 def fused_mosaic_host(mosaic, n=1.5, want_iun=False, want_normals=True, out=None, chunk_frames=0, device=None):
     """Host (ideally pinned) uint8 mosaics -> host float32 outputs; copies are pipelined inside the library."""
     if not isinstance(mosaic, torch.Tensor) or mosaic.is_cuda or mosaic.dtype != torch.uint8:

@@ -21,3 +21,10 @@ def golden():
     path = os.path.join(ROOT, "tests", "golden", "reference_outputs.npz")
     with np.load(path) as z:
         return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def resize_golden():
+    path = os.path.join(ROOT, "tests", "golden", "resize_golden.npz")
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}

@@ -130,6 +130,29 @@ def test_steep_end_segments_are_evaluated_in_float64(L):
         L.polcue_lut_destroy(h)
 
 
+@pytest.mark.parametrize("geometry", [(832, 1088, 320, 480), (1024, 1224, 320, 480), (33, 47, 66, 94), (50, 70, 50, 30), (7, 9, 3, 2),
+                                      (2048, 2448, 192, 640), (5, 5, 5, 5)])
+def test_resize_plan_weights_equal_the_pillow_restatement(L, geometry):
+    """The library's Lanczos weights (host C++, libm) against the oracle's numpy restatement of Resample.c, integer for integer."""
+    ih, iw, oh, ow = geometry
+    h = C.c_void_p()
+    assert L.polcue_resize_plan_host_build(ih, iw, oh, ow, C.byref(h)) == 0
+    for axis, (n_in, n_out) in enumerate(((iw, ow), (ih, oh))):
+        ksize = L.polcue_resize_plan_coeffs(h, axis, None, None, 0)
+        bounds = np.empty((n_out, 2), np.int32)
+        kk = np.empty((n_out, ksize), np.int32)
+        assert L.polcue_resize_plan_coeffs(h, axis, bounds.ctypes.data, kk.ctypes.data, kk.size) == ksize
+        if n_in == n_out:        # Pillow skips the pass; the library runs it with single-tap identity weights
+            assert ksize == 1 and (kk == 1 << 22).all() and np.array_equal(bounds[:, 0], np.arange(n_out)) and (bounds[:, 1] == 1).all()
+            continue
+        ks, b_ref, kk_ref = O.lanczos_coeffs_8bpc(n_in, n_out)
+        assert ks == ksize and np.array_equal(bounds, b_ref) and np.array_equal(kk, kk_ref)
+        assert (np.abs(kk.sum(axis=1) - (1 << 22)) <= ksize).all()          # weights sum to one in fixed point
+    assert L.polcue_resize_workspace_bytes(h, 8) == 8 * ih * ow
+    L.polcue_resize_plan_destroy(h)
+    assert L.polcue_resize_plan_host_build(0, 4, 4, 4, C.byref(h)) == -22
+
+
 def test_table_anchor_values(L):
     rc, h = _host_lut(L, 1.5)
     anchors = {0.0: (0.0, 0.0, 1.570796327), 0.01: (0.410434783, 0.086477641, 1.566324189), 0.3: (1.472298774, 0.460030611, 1.436485518),

@@ -735,3 +735,75 @@ def test_launch_counter_counts_kernels():
     before = _lib.launch_count()
     ops.fused_mosaic(dev(synth.gen_u_mosaic(0, 32, 48))[None], 1.5)
     assert _lib.launch_count() == before + 1
+
+
+# ------------------------------------------------------------------------------------------------
+# loader front end: Pillow-exact Lanczos resize, then XOLP + normals
+# ------------------------------------------------------------------------------------------------
+def test_lanczos_resize_bit_exact_vs_reference_outputs(resize_golden):
+    g = resize_golden
+    for i, (ih, iw, oh, ow) in enumerate(g["case_shapes"]):
+        img = g[f"in_{i}"]
+        got = ops.lanczos_resize(dev(img), (int(oh), int(ow)))
+        assert np.array_equal(got.cpu().numpy(), g[f"out_{i}"]), (i, ih, iw, oh, ow)
+        both = ops.lanczos_resize(dev(np.stack((img, img))), (int(oh), int(ow)), flip=[False, True]).cpu().numpy()
+        assert np.array_equal(both[0], g[f"out_{i}"]) and np.array_equal(both[1], g[f"outflip_{i}"]), i
+
+
+def test_lanczos_resize_hammer_geometry_vs_reference_digest(resize_golden):
+    import hashlib
+    planes = synth.gen_p_planes(4242, 832, 1088)
+    small = ops.lanczos_resize(dev(np.stack(planes)), (320, 480), flip=[False, True, False, True]).cpu().numpy()
+    for k in range(4):
+        assert np.array_equal(small[k][::8, ::8], resize_golden[f"hammer_sample_{k}"])
+        assert hashlib.sha256(small[k].tobytes()).hexdigest() == resize_golden["hammer_sha256"][k]
+
+
+def test_lanczos_resize_random_geometries_vs_oracle():
+    """Every tap-count class (<= 16, <= 32, generic), upscaling, identity axes, odd widths (scalar paths), saturating inputs."""
+    rng = np.random.default_rng(11)
+    shapes = [(40, 52, 17, 23), (90, 130, 9, 10), (256, 300, 8, 9), (12, 10, 30, 41), (31, 64, 31, 16), (64, 31, 16, 31), (1, 1, 1, 1),
+              (3, 200, 3, 7), (200, 3, 7, 3), (17, 16, 16, 16)]
+    shapes += [tuple(int(v) for v in rng.integers(1, 140, 4)) for _ in range(12)]
+    for ih, iw, oh, ow in shapes:
+        imgs = rng.integers(0, 256, (3, ih, iw), dtype=np.uint8)
+        imgs[1] = rng.choice([0, 255], (ih, iw))
+        flips = [False, True, True]
+        got = ops.lanczos_resize(dev(imgs), (oh, ow), flip=flips).cpu().numpy()
+        for k in range(3):
+            src = np.ascontiguousarray(imgs[k][:, ::-1]) if flips[k] else imgs[k]
+            assert np.array_equal(got[k], O.resize_lanczos_u8(src, (oh, ow))), (ih, iw, oh, ow, k)
+
+
+@pytest.mark.parametrize("geometry", [(104, 136, 40, 60), (61, 83, 23, 31), (208, 272, 80, 120)])
+def test_loader_front_end_vs_oracle(geometry):
+    ih, iw, oh, ow = geometry
+    b = 3
+    planes = [np.stack([synth.gen_p_planes(50 + f, ih, iw)[k] for f in range(b)]) for k in range(4)]
+    flips = [False, True, False]
+    out = ops.loader_front_end(*(dev(p) for p in planes), (oh, ow), n=1.5, flip=flips, want_iun=True)
+    assert out["planes"].shape == (b, 4, oh, ow) and out["xolp"].shape == (b, 2, oh, ow) and out["normals"].shape == (b, 9, oh, ow)
+    for f in range(b):
+        small, xolp, normals = O.loader_front_end(*(p[f] for p in planes), (oh, ow), n=1.5, flip=flips[f])
+        assert np.array_equal(out["planes"][f].cpu().numpy(), small), "resized planes are not bit-exact"
+        P.assert_dolp_close(out["xolp"][f, 0].cpu().numpy(), xolp[0])
+        P.assert_aolp_close(out["xolp"][f, 1].cpu().numpy(), xolp[1])
+        P.assert_normals_close(out["normals"][f].cpu().numpy().reshape(3, 3, oh, ow), normals.reshape(3, 3, oh, ow), axis=1)
+    # the same numbers as the two-step path through the public pieces
+    small = ops.lanczos_resize(dev(np.stack(planes, axis=1)), (oh, ow), flip=np.repeat(flips, 4).tolist())
+    assert torch.equal(small, out["planes"])
+    two = ops.fused_planes(*(small[:, k].contiguous() for k in range(4)), want_iun=True)
+    for key in ("xolp", "normals", "iun"):
+        assert torch.equal(two[key], out[key]), key
+
+
+def test_loader_front_end_rejects_bad_arguments():
+    a = torch.zeros((2, 8, 8), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        ops.loader_front_end(a, a, a, a[:1], (4, 4))
+    with pytest.raises(ValueError):
+        ops.loader_front_end(a, a, a, a, (4, 4), flip=[True])
+    with pytest.raises(TypeError):
+        ops.lanczos_resize(a.cpu(), (4, 4))
+    with pytest.raises(_lib.PolcueError):
+        ops.lanczos_resize(a, (0, 4))

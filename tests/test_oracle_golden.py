@@ -163,3 +163,45 @@ def test_depth_errors_per_image_vs_reference(golden):
     rows_m, _ = O.depth_errors_per_image(gt, pred, 0.1, 2.0, inst, 40)
     assert rows_m.shape == (3, 7)
     assert all(np.isnan(v) for v in O.compute_depth_errors(np.zeros(0), np.zeros(0)))
+
+
+# ------------------------------------------------------------------------------------------------
+# loader front end: Pillow's 8-bit Lanczos resize
+# ------------------------------------------------------------------------------------------------
+def test_lanczos_resize_restatement_is_bit_exact_with_the_reference_call_chain(resize_golden):
+    import hashlib
+    from polcue import synth
+    g = resize_golden
+    for i, (ih, iw, oh, ow) in enumerate(g["case_shapes"]):
+        img = g[f"in_{i}"]
+        assert img.shape == (ih, iw)
+        assert np.array_equal(O.resize_lanczos_u8(img, (oh, ow)), g[f"out_{i}"]), i
+        assert np.array_equal(O.resize_lanczos_u8(np.ascontiguousarray(img[:, ::-1]), (oh, ow)), g[f"outflip_{i}"]), i
+    planes = synth.gen_p_planes(4242, 832, 1088)       # HAMMER geometry, inputs regenerated from the seed
+    for k in range(4):
+        assert hashlib.sha256(planes[k].tobytes()).hexdigest() == g["hammer_in_sha256"][k]
+        src = np.ascontiguousarray(planes[k][:, ::-1]) if k & 1 else planes[k]
+        small = O.resize_lanczos_u8(src, (320, 480))
+        assert np.array_equal(small[::8, ::8], g[f"hammer_sample_{k}"])
+        assert hashlib.sha256(small.tobytes()).hexdigest() == g["hammer_sha256"][k]
+
+
+def test_lanczos_resize_restatement_vs_installed_pillow():
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(5)
+    for _ in range(25):
+        ih, iw, oh, ow = (int(v) for v in rng.integers(1, 120, 4))
+        img = rng.integers(0, 256, (ih, iw), dtype=np.uint8)
+        if rng.random() < 0.3:
+            img[:] = rng.choice([0, 255], img.shape)      # ringing: exercises both clamps of clip8
+        ref = np.asarray(Image.fromarray(img, "L").resize((ow, oh), Image.LANCZOS))
+        assert np.array_equal(O.resize_lanczos_u8(img, (oh, ow)), ref), (ih, iw, oh, ow)
+
+
+def test_loader_front_end_oracle_composition():
+    from polcue import synth
+    planes = synth.gen_p_planes(3, 52, 68)
+    small, xolp, normals = O.loader_front_end(planes[0], planes[1], planes[2], planes[3], (20, 30), flip=True)
+    assert small.shape == (4, 20, 30) and xolp.shape == (2, 20, 30) and normals.shape == (9, 20, 30)
+    assert np.array_equal(small[2], O.resize_lanczos_u8(np.ascontiguousarray(planes[2][:, ::-1]), (20, 30)))
+    assert np.allclose(np.linalg.norm(normals.reshape(3, 3, 20, 30), axis=1), 1.0)

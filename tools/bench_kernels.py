@@ -160,6 +160,25 @@ def main():
         del gt, pred, inst, depth, gflat, pflat
         torch.cuda.empty_cache()
 
+    # ---- loader front end: Pillow-exact Lanczos resize of the four polarizer images + XOLP + normals (cfg4 geometry) ----
+    B, ih, iw, oh, ow = 32, 832, 1088, 320, 480            # HAMMER quadrants -> training resolution
+    full = [torch.from_numpy(np.stack([synth.gen_p_planes(f % 4, ih, iw)[k] for f in range(4)] * (B // 4))).to(dev) for k in range(4)]
+    stacked = torch.stack(full, dim=1).contiguous()
+    ws = torch.empty(4 * B * ih * ow, dtype=torch.uint8, device=dev)
+    in_bytes, opx = 4 * B * ih * iw, B * oh * ow
+    emit("loader/lanczos_resize", f"u8 [{B},4,{ih},{iw}] -> u8 [{B},4,{oh},{ow}] (2 launches; integer-MAC bound, bytes = in + out)",
+         in_bytes + 4 * opx, lambda: ops.lanczos_resize(stacked, (oh, ow), workspace=ws), True)
+    keep = {}
+    keep.update(ops.loader_front_end(*full, (oh, ow)))
+    emit("loader/front_end", f"4 x u8 [{B},{ih},{iw}] -> planes u8 + xolp f32 + normals f32 at {oh}x{ow} (3 launches)",
+         in_bytes + (4 + 44) * opx, lambda: ops.loader_front_end(*full, (oh, ow), out=keep), True)
+    small = keep["planes"]
+    p4 = [small[:, k].contiguous() for k in range(4)]
+    keep2 = {}
+    keep2.update(ops.fused_planes(*p4))
+    emit("loader/fused_planes", f"4 x u8 [{B},{oh},{ow}] -> xolp + normals (the front end's last launch alone)", 48 * opx,
+         lambda: ops.fused_planes(*p4, out=keep2), True)
+
 
 if __name__ == "__main__":
     main()
