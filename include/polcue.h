@@ -121,7 +121,7 @@ POLCUE_API int polcue_fused_planes_u8(const uint8_t* i0, const uint8_t* i45, con
  * Arithmetic: Pillow (6.2.1 pinned, environment.yml:14) src/libImaging/Resample.c -- float64 Lanczos-3 weights,
  * 22-bit fixed point, horizontal pass into an 8-bit intermediate, vertical pass.
  * A plan holds the weights of one (in_h, in_w) -> (out_h, out_w) geometry on the CURRENT device.
- * workspace: polcue_resize_workspace_bytes(plan, images) device bytes (the 8-bit intermediate, images x in_h x out_w).
+ * workspace: polcue_resize_workspace_bytes(plan, images) device bytes (the 8-bit intermediate, images x in_h x out_w, + 32 rows).
  * flip: NULL or one device byte per image (polcue_resize_lanczos_u8) / per sample (front end): non-zero mirrors the
  *       image left-right before the resize, as hammer_dataset.py:72-73 does.
  * ------------------------------------------------------------------------------------------- */
@@ -131,6 +131,11 @@ POLCUE_API int polcue_resize_plan_host_build(int in_h, int in_w, int out_h, int 
 POLCUE_API void polcue_resize_plan_destroy(polcue_resize_plan* plan);
 /* Host introspection: returns ksize of axis (0 horizontal, 1 vertical); bounds = out x (first, count), kk = out x ksize. */
 POLCUE_API int polcue_resize_plan_coeffs(const polcue_resize_plan* plan, int axis, int* bounds, int* kk, size_t kk_capacity);
+/* Tests only: 1 = run the horizontal pass in its byte-load form even where the dp4a form applies. */
+POLCUE_API int polcue_debug_resize_force_bytes(int on);
+/* Profiling aid: enable = 1 records CUDA events around the two passes of every resize call; a later call with non-null
+ * pointers waits for the last resize and returns the device time of its horizontal and vertical pass. */
+POLCUE_API int polcue_debug_resize_pass_times(int enable, float* ms_h, float* ms_v);
 POLCUE_API size_t polcue_resize_workspace_bytes(const polcue_resize_plan* plan, int images);
 /* src: images x in_h x in_w uint8 -> dst: images x out_h x out_w uint8 (two launches). */
 POLCUE_API int polcue_resize_lanczos_u8(const polcue_resize_plan* plan, const uint8_t* src, int images, const uint8_t* flip,

@@ -45,6 +45,8 @@ _SIGNATURES = {
     "polcue_resize_plan_host_build": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "polcue_resize_plan_destroy": (None, [C.c_void_p]),
     "polcue_resize_plan_coeffs": (C.c_int, [C.c_void_p, C.c_int, _vp, _vp, C.c_size_t]),
+    "polcue_debug_resize_force_bytes": (C.c_int, [C.c_int]),
+    "polcue_debug_resize_pass_times": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "polcue_resize_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "polcue_resize_lanczos_u8": (C.c_int, [C.c_void_p, _u8p, C.c_int, _u8p, _u8p, _u8p, _vp]),
     "polcue_loader_front_end_u8": (C.c_int, [C.c_void_p, _u8p, _u8p, _u8p, _u8p, C.c_int, _u8p, C.c_void_p, _u8p, _u8p, _f32p, _f32p,

@@ -759,8 +759,17 @@ def test_lanczos_resize_hammer_geometry_vs_reference_digest(resize_golden):
         assert hashlib.sha256(small[k].tobytes()).hexdigest() == resize_golden["hammer_sha256"][k]
 
 
-def test_lanczos_resize_random_geometries_vs_oracle():
-    """Every tap-count class (<= 16, <= 32, generic), upscaling, identity axes, odd widths (scalar paths), saturating inputs."""
+@pytest.fixture
+def byte_form(request):
+    _lib.lib().polcue_debug_resize_force_bytes(1 if request.param else 0)
+    yield request.param
+    _lib.lib().polcue_debug_resize_force_bytes(0)
+
+
+@pytest.mark.parametrize("byte_form", [False, True], indirect=True)
+def test_lanczos_resize_random_geometries_vs_oracle(byte_form):
+    """Every tap-count class (<= 16, <= 32, generic), upscaling, identity axes, odd widths (scalar paths), saturating inputs;
+    the horizontal pass in its dp4a form and in its byte-load form."""
     rng = np.random.default_rng(11)
     shapes = [(40, 52, 17, 23), (90, 130, 9, 10), (256, 300, 8, 9), (12, 10, 30, 41), (31, 64, 31, 16), (64, 31, 16, 31), (1, 1, 1, 1),
               (3, 200, 3, 7), (200, 3, 7, 3), (17, 16, 16, 16)]

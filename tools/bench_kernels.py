@@ -164,10 +164,25 @@ def main():
     B, ih, iw, oh, ow = 32, 832, 1088, 320, 480            # HAMMER quadrants -> training resolution
     full = [torch.from_numpy(np.stack([synth.gen_p_planes(f % 4, ih, iw)[k] for f in range(4)] * (B // 4))).to(dev) for k in range(4)]
     stacked = torch.stack(full, dim=1).contiguous()
-    ws = torch.empty(4 * B * ih * ow, dtype=torch.uint8, device=dev)
+    ws = torch.empty((4 * B * ih + 32) * ow, dtype=torch.uint8, device=dev)
     in_bytes, opx = 4 * B * ih * iw, B * oh * ow
     emit("loader/lanczos_resize", f"u8 [{B},4,{ih},{iw}] -> u8 [{B},4,{oh},{ow}] (2 launches; integer-MAC bound, bytes = in + out)",
          in_bytes + 4 * opx, lambda: ops.lanczos_resize(stacked, (oh, ow), workspace=ws), True)
+    if not args.once and (not only or "loader" in only):
+        import ctypes as C
+        L = _lib.lib()
+        L.polcue_debug_resize_pass_times(1, None, None)
+        th, tv = [], []
+        for _ in range(8):
+            flush_buf.fill_(1)
+            ops.lanczos_resize(stacked, (oh, ow), workspace=ws)
+            a, b = C.c_float(), C.c_float()
+            L.polcue_debug_resize_pass_times(1, C.byref(a), C.byref(b))
+            th.append(a.value)
+            tv.append(b.value)
+        L.polcue_debug_resize_pass_times(0, None, None)
+        print(json.dumps({"kernel": "loader/lanczos_resize passes", "horizontal_ms": sorted(th)[len(th) // 2], "vertical_ms": sorted(tv)[len(tv) // 2],
+                          "note": "CUDA events between the two launches of one call, L2 flushed before the call"}), flush=True)
     keep = {}
     keep.update(ops.loader_front_end(*full, (oh, ow)))
     emit("loader/front_end", f"4 x u8 [{B},{ih},{iw}] -> planes u8 + xolp f32 + normals f32 at {oh}x{ow} (3 launches)",
