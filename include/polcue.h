@@ -143,10 +143,14 @@ POLCUE_API int polcue_resize_lanczos_u8(const polcue_resize_plan* plan, const ui
 /* The polarization branch of __getitem__ + the encoder front end for a batch: the four full-resolution gray images
  * (each B x in_h x in_w; i0 = pol00, i45 = pol01, i90 = pol10, i135 = pol11, indoor_dataset.py:435-438) are resized
  * into planes (B x 4 x out_h x out_w, angle order, required), then get_xolp (:430-442) and get_normals
- * (pre_encoders.py:99-113) run on them as in polcue_fused_planes_u8.  workspace: 4 * B images.  Three launches. */
+ * (pre_encoders.py:99-113) run on them as in polcue_fused_planes_u8.  workspace: 4 * B images.  Three launches.
+ * xolp_norm (B x 2 x out_h x out_w, or NULL) additionally receives ShallowEncoder.normalizeInput(xolp, 'XOLP')
+ * (pre_encoders.py:75-83) = (xolp - mean) / std with xolp_mean_std = 2 HOST floats {mean, std}
+ * ({0.08693199701957657, 0.44430732785457433} in the reference), folded into the kernel's store. */
 POLCUE_API int polcue_loader_front_end_u8(const polcue_resize_plan* plan, const uint8_t* i0, const uint8_t* i45, const uint8_t* i90,
                                const uint8_t* i135, int B, const uint8_t* flip, const polcue_lut* lut, uint8_t* workspace,
-                               uint8_t* planes, float* iun, float* xolp, float* normals, polcue_stream_t stream);
+                               uint8_t* planes, float* iun, float* xolp, float* normals, const float* xolp_mean_std,
+                               float* xolp_norm, polcue_stream_t stream);
 
 /* Same pipeline with HOST buffers (pinned or pageable): chunks of frames are copied in, processed
  * and copied out on three streams so H2D, the kernel and D2H overlap.  Blocks until done.

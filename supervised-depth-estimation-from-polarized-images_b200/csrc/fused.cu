@@ -109,6 +109,8 @@ struct FusedParams {
     uint8_t* planes;   // may be null
     float* iun;        // may be null
     float* xolp;
+    float* xolp_norm;  // may be null: (xolp - norm_mean) / norm_std, ShallowEncoder.normalizeInput (pre_encoders.py:75-83)
+    float norm_mean, norm_inv_std;
     float* normals;    // may be null
     LutArgs lut;
     uint32_t groups_total;   // B * Hs * (Ws / VEC)
@@ -265,6 +267,18 @@ __device__ __forceinline__ void process_group(const FusedParams& p, const LutSha
     xo += p.plane;
     st_stream_vec<VEC>(xo, phi);
     if (p.iun) st_stream_vec<VEC>(p.iun + ((size_t)b * p.plane + pix), iun);
+    if (p.xolp_norm) {      // the encoder's input normalisation folded into the store, rounded as torch's CUDA kernels round it:
+                            // x - float(mean), then times float(1 / std) (BinaryDivTrueKernel multiplies by the reciprocal of a scalar)
+        float nr[VEC], nf[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            nr[j] = __fmul_rn(__fsub_rn(rho[j], p.norm_mean), p.norm_inv_std);
+            nf[j] = __fmul_rn(__fsub_rn(phi[j], p.norm_mean), p.norm_inv_std);
+        }
+        float* xn = p.xolp_norm + ((size_t)(2 * b) * p.plane + pix);
+        st_stream_vec<VEC>(xn, nr);
+        st_stream_vec<VEC>(xn + p.plane, nf);
+    }
 
     if constexpr (NORMALS) {
         float nrm[9][VEC];
@@ -705,6 +719,9 @@ static int fused_mosaic_common(const uint8_t* mosaic, int B, int H, int W, bool 
     p.planes = planes;
     p.iun = iun;
     p.xolp = xolp;
+    p.xolp_norm = nullptr;
+    p.norm_mean = 0.0f;
+    p.norm_inv_std = 1.0f;
     p.normals = normals;
     if (normals) p.lut = lut_args(lut);
     else p.lut = LutArgs{};
@@ -746,13 +763,15 @@ int polcue_fused_superpixel_u8(const uint8_t* mosaic, int B, int H, int W, const
 // Four sample planes at `i0 + {0, off45, off90, off135}`, consecutive frames `frame_stride` bytes apart.
 static int fused_planes_common(const uint8_t* i0, long long off45, long long off90, long long off135, unsigned long long frame_stride,
                                bool aligned4, bool aligned2, int B, int H, int W, const polcue_lut* lut, float* iun, float* xolp,
-                               float* normals, polcue_stream_t stream) {
+                               float* normals, polcue_stream_t stream, float* xolp_norm = nullptr, float norm_mean = 0.0f,
+                               float norm_std = 1.0f) {
     if (normals && (!lut || !lut->d_blob)) return POLCUE_EINVAL;
+    if (xolp_norm && !(norm_std != 0.0f)) return POLCUE_EINVAL;
     if (B == 0) return POLCUE_OK;
     int vec = 1;
-    if (W % 4 == 0 && aligned4 && aligned(xolp, 16) && aligned(normals, 16) && aligned(iun, 16)) vec = 4;
-    else if (W % 2 == 0 && aligned2 && aligned(xolp, 8) && aligned(normals, 8) && aligned(iun, 8)) vec = 2;
-    else if (!aligned(xolp, 4) || !aligned(normals, 4) || !aligned(iun, 4)) return POLCUE_EINVAL;
+    if (W % 4 == 0 && aligned4 && aligned(xolp, 16) && aligned(normals, 16) && aligned(iun, 16) && aligned(xolp_norm, 16)) vec = 4;
+    else if (W % 2 == 0 && aligned2 && aligned(xolp, 8) && aligned(normals, 8) && aligned(iun, 8) && aligned(xolp_norm, 8)) vec = 2;
+    else if (!aligned(xolp, 4) || !aligned(normals, 4) || !aligned(iun, 4) || !aligned(xolp_norm, 4)) return POLCUE_EINVAL;
     const unsigned long long groups = (unsigned long long)B * H * (W / vec);
     if (groups >= (1ull << 31) || frame_stride >= (1ull << 30)) return POLCUE_E2BIG;
     FusedParams p;
@@ -765,6 +784,9 @@ static int fused_planes_common(const uint8_t* i0, long long off45, long long off
     p.planes = nullptr;
     p.iun = iun;
     p.xolp = xolp;
+    p.xolp_norm = xolp_norm;
+    p.norm_mean = norm_mean;
+    p.norm_inv_std = 1.0f / norm_std;
     p.normals = normals;
     if (normals) p.lut = lut_args(lut);
     else p.lut = LutArgs{};
@@ -930,9 +952,10 @@ int polcue_calc_normals_channel_f32(const float* phi, const float* theta, const 
 
 // planes: B x 4 x H x W (angle order) -- the layout the loader front end produces (resize.cu)
 int polcue::fused_planes_strided(const uint8_t* planes, int B, int H, int W, const polcue_lut* lut, float* iun, float* xolp,
-                                 float* normals, cudaStream_t stream) {
+                                 float* normals, cudaStream_t stream, float* xolp_norm, float norm_mean, float norm_std) {
     if (!planes || !xolp || B < 0 || H <= 0 || W <= 0) return POLCUE_EINVAL;
     const long long hw = (long long)H * W;
     return fused_planes_common(planes, hw, 2 * hw, 3 * hw, 4ull * hw, aligned(planes, 4) && hw % 4 == 0,
-                               aligned(planes, 2) && hw % 2 == 0, B, H, W, lut, iun, xolp, normals, (polcue_stream_t)stream);
+                               aligned(planes, 2) && hw % 2 == 0, B, H, W, lut, iun, xolp, normals, (polcue_stream_t)stream, xolp_norm,
+                               norm_mean, norm_std);
 }

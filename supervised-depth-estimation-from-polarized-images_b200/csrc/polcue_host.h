@@ -43,7 +43,8 @@ const DeviceInfo& device_info();  // of the current device (cached per device)
 
 // fused.cu: XOLP + normals from planes laid out B x 4 x H x W (used by the loader front end, resize.cu)
 int fused_planes_strided(const uint8_t* planes, int B, int H, int W, const polcue_lut* lut, float* iun, float* xolp,
-                         float* normals, cudaStream_t stream);
+                         float* normals, cudaStream_t stream, float* xolp_norm = nullptr, float norm_mean = 0.0f,
+                         float norm_std = 1.0f);
 
 // magic numbers for polcue::FastDiv (exact for numerators < 2^31)
 inline void make_fastdiv(uint32_t d, uint32_t& mul, uint32_t& shift) {

@@ -803,13 +803,15 @@ int polcue_resize_lanczos_u8(const polcue_resize_plan* plan, const uint8_t* src,
 
 int polcue_loader_front_end_u8(const polcue_resize_plan* plan, const uint8_t* i0, const uint8_t* i45, const uint8_t* i90,
                                const uint8_t* i135, int B, const uint8_t* flip, const polcue_lut* lut, uint8_t* workspace,
-                               uint8_t* planes, float* iun, float* xolp, float* normals, polcue_stream_t stream) {
-    if (!plan || !planes || !xolp || B < 0) return POLCUE_EINVAL;
+                               uint8_t* planes, float* iun, float* xolp, float* normals, const float* xolp_mean_std, float* xolp_norm,
+                               polcue_stream_t stream) {
+    if (!plan || !planes || !xolp || B < 0 || (xolp_norm && !xolp_mean_std)) return POLCUE_EINVAL;
     if (B == 0) return POLCUE_OK;
     const uint8_t* four[4] = {i0, i45, i90, i135};
     int rc = launch_resize(plan, four, 4, (long long)plan->in_h * plan->in_w, 4 * B, flip, workspace, planes, (cudaStream_t)stream);
     if (rc != POLCUE_OK) return rc;
-    return fused_planes_strided(planes, B, plan->out_h, plan->out_w, lut, iun, xolp, normals, (cudaStream_t)stream);
+    return fused_planes_strided(planes, B, plan->out_h, plan->out_w, lut, iun, xolp, normals, (cudaStream_t)stream, xolp_norm,
+                                xolp_norm ? xolp_mean_std[0] : 0.0f, xolp_norm ? xolp_mean_std[1] : 1.0f);
 }
 
 }  // extern "C"

@@ -215,10 +215,15 @@ def lanczos_resize(images, out_hw, flip=None, workspace=None):
     return out
 
 
-def loader_front_end(i0, i45, i90, i135, out_hw, n=1.5, flip=None, want_iun=False, want_normals=True, out=None):
+XOLP_MEAN_STD = (0.08693199701957657, 0.44430732785457433)     # ShallowEncoder.normalizeInput, pre_encoders.py:79
+
+
+def loader_front_end(i0, i45, i90, i135, out_hw, n=1.5, flip=None, want_iun=False, want_normals=True, out=None, normalize_xolp=None):
     """The polarization branch of ``__getitem__`` for a batch, on the GPU: four full-resolution uint8 images (B x H x W each;
     pol00, pol01, pol10, pol11 = 0, 45, 90, 135 deg) -> dict(planes u8 [B,4,h,w] (the resized images), xolp [B,2,h,w],
-    normals [B,9,h,w], iun).  indoor_dataset.py:335-349 + get_xolp (:430-442) + get_normals (pre_encoders.py:99-113)."""
+    normals [B,9,h,w], iun).  indoor_dataset.py:335-349 + get_xolp (:430-442) + get_normals (pre_encoders.py:99-113).
+    `normalize_xolp`: (mean, std), e.g. XOLP_MEAN_STD, adds `xolp_norm` = ShallowEncoder.normalizeInput(xolp, 'XOLP')
+    (pre_encoders.py:75-83), written by the same kernel."""
     planes = [_need_cuda(p, "image", torch.uint8) for p in (i0, i45, i90, i135)]
     shape = planes[0].shape
     if any(p.shape != shape or p.device != planes[0].device for p in planes) or len(shape) != 3:
@@ -247,9 +252,12 @@ def loader_front_end(i0, i45, i90, i135, out_hw, n=1.5, flip=None, want_iun=Fals
         ws = out["workspace"] = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
     flags = _flip_flags(flip, b, dev)
     lut = lut_for(n, dev) if want_normals else C.c_void_p(0)
+    xnorm = buf("xolp_norm", (b, 2, oh, ow)) if normalize_xolp is not None else None
+    mean_std = (C.c_float * 2)(*[float(v) for v in normalize_xolp]) if normalize_xolp is not None else None
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().polcue_loader_front_end_u8(plan, *(_ptr(p) for p in planes), b, _ptr(flags), lut, _ptr(ws), _ptr(small),
-                                                         _ptr(iun), _ptr(xolp), _ptr(normals), _stream(planes[0])),
+                                                         _ptr(iun), _ptr(xolp), _ptr(normals), mean_std, _ptr(xnorm),
+                                                         _stream(planes[0])),
                    "polcue_loader_front_end_u8")
     return out
 

@@ -790,7 +790,9 @@ def test_loader_front_end_vs_oracle(geometry):
     b = 3
     planes = [np.stack([synth.gen_p_planes(50 + f, ih, iw)[k] for f in range(b)]) for k in range(4)]
     flips = [False, True, False]
-    out = ops.loader_front_end(*(dev(p) for p in planes), (oh, ow), n=1.5, flip=flips, want_iun=True)
+    out = ops.loader_front_end(*(dev(p) for p in planes), (oh, ow), n=1.5, flip=flips, want_iun=True, normalize_xolp=ops.XOLP_MEAN_STD)
+    # ShallowEncoder.normalizeInput(x, 'XOLP') (pre_encoders.py:79) on the float32 tensor, bit for bit
+    assert torch.equal(out["xolp_norm"], (out["xolp"] - 0.08693199701957657) / 0.44430732785457433)
     assert out["planes"].shape == (b, 4, oh, ow) and out["xolp"].shape == (b, 2, oh, ow) and out["normals"].shape == (b, 9, oh, ow)
     for f in range(b):
         small, xolp, normals = O.loader_front_end(*(p[f] for p in planes), (oh, ow), n=1.5, flip=flips[f])
@@ -816,3 +818,47 @@ def test_loader_front_end_rejects_bad_arguments():
         ops.lanczos_resize(a.cpu(), (4, 4))
     with pytest.raises(_lib.PolcueError):
         ops.lanczos_resize(a, (0, 4))
+
+
+@pytest.mark.parametrize("geometry", [(104, 144, 40, 60), (61, 83, 23, 31), (96, 16, 8, 16), (12, 10, 30, 41), (90, 130, 9, 10)])
+def test_resize_kernels_never_write_outside_their_outputs(geometry):
+    """Canary bands around the workspace, the resized planes and every float output of the front end (TMA-pipelined,
+    manually staged, identity-axis, upscaling and generic-tap-count geometries), through the C ABI."""
+    import ctypes as C
+    ih, iw, oh, ow = geometry
+    L = _lib.lib()
+    b = 3
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(4)
+    full = [dev(rng.integers(0, 256, (b, ih, iw), dtype=np.uint8)) for _ in range(4)]
+    flips = dev(np.array([0, 1, 0], np.uint8))
+    plan = ops.resize_plan((ih, iw), (oh, ow), full[0].device)
+    lut = ops.lut_for(1.5, full[0].device)
+    need = int(L.polcue_resize_workspace_bytes(plan, 4 * b))
+    wb, wsp, wpad = _guarded((need,), torch.uint8, 201)
+    pb, planes, ppad = _guarded((b, 4, oh, ow), torch.uint8, 201)
+    xb, xolp, xp = _guarded((b, 2, oh, ow), torch.float32, -7.0)
+    qb, xnorm, qp = _guarded((b, 2, oh, ow), torch.float32, -7.0)
+    nb, nrm, npad = _guarded((b, 9, oh, ow), torch.float32, -7.0)
+    ib, iun, ipad = _guarded((b, oh, ow), torch.float32, -7.0)
+    mean_std = (C.c_float * 2)(*ops.XOLP_MEAN_STD)
+    assert L.polcue_loader_front_end_u8(plan, *(f.data_ptr() for f in full), b, flips.data_ptr(), lut, wsp.data_ptr(), planes.data_ptr(),
+                                        iun.data_ptr(), xolp.data_ptr(), nrm.data_ptr(), mean_std, xnorm.data_ptr(), stream) == 0
+    torch.cuda.synchronize()
+    assert _bands_intact(wb, wpad, 201) and _bands_intact(pb, ppad, 201) and _bands_intact(xb, xp, -7.0) and _bands_intact(qb, qp, -7.0)
+    assert _bands_intact(nb, npad, -7.0) and _bands_intact(ib, ipad, -7.0)
+    assert not bool((nrm == -7.0).any()) and not bool((xolp == -7.0).any()) and not bool((xnorm == -7.0).any())
+    for f in range(b):
+        small, _, _ = O.loader_front_end(*(p[f].cpu().numpy() for p in full), (oh, ow), flip=bool(flips[f]))
+        assert np.array_equal(planes[f].cpu().numpy(), small)
+    # single-tensor entry point with its own guards
+    ob, outp, opad = _guarded((b, oh, ow), torch.uint8, 201)
+    wb2, wsp2, wpad2 = _guarded((int(L.polcue_resize_workspace_bytes(plan, b)),), torch.uint8, 201)
+    assert L.polcue_resize_lanczos_u8(plan, full[1].data_ptr(), b, None, wsp2.data_ptr(), outp.data_ptr(), stream) == 0
+    torch.cuda.synchronize()
+    assert _bands_intact(ob, opad, 201) and _bands_intact(wb2, wpad2, 201)
+    assert np.array_equal(outp[1].cpu().numpy(), O.resize_lanczos_u8(full[1][1].cpu().numpy(), (oh, ow)))
+    # rejected arguments launch nothing
+    assert L.polcue_resize_lanczos_u8(plan, None, b, None, wsp2.data_ptr(), outp.data_ptr(), stream) == -22
+    assert L.polcue_loader_front_end_u8(plan, *(f.data_ptr() for f in full), b, None, lut, wsp.data_ptr(), planes.data_ptr(), None,
+                                        xolp.data_ptr(), nrm.data_ptr(), None, xnorm.data_ptr(), stream) == -22

@@ -38,5 +38,14 @@ for (h, w) in ((64, 96), (37, 131), (5, 3)):                        # TMA path, 
     ops.depth_error_sums(gt[mk], pred[mk])
     dp = pred[:, None].clone().requires_grad_(True)
     ops.normals_loss(torch.where(gt > 0, gt, torch.full_like(gt, 0.7))[:, None], dp, k, (gt > 0).float()[:, None]).backward()
+rng = np.random.default_rng(0)
+for (ih, iw, oh, ow) in ((96, 128, 40, 60), (61, 83, 23, 31), (200, 16, 7, 16), (12, 10, 30, 41), (256, 300, 8, 9)):
+    # TMA-pipelined + cp.async passes, manual staging, identity axis, upscaling, generic tap counts
+    full = [t(rng.integers(0, 256, (3, ih, iw), dtype=np.uint8)) for _ in range(4)]
+    ops.loader_front_end(*full, (oh, ow), flip=[False, True, False], want_iun=True, normalize_xolp=ops.XOLP_MEAN_STD)
+    ops.lanczos_resize(full[0], (oh, ow), flip=True)
+m = t(synth.gen_batch("U", 0, 2, 60, 144))
+ops.fused_mosaic(m, 1.8)                                            # steep end segment: float64 out-of-line path
+ops.fused_mosaic(m, 1.5, superpixel=(2, 1, 3, 0), want_planes=True)
 torch.cuda.synchronize()
 print("sanitize_all: every entry point ran")
