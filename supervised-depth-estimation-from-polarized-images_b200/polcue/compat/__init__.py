@@ -12,6 +12,7 @@ module it replaces, so a call site changes only its import line (INTEGRATION.md 
   manydepth/networks/pre_encoders.py (get_normals)  polcue.compat.pre_encoders
   manydepth/layers.py (compute_depth_errors*)    polcue.compat.layers
   kornia.geometry.depth (depth_to_normals)       polcue.compat.depth
+  manydepth/datasets/indoor_dataset.py (resize_pol, get_xolp)  polcue.compat.indoor_dataset
 
 numpy-signature functions take numpy arrays and return numpy float64 like the reference (the data makes one
 round trip through the GPU); torch-signature functions take and return CUDA tensors.

@@ -808,6 +808,36 @@ def test_loader_front_end_vs_oracle(geometry):
         assert torch.equal(two[key], out[key]), key
 
 
+def test_indoor_dataset_mirrors(resize_golden):
+    """ResizePol and get_xolp used exactly as indoor_dataset.py:335-349, :354 use the originals."""
+    from PIL import Image
+    from polcue.compat import indoor_dataset as c_ds
+    g = resize_golden
+    ih, iw, oh, ow = (int(v) for v in g["case_shapes"][0])
+    resize_pol = c_ds.ResizePol((oh, ow))
+    out = resize_pol(Image.fromarray(g["in_0"]).convert("L"))
+    assert out.mode == "L" and out.size == (ow, oh) and np.array_equal(np.asarray(out), g["out_0"])
+    assert np.array_equal(resize_pol(g["in_0"]), g["out_0"])
+    with pytest.raises(ValueError):
+        resize_pol(Image.fromarray(g["in_0"]).convert("RGB"))
+    planes = synth.gen_p_planes(8, 2 * oh, 2 * ow)
+    inputs = {}
+    for name, k in (("pol00", 0), ("pol01", 1), ("pol10", 2), ("pol11", 3)):       # 0, 45, 90, 135 deg
+        inputs[(name + "_gray", 0, 0)] = resize_pol(Image.fromarray(planes[k], "L"))
+    c_ds.get_xolp(None, inputs, 0)
+    xolp = inputs[("xolp", 0, 0)]
+    assert xolp.shape == (2, oh, ow) and xolp.dtype == torch.float64 and not xolp.is_cuda
+    small = np.stack([np.asarray(inputs[(name + "_gray", 0, 0)]) for name in ("pol00", "pol01", "pol10", "pol11")], axis=2)
+    _, rho, phi = O.iun_and_xolp_closed(small)
+    P.assert_dolp_close(xolp[0].numpy(), rho)
+    P.assert_aolp_close(xolp[1].numpy(), phi)
+    # batched form, loader argument order (pol00, pol10, pol01, pol11)
+    full = [dev(p[None]) for p in planes]
+    both = c_ds.polarization_inputs(full[0], full[2], full[1], full[3], (oh, ow))
+    assert np.array_equal(both["planes"][0].cpu().numpy(), small.transpose(2, 0, 1))
+    assert torch.allclose(both["xolp"][0].cpu().double(), xolp, atol=0, rtol=0)
+
+
 def test_loader_front_end_rejects_bad_arguments():
     a = torch.zeros((2, 8, 8), dtype=torch.uint8, device="cuda")
     with pytest.raises(ValueError):
