@@ -59,7 +59,9 @@ __device__ __forceinline__ void acc_add(Acc& a, float gt, float pred) {
     a.c3 += ratio_below(hi, lo, 1.953125f, thr);
     const float d = gt - pred, d2 = d * d;
     const float inv_gt = rcp_approx(gt);
-    const float dl = lg2_approx(hi) - lg2_approx(lo);    // |log gt - log pred| / ln 2; ln^2 2 is applied at the flush
+    const float dl = lg2_approx(pred * inv_gt);          // (log pred - log gt) / ln 2 (only its square is used); ln^2 2 is
+                                                         // applied at the flush.  One MUFU less than lg2(hi) - lg2(lo); the
+                                                         // neutral pair gives lg2(1 * rcp(1)) = 0 exactly
     a.f[0] += d2;
     a.f[1] = fmaf(dl, dl, a.f[1]);
     a.f[2] = fmaf(fabsf(d), inv_gt, a.f[2]);
@@ -176,7 +178,15 @@ __global__ void __launch_bounds__(kMetricThreads) depth_errors_kernel(const floa
         __shared__ double lane_rows[32][8];
         const unsigned k = threadIdx.x & 7, lane = threadIdx.x >> 3;
         double v = 0.0;
-        for (unsigned blk = lane; blk < gridDim.x; blk += 32) v += __ldcg(partials + (size_t)blk * 8 + k);
+        unsigned blk = lane;
+        for (; blk + 7 * 32 < gridDim.x; blk += 8 * 32) {      // eight loads in flight, added in the same fixed order
+            double t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = __ldcg(partials + (size_t)(blk + 32 * j) * 8 + k);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v += t[j];
+        }
+        for (; blk < gridDim.x; blk += 32) v += __ldcg(partials + (size_t)blk * 8 + k);
         lane_rows[lane][k] = v;
         __syncthreads();
         if (threadIdx.x < 8) {
@@ -296,7 +306,7 @@ __device__ __forceinline__ Contrib make_contrib(float gt, float pred, bool keep)
     c.c2 = (int)keep & (int)ratio_below(hi, lo, 1.5625f, thr);
     c.c3 = (int)keep & (int)ratio_below(hi, lo, 1.953125f, thr);
     const float d = gt - pred, d2 = d * d, inv_gt = rcp_approx(gt);
-    const float dl = lg2_approx(hi) - lg2_approx(lo);
+    const float dl = lg2_approx(pred * inv_gt);
     c.f[0] = d2;
     c.f[1] = dl * dl;
     c.f[2] = fabsf(d) * inv_gt;

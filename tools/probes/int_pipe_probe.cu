@@ -34,6 +34,52 @@ __global__ void probe(unsigned* out, unsigned a0, unsigned b0, int iters) {
     if (s == 0x12345678u) out[0] = s;
 }
 
+// Packed FP32 (Blackwell): two FMAs per instruction.  Four 64-bit chains per thread.
+template <int OP>
+__global__ void probe2(unsigned long long* out, unsigned long long a0, unsigned long long b0, int iters) {
+    unsigned long long acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = threadIdx.x + i;
+    unsigned long long a = a0 + threadIdx.x, b = b0;
+    unsigned x[4] = {threadIdx.x, threadIdx.x + 1, threadIdx.x + 2, threadIdx.x + 3};
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (OP == 0) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(a), "l"(b));
+            else if (OP == 1) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(acc[i]) : "l"(a));
+            else if (OP == 2) { asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(a), "l"(b)); asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"((unsigned)a), "r"((unsigned)b)); }
+            else if (OP == 3) { asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(a), "l"(b)); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"((unsigned)a), "r"((unsigned)b)); }
+        }
+    }
+    unsigned long long s = x[0] ^ x[1] ^ x[2] ^ x[3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s ^= acc[i];
+    if (s == 0x12345678u) out[0] = s;
+}
+
+template <int OP>
+void run2(const char* name, int per_iter) {
+    unsigned long long* out;
+    cudaMalloc(&out, 8);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int iters = 4096, threads = 1024, blocks = sms * 2;
+    probe2<OP><<<blocks, threads>>>(out, 3, 5, 16);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    probe2<OP><<<blocks, threads>>>(out, 3, 5, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    const double instr = (double)blocks * threads * iters * per_iter;
+    printf("%-10s %8.3f ms  %7.1f thread-instr/clk/SM (at %d MHz nominal)\n", name, ms, instr / (ms * 1e-3) / (khz * 1e3) / sms, khz / 1000);
+    cudaFree(out);
+}
+
 template <int OP>
 void run(const char* name) {
     unsigned* out;
@@ -70,5 +116,9 @@ int main() {
     run<13>("IDP+IADD");
     run<14>("IDP+FFMA");
     run<15>("IMNMX+PRMT");
+    run2<0>("FFMA2", 4);
+    run2<1>("FADD2", 4);
+    run2<2>("FFMA2+PRMT", 8);
+    run2<3>("FFMA2+FFMA", 8);
     return 0;
 }
