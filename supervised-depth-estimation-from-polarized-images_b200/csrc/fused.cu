@@ -8,9 +8,9 @@
 // Layout: every output is planar (B x C x Hs x Ws) so each of the 11 float planes is written as
 // one contiguous 512-byte run per warp instruction.  A thread owns VEC consecutive pixels of one
 // row: it reads VEC bytes from each of the four quadrants (one 32-bit load each for VEC = 4) and
-// writes one 16-byte vector per plane.  The grid is persistent (resident CTAs x SMs) and strides
-// over the flat list of pixel groups; the zenith tables (~85 KB for n = 1.5) are staged once per
-// CTA into shared memory with a single bulk-async (TMA) copy.
+// writes one 16-byte vector per plane.  One CTA per tile of 256 pixel groups; resident CTAs take over
+// pending tiles through cluster launch control (polcue_device.cuh), so the zenith tables (49 KB for
+// n = 1.5) are staged once per RESIDENT CTA into shared memory with a single bulk-async (TMA) copy.
 #include <cfloat>
 
 #include "polcue_device.cuh"
