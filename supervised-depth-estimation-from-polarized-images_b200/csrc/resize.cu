@@ -212,7 +212,7 @@ __device__ __forceinline__ void hpass_columns_dp4a(const HParams& p, uint32_t ti
     }
 }
 
-template <int KMAX>
+template <int KW>   // KW > 0: window of 4 KW taps (dp4a form when the weights pack, else bytes with weights in registers); 0: any tap count
 __global__ void __launch_bounds__(512) resize_h_kernel(const __grid_constant__ HParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint8_t* tile = smem_raw + kPadH;
@@ -239,14 +239,14 @@ __global__ void __launch_bounds__(512) resize_h_kernel(const __grid_constant__ H
     __syncthreads();
     uint8_t* dst_rows = p.dst + ((size_t)img * p.in_h + row0) * p.out_w;
     const bool flip = p.flip && p.flip[img / p.nsrc];
-    if constexpr (KMAX > 0) {
+    if constexpr (KW > 0) {
         if (p.pack) {
-            hpass_columns_dp4a<KMAX / 4>(p, smem_u32(tile), rows, dst_rows, flip);
+            hpass_columns_dp4a<KW>(p, smem_u32(tile), rows, dst_rows, flip);
             return;
         }
     }
-    if (flip) hpass_columns<KMAX, true>(p, tile, rows, dst_rows);
-    else hpass_columns<KMAX, false>(p, tile, rows, dst_rows);
+    if (flip) hpass_columns<4 * KW, true>(p, tile, rows, dst_rows);
+    else hpass_columns<4 * KW, false>(p, tile, rows, dst_rows);
 }
 
 // The same pass as a pipeline: a CTA owns one output column per thread (weights stay in registers) and walks a run of
@@ -258,6 +258,7 @@ struct HPipeParams {
     int tiles_per_image, images;        // row tiles per image; images
     int step_img, step_t;               // grid size as (whole images, remaining tiles): one step of a CTA's tile walk
     int nsrc_shift;                     // log2(nsrc)
+    int tile_rows;                      // rows per tile: 32, or 16 for wide images (three stages must fit twice per SM)
     uint32_t buf_stride;        // bytes between the two staging buffers (multiple of 16)
 };
 
@@ -281,7 +282,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 constexpr int kStagesH = 3;
-constexpr int kRowsHP = 32;    // rows per tile of the pipelined kernel
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -298,7 +298,8 @@ __global__ void __launch_bounds__(512, 2) resize_h_pipe_kernel(const __grid_cons
     const int consumer_warps = blockDim.x / 32 - 1;
     const int warp = threadIdx.x / 32;
     const uint32_t buf0 = smem_u32(smem_raw), full0 = smem_u32(&full[0]), empty0 = smem_u32(&empty[0]);
-    const int tile_bytes = kRowsHP * p.in_w;
+    const int tile_rows = pp.tile_rows;
+    const int tile_bytes = tile_rows * p.in_w;
     for (int i = threadIdx.x; i < kPadH * kStagesH; i += blockDim.x) {     // zero-weight taps multiply these
         const int st = i / kPadH, o = i - st * kPadH;
         smem_raw[st * pp.buf_stride + o] = 0;
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(512, 2) resize_h_pipe_kernel(const __grid_cons
                 const int st = k % kStagesH;
                 mbar_wait(empty0 + 8 * st, ((k / kStagesH) & 1) ^ 1);              // passes at once on a fresh barrier
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // consumers' reads before the async write
-                const int rows = min(kRowsHP, p.in_h - t * kRowsHP);
+                const int rows = min(tile_rows, p.in_h - t * tile_rows);
                 const uint8_t* src = p.src[img & nsrc_mask] + (size_t)(img >> pp.nsrc_shift) * p.image_stride + (size_t)t * tile_bytes;
                 bulk_load(buf0 + st * pp.buf_stride + kPadH, src, (uint32_t)(rows * p.in_w), full0 + 8 * st);
             }
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(512, 2) resize_h_pipe_kernel(const __grid_cons
     int start = 0, have = -1;       // have: which weight order is loaded (0 normal, 1 mirrored)
     int st = 0, parity = 0;
     for (; img < pp.images; advance()) {
-        const int rows = min(kRowsHP, p.in_h - t * kRowsHP);
+        const int rows = min(tile_rows, p.in_h - t * tile_rows);
         const int flip = (p.flip && p.flip[img >> pp.nsrc_shift]) ? 1 : 0;
         if (active && flip != have) {
             have = flip;
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(512, 2) resize_h_pipe_kernel(const __grid_cons
         mbar_wait(full0 + 8 * st, parity);
         if (active) {
             uint32_t addr = buf0 + st * pp.buf_stride + kPadH + (uint32_t)start;
-            uint8_t* out = p.dst + ((size_t)img * p.in_h + (size_t)t * kRowsHP) * p.out_w + xx;
+            uint8_t* out = p.dst + ((size_t)img * p.in_h + (size_t)t * tile_rows) * p.out_w + xx;
             uint32_t sel = 0x3210u + 0x1111u * (addr & 3u);
             if constexpr (ROW4) addr &= ~3u;
 #pragma unroll 2
@@ -571,11 +572,18 @@ int launch_resize(const polcue_resize_plan* plan, const uint8_t* const* src, int
     if ((unsigned long long)plan->in_h * plan->in_w >= (1ull << 31) || (unsigned long long)kRowsH * plan->in_w > 100 * 1024)
         return POLCUE_E2BIG;
     HParams h;
-    bool v16 = plan->in_w % 16 == 0 && image_stride % 16 == 0;
+    bool base16 = image_stride % 16 == 0;
     for (int s = 0; s < 4; ++s) {
         h.src[s] = src[s < nsrc ? s : 0];
-        v16 = v16 && aligned(h.src[s], 16);
+        base16 = base16 && aligned(h.src[s], 16);
     }
+    const bool v16 = base16 && plan->in_w % 16 == 0;
+    // A 32-row tile is one contiguous run of 32 in_w bytes: always a 16-byte multiple, and 16-byte aligned when the
+    // image is; only a shorter last tile needs (in_h % 32) in_w to be one as well.  (1224-wide quadrants qualify.)
+    const size_t stage_budget = 110 * 1024;      // per CTA, so that two CTAs share an SM
+    const int tile_rows = kStagesH * (32 * (size_t)plan->in_w + 2 * kPadH + 16) <= stage_budget ? 32 : 16;
+    const bool tma_tiles = base16 && ((long long)(plan->in_h % tile_rows) * plan->in_w) % 16 == 0 &&
+                           kStagesH * (tile_rows * (size_t)plan->in_w + 2 * kPadH + 16) <= stage_budget;
     h.nsrc = nsrc;
     h.image_stride = image_stride;
     h.flip = flip;
@@ -599,16 +607,16 @@ int launch_resize(const polcue_resize_plan* plan, const uint8_t* const* src, int
     };
     int rc;
     if (g_resize_timing) cudaEventRecord(g_resize_ev[0], stream);
-    if (h.pack && plan->out_w <= 480 && h.vec16 && (nsrc == 1 || nsrc == 4) &&
-        (size_t)kStagesH * (kRowsHP * (size_t)plan->in_w + 2 * kPadH + 16) <= 110 * 1024) {
+    if (h.pack && plan->out_w <= 480 && tma_tiles && (nsrc == 1 || nsrc == 4)) {
         HPipeParams pp;
         pp.h = h;
-        pp.tiles_per_image = (plan->in_h + kRowsHP - 1) / kRowsHP;
+        pp.tile_rows = tile_rows;
+        pp.tiles_per_image = (plan->in_h + tile_rows - 1) / tile_rows;
         if ((long long)pp.tiles_per_image * images >= (1ll << 30)) return POLCUE_E2BIG;
         const int tiles_total = pp.tiles_per_image * images;
         pp.images = images;
         pp.nsrc_shift = nsrc == 4 ? 2 : 0;
-        pp.buf_stride = (uint32_t)(((size_t)kRowsHP * plan->in_w + 2 * kPadH + 15) / 16 * 16);
+        pp.buf_stride = (uint32_t)(((size_t)tile_rows * plan->in_w + 2 * kPadH + 15) / 16 * 16);
         const size_t smem2 = kStagesH * (size_t)pp.buf_stride;
         const int threads_p = (plan->out_w + 31) / 32 * 32 + 32;                  // + the producer warp
         auto launch_p = [&](auto kern) -> int {
@@ -623,11 +631,23 @@ int launch_resize(const polcue_resize_plan* plan, const uint8_t* const* src, int
             kern<<<grid_p, threads_p, smem2, stream>>>(pp);
             return launch_status();
         };
-        if (plan->in_w % 4 == 0) rc = plan->pack_words == 4 ? launch_p(resize_h_pipe_kernel<4, true>) : launch_p(resize_h_pipe_kernel<8, true>);
-        else rc = plan->pack_words == 4 ? launch_p(resize_h_pipe_kernel<4, false>) : launch_p(resize_h_pipe_kernel<8, false>);
-    } else if (h.ksize <= 16) rc = launch_h(resize_h_kernel<16>);
-    else if (h.ksize <= 32) rc = launch_h(resize_h_kernel<32>);
-    else rc = launch_h(resize_h_kernel<0>);
+        const bool row4 = plan->in_w % 4 == 0;
+        switch (plan->pack_words) {
+#define POLCUE_H_CASE(K) case K: rc = row4 ? launch_p(resize_h_pipe_kernel<K, true>) : launch_p(resize_h_pipe_kernel<K, false>); break
+            POLCUE_H_CASE(4); POLCUE_H_CASE(5); POLCUE_H_CASE(6); POLCUE_H_CASE(7); POLCUE_H_CASE(8);
+#undef POLCUE_H_CASE
+            default: return POLCUE_EINVAL;
+        }
+    } else {
+        switch (h.ksize <= 32 ? std::max(4, (h.ksize + 3) / 4) : 0) {      // the same word count the weights were packed with
+            case 4: rc = launch_h(resize_h_kernel<4>); break;
+            case 5: rc = launch_h(resize_h_kernel<5>); break;
+            case 6: rc = launch_h(resize_h_kernel<6>); break;
+            case 7: rc = launch_h(resize_h_kernel<7>); break;
+            case 8: rc = launch_h(resize_h_kernel<8>); break;
+            default: rc = launch_h(resize_h_kernel<0>); break;
+        }
+    }
     if (rc != POLCUE_OK) return rc;
     if (g_resize_timing) cudaEventRecord(g_resize_ev[1], stream);
 
@@ -699,7 +719,7 @@ int polcue_resize_plan_create(int in_h, int in_w, int out_h, int out_w, polcue_r
     plan->off_kk_v = plan->off_bounds_v + (size_t)2 * out_h;
     plan->blob_ints = plan->off_kk_v + (size_t)kv * out_h;
     // byte planes of the horizontal weights for the dp4a form: window words KW = 4 (<= 16 taps) or 8 (<= 32 taps)
-    const int kw = kh <= 16 ? 4 : (kh <= 32 ? 8 : 0);
+    const int kw = kh <= 32 ? std::max(4, (kh + 3) / 4) : 0;      // 4-tap words of the window: 4..8
     bool packable = kw > 0;
     for (int v : plan->kk[0]) packable = packable && (v >> 16) >= -128 && (v >> 16) <= 127;
     plan->pack_words = packable ? kw : 0;
