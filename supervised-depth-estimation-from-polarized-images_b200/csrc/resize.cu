@@ -291,7 +291,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // 32 output columns.  Stages are handed over through full/empty mbarriers, so no CTA-wide barrier sits in the loop and
 // warps drift up to kStagesH - 1 tiles apart.
 template <int KW, bool ROW4>   // ROW4: in_w % 4 == 0, so a column's window has the same word alignment in every row
-__global__ void __launch_bounds__(512, 2) resize_h_pipe_kernel(const __grid_constant__ HPipeParams pp) {
+__global__ void __launch_bounds__(1024, 1) resize_h_pipe_kernel(const __grid_constant__ HPipeParams pp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t full[kStagesH], empty[kStagesH];
     const HParams& p = pp.h;
@@ -607,7 +607,7 @@ int launch_resize(const polcue_resize_plan* plan, const uint8_t* const* src, int
     };
     int rc;
     if (g_resize_timing) cudaEventRecord(g_resize_ev[0], stream);
-    if (h.pack && plan->out_w <= 480 && tma_tiles && (nsrc == 1 || nsrc == 4)) {
+    if (h.pack && plan->out_w <= 992 && tma_tiles && (nsrc == 1 || nsrc == 4)) {      // one output column per consumer thread
         HPipeParams pp;
         pp.h = h;
         pp.tile_rows = tile_rows;

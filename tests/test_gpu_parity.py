@@ -774,7 +774,8 @@ def test_lanczos_resize_random_geometries_vs_oracle(byte_form):
     shapes = [(40, 52, 17, 23), (90, 130, 9, 10), (256, 300, 8, 9), (12, 10, 30, 41), (31, 64, 31, 16), (64, 31, 16, 31), (1, 1, 1, 1),
               (3, 200, 3, 7), (200, 3, 7, 3), (17, 16, 16, 16),
               # bulk-copy (TMA) tiles whose rows are not 16-byte multiples: word-aligned rows, unaligned rows, 17..32 taps, short last tile
-              (64, 72, 20, 30), (64, 70, 20, 30), (96, 1224, 40, 480), (70, 72, 20, 30), (70, 70, 20, 30)]
+              (64, 72, 20, 30), (64, 70, 20, 30), (96, 1224, 40, 480), (70, 72, 20, 30), (70, 70, 20, 30), (48, 1248, 19, 640), (40, 2000, 11, 992),
+              (40, 2000, 11, 1000)]
     shapes += [tuple(int(v) for v in rng.integers(1, 140, 4)) for _ in range(12)]
     for ih, iw, oh, ow in shapes:
         imgs = rng.integers(0, 256, (3, ih, iw), dtype=np.uint8)
