@@ -153,6 +153,26 @@ def test_resize_plan_weights_equal_the_pillow_restatement(L, geometry):
     assert L.polcue_resize_plan_host_build(0, 4, 4, 4, C.byref(h)) == -22
 
 
+def test_tables_for_random_refractive_indices(L):
+    """Any n the builder accepts: float32 cells + float64 steep segments reproduce scipy's interpolant to float32 rounding
+    of theta (+ 2e-6), in-table, at the peak and in both extrapolation ranges.  (A 78-index sweep found n = 1.5548 with an
+    end slope of -53 006.)"""
+    rng = np.random.default_rng(7)
+    for n in np.concatenate((rng.uniform(1.02, 3.0, 10), [1.5548, 1.8])):
+        rc, h = _host_lut(L, n)
+        assert rc == 0, n
+        knots = O.sorted_knots(float(n))
+        q = np.concatenate((rng.uniform(0, 1, 8000) ** 2, rng.uniform(0, 2.2, 3000), 1 - rng.uniform(0, 1, 3000) ** 3 * 1e-3,
+                            [0.0, 1.0, 2.0])).astype(np.float32)
+        for t, name in enumerate(("diffuse", "spec1", "spec2")):
+            xk, yk = knots[name]
+            theta = np.empty(q.size, np.float32)
+            assert L.polcue_lut_eval_host(h, t, q.ctypes.data, q.size, theta.ctypes.data) == 0
+            ref = O.interp_linear_extrap(xk, yk, q.astype(np.float64))
+            assert (np.abs(theta - ref) <= 1.2e-7 * np.abs(ref) + 2e-5).all(), (n, name)
+        L.polcue_lut_destroy(h)
+
+
 def test_table_anchor_values(L):
     rc, h = _host_lut(L, 1.5)
     anchors = {0.0: (0.0, 0.0, 1.570796327), 0.01: (0.410434783, 0.086477641, 1.566324189), 0.3: (1.472298774, 0.460030611, 1.436485518),

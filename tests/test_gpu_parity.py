@@ -327,6 +327,26 @@ def test_steep_end_segment_is_evaluated_in_float64(mufu):
         _lib.lib().polcue_debug_set_trig(1)
 
 
+def test_get_normals_random_refractive_indices():
+    """Differential sweep over n (incl. 1.5548, whose second specular branch ends with slope -53 006, and n near 1):
+    XOLP-fed and byte-fed kernels against the float64 oracle on rho in [0, 2.2], both sincos variants."""
+    rng = np.random.default_rng(23)
+    for i, n in enumerate(np.concatenate((rng.uniform(1.02, 3.0, 8), [1.5548, 1.01]))):
+        shape = (2, int(rng.integers(3, 40)), int(rng.integers(3, 60)))
+        rho = np.where(rng.random(shape) < 0.5, rng.uniform(0, 1, shape) ** 2, rng.uniform(0, 2.2, shape))
+        rho = np.where(rng.random(shape) < 0.1, 1 - rng.uniform(0, 1, shape) ** 3 * 1e-3, rho).astype(np.float32)
+        x = np.stack((rho, rng.uniform(-np.pi / 2, np.pi / 2, shape).astype(np.float32)), axis=1)
+        _lib.lib().polcue_debug_set_trig(i & 1)
+        try:
+            got = ops.get_normals(dev(x), float(n)).cpu().numpy()
+        finally:
+            _lib.lib().polcue_debug_set_trig(1)
+        ref = O.get_normals(x, float(n))
+        b, h, w = shape
+        P.assert_normals_close(got.reshape(b, 3, 3, h, w), ref.reshape(b, 3, 3, h, w), axis=2, what=f"n={n:.4f}")
+        check_fused(rng.integers(0, 256, (1, 2 * h, 2 * w), dtype=np.uint8), n=float(n), mufu=bool(i & 1))
+
+
 def test_numpy_chain_mirror(golden):
     st = golden["xolp_p_in"]
     mosaic = synth.tile_mosaic([st[..., k] for k in range(4)])
