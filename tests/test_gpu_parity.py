@@ -442,6 +442,56 @@ def test_depth_to_normals(shape):
     assert ((np.abs(nrm - 1) < 1e-5) | (nrm < 1e-5)).all()
 
 
+def test_stencil_metrics_and_loss_randomized_shapes_and_cameras():
+    """Differential sweep: 16 random (batch, shape, camera, depth range, mask) cases through the stencil, the per-image
+    metrics (range + material filter), the flat metric sums and the normals loss with its gradient."""
+    rng = np.random.default_rng(99)
+    for case in range(16):
+        b, h, w = int(rng.integers(1, 4)), int(rng.integers(1, 70)), int(rng.integers(1, 200))
+        if case % 4 == 0:
+            w = 4 * max(1, w // 4)                                     # 16-byte rows: TMA staging
+        v, u = np.mgrid[0:h, 0:w].astype(np.float64)
+        depth = np.stack([0.3 + rng.uniform(0.2, 1.5) * (1 + 0.3 * np.sin(u / rng.uniform(5, 60) + rng.uniform(0, 6)) *
+                                                          np.cos(v / rng.uniform(5, 60))) + rng.uniform(-2e-3, 2e-3) * u
+                          for _ in range(b)]).astype(np.float32)
+        k = np.stack([np.array([[rng.uniform(200, 900), 0, rng.uniform(0, w)], [0, rng.uniform(200, 900), rng.uniform(0, h)], [0, 0, 1]])
+                      for _ in range(b)]).astype(np.float32)
+        got = ops.depth_to_normals(dev(depth)[:, None], dev(k)).cpu().numpy()
+        P.assert_normals_close(got, O.depth_to_normals(depth[:, None], k), axis=1, tol=2e-3, what=f"stencil case {case}")
+        # metrics: prediction = noisy depth, 15 % invalid ground truth, random range and material
+        pred = (depth * (1 + 0.1 * rng.standard_normal(depth.shape))).clip(0.05, 4).astype(np.float32)
+        gt = np.where(rng.random(depth.shape) < 0.15, 0, depth).astype(np.float32)
+        inst = (20 * rng.integers(0, 11, depth.shape)).astype(np.uint8)
+        lo, hi = np.float32(rng.uniform(0.05, 0.4)), np.float32(rng.uniform(1.0, 3.0))
+        for inst_id in (None, int(20 * rng.integers(0, 11))):
+            sums, metrics = ops.depth_errors_per_image(dev(gt), dev(pred), float(lo), float(hi), dev(inst) if inst_id is not None else None, inst_id)
+            rows, _ = O.depth_errors_per_image(gt, pred, lo, hi, inst, inst_id)
+            gm = metrics.cpu().numpy().astype(np.float64)
+            assert np.array_equal(np.isnan(gm), np.isnan(rows)), case
+            assert np.allclose(gm, rows, rtol=1e-5, equal_nan=True), (case, np.nanmax(np.abs(gm / rows - 1)))
+        m = gt > 0
+        if m.any():
+            flat = [float(x) for x in ops.compute_depth_errors(dev(gt[m]), dev(pred[m]))]
+            assert np.allclose(flat, O.compute_depth_errors(gt[m], pred[m]), rtol=2e-5), case
+        # loss + gradient against the float64 autograd oracle
+        mask = (rng.random(depth.shape) < 0.8).astype(np.float32)
+        if mask.sum() == 0 or min(h, w) < 2:
+            continue        # one-pixel-wide images: every normal is the zero vector and the reference's gradient is round-off noise
+        t64 = lambda a: torch.from_numpy(a.astype(np.float64))
+        p64 = t64(pred)[:, None].requires_grad_(True)
+        ref_loss = O.normals_loss_torch(t64(depth)[:, None], p64, t64(k), t64(mask)[:, None])
+        ref_loss.backward()
+        ref_grad = p64.grad[:, 0].numpy()
+        dp = dev(pred)[:, None].clone().requires_grad_(True)
+        loss = ops.normals_loss(dev(depth)[:, None], dp, dev(k), dev(mask)[:, None])
+        loss.backward()
+        assert abs(float(loss.detach()) - float(ref_loss.detach())) < 3e-5 * max(1.0, abs(float(ref_loss.detach()))), case
+        g = dp.grad[:, 0].cpu().numpy().astype(np.float64)
+        scale = np.abs(ref_grad).max() + 1e-30
+        err = np.abs(g - ref_grad) / scale          # float32 kernel vs float64 autograd, as in the fixed-shape test below
+        assert err.max() < 2e-3 and np.sqrt((err ** 2).mean()) < 2e-4, (case, float(err.max()))
+
+
 def test_depth_to_normals_uses_tma_staging_when_rows_are_16_byte_multiples():
     L = _lib.lib()
     gt, _, _, k = synth.gen_depth_batch(0, 2, 64, 96)
