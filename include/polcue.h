@@ -152,6 +152,15 @@ POLCUE_API int polcue_loader_front_end_u8(const polcue_resize_plan* plan, const 
                                uint8_t* planes, float* iun, float* xolp, float* normals, const float* xolp_mean_std,
                                float* xolp_norm, polcue_stream_t stream);
 
+/* The loader front end with HOST buffers (pinned or pageable): the four image stacks (each B x in_h x in_w) are copied
+ * in by chunks of `chunk_samples` (<= 0: default), resized and reduced on the device, and planes (B x 4 x out_h x out_w,
+ * or NULL), xolp, normals (or NULL) and xolp_norm (or NULL) are copied back, copies and kernels overlapping on three
+ * streams.  h_flip: NULL or B host bytes.  Blocks until done.  The weights of the geometry are cached between calls. */
+POLCUE_API int polcue_loader_front_end_u8_host(int in_h, int in_w, int out_h, int out_w, const uint8_t* h_i0, const uint8_t* h_i45,
+                                    const uint8_t* h_i90, const uint8_t* h_i135, int B, const uint8_t* h_flip, const polcue_lut* lut,
+                                    uint8_t* h_planes, float* h_xolp, float* h_normals, const float* xolp_mean_std,
+                                    float* h_xolp_norm, int chunk_samples);
+
 /* Same pipeline with HOST buffers (pinned or pageable): chunks of frames are copied in, processed
  * and copied out on three streams so H2D, the kernel and D2H overlap.  Blocks until done.
  * `chunk_frames` <= 0 picks a default.  This is the call bench.py's `e2e` figure times. */

@@ -51,6 +51,8 @@ _SIGNATURES = {
     "polcue_resize_lanczos_u8": (C.c_int, [C.c_void_p, _u8p, C.c_int, _u8p, _u8p, _u8p, _vp]),
     "polcue_loader_front_end_u8": (C.c_int, [C.c_void_p, _u8p, _u8p, _u8p, _u8p, C.c_int, _u8p, C.c_void_p, _u8p, _u8p, _f32p, _f32p,
                                             _f32p, C.POINTER(C.c_float), _f32p, _vp]),
+    "polcue_loader_front_end_u8_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _u8p, _u8p, _u8p, C.c_int, _u8p, C.c_void_p, _u8p,
+                                                 _f32p, _f32p, C.POINTER(C.c_float), _f32p, C.c_int]),
     "polcue_fused_mosaic_u8_host": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _f32p, _f32p, _f32p, C.c_int]),
     "polcue_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "polcue_host_free": (C.c_int, [C.c_void_p]),

@@ -290,6 +290,47 @@ def fused_mosaic_host(mosaic, n=1.5, want_iun=False, want_normals=True, out=None
     return out
 
 
+def loader_front_end_host(i0, i45, i90, i135, out_hw, n=1.5, flip=None, want_planes=True, want_normals=True, normalize_xolp=None,
+                          out=None, chunk_samples=0, device=None):
+    """`loader_front_end` for HOST tensors (ideally pinned): four B x H x W uint8 CPU stacks in, host outputs; the copies are
+    pipelined against the kernels inside the library (`polcue_loader_front_end_u8_host`)."""
+    imgs = []
+    for t in (i0, i45, i90, i135):
+        if not isinstance(t, torch.Tensor) or t.is_cuda or t.dtype != torch.uint8:
+            raise TypeError("images must be CPU uint8 tensors")
+        imgs.append(t.contiguous())
+    shape = imgs[0].shape
+    if any(t.shape != shape for t in imgs) or len(shape) != 3:
+        raise ValueError("images must share one B x H x W shape")
+    b, h, w = shape
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    out = dict(out or {})
+
+    def buf(key, shp, dtype=torch.float32):
+        t = out.get(key)
+        if t is None:
+            t = out[key] = torch.empty(shp, dtype=dtype, pin_memory=True)
+        return t
+
+    xolp = buf("xolp", (b, 2, oh, ow))
+    planes = buf("planes", (b, 4, oh, ow), torch.uint8) if want_planes else None
+    normals = buf("normals", (b, 9, oh, ow)) if want_normals else None
+    xnorm = buf("xolp_norm", (b, 2, oh, ow)) if normalize_xolp is not None else None
+    mean_std = (C.c_float * 2)(*[float(v) for v in normalize_xolp]) if normalize_xolp is not None else None
+    flags = None
+    if flip is not None:
+        flags = torch.as_tensor([flip] * b if isinstance(flip, bool) else flip).to(torch.uint8).contiguous()
+        if flags.numel() != b:
+            raise ValueError(f"flip needs one flag per sample ({b})")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lut = lut_for(n, dev) if want_normals else C.c_void_p(0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().polcue_loader_front_end_u8_host(h, w, oh, ow, *(_ptr(t) for t in imgs), b, _ptr(flags), lut, _ptr(planes),
+                                                              _ptr(xolp), _ptr(normals), mean_std, _ptr(xnorm), int(chunk_samples)),
+                   "polcue_loader_front_end_u8_host")
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # XOLP
 # ------------------------------------------------------------------------------------------

@@ -911,6 +911,21 @@ def test_indoor_dataset_mirrors(resize_golden):
     assert torch.allclose(both["xolp"][0].cpu().double(), xolp, atol=0, rtol=0)
 
 
+def test_loader_front_end_host_entry_point_matches_device_entry_point():
+    rng = np.random.default_rng(12)
+    b, ih, iw, oh, ow = 11, 104, 144, 40, 60                          # 11 samples in chunks of 4: 3 ring slots + a short last chunk
+    full = [torch.from_numpy(rng.integers(0, 256, (b, ih, iw), dtype=np.uint8)) for _ in range(4)]
+    flips = [bool(v) for v in rng.integers(0, 2, b)]
+    host = ops.loader_front_end_host(*(t.pin_memory() for t in full), (oh, ow), flip=flips, normalize_xolp=ops.XOLP_MEAN_STD, chunk_samples=4)
+    devo = ops.loader_front_end(*(t.cuda() for t in full), (oh, ow), flip=flips, normalize_xolp=ops.XOLP_MEAN_STD)
+    for key in ("planes", "xolp", "xolp_norm", "normals"):
+        assert not host[key].is_cuda and torch.equal(host[key], devo[key].cpu()), key
+    again = ops.loader_front_end_host(*full, (oh, ow), flip=flips, want_planes=False, want_normals=False)      # pageable, cached ring
+    assert set(again) == {"xolp"} and torch.equal(again["xolp"], host["xolp"])
+    with pytest.raises(TypeError):
+        ops.loader_front_end_host(*(t.cuda() for t in full), (oh, ow))
+
+
 def test_loader_front_end_rejects_bad_arguments():
     a = torch.zeros((2, 8, 8), dtype=torch.uint8, device="cuda")
     with pytest.raises(ValueError):
