@@ -2,7 +2,8 @@
 """Per-kernel roofline readings for every CUDA entry point of libpolcue.so other than the headline fused kernel
 (bench.py covers that one).  For each kernel: algorithmic bytes per launch / mean launch time (CUDA
 events on the launching stream) against the measured HBM copy peak.  Working sets smaller than ~2x the L2 are
-preceded by an L2 flush (a 512 MB write) inside the loop but outside the timed events.
+preceded by an L2 flush (a 512 MB read, so that no dirty lines are left for the kernel to write back) inside the loop;
+the separately measured cost of the flushes is subtracted.
 
   python tools/bench_kernels.py [--reps 10] [--only stencil,metrics] > profiles/kernels_rNN.jsonl
 """
@@ -47,11 +48,15 @@ def timeit(fn, reps, flush):
     if flush is None:
         return run(fn), run(fn)
 
+    # The flush READS 512 MB (a reduction), so L2 ends up full of CLEAN lines of the flush buffer.  A write flush would
+    # leave ~126 MB of dirty lines whose write-back the measured kernel then pays for (about 20 us of DRAM traffic).
+    view = flush.view(torch.int32)
+
     def both():
-        flush.fill_(1)
+        view.sum()
         fn()
 
-    t_flush = min(run(lambda: flush.fill_(1)) for _ in range(2))
+    t_flush = min(run(lambda: view.sum()) for _ in range(2))
     t_both = min(run(both) for _ in range(2))
     return t_both - t_flush, t_both - t_flush
 
