@@ -271,6 +271,25 @@ POLCUE_API size_t polcue_channel_stats_workspace_bytes(int B, int C, size_t hw);
 POLCUE_API int polcue_channel_stats_f32(const float* x, int B, int C, size_t hw, void* workspace, double* stats,
                              polcue_stream_t stream);
 
+/* The evaluation loops in full (manydepth/trainer.py:1356-1430, manydepth/evaluation.py:215-288), one mask group per call:
+ *   mask      = (gt > min_d) & (gt < max_d) [& inst_lo <= inst <= inst_hi]      (inst NULL: no material filter;
+ *               evaluation.py's "objects" group is the id RANGE 20..160, every other group has inst_lo == inst_hi)
+ *   clamp_first != 0: pred is clamped to [min_d, max_d] first, as both loops clamp the whole batch (trainer.py:1368-1370)
+ *   median scaling (trainer.py:1413-1414, the configurations without depth supervision):
+ *               pred *= np.median(gt[mask]) / np.median(pred[mask])
+ *   pred clamped to [min_d, max_d], then the seven metrics per image.
+ * polcue_masked_median_scale_f32: medians[B][2] = (median of gt[mask], median of pred[mask]) exactly as np.median gives them
+ * for float32 arrays (radix select; an even count averages the two middle values in float32) and scale[B] (or NULL) = their
+ * float32 ratio; an empty mask gives NaN.
+ * polcue_depth_errors_images_scaled_f32: the per-image metrics with pred multiplied by pred_scale[image] (device floats,
+ * NULL = no scaling) between the two clamps. */
+POLCUE_API int polcue_masked_median_scale_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px, float min_d,
+                                   float max_d, int inst_lo, int inst_hi, int clamp_first, float* medians, float* scale,
+                                   polcue_stream_t stream);
+POLCUE_API int polcue_depth_errors_images_scaled_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px,
+                                          float min_d, float max_d, int inst_lo, int inst_hi, int clamp_first,
+                                          const float* pred_scale, double* sums, float* metrics, polcue_stream_t stream);
+
 /* All mask groups of the evaluation loop in ONE launch (the reference makes 11-12 CPU passes, manydepth/trainer.py:920-980,
  * evaluation.py:169-213): group_ids[g] = instance id of group g (20, 40, ... 200, trainer.py:1389-1411) or -1 for
  * object == "all"; n_groups <= 16 HOST ints.  sums: B x n_groups x 8 doubles, metrics: B x n_groups x 7 floats or NULL.

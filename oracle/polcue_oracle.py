@@ -379,9 +379,12 @@ def depth_error_sums(gt, pred):
                          (np.abs(diff) / gt).sum(), (diff ** 2 / gt).sum()], dtype=np.float64)
 
 
-def depth_errors_per_image(gt, pred, min_depth, max_depth, inst=None, inst_id=None):
-    """Per-image masked metrics of Trainer.compute_depth_losses_from_list, manydepth/trainer.py:1376-1428
-    (supervised configuration: no median scaling).
+def depth_errors_per_image(gt, pred, min_depth, max_depth, inst=None, inst_id=None, median_scaling=False, clamp_first=False):
+    """Per-image masked metrics of Trainer.compute_depth_losses_from_list, manydepth/trainer.py:1376-1428.
+    `median_scaling` = the branch of :1413-1414 (`not depth_supervision and not train_stereo_only`):
+    depth_pred *= np.median(depth_gt) / np.median(depth_pred) on the masked arrays, before the clamp.
+    `inst_id` may be an inclusive (lo, hi) range (evaluation.py:259-262, "objects" = 20..160); `clamp_first` = the
+    batch-level torch.clamp of trainer.py:1368-1370 / evaluation.py:223-225 ahead of everything else.
 
     gt, pred: B x H x W float; inst: B x H x W instance-id map or None; inst_id: material level
     (20, 40, ... 200; trainer.py:1389-1411) or None for object == "all".
@@ -396,8 +399,13 @@ def depth_errors_per_image(gt, pred, min_depth, max_depth, inst=None, inst_id=No
     for b in range(gt.shape[0]):
         m = (gt[b] > min_depth) & (gt[b] < max_depth)
         if inst is not None and inst_id is not None:
-            m &= np.asarray(inst[b]) == inst_id
-        rows.append(compute_depth_errors(gt[b][m], np.clip(pred[b][m], min_depth, max_depth)))
+            lo, hi = (inst_id if isinstance(inst_id, (tuple, list)) else (inst_id, inst_id))
+            m &= (np.asarray(inst[b]) >= lo) & (np.asarray(inst[b]) <= hi)
+        g, q = gt[b][m], (np.clip(pred[b], min_depth, max_depth) if clamp_first else pred[b])[m]
+        if median_scaling:
+            with np.errstate(all="ignore"):
+                q = q * (np.median(g) / np.median(q)) if g.size else q
+        rows.append(compute_depth_errors(g, np.clip(q, min_depth, max_depth)))
     rows = np.array(rows, dtype=np.float64).reshape(gt.shape[0], 7)
     return rows, rows.mean(axis=0)
 

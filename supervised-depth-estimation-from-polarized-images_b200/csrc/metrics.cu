@@ -210,6 +210,9 @@ struct ImageParams {
     const float* gt;
     const float* pred;
     const uint8_t* inst;  // may be null
+    const float* pred_scale;   // may be null: per-image factor applied to pred before the clamp (median scaling, trainer.py:1413-1414)
+    int want_hi;               // material filter is group_ids[0] <= id <= want_hi (evaluation.py:259-262: "objects" = 20..160)
+    int clamp_first;           // clamp pred to [min_d, max_d] BEFORE the scaling as well (the batch-level clamp of trainer.py:1368-1370)
     size_t px;
     float min_d, max_d;
     int n_groups;         // mask groups evaluated in this launch (grid.y); outputs are [B][n_groups][...]
@@ -219,10 +222,12 @@ struct ImageParams {
     bool vec4;
 };
 
-__device__ __forceinline__ void acc_masked(Acc& a, const ImageParams& p, int want_id, float g, float q, int id) {
-    // trainer.py:1380 mask, :1410-1411 material filter, :1417-1418 clamp of the prediction
-    const bool keep = (g > p.min_d) & (g < p.max_d) & ((want_id < 0) | (id == want_id));
-    acc_add(a, keep ? g : 1.0f, keep ? fminf(fmaxf(q, p.min_d), p.max_d) : 1.0f);   // rejected -> the neutral pair (1, 1)
+__device__ __forceinline__ void acc_masked(Acc& a, const ImageParams& p, int want_id, float g, float q, int id, float scale) {
+    // trainer.py:1380 mask, :1410-1411 material filter, :1413-1414 median scaling (scale = 1 without it: exact),
+    // :1417-1418 clamp of the prediction
+    const bool keep = (g > p.min_d) & (g < p.max_d) & ((want_id < 0) | ((id >= want_id) & (id <= p.want_hi)));
+    if (p.clamp_first) q = fminf(fmaxf(q, p.min_d), p.max_d);
+    acc_add(a, keep ? g : 1.0f, keep ? fminf(fmaxf(__fmul_rn(q, scale), p.min_d), p.max_d) : 1.0f);   // rejected -> the neutral pair (1, 1)
     a.n += keep;
     a.seen += 1;
 }
@@ -237,6 +242,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     const float* gt = p.gt + b * p.px;
     const float* pred = p.pred + b * p.px;
     const uint8_t* inst = (p.inst && want_id >= 0) ? p.inst + b * p.px : nullptr;
+    const float scale = p.pred_scale ? __ldg(p.pred_scale + b) : 1.0f;
 
     Acc a;
     acc_clear(a);
@@ -249,10 +255,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
             const float4 g = ld_stream_f32x4(gt + 4 * i), q = ld_stream_f32x4(pred + 4 * i);
             uint32_t ids = 0;
             if (inst) ids = ld_stream_u32(inst + 4 * i);
-            acc_masked(a, p, want_id, g.x, q.x, ids & 0xff);
-            acc_masked(a, p, want_id, g.y, q.y, (ids >> 8) & 0xff);
-            acc_masked(a, p, want_id, g.z, q.z, (ids >> 16) & 0xff);
-            acc_masked(a, p, want_id, g.w, q.w, ids >> 24);
+            acc_masked(a, p, want_id, g.x, q.x, ids & 0xff, scale);
+            acc_masked(a, p, want_id, g.y, q.y, (ids >> 8) & 0xff, scale);
+            acc_masked(a, p, want_id, g.z, q.z, (ids >> 16) & 0xff, scale);
+            acc_masked(a, p, want_id, g.w, q.w, ids >> 24, scale);
             if (++since == 16) {
                 flush(s, a);
                 since = 0;
@@ -260,7 +266,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
         }
     } else {
         for (size_t i = tid; i < p.px; i += stride) {
-            acc_masked(a, p, want_id, gt[i], pred[i], inst ? inst[i] : 0);
+            acc_masked(a, p, want_id, gt[i], pred[i], inst ? inst[i] : 0, scale);
             if (++since == 64) {
                 flush(s, a);
                 since = 0;
@@ -281,6 +287,112 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     }
     cluster.sync();  // keep remote shared memory alive until rank 0 has read it
     if (rank == 0 && threadIdx.x == 0 && p.metrics) finalize(warp_rows[1], p.metrics + b * 7);
+}
+
+// ------------------------------------------------------------------------------------------
+// median scaling (trainer.py:1413-1414, self-supervised configurations only):
+//     depth_pred *= np.median(depth_gt[mask]) / np.median(depth_pred[mask])
+// One CTA per (image, array).  The k-th smallest masked value is found by a three-pass radix select on the order-
+// preserving 32-bit key of the float (11 + 11 + 10 bits, shared-memory histogram with integer atomics: exact and
+// order-independent); an even count averages the two middle values in float32 as np.median does.
+// ------------------------------------------------------------------------------------------
+constexpr int kMedianThreads = 1024;
+
+struct MedianParams {
+    const float* gt;
+    const float* pred;
+    const uint8_t* inst;   // may be null
+    size_t px;
+    float min_d, max_d;
+    int want_id, want_hi;  // want_id = -1: range mask only, else want_id <= id <= want_hi
+    int clamp_first;       // the prediction is clamped to [min_d, max_d] before its median is taken
+    float* medians;        // [B][2]: median of gt[mask], of pred[mask]
+};
+
+__device__ __forceinline__ uint32_t order_key(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k) {
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+
+__global__ void __launch_bounds__(kMedianThreads) masked_median_kernel(const MedianParams p) {
+    __shared__ unsigned hist[2048];
+    __shared__ unsigned warp_tot[kMedianThreads / 32];
+    __shared__ unsigned sel_bin, sel_rank, total;
+    const size_t b = blockIdx.y;
+    const float* gt = p.gt + b * p.px;
+    const float* key_src = (blockIdx.x == 0 ? p.gt : p.pred) + b * p.px;
+    const uint8_t* inst = (p.inst && p.want_id >= 0) ? p.inst + b * p.px : nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float middle[2] = {0.0f, 0.0f};
+    unsigned n = 0;
+    for (int which = 0; which < 2; ++which) {             // lower and upper middle element
+        uint32_t prefix = 0;
+        unsigned rank = 0;
+        for (int pass = 0; pass < 3; ++pass) {
+            const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+            const int bits = pass == 2 ? 10 : 11;
+            for (int i = threadIdx.x; i < 2048; i += kMedianThreads) hist[i] = 0;
+            __syncthreads();
+            for (size_t i = threadIdx.x; i < p.px; i += kMedianThreads) {
+                const float g = gt[i];
+                const bool keep = (g > p.min_d) & (g < p.max_d) & (!inst || ((int)inst[i] >= p.want_id) & ((int)inst[i] <= p.want_hi));
+                if (!keep) continue;
+                float v = key_src[i];
+                if (p.clamp_first && blockIdx.x == 1) v = fminf(fmaxf(v, p.min_d), p.max_d);
+                const uint32_t k = order_key(v);
+                if (pass > 0 && (k >> (shift + bits)) != prefix) continue;
+                atomicAdd(&hist[(k >> shift) & ((1u << bits) - 1)], 1u);
+            }
+            __syncthreads();
+            // exclusive scan over the 2048 bins (two per thread) to find the bin that holds `rank`
+            const unsigned h0 = hist[2 * threadIdx.x], h1 = hist[2 * threadIdx.x + 1];
+            unsigned incl = h0 + h1;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
+            }
+            if (lane == 31) warp_tot[warp] = incl;
+            __syncthreads();
+            unsigned base = 0;
+            for (int w = 0; w < warp; ++w) base += warp_tot[w];
+            if (pass == 0 && which == 0 && threadIdx.x == kMedianThreads - 1) total = base + incl;
+            __syncthreads();
+            if (pass == 0) {
+                n = total;
+                if (n == 0) break;
+                rank = which == 0 ? (n - 1) / 2 : n / 2;
+            }
+            const unsigned before = base + incl - (h0 + h1);
+            if (rank >= before && rank < before + h0) {
+                sel_bin = 2 * threadIdx.x;
+                sel_rank = rank - before;
+            } else if (rank >= before + h0 && rank < before + h0 + h1) {
+                sel_bin = 2 * threadIdx.x + 1;
+                sel_rank = rank - before - h0;
+            }
+            __syncthreads();
+            prefix = (prefix << bits) | sel_bin;
+            rank = sel_rank;
+            __syncthreads();
+        }
+        if (n == 0) break;
+        middle[which] = key_value(prefix);
+        if ((n & 1) && which == 0) {      // odd count: one middle element
+            middle[1] = middle[0];
+            break;
+        }
+    }
+    if (threadIdx.x == 0)
+        p.medians[b * 2 + blockIdx.x] = n ? __fmul_rn(__fadd_rn(middle[0], middle[1]), 0.5f) : __int_as_float(0x7fc00000);
+}
+
+__global__ void median_ratio_kernel(const float* medians, int B, float* scale) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) scale[b] = __fdiv_rn(medians[2 * b], medians[2 * b + 1]);     // np.float32 / np.float32
 }
 
 // ------------------------------------------------------------------------------------------
@@ -459,7 +571,8 @@ int polcue_depth_errors_f32(const float* gt, const float* pred, size_t count, vo
 }
 
 static int launch_images(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px, float min_d, float max_d,
-                         const int* group_ids, int n_groups, double* sums, float* metrics, polcue_stream_t stream) {
+                         const int* group_ids, int n_groups, double* sums, float* metrics, polcue_stream_t stream,
+                         const float* pred_scale = nullptr, int inst_hi = -1, int clamp_first = 0) {
     if (!gt || !pred || !sums || B < 0 || B > 65535 || n_groups < 1 || n_groups > 16) return POLCUE_EINVAL;
     if (reinterpret_cast<uintptr_t>(sums) & 7) return POLCUE_EINVAL;
     if (B == 0) return POLCUE_OK;
@@ -467,6 +580,9 @@ static int launch_images(const float* gt, const float* pred, const uint8_t* inst
     p.gt = gt;
     p.pred = pred;
     p.inst = inst;
+    p.pred_scale = pred_scale;
+    p.want_hi = (inst && inst_hi >= 0) ? inst_hi : ((inst && n_groups >= 1) ? group_ids[0] : -1);
+    p.clamp_first = clamp_first;
     p.px = px;
     p.min_d = min_d;
     p.max_d = max_d;
@@ -484,6 +600,38 @@ int polcue_depth_errors_images_f32(const float* gt, const float* pred, const uin
                                    float max_d, int inst_id, double* sums, float* metrics, polcue_stream_t stream) {
     const int id = inst ? inst_id : -1;
     return launch_images(gt, pred, inst, B, px, min_d, max_d, &id, 1, sums, metrics, stream);
+}
+
+int polcue_depth_errors_images_scaled_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px, float min_d,
+                                          float max_d, int inst_lo, int inst_hi, int clamp_first, const float* pred_scale,
+                                          double* sums, float* metrics, polcue_stream_t stream) {
+    if (inst && (inst_lo < 0 || inst_hi < inst_lo)) return POLCUE_EINVAL;
+    const int id = inst ? inst_lo : -1;
+    return launch_images(gt, pred, inst, B, px, min_d, max_d, &id, 1, sums, metrics, stream, pred_scale, inst_hi, clamp_first);
+}
+
+int polcue_masked_median_scale_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px, float min_d,
+                                   float max_d, int inst_lo, int inst_hi, int clamp_first, float* medians, float* scale,
+                                   polcue_stream_t stream) {
+    if (!gt || !pred || !medians || B < 0 || B > 65535) return POLCUE_EINVAL;
+    if (inst && (inst_lo < 0 || inst_hi < inst_lo)) return POLCUE_EINVAL;
+    if (B == 0) return POLCUE_OK;
+    MedianParams p;
+    p.gt = gt;
+    p.pred = pred;
+    p.inst = inst;
+    p.px = px;
+    p.min_d = min_d;
+    p.max_d = max_d;
+    p.want_id = inst ? inst_lo : -1;
+    p.want_hi = inst_hi;
+    p.clamp_first = clamp_first;
+    p.medians = medians;
+    masked_median_kernel<<<dim3(2, B, 1), kMedianThreads, 0, (cudaStream_t)stream>>>(p);
+    int rc = launch_status();
+    if (rc != POLCUE_OK || !scale) return rc;
+    median_ratio_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(medians, B, scale);
+    return launch_status();
 }
 
 int polcue_depth_errors_groups_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px, float min_d,

@@ -73,6 +73,10 @@ _SIGNATURES = {
     "polcue_depth_errors_f32": (C.c_int, [_f32p, _f32p, C.c_size_t, _vp, _f64p, _f32p, _vp]),
     "polcue_depth_errors_images_f32": (C.c_int, [_f32p, _f32p, _u8p, C.c_int, C.c_size_t, C.c_float, C.c_float, C.c_int,
                                                   _f64p, _f32p, _vp]),
+    "polcue_masked_median_scale_f32": (C.c_int, [_f32p, _f32p, _u8p, C.c_int, C.c_size_t, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                                                _f32p, _f32p, _vp]),
+    "polcue_depth_errors_images_scaled_f32": (C.c_int, [_f32p, _f32p, _u8p, C.c_int, C.c_size_t, C.c_float, C.c_float, C.c_int, C.c_int,
+                                                       C.c_int, _f32p, _f64p, _f32p, _vp]),
     "polcue_depth_errors_groups_f32": (C.c_int, [_f32p, _f32p, _u8p, C.c_int, C.c_size_t, C.c_float, C.c_float, C.POINTER(C.c_int),
                                                   C.c_int, _f64p, _f32p, _vp]),
     "polcue_channel_stats_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_size_t]),

@@ -13,6 +13,7 @@ module it replaces, so a call site changes only its import line (INTEGRATION.md 
   manydepth/layers.py (compute_depth_errors*)    polcue.compat.layers
   kornia.geometry.depth (depth_to_normals)       polcue.compat.depth
   manydepth/datasets/indoor_dataset.py (resize_pol, get_xolp)  polcue.compat.indoor_dataset
+  manydepth/trainer.py, manydepth/evaluation.py (compute_depth_losses_from_list)  polcue.compat.trainer
 
 numpy-signature functions take numpy arrays and return numpy float64 like the reference (the data makes one
 round trip through the GPU); torch-signature functions take and return CUDA tensors.

@@ -515,8 +515,45 @@ def compute_depth_errors(gt, pred):
     return tuple(metrics.unbind(0))
 
 
-def depth_errors_per_image(gt, pred, min_depth, max_depth, inst=None, inst_id=None):
+def _inst_range(inst_id):
+    """None -> no filter; int -> that id; (lo, hi) -> the id range (evaluation.py:259-262 "objects" = (20, 160))."""
+    if inst_id is None:
+        return None
+    if isinstance(inst_id, (tuple, list)):
+        lo, hi = int(inst_id[0]), int(inst_id[1])
+    else:
+        lo = hi = int(inst_id)
+    return lo, hi
+
+
+def masked_median_scale(gt, pred, min_depth, max_depth, inst=None, inst_id=None, clamp_first=False):
+    """Per image: (medians [B,2] = np.median(gt[mask]), np.median(pred[mask]); scale [B] = their float32 ratio), the factor of
+    the reference's median scaling (trainer.py:1413-1414).  Same mask as `depth_errors_per_image`."""
+    gt = _need_cuda(gt, "gt").float().contiguous()
+    pred = _need_cuda(pred, "pred").float().contiguous()
+    b = gt.shape[0]
+    px = gt.numel() // b if b else 0
+    if pred.numel() != gt.numel():
+        raise ValueError("gt and pred must have the same shape")
+    rng = _inst_range(inst_id) if inst is not None else None
+    use_inst = rng is not None
+    if use_inst:
+        inst = _need_cuda(inst, "inst", torch.uint8)
+    lo, hi = rng if use_inst else (0, 0)
+    medians = torch.empty((b, 2), dtype=torch.float32, device=gt.device)
+    scale = torch.empty((b,), dtype=torch.float32, device=gt.device)
+    with torch.cuda.device(gt.device):
+        _lib.check(_lib.lib().polcue_masked_median_scale_f32(_ptr(gt), _ptr(pred), _ptr(inst) if use_inst else C.c_void_p(0), b, px,
+                                                             float(min_depth), float(max_depth), lo, hi, int(bool(clamp_first)),
+                                                             _ptr(medians), _ptr(scale), _stream(gt)), "polcue_masked_median_scale_f32")
+    return medians, scale
+
+
+def depth_errors_per_image(gt, pred, min_depth, max_depth, inst=None, inst_id=None, median_scaling=False, clamp_first=False):
     """Per-image masked metrics (trainer.py:1376-1428): gt/pred B x H x W (or B x 1 x H x W), inst uint8 or None.
+    `inst_id`: None, one material id, or an inclusive (lo, hi) id range (evaluation.py's "objects" group = (20, 160)).
+    `median_scaling`: multiply each image's prediction by median(gt[mask]) / median(pred[mask]) first (trainer.py:1413-1414,
+    the configurations without depth supervision); `clamp_first`: clamp the prediction before that too (trainer.py:1368-1370).
 
     Returns (sums [B,8] float64, metrics [B,7] float32) on device.
     """
@@ -526,18 +563,22 @@ def depth_errors_per_image(gt, pred, min_depth, max_depth, inst=None, inst_id=No
     px = gt.numel() // b if b else 0
     if pred.numel() != gt.numel():
         raise ValueError("gt and pred must have the same shape")
-    use_inst = inst is not None and inst_id is not None
+    rng = _inst_range(inst_id) if inst is not None else None
+    use_inst = rng is not None
     if use_inst:
         inst = _need_cuda(inst, "inst", torch.uint8)
         if inst.numel() != gt.numel():
             raise ValueError("inst must have the same shape as gt")
+    lo, hi = rng if use_inst else (0, 0)
     sums = torch.empty((b, 8), dtype=torch.float64, device=gt.device)
     metrics = torch.empty((b, 7), dtype=torch.float32, device=gt.device)
+    scale = (masked_median_scale(gt, pred, min_depth, max_depth, inst if use_inst else None, inst_id, clamp_first)[1]
+             if median_scaling else None)
     with torch.cuda.device(gt.device):
-        _lib.check(_lib.lib().polcue_depth_errors_images_f32(_ptr(gt), _ptr(pred), _ptr(inst) if use_inst else C.c_void_p(0), b,
-                                                             px, float(min_depth), float(max_depth),
-                                                             int(inst_id) if use_inst else 0, _ptr(sums), _ptr(metrics),
-                                                             _stream(gt)), "polcue_depth_errors_images_f32")
+        _lib.check(_lib.lib().polcue_depth_errors_images_scaled_f32(_ptr(gt), _ptr(pred), _ptr(inst) if use_inst else C.c_void_p(0), b,
+                                                                    px, float(min_depth), float(max_depth), lo, hi,
+                                                                    int(bool(clamp_first)), _ptr(scale), _ptr(sums), _ptr(metrics),
+                                                                    _stream(gt)), "polcue_depth_errors_images_scaled_f32")
     return sums, metrics
 
 

@@ -657,6 +657,76 @@ def test_depth_errors_per_image(golden, shape):
         assert np.allclose(metrics.cpu().numpy(), golden["met_img_rows"], rtol=2e-5)
 
 
+@pytest.mark.parametrize("shape", [(320, 480), (33, 47), (1, 5), (2, 2)])
+def test_median_scaling_of_the_self_supervised_configurations(shape):
+    """trainer.py:1413-1414: the masked medians are exact (radix select), even and odd counts, ties, empty masks."""
+    h, w = shape
+    gt, pred, inst, _ = synth.gen_depth_batch(2, 6, h, w)
+    pred = (pred * np.float32(1.7)).astype(np.float32)                 # a scale-ambiguous prediction, as a self-supervised model gives
+    pred[1] = np.round(pred[1], 1)                                     # many equal values around the median
+    gt[2, : max(1, h // 2)] = 0                                        # changes the count's parity
+    gt[3] = 0                                                          # empty mask
+    inst[4] = 40
+    for inst_id in (None, 40):
+        med, scale = ops.masked_median_scale(dev(gt), dev(pred), 0.1, 2.0, dev(inst) if inst_id is not None else None, inst_id)
+        med, scale = med.cpu().numpy(), scale.cpu().numpy()
+        for b in range(6):
+            m = (gt[b] > np.float32(0.1)) & (gt[b] < np.float32(2.0))
+            if inst_id is not None:
+                m &= inst[b] == inst_id
+            if m.sum() == 0:
+                assert np.isnan(med[b]).all() and np.isnan(scale[b])
+                continue
+            assert med[b, 0] == np.median(gt[b][m]) and med[b, 1] == np.median(pred[b][m]), (b, m.sum())      # bit-exact
+            assert scale[b] == np.median(gt[b][m]) / np.median(pred[b][m])
+        _, metrics = ops.depth_errors_per_image(dev(gt), dev(pred), 0.1, 2.0, dev(inst) if inst_id is not None else None, inst_id,
+                                                median_scaling=True)
+        rows, _ = O.depth_errors_per_image(gt, pred, 0.1, 2.0, inst, inst_id, median_scaling=True)
+        got = metrics.cpu().numpy().astype(np.float64)
+        assert np.array_equal(np.isnan(got), np.isnan(rows))
+        assert np.allclose(got, rows, rtol=1e-5, equal_nan=True)
+    # without scaling the scaled entry point is the plain one, bit for bit
+    a = ops.depth_errors_per_image(dev(gt), dev(pred), 0.1, 2.0)[0]
+    L = _lib.lib()
+    import ctypes as C
+    sums = torch.empty((6, 8), dtype=torch.float64, device="cuda")
+    assert L.polcue_depth_errors_images_f32(dev(gt).data_ptr(), dev(pred).data_ptr(), None, 6, h * w, C.c_float(0.1), C.c_float(2.0), 0,
+                                            sums.data_ptr(), None, C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+    assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(sums))
+
+
+@pytest.mark.parametrize("supervised", [True, False])
+def test_evaluation_loop_mirror(supervised, capsys):
+    """compute_depth_losses_from_list called the way Trainer.test / Evaluation.test call it (lists of CPU batches, one call
+    per material group incl. evaluation.py's id RANGE "objects"), against a numpy transcription of the reference loop."""
+    import types
+    from polcue.compat import trainer as c_tr
+    h, w, bsz = 64, 96, 3
+    opt = types.SimpleNamespace(min_depth=0.1, max_depth=2.0, height=h, width=w, batch_size=bsz, depth_supervision=supervised,
+                                train_stereo_only=False)
+    me = types.SimpleNamespace(opt=opt, depth_metric_names=list(c_tr.DEPTH_METRIC_NAMES))
+    gts, preds, masks = [], [], []
+    for k in range(2):
+        gt, pred, inst, _ = synth.gen_depth_batch(10 * k, bsz, h, w)
+        pred = (pred * np.float32(1.0 if supervised else 1.6) + np.float32(0.0)).astype(np.float32)
+        pred[0, :4] = 5.0                                              # beyond max_depth: exercises the batch-level clamp
+        gts.append(torch.from_numpy(gt)[:, None]); preds.append(torch.from_numpy(pred)[:, None])
+        masks.append(torch.from_numpy(inst.astype(np.int32))[:, None])
+    for obj in ("all", "bottle", "wall", "objects"):
+        losses = {}
+        got = c_tr.compute_depth_losses_from_list(me, gts, preds, losses, masks, object=obj)
+        rows = []
+        inst_id = None if obj == "all" else c_tr.OBJECT_IDS[obj]
+        for k in range(2):
+            r, _ = O.depth_errors_per_image(gts[k][:, 0].numpy(), preds[k][:, 0].numpy(), 0.1, 2.0, masks[k][:, 0].numpy(), inst_id,
+                                            median_scaling=not supervised, clamp_first=True)
+            rows.append(r)
+        ref = np.concatenate(rows).mean(0)
+        assert np.allclose(got, ref, rtol=1e-5, equal_nan=True), (obj, got, ref)
+        assert set(losses) == set(c_tr.DEPTH_METRIC_NAMES) and losses["de/abs_rel"].shape == ()
+    assert "abs_rel |" in capsys.readouterr().out
+
+
 @pytest.mark.parametrize("shape", [(3, 2, 64, 96), (2, 9, 33, 47), (5, 11, 320, 480), (1, 1, 1, 1)])
 def test_channel_stats_and_xolp_statistics(shape):
     rng = np.random.default_rng(sum(shape))
