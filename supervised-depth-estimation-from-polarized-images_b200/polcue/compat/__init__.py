@@ -44,7 +44,8 @@ def install(verbose=False):
       manydepth.networks.pre_encoders.{rho_diffuse, rho_spec, calc_normals} and ShallowNormalsEncoder.get_normals
       manydepth.layers.{compute_depth_errors, compute_depth_errors_numpy}
       manydepth.trainer.{compute_depth_errors, compute_depth_errors_numpy, Iun_and_xolp} and
-          Trainer.compute_supervised_normals_losses (the GT + predicted stencils, cosine and masked mean, with backward)
+          Trainer.compute_supervised_normals_losses (the GT + predicted stencils, cosine and masked mean, with backward),
+          Trainer.compute_depth_losses_from_list / manydepth.evaluation.Evaluation.compute_depth_losses_from_list
       manydepth.datasets.indoor_dataset.Iun_and_xolp, polarisation.* and ppp_code.physical_normals_channels.* if imported.
     Returns the list of "module.attribute" names that were replaced.
     """
@@ -73,6 +74,8 @@ def install(verbose=False):
     patch("manydepth.trainer", "compute_supervised_normals_losses",
           lambda self, depth_gt, depth_pred, intrinsics, mask: trainer.compute_supervised_normals_losses(depth_gt, depth_pred, intrinsics, mask),
           owner="Trainer")
+    patch("manydepth.trainer", "compute_depth_losses_from_list", trainer.compute_depth_losses_from_list, owner="Trainer")
+    patch("manydepth.evaluation", "compute_depth_losses_from_list", trainer.compute_depth_losses_from_list, owner="Evaluation")
     for mod_name in ("polarisation.pol_split_and_save", "polarisation.xolp_and_normals"):
         patch(mod_name, "split_pol", pol_split_and_save.split_pol)
     for name in ("rho_diffuse", "rho_spec", "calc_normals"):
