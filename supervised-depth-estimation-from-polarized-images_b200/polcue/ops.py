@@ -585,7 +585,8 @@ def depth_errors_per_image(gt, pred, min_depth, max_depth, inst=None, inst_id=No
 def depth_errors_groups(gt, pred, inst, min_depth, max_depth, group_ids):
     """Every mask group of the reference's evaluation loop in one launch.  group_ids: iterable of instance ids
     (20 ... 200, trainer.py:1389-1411) with None / -1 meaning object == "all".
-    Returns (sums [B, G, 8] float64, metrics [B, G, 7] float32) on device."""
+    Returns (sums [B, G, 8] float64, metrics [B, G, 7] float32) on device.  The accumulators are additive, so a union of
+    materials (evaluation.py's "objects" = ids 20..160) is `metrics_from_sums(sums[:, those groups].sum(1))`."""
     gt = _need_cuda(gt, "gt").float().contiguous()
     pred = _need_cuda(pred, "pred").float().contiguous()
     ids = [(-1 if g is None else int(g)) for g in group_ids]

@@ -725,6 +725,14 @@ def test_evaluation_loop_mirror(supervised, capsys):
         assert np.allclose(got, ref, rtol=1e-5, equal_nan=True), (obj, got, ref)
         assert set(losses) == set(c_tr.DEPTH_METRIC_NAMES) and losses["de/abs_rel"].shape == ()
     assert "abs_rel |" in capsys.readouterr().out
+    if supervised:      # the id-range group equals the sum of its materials' accumulators from the single-pass kernel
+        gt, pred, inst = (dev(t[0][:, 0].numpy()) for t in (gts, preds, masks))
+        inst = inst.to(torch.uint8)
+        levels = list(range(20, 161, 20))
+        sums, _ = ops.depth_errors_groups(gt, pred.clamp(0.1, 2.0), inst, 0.1, 2.0, levels)
+        union = ops.metrics_from_sums(sums.sum(1)).cpu().numpy()
+        _, direct = ops.depth_errors_per_image(gt, pred, 0.1, 2.0, inst, (20, 160), clamp_first=True)
+        assert np.allclose(union, direct.cpu().numpy(), rtol=1e-6, equal_nan=True)
 
 
 @pytest.mark.parametrize("shape", [(3, 2, 64, 96), (2, 9, 33, 47), (5, 11, 320, 480), (1, 1, 1, 1)])
