@@ -176,39 +176,61 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // a u
     return d;
 }
 
+// One output column's byte-plane weights (normal or mirrored order) and the first byte of its window.
+template <int KW>
+struct ColumnWeights {
+    uint32_t lo[KW], mid[KW], hi[KW];
+    int start;
+    __device__ __forceinline__ void load(const HParams& p, int xx, bool flip) {
+        const uint32_t* pk = p.pack + (size_t)(flip ? 3 * KW : 0) * p.out_w + xx;
+#pragma unroll
+        for (int i = 0; i < KW; ++i) {
+            lo[i] = __ldg(pk + (size_t)i * p.out_w);
+            mid[i] = __ldg(pk + (size_t)(KW + i) * p.out_w);
+            hi[i] = __ldg(pk + (size_t)(2 * KW + i) * p.out_w);
+        }
+        const int xmin = p.bounds[xx].x;
+        start = flip ? p.in_w - 1 - xmin - (4 * KW - 1) : xmin;
+    }
+};
+
+// `rows` rows of one output column: per row KW + 1 aligned LDS.32 cover the 4 KW-byte window at shared address `addr`,
+// PRMT funnels them to the window's alignment, 3 KW dp4a reduce them.  ROW4: in_w % 4 == 0, so the alignment is the same
+// in every row and the selector is computed once.
+template <int KW, bool ROW4>
+__device__ __forceinline__ void dp4a_column_rows(const ColumnWeights<KW>& k, uint32_t addr, int rows, int in_w, uint8_t* out, int out_w) {
+    uint32_t sel = 0x3210u + 0x1111u * (addr & 3u);
+    if constexpr (ROW4) addr &= ~3u;
+#pragma unroll 2
+    for (int r = 0; r < rows; ++r) {
+        uint32_t a = addr;
+        if constexpr (!ROW4) {
+            a = addr & ~3u;
+            sel = 0x3210u + 0x1111u * (addr & 3u);
+        }
+        uint32_t w[KW + 1];
+#pragma unroll
+        for (int i = 0; i <= KW; ++i) w[i] = lds_u32(a + 4 * i);
+        int lo = kHalf, mid = 0, hi = 0;
+#pragma unroll
+        for (int i = 0; i < KW; ++i) {
+            const uint32_t v = __byte_perm(w[i], w[i + 1], sel);
+            lo = dp4a_uu(v, k.lo[i], lo);
+            mid = dp4a_uu(v, k.mid[i], mid);
+            hi = dp4a_us(v, k.hi[i], hi);
+        }
+        *out = (uint8_t)clip8(lo + (mid << 8) + (hi << 16));
+        out += out_w;
+        addr += in_w;
+    }
+}
+
 template <int KW>
 __device__ __forceinline__ void hpass_columns_dp4a(const HParams& p, uint32_t tile_addr, int rows, uint8_t* dst_rows, bool flip) {
     for (int xx = threadIdx.x; xx < p.out_w; xx += blockDim.x) {
-        const int2 bd = p.bounds[xx];
-        const uint32_t* pk = p.pack + (size_t)(flip ? 3 * KW : 0) * p.out_w + xx;
-        uint32_t klo[KW], kmid[KW], khi[KW];
-#pragma unroll
-        for (int i = 0; i < KW; ++i) {
-            klo[i] = __ldg(pk + (size_t)i * p.out_w);
-            kmid[i] = __ldg(pk + (size_t)(KW + i) * p.out_w);
-            khi[i] = __ldg(pk + (size_t)(2 * KW + i) * p.out_w);
-        }
-        const int start = flip ? p.in_w - 1 - bd.x - (4 * KW - 1) : bd.x;
-        uint32_t addr = tile_addr + (uint32_t)start;
-        uint8_t* out = dst_rows + xx;
-        for (int r = 0; r < rows; ++r) {
-            const uint32_t a = addr & ~3u;
-            const uint32_t sel = 0x3210u + 0x1111u * (addr & 3u);
-            uint32_t w[KW + 1];
-#pragma unroll
-            for (int i = 0; i <= KW; ++i) w[i] = lds_u32(a + 4 * i);
-            int lo = 0, mid = 0, hi = 0;
-#pragma unroll
-            for (int i = 0; i < KW; ++i) {
-                const uint32_t v = __byte_perm(w[i], w[i + 1], sel);
-                lo = dp4a_uu(v, klo[i], lo);
-                mid = dp4a_uu(v, kmid[i], mid);
-                hi = dp4a_us(v, khi[i], hi);
-            }
-            *out = (uint8_t)clip8(kHalf + lo + (mid << 8) + (hi << 16));
-            out += p.out_w;
-            addr += p.in_w;
-        }
+        ColumnWeights<KW> k;
+        k.load(p, xx, flip);
+        dp4a_column_rows<KW, false>(k, tile_addr + (uint32_t)k.start, rows, p.in_w, dst_rows + xx, p.out_w);
     }
 }
 
@@ -341,53 +363,21 @@ __global__ void __launch_bounds__(1024, 1) resize_h_pipe_kernel(const __grid_con
     }
     const int xx = threadIdx.x;
     const bool active = xx < p.out_w;
-    uint32_t klo[KW], kmid[KW], khi[KW];
-    int start = 0, have = -1;       // have: which weight order is loaded (0 normal, 1 mirrored)
+    ColumnWeights<KW> k;
+    k.start = 0;
+    int have = -1;                  // which weight order is loaded (0 normal, 1 mirrored)
     int st = 0, parity = 0;
     for (; img < pp.images; advance()) {
         const int rows = min(tile_rows, p.in_h - t * tile_rows);
         const int flip = (p.flip && p.flip[img >> pp.nsrc_shift]) ? 1 : 0;
         if (active && flip != have) {
             have = flip;
-            const uint32_t* pk = p.pack + (size_t)(flip ? 3 * KW : 0) * p.out_w + xx;
-#pragma unroll
-            for (int i = 0; i < KW; ++i) {
-                klo[i] = __ldg(pk + (size_t)i * p.out_w);
-                kmid[i] = __ldg(pk + (size_t)(KW + i) * p.out_w);
-                khi[i] = __ldg(pk + (size_t)(2 * KW + i) * p.out_w);
-            }
-            const int xmin = p.bounds[xx].x;
-            start = flip ? p.in_w - 1 - xmin - (4 * KW - 1) : xmin;
+            k.load(p, xx, flip != 0);
         }
         mbar_wait(full0 + 8 * st, parity);
-        if (active) {
-            uint32_t addr = buf0 + st * pp.buf_stride + kPadH + (uint32_t)start;
-            uint8_t* out = p.dst + ((size_t)img * p.in_h + (size_t)t * tile_rows) * p.out_w + xx;
-            uint32_t sel = 0x3210u + 0x1111u * (addr & 3u);
-            if constexpr (ROW4) addr &= ~3u;
-#pragma unroll 2
-            for (int r = 0; r < rows; ++r) {
-                uint32_t a = addr;
-                if constexpr (!ROW4) {
-                    a = addr & ~3u;
-                    sel = 0x3210u + 0x1111u * (addr & 3u);
-                }
-                uint32_t w[KW + 1];
-#pragma unroll
-                for (int i = 0; i <= KW; ++i) w[i] = lds_u32(a + 4 * i);
-                int lo = kHalf, mid = 0, hi = 0;
-#pragma unroll
-                for (int i = 0; i < KW; ++i) {
-                    const uint32_t v = __byte_perm(w[i], w[i + 1], sel);
-                    lo = dp4a_uu(v, klo[i], lo);
-                    mid = dp4a_uu(v, kmid[i], mid);
-                    hi = dp4a_us(v, khi[i], hi);
-                }
-                *out = (uint8_t)clip8(lo + (mid << 8) + (hi << 16));
-                out += p.out_w;
-                addr += p.in_w;
-            }
-        }
+        if (active)
+            dp4a_column_rows<KW, ROW4>(k, buf0 + st * pp.buf_stride + kPadH + (uint32_t)k.start, rows, p.in_w,
+                                       p.dst + ((size_t)img * p.in_h + (size_t)t * tile_rows) * p.out_w + xx, p.out_w);
         __syncwarp();
         if (threadIdx.x % 32 == 0) mbar_arrive(empty0 + 8 * st);    // this warp is done with the stage
         if (++st == kStagesH) {
