@@ -161,6 +161,15 @@ def run_loader_full(args, rank, world, dev):
     e.record()
     torch.cuda.synchronize()
     ms_kernels = D.max_over_ranks(a.elapsed_time(e) / args.reps, dev)
+    # the C-ABI host entry point: every output (planes, xolp, xolp_norm, normals) back in pinned host memory
+    host_out = {}
+    for _ in range(2):
+        host_out = ops.loader_front_end_host(*pool, (h, w), n=1.5, normalize_xolp=ops.XOLP_MEAN_STD, out=host_out)
+    t0 = time.perf_counter()
+    host_reps = max(1, args.reps // 5)
+    for _ in range(host_reps):
+        host_out = ops.loader_front_end_host(*pool, (h, w), n=1.5, normalize_xolp=ops.XOLP_MEAN_STD, out=host_out)
+    ms_host = D.max_over_ranks((time.perf_counter() - t0) / host_reps * 1e3, dev)
     if rank == 0:
         import multiprocessing as mp
         cores = os.cpu_count() or 1
@@ -175,6 +184,9 @@ def run_loader_full(args, rank, world, dev):
                           "n_gpus": world, "us_per_batch": ms * 1e3, "samples_per_s": world * b / (ms * 1e-3),
                           "us_per_batch_kernels_only": ms_kernels * 1e3, "h2d_bytes_per_batch": 4 * b * ih * iw,
                           "h2d_gbs": 4 * b * ih * iw / (ms * 1e-3) / 1e9,
+                          "host_entry_point": {"api": "polcue_loader_front_end_u8_host (all outputs returned to pinned host memory)",
+                                               "us_per_batch": ms_host * 1e3, "samples_per_s": world * b / (ms_host * 1e-3),
+                                               "d2h_bytes_per_batch": b * h * w * (4 + 8 + 8 + 36)},
                           "cpu_reference": {"samples_per_s": 2 * cores / cpu_s, "cores": cores,
                                             "what": "PIL Lanczos resize of the four images + lstsq XOLP per sample, one process per core"}}),
               flush=True)
