@@ -31,7 +31,8 @@ namespace polcue {
 namespace {
 
 constexpr int kLW = 128, kLossThreads = 256;
-constexpr int kFwdH = 32, kBwdH = 8;                         // tile heights: forward keeps two depth tiles, backward also six adjoint fields
+constexpr int kFwdH = 32, kBwdH = 14;                        // tile heights: forward keeps two depth tiles, backward also six adjoint fields;
+                                                             // 14 + 2 ring rows = 16 rows x 32 pixel groups = two full rounds of 256 threads in phase 1
 constexpr int kHalo = 2;
 constexpr int kLBoxW = kLW + 8;                              // interior at column 4, row 2
 constexpr int kLCol = 4, kLRow = kHalo;
