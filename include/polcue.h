@@ -240,6 +240,21 @@ POLCUE_API int polcue_normals_loss_bwd_f32(const float* depth_gt, const float* d
                                 int B, int H, int W, const double* sums2, const float* grad_out, float* grad_pred,
                                 polcue_stream_t stream);
 
+/* The whole supervised block of Trainer.compute_losses for one scale (manydepth/trainer.py:1240-1251):
+ *     mask = (gt >= min_d).float() * (gt <= max_d).float()
+ *     supervised_depth_loss   = (|gt - pred| * mask).sum() / mask.sum()
+ *     supervised_normals_loss = compute_supervised_normals_losses(gt, pred, K, mask)          (:1298-1309)
+ * in the same forward kernel (the mask is derived from the staged GT tile, no mask tensor is read) and the same backward
+ * kernel.  sums3 = {sum (2 - cos) m, sum m, sum |gt - pred| m} (device doubles); losses2 = {normals loss, depth loss} or
+ * NULL.  Backward: grad_pred = grad_normals * d(normals loss) + grad_depth * sign(pred - gt) m / sum m (device scalars).
+ * workspace: polcue_normals_loss_workspace_bytes(). */
+POLCUE_API int polcue_supervised_losses_fwd_f32(const float* depth_gt, const float* depth_pred, const float* K, float min_d, float max_d,
+                                     int B, int H, int W, void* workspace, double* sums3, float* losses2,
+                                     polcue_stream_t stream);
+POLCUE_API int polcue_supervised_losses_bwd_f32(const float* depth_gt, const float* depth_pred, const float* K, float min_d, float max_d,
+                                     int B, int H, int W, const double* sums3, const float* grad_normals,
+                                     const float* grad_depth, float* grad_pred, polcue_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Depth error metrics.
  *   manydepth/layers.py:539-557 compute_depth_errors / :559-577 compute_depth_errors_numpy

@@ -48,15 +48,18 @@ struct LossParams {
     const float* gt;
     const float* pred;
     const float* K;
-    const float* mask;
+    const float* mask;     // may be null when range_mask: mask = (min_d <= gt <= max_d), trainer.py:1241-1242
+    int range_mask;
+    float min_d, max_d;
     int H, W;
     // forward
     unsigned long long* ticket;
-    double* partials;      // [ctas][2]
-    double* sums2;         // S = sum (2 - cos) m, M = sum m
+    double* partials;      // [ctas][3]
+    double* sums2;         // S = sum (2 - cos) m, M = sum m (and, with the L1 term, [2] = sum |gt - pred| m)
     float* loss;           // S / M
     // backward
     const float* grad_out; // device scalar
+    const float* grad_l1;  // device scalar: upstream gradient of the supervised depth loss (L1 variant), may be null
     float* grad_pred;
 };
 
@@ -248,13 +251,22 @@ __device__ __forceinline__ void adjoint_px(const float (&ug)[3], const float (&v
     gvb[2] = nb[0] * up[1] - nb[1] * up[0];
 }
 
-template <bool TMA>
+// mask of one pixel: the caller's float mask, or the supervised range test on the GT depth (trainer.py:1241-1242)
+template <bool RANGE>   // RANGE is what the supervised (L1) entry points use; the plain ones read the caller's mask
+__device__ __forceinline__ float mask_value(const LossParams& p, size_t idx, float gt_depth) {
+    if constexpr (RANGE) return (gt_depth >= p.min_d && gt_depth <= p.max_d) ? 1.0f : 0.0f;
+    else return __ldg(p.mask + idx);
+}
+
+// L1 = true adds the supervised depth loss of the same block of the trainer (trainer.py:1246):
+//     supervised_depth_loss = (|gt - pred| * mask).sum() / mask.sum()
+template <bool TMA, bool L1>
 __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const __grid_constant__ CUtensorMap tm_gt,
                                                                         const __grid_constant__ CUtensorMap tm_pred, const LossParams p) {
     __shared__ __align__(128) float tg[box_rows(kFwdH)][kLBoxW];
     __shared__ __align__(128) float tp[box_rows(kFwdH)][kLBoxW];
     __shared__ uint64_t bar;
-    __shared__ double red[kLossThreads / 32][2];
+    __shared__ double red[kLossThreads / 32][3];
     __shared__ bool last;
     const int b = blockIdx.z, x0 = blockIdx.x * kLW, y0 = blockIdx.y * kFwdH;
     const size_t hw = (size_t)p.H * p.W;
@@ -273,7 +285,7 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const
         __syncthreads();
     }
     const Cam cam = load_cam(p.K, b);
-    float s = 0.0f, m = 0.0f;          // at most 16 pixels per thread: float32 partials, float64 from the warp level on
+    float s = 0.0f, m = 0.0f, l1 = 0.0f;   // at most 16 pixels per thread: float32 partials, float64 from the warp level on
     for (int i = threadIdx.x; i < (kLW / 4) * kFwdH; i += kLossThreads) {
         const int ty = i / (kLW / 4), tx0 = 4 * (i - ty * (kLW / 4));
         const int x = x0 + tx0, y = y0 + ty;
@@ -297,11 +309,13 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const
             normalize3(n, un);
             b4[0][j] = un[0]; b4[1][j] = un[1]; b4[2][j] = un[2];
         }
-        float fs = 0.0f, fm = 0.0f;
+        float fs = 0.0f, fm = 0.0f, fl = 0.0f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (x + j < p.W) {
-                const float mk = __ldg(p.mask + b * hw + (size_t)y * p.W + x + j);
+                const float zg = tg[kLRow + ty][kLCol + tx0 + j];
+                const float mk = mask_value<L1>(p, b * hw + (size_t)y * p.W + x + j, zg);
+                if constexpr (L1) fl = fmaf(fabsf(zg - tp[kLRow + ty][kLCol + tx0 + j]), mk, fl);
                 const float a[3] = {a4[0][j], a4[1][j], a4[2][j]}, bb3[3] = {b4[0][j], b4[1][j], b4[2][j]};
                 float inv_den, ab, bb;
                 bool clamped;
@@ -312,66 +326,80 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const
         }
         s += fs;
         m += fm;
+        l1 += fl;
     }
     // deterministic reduction: warp shuffle -> shared -> per-CTA partial -> last CTA folds in fixed order
-    double sd = s, md = m;
+    double sd = s, md = m, ld = l1;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         sd += __shfl_down_sync(0xffffffffu, sd, off);
         md += __shfl_down_sync(0xffffffffu, md, off);
+        if constexpr (L1) ld += __shfl_down_sync(0xffffffffu, ld, off);
     }
     if ((threadIdx.x & 31) == 0) {
         red[threadIdx.x >> 5][0] = sd;
         red[threadIdx.x >> 5][1] = md;
+        red[threadIdx.x >> 5][2] = ld;
     }
     __syncthreads();
     const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     const unsigned ctas = gridDim.x * gridDim.y * gridDim.z;
     if (threadIdx.x == 0) {
-        double ts = 0.0, tmk = 0.0;
+        double ts = 0.0, tmk = 0.0, tl = 0.0;
         for (int w = 0; w < kLossThreads / 32; ++w) {
             ts += red[w][0];
             tmk += red[w][1];
+            tl += red[w][2];
         }
-        p.partials[2 * (size_t)cta] = ts;
-        p.partials[2 * (size_t)cta + 1] = tmk;
+        p.partials[3 * (size_t)cta] = ts;
+        p.partials[3 * (size_t)cta + 1] = tmk;
+        p.partials[3 * (size_t)cta + 2] = tl;
         __threadfence();
         last = atomicAdd(p.ticket, 1ull) == ctas - 1;
     }
     __syncthreads();
     if (!last) return;
     __threadfence();
-    double fs = 0.0, fm = 0.0;
+    double fs = 0.0, fm = 0.0, fl1 = 0.0;
     for (unsigned j = threadIdx.x; j < ctas; j += kLossThreads) {
-        fs += __ldcg(p.partials + 2 * (size_t)j);
-        fm += __ldcg(p.partials + 2 * (size_t)j + 1);
+        fs += __ldcg(p.partials + 3 * (size_t)j);
+        fm += __ldcg(p.partials + 3 * (size_t)j + 1);
+        if constexpr (L1) fl1 += __ldcg(p.partials + 3 * (size_t)j + 2);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         fs += __shfl_down_sync(0xffffffffu, fs, off);
         fm += __shfl_down_sync(0xffffffffu, fm, off);
+        if constexpr (L1) fl1 += __shfl_down_sync(0xffffffffu, fl1, off);
     }
     __syncthreads();
     if ((threadIdx.x & 31) == 0) {
         red[threadIdx.x >> 5][0] = fs;
         red[threadIdx.x >> 5][1] = fm;
+        red[threadIdx.x >> 5][2] = fl1;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double ts = 0.0, tmk = 0.0;
+        double ts = 0.0, tmk = 0.0, tl = 0.0;
         for (int w = 0; w < kLossThreads / 32; ++w) {
             ts += red[w][0];
             tmk += red[w][1];
+            tl += red[w][2];
         }
         p.sums2[0] = ts;
         p.sums2[1] = tmk;
-        if (p.loss) *p.loss = (float)(ts / tmk);
+        if constexpr (L1) p.sums2[2] = tl;
+        if (p.loss) {
+            p.loss[0] = (float)(ts / tmk);
+            if constexpr (L1) p.loss[1] = (float)(tl / tmk);
+        }
         *p.ticket = 0ull;
     }
 }
 
-template <bool TMA>
-__global__ void __launch_bounds__(kLossThreads, 4) normals_loss_bwd_kernel(const __grid_constant__ CUtensorMap tm_gt,
+// 72 KB of shared memory per CTA: three CTAs per SM, so up to 85 registers per thread (no spills)
+template <bool TMA, bool L1>
+__global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_kernel(const __grid_constant__ CUtensorMap tm_gt,
                                                                         const __grid_constant__ CUtensorMap tm_pred, const LossParams p) {
     // dynamic shared memory: two halo'd depth tiles and the six adjoint fields of the tile + 1-pixel ring (46 KB)
     extern __shared__ __align__(128) unsigned char bwd_smem[];
@@ -397,6 +425,7 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_bwd_kernel(const
     }
     const Cam cam = load_cam(p.K, b);
     const float scale = -__ldg(p.grad_out) / (float)p.sums2[1];    // -grad_out / sum(mask)
+    const float l1_scale = (L1 && p.grad_l1) ? __ldg(p.grad_l1) / (float)p.sums2[1] : 0.0f;
 
     // phase 1: adjoint of the two gradients at every pixel of the tile and its 1-pixel ring.
     // Core columns go four pixels at a time (shared 3 x 6 windows), the two ring columns one pixel at a time.
@@ -415,7 +444,7 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_bwd_kernel(const
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (x + j < p.W) {
-                    const float k = scale * __ldg(p.mask + b * hw + (size_t)y * p.W + x + j);
+                    const float k = scale * mask_value<L1>(p, b * hw + (size_t)y * p.W + x + j, tg[kLRow + ty][kLCol + tx0 + j]);
                     const float ug[3] = {gug[0][j], gug[1][j], gug[2][j]}, vg[3] = {gvg[0][j], gvg[1][j], gvg[2][j]};
                     const float up[3] = {gup[0][j], gup[1][j], gup[2][j]}, vp[3] = {gvp[0][j], gvp[1][j], gvp[2][j]};
                     float gub[3], gvb[3];
@@ -439,7 +468,7 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_bwd_kernel(const
         const int x = x0 + tx, y = y0 + ty;
         float gub[3] = {0.f, 0.f, 0.f}, gvb[3] = {0.f, 0.f, 0.f};
         if (x >= 0 && x < p.W && y >= 0 && y < p.H) {
-            const float k = scale * __ldg(p.mask + b * hw + (size_t)y * p.W + x);
+            const float k = scale * mask_value<L1>(p, b * hw + (size_t)y * p.W + x, tg[kLRow + ty][kLCol + tx]);
             float ug[3], vg[3], up[3], vp[3];
             gradients(tg, ty, tx, x, y, p.H, p.W, cam, ug, vg);
             gradients(tp, ty, tx, x, y, p.H, p.W, cam, up, vp);
@@ -498,6 +527,14 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_bwd_kernel(const
             }
             const float fxq = ((float)xj - cam.cx) * cam.inv_fx;
             res[j] = fmaf(fxq, A[0], fmaf(fyq, A[1], A[2]));
+            if constexpr (L1) {     // d/dpred of sum |gt - pred| m / sum m: sign(pred - gt) m / sum m (sign(0) = 0, as torch.abs)
+                if (xj < p.W) {
+                    const float zg = tg[kLRow + ty][kLCol + tx0 + j], zp = tp[kLRow + ty][kLCol + tx0 + j];
+                    const float mk = mask_value<L1>(p, b * hw + (size_t)y * p.W + xj, zg);
+                    const float sgn = (zp > zg) ? 1.0f : ((zp < zg) ? -1.0f : 0.0f);
+                    res[j] = fmaf(l1_scale * mk, sgn, res[j]);
+                }
+            }
         }
         float* o = p.grad_pred + b * hw + (size_t)y * p.W + x;
         if (x + 3 < p.W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
@@ -558,14 +595,15 @@ using namespace polcue;
 
 extern "C" {
 
-size_t polcue_normals_loss_workspace_bytes(void) { return 64 + (size_t)kMaxLossBlocks * 2 * sizeof(double); }
+size_t polcue_normals_loss_workspace_bytes(void) { return 64 + (size_t)kMaxLossBlocks * 3 * sizeof(double); }
 
-int polcue_normals_loss_fwd_f32(const float* depth_gt, const float* depth_pred, const float* K, const float* mask, int B, int H,
-                                int W, void* workspace, double* sums2, float* loss, polcue_stream_t stream) {
+static int loss_forward(const float* depth_gt, const float* depth_pred, const float* K, const float* mask, bool range_mask, float min_d,
+                        float max_d, bool with_l1, int B, int H, int W, void* workspace, double* sums, float* loss,
+                        polcue_stream_t stream) {
     dim3 grid;
-    const int rc = check_common(depth_gt, depth_pred, K, mask, B, H, W, kFwdH, true, grid);
+    const int rc = check_common(depth_gt, depth_pred, K, range_mask ? depth_gt : mask, B, H, W, kFwdH, true, grid);
     if (rc != POLCUE_OK) return rc;
-    if (!workspace || !sums2 || (reinterpret_cast<uintptr_t>(workspace) & 63) || (reinterpret_cast<uintptr_t>(sums2) & 7))
+    if (!workspace || !sums || (reinterpret_cast<uintptr_t>(workspace) & 63) || (reinterpret_cast<uintptr_t>(sums) & 7))
         return POLCUE_EINVAL;
     if (B == 0) return POLCUE_EINVAL;   // the loss of an empty batch is 0/0; let the caller decide
     LossParams p{};
@@ -573,46 +611,82 @@ int polcue_normals_loss_fwd_f32(const float* depth_gt, const float* depth_pred, 
     p.pred = depth_pred;
     p.K = K;
     p.mask = mask;
+    p.range_mask = range_mask ? 1 : 0;
+    p.min_d = min_d;
+    p.max_d = max_d;
     p.H = H;
     p.W = W;
     p.ticket = static_cast<unsigned long long*>(workspace);
     p.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 64);
-    p.sums2 = sums2;
+    p.sums2 = sums;
     p.loss = loss;
     CUtensorMap mg, mp;
     cudaStream_t s = (cudaStream_t)stream;
-    if (make_map(&mg, depth_gt, B, H, W, kFwdH) && make_map(&mp, depth_pred, B, H, W, kFwdH))
-        normals_loss_fwd_kernel<true><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
-    else
-        normals_loss_fwd_kernel<false><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
+    const bool tma = make_map(&mg, depth_gt, B, H, W, kFwdH) && make_map(&mp, depth_pred, B, H, W, kFwdH);
+    if (with_l1) {
+        if (tma) normals_loss_fwd_kernel<true, true><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
+        else normals_loss_fwd_kernel<false, true><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
+    } else {
+        if (tma) normals_loss_fwd_kernel<true, false><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
+        else normals_loss_fwd_kernel<false, false><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
+    }
     return launch_status();
 }
 
-int polcue_normals_loss_bwd_f32(const float* depth_gt, const float* depth_pred, const float* K, const float* mask, int B, int H,
-                                int W, const double* sums2, const float* grad_out, float* grad_pred, polcue_stream_t stream) {
+static int loss_backward(const float* depth_gt, const float* depth_pred, const float* K, const float* mask, bool range_mask, float min_d,
+                         float max_d, bool with_l1, int B, int H, int W, const double* sums, const float* grad_out,
+                         const float* grad_l1, float* grad_pred, polcue_stream_t stream) {
     dim3 grid;
-    const int rc = check_common(depth_gt, depth_pred, K, mask, B, H, W, kBwdH, false, grid);
+    const int rc = check_common(depth_gt, depth_pred, K, range_mask ? depth_gt : mask, B, H, W, kBwdH, false, grid);
     if (rc != POLCUE_OK) return rc;
-    if (!sums2 || !grad_out || !grad_pred || (reinterpret_cast<uintptr_t>(grad_pred) & 3)) return POLCUE_EINVAL;
+    if (!sums || !grad_out || !grad_pred || (reinterpret_cast<uintptr_t>(grad_pred) & 3)) return POLCUE_EINVAL;
     if (B == 0) return POLCUE_OK;
     LossParams p{};
     p.gt = depth_gt;
     p.pred = depth_pred;
     p.K = K;
     p.mask = mask;
+    p.range_mask = range_mask ? 1 : 0;
+    p.min_d = min_d;
+    p.max_d = max_d;
     p.H = H;
     p.W = W;
-    p.sums2 = const_cast<double*>(sums2);
+    p.sums2 = const_cast<double*>(sums);
     p.grad_out = grad_out;
+    p.grad_l1 = grad_l1;
     p.grad_pred = grad_pred;
     CUtensorMap mg, mp;
     cudaStream_t s = (cudaStream_t)stream;
     const bool tma = make_map(&mg, depth_gt, B, H, W, kBwdH) && make_map(&mp, depth_pred, B, H, W, kBwdH);
-    auto kern = tma ? normals_loss_bwd_kernel<true> : normals_loss_bwd_kernel<false>;
+    auto kern = with_l1 ? (tma ? normals_loss_bwd_kernel<true, true> : normals_loss_bwd_kernel<false, true>)
+                        : (tma ? normals_loss_bwd_kernel<true, false> : normals_loss_bwd_kernel<false, false>);
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
     if (e != cudaSuccess) return (int)e;
     kern<<<grid, kLossThreads, kBwdSmem, s>>>(mg, mp, p);
     return launch_status();
+}
+
+int polcue_normals_loss_fwd_f32(const float* depth_gt, const float* depth_pred, const float* K, const float* mask, int B, int H,
+                                int W, void* workspace, double* sums2, float* loss, polcue_stream_t stream) {
+    return loss_forward(depth_gt, depth_pred, K, mask, false, 0.0f, 0.0f, false, B, H, W, workspace, sums2, loss, stream);
+}
+
+int polcue_normals_loss_bwd_f32(const float* depth_gt, const float* depth_pred, const float* K, const float* mask, int B, int H,
+                                int W, const double* sums2, const float* grad_out, float* grad_pred, polcue_stream_t stream) {
+    return loss_backward(depth_gt, depth_pred, K, mask, false, 0.0f, 0.0f, false, B, H, W, sums2, grad_out, nullptr, grad_pred, stream);
+}
+
+int polcue_supervised_losses_fwd_f32(const float* depth_gt, const float* depth_pred, const float* K, float min_d, float max_d, int B,
+                                     int H, int W, void* workspace, double* sums3, float* losses2, polcue_stream_t stream) {
+    return loss_forward(depth_gt, depth_pred, K, nullptr, true, min_d, max_d, true, B, H, W, workspace, sums3, losses2, stream);
+}
+
+int polcue_supervised_losses_bwd_f32(const float* depth_gt, const float* depth_pred, const float* K, float min_d, float max_d, int B,
+                                     int H, int W, const double* sums3, const float* grad_normals, const float* grad_depth,
+                                     float* grad_pred, polcue_stream_t stream) {
+    if (!grad_depth) return POLCUE_EINVAL;
+    return loss_backward(depth_gt, depth_pred, K, nullptr, true, min_d, max_d, true, B, H, W, sums3, grad_normals, grad_depth, grad_pred,
+                         stream);
 }
 
 }  // extern "C"

@@ -69,6 +69,9 @@ _SIGNATURES = {
     "polcue_normals_loss_workspace_bytes": (C.c_size_t, []),
     "polcue_normals_loss_fwd_f32": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _vp, _f64p, _f32p, _vp]),
     "polcue_normals_loss_bwd_f32": (C.c_int, [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f64p, _f32p, _f32p, _vp]),
+    "polcue_supervised_losses_fwd_f32": (C.c_int, [_f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, _vp, _f64p, _f32p, _vp]),
+    "polcue_supervised_losses_bwd_f32": (C.c_int, [_f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, _f64p, _f32p, _f32p,
+                                                  _f32p, _vp]),
     "polcue_depth_errors_workspace_bytes": (C.c_size_t, []),
     "polcue_depth_errors_f32": (C.c_int, [_f32p, _f32p, C.c_size_t, _vp, _f64p, _f32p, _vp]),
     "polcue_depth_errors_images_f32": (C.c_int, [_f32p, _f32p, _u8p, C.c_int, C.c_size_t, C.c_float, C.c_float, C.c_int,

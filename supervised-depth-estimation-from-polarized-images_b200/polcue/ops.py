@@ -705,6 +705,56 @@ class _NormalsLoss(torch.autograd.Function):
         return None, grad_pred, None, None
 
 
+class _SupervisedLosses(torch.autograd.Function):
+    """(depth L1 loss, normals loss) of trainer.py:1240-1251 with mask = (min <= gt <= max); gradients flow to depth_pred."""
+
+    @staticmethod
+    def forward(ctx, depth_gt, depth_pred, camera_matrix, min_depth, max_depth):
+        b, _, h, w = depth_pred.shape
+        sums = torch.empty(3, dtype=torch.float64, device=depth_pred.device)
+        losses = torch.empty(2, dtype=torch.float32, device=depth_pred.device)
+        with torch.cuda.device(depth_pred.device):
+            _lib.check(_lib.lib().polcue_supervised_losses_fwd_f32(_ptr(depth_gt), _ptr(depth_pred), _ptr(camera_matrix), min_depth,
+                                                                   max_depth, b, h, w, _ptr(_loss_workspace(depth_pred.device)),
+                                                                   _ptr(sums), _ptr(losses), _stream(depth_pred)),
+                       "polcue_supervised_losses_fwd_f32")
+        ctx.save_for_backward(depth_gt, depth_pred, camera_matrix, sums)
+        ctx.range = (min_depth, max_depth)
+        return losses[1], losses[0]          # (supervised_depth_loss, supervised_normals_loss)
+
+    @staticmethod
+    def backward(ctx, grad_depth, grad_normals):
+        depth_gt, depth_pred, camera_matrix, sums = ctx.saved_tensors
+        b, _, h, w = depth_pred.shape
+        zero = torch.zeros((), dtype=torch.float32, device=depth_pred.device)
+        grad_depth = zero if grad_depth is None else grad_depth.to(torch.float32).contiguous()
+        grad_normals = zero if grad_normals is None else grad_normals.to(torch.float32).contiguous()
+        grad_pred = torch.empty_like(depth_pred)
+        with torch.cuda.device(depth_pred.device):
+            _lib.check(_lib.lib().polcue_supervised_losses_bwd_f32(_ptr(depth_gt), _ptr(depth_pred), _ptr(camera_matrix), ctx.range[0],
+                                                                   ctx.range[1], b, h, w, _ptr(sums), _ptr(grad_normals),
+                                                                   _ptr(grad_depth), _ptr(grad_pred), _stream(depth_pred)),
+                       "polcue_supervised_losses_bwd_f32")
+        return None, grad_pred, None, None, None
+
+
+def supervised_losses(depth_gt, depth_pred, camera_matrix, min_depth, max_depth):
+    """The supervised block of Trainer.compute_losses (manydepth/trainer.py:1240-1251) for one scale in one forward and
+    one backward kernel:
+        mask = (gt >= min_depth).float() * (gt <= max_depth).float()
+        supervised_depth_loss   = (|gt - pred| * mask).sum() / mask.sum()
+        supervised_normals_loss = compute_supervised_normals_losses(gt, pred, K, mask)
+    Returns (supervised_depth_loss, supervised_normals_loss), zero-dim float32, differentiable w.r.t. depth_pred."""
+    depth_gt = _need_cuda(depth_gt, "depth_gt").detach().float().contiguous()
+    depth_pred = _need_cuda(depth_pred, "depth_pred").float().contiguous()
+    camera_matrix = _need_cuda(camera_matrix, "camera_matrix").detach().float().contiguous()
+    if depth_pred.dim() != 4 or depth_pred.shape[1] != 1 or depth_gt.shape != depth_pred.shape:
+        raise ValueError("depth_gt and depth_pred must share one B x 1 x H x W shape")
+    if camera_matrix.shape != (depth_pred.shape[0], 3, 3):
+        raise ValueError("camera_matrix must be B x 3 x 3")
+    return _SupervisedLosses.apply(depth_gt, depth_pred, camera_matrix, float(min_depth), float(max_depth))
+
+
 def normals_loss(depth_gt, depth_pred, camera_matrix, mask):
     """Trainer.compute_supervised_normals_losses (manydepth/trainer.py:1298-1309): zero-dim float32 loss, differentiable
     w.r.t. depth_pred.  depth_gt / depth_pred / mask: B x 1 x H x W, camera_matrix: B x 3 x 3 (CUDA)."""

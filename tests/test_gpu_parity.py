@@ -538,6 +538,49 @@ def test_normals_loss_forward_and_backward_vs_autograd_oracle(shape):
     assert np.sqrt((err ** 2).mean()) < 2e-4 * scale
 
 
+@pytest.mark.parametrize("shape", [(320, 480), (37, 131), (16, 128), (2, 5)])
+def test_supervised_depth_and_normals_losses_fused(shape):
+    """trainer.py:1240-1251 for one scale: mask from the GT range, masked L1 depth loss and the normals loss, both with
+    gradients, against float64 torch autograd; and the normals part bit-identical to the stand-alone kernels."""
+    from polcue.compat import trainer as c_tr
+    gt, pred, _, k = _loss_case(shape)
+    gt = gt.copy()
+    gt[:, : max(1, shape[0] // 8)] += 1.2                             # beyond max_depth: outside the range mask
+    lo, hi = 0.1, 1.6
+    t64 = lambda a: torch.from_numpy(a.astype(np.float64))
+    g64, p64 = t64(gt)[:, None], t64(pred)[:, None].requires_grad_(True)
+    m64 = (g64 >= lo).double() * (g64 <= hi).double()
+    ref_depth = ((g64 - p64).abs() * m64).sum() / m64.sum()
+    ref_normals = O.normals_loss_torch(g64, p64, t64(k), m64)
+    (0.7 * ref_depth + 1.3 * ref_normals).backward()
+    ref_grad = p64.grad[:, 0].numpy()
+
+    k44 = torch.eye(4).repeat(gt.shape[0], 1, 1)
+    k44[:, :3, :3] = torch.from_numpy(k)
+    d_pred = dev(pred)[:, None].requires_grad_(True)
+    depth_loss, normals_loss = c_tr.compute_supervised_losses(dev(gt)[:, None], d_pred, k44.cuda(), lo, hi)
+    assert abs(float(depth_loss.detach()) - float(ref_depth.detach())) < 2e-6 * max(1.0, abs(float(ref_depth.detach())))
+    assert abs(float(normals_loss.detach()) - float(ref_normals.detach())) < 2e-5 * max(1.0, abs(float(ref_normals.detach())))
+    (0.7 * depth_loss + 1.3 * normals_loss).backward()
+    got = d_pred.grad[:, 0].cpu().numpy()
+    scale = np.abs(ref_grad).max() + 1e-30
+    err = np.abs(got - ref_grad)
+    assert err.max() < 2e-3 * scale and np.sqrt((err ** 2).mean()) < 2e-4 * scale, (err.max(), scale)
+    # the normals half equals the stand-alone kernels given the same mask, bit for bit; the L1 gradient is exact
+    mask = ((dev(gt) >= lo).float() * (dev(gt) <= hi).float())[:, None]
+    d2 = dev(pred)[:, None].requires_grad_(True)
+    alone = ops.normals_loss(dev(gt)[:, None], d2, dev(k), mask)
+    assert torch.equal(alone.detach(), normals_loss.detach())
+    alone.backward()
+    d3 = dev(pred)[:, None].requires_grad_(True)
+    ops.supervised_losses(dev(gt)[:, None], d3, dev(k), lo, hi)[1].backward()
+    assert torch.equal(d3.grad, d2.grad)
+    d4 = dev(pred)[:, None].requires_grad_(True)
+    ops.supervised_losses(dev(gt)[:, None], d4, dev(k), lo, hi)[0].backward()
+    expect = torch.sign(d4.detach() - dev(gt)[:, None]) * mask / mask.sum()
+    assert torch.allclose(d4.grad, expect, rtol=1e-6, atol=0)
+
+
 def test_normals_loss_matches_composition_of_public_ops_and_is_deterministic():
     gt, pred, mask, k = _loss_case((64, 96))
     args = (dev(gt)[:, None], dev(pred)[:, None], dev(k), dev(mask)[:, None])
