@@ -452,17 +452,19 @@ __device__ __forceinline__ void run_add(Run& r, const Contrib& c, bool on) {
     r.c2 += on ? c.c2 : 0;
     r.c3 += on ? c.c3 : 0;
 }
-// table layout: [slot][8][kMetricThreads] floats; counts are exact in float32 below 2^24 pixels per thread
+// table layout: [slot][kGroupRows][kMetricThreads] 32-bit words.  Rows 0-1 hold the four counts as 16-bit pairs
+// (n | c1 << 16, c2 | c3 << 16: a thread sees at most px / 2048 <= 65535 pixels, checked on the host), rows 2-5 the four
+// float sums: 6 words per thread and group instead of 8, which is what lets three CTAs instead of two share an SM.
+constexpr int kGroupRows = 6;
 __device__ __forceinline__ void run_flush(float* table, int slot, Run& r) {
-    float* col = table + (size_t)slot * 8 * kMetricThreads + threadIdx.x;
-    col[0 * kMetricThreads] += (float)r.n;
-    col[1 * kMetricThreads] += (float)r.c1;
-    col[2 * kMetricThreads] += (float)r.c2;
-    col[3 * kMetricThreads] += (float)r.c3;
-    col[4 * kMetricThreads] += r.f[0];
-    col[5 * kMetricThreads] += r.f[1];
-    col[6 * kMetricThreads] += r.f[2];
-    col[7 * kMetricThreads] += r.f[3];
+    float* col = table + (size_t)slot * kGroupRows * kMetricThreads + threadIdx.x;
+    unsigned* cnt = reinterpret_cast<unsigned*>(col);
+    cnt[0 * kMetricThreads] += (unsigned)r.n | ((unsigned)r.c1 << 16);
+    cnt[1 * kMetricThreads] += (unsigned)r.c2 | ((unsigned)r.c3 << 16);
+    col[2 * kMetricThreads] += r.f[0];
+    col[3 * kMetricThreads] += r.f[1];
+    col[4 * kMetricThreads] += r.f[2];
+    col[5 * kMetricThreads] += r.f[3];
     run_clear(r);
 }
 
@@ -482,7 +484,7 @@ struct GroupParams {
 
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThreads)
     depth_errors_groups_kernel(const __grid_constant__ GroupParams p) {
-    extern __shared__ __align__(16) float table[];          // [n_groups][8][kMetricThreads]
+    extern __shared__ __align__(16) float table[];          // [n_groups][kGroupRows][kMetricThreads], see run_flush
     __shared__ double cta_tot[16][8];
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned rank = cluster.block_rank();
@@ -490,7 +492,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     const float* gt = p.gt + b * p.px;
     const float* pred = p.pred + b * p.px;
     const uint8_t* inst = p.inst ? p.inst + b * p.px : nullptr;
-    for (int i = threadIdx.x; i < p.n_groups * 8 * kMetricThreads; i += kMetricThreads) table[i] = 0.0f;
+    for (int i = threadIdx.x; i < p.n_groups * kGroupRows * kMetricThreads; i += kMetricThreads) table[i] = 0.0f;   // 0.0f == 0u
     // (each thread only ever touches its own column, no barrier needed before use)
 
     Run all, mat;
@@ -544,18 +546,39 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     if (cur != 0xFF) run_flush(table, cur, mat);
     if (p.all_slot >= 0) run_flush(table, p.all_slot, all);
     __syncthreads();
-    // CTA fold over threads in a fixed order: a warp takes (slot, accumulator) pairs warp, warp + 8, ...; each lane adds its
-    // eight columns (bank-conflict free), then a fixed shuffle tree
+    // CTA fold over threads in a fixed order: a warp takes (slot, row) pairs warp, warp + 8, ...; each lane adds its
+    // eight columns (bank-conflict free), then a fixed shuffle tree.  Count rows are summed as exact integers.
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int pair = warp; pair < p.n_groups * 8; pair += kMetricThreads / 32) {
+        for (int pair = warp; pair < p.n_groups * kGroupRows; pair += kMetricThreads / 32) {
+            const int slot = pair / kGroupRows, row = pair - slot * kGroupRows;
             const float* col = table + (size_t)pair * kMetricThreads;
-            double v = 0.0;
+            if (row < 2) {
+                const unsigned* cnt = reinterpret_cast<const unsigned*>(col);
+                unsigned lo = 0, hi = 0;
 #pragma unroll
-            for (int j = 0; j < kMetricThreads / 32; ++j) v += (double)col[lane + 32 * j];
+                for (int j = 0; j < kMetricThreads / 32; ++j) {
+                    const unsigned w = cnt[lane + 32 * j];
+                    lo += w & 0xffffu;
+                    hi += w >> 16;
+                }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-            if (lane == 0) cta_tot[pair >> 3][pair & 7] = ((pair & 7) == 5) ? v * 0.4804530139182014 : v;   // ln(2)^2 on the log2 term
+                for (int off = 16; off > 0; off >>= 1) {
+                    lo += __shfl_down_sync(0xffffffffu, lo, off);
+                    hi += __shfl_down_sync(0xffffffffu, hi, off);
+                }
+                if (lane == 0) {
+                    cta_tot[slot][2 * row] = (double)lo;
+                    cta_tot[slot][2 * row + 1] = (double)hi;
+                }
+            } else {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < kMetricThreads / 32; ++j) v += (double)col[lane + 32 * j];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+                if (lane == 0) cta_tot[slot][row + 2] = (row == 3) ? v * 0.4804530139182014 : v;   // ln(2)^2 on the log2 term
+            }
         }
     }
     cluster.sync();
@@ -695,7 +718,8 @@ int polcue_depth_errors_groups_f32(const float* gt, const float* pred, const uin
     p.metrics = metrics;
     p.vec4 = (px % 4 == 0) && (((reinterpret_cast<uintptr_t>(gt) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(inst) & 3) == 0);
-    const size_t smem = (size_t)n_groups * 8 * kMetricThreads * sizeof(float);
+    if (px / ((size_t)kCluster * kMetricThreads) + 8 > 65535) return POLCUE_E2BIG;   // 16-bit per-thread counts (run_flush)
+    const size_t smem = (size_t)n_groups * kGroupRows * kMetricThreads * sizeof(float);
     const cudaError_t e = cudaFuncSetAttribute(depth_errors_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     depth_errors_groups_kernel<<<dim3(kCluster, B, 1), kMetricThreads, smem, (cudaStream_t)stream>>>(p);
