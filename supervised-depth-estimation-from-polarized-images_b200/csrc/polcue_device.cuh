@@ -308,6 +308,103 @@ __device__ __forceinline__ Cues cues_from_u8(float i0, float i45, float i90, flo
     return q;
 }
 
+// ------------------------------------------------------------------------------------------
+// Packed FP32 (Blackwell FFMA2 / FADD2 / FMUL2): two pixels per instruction.  tools/probes/int_pipe_probe.cu measures
+// FFMA2 at the scalar FFMA FLOP rate in half the issue slots (60.7 packed instructions/clk/SM; immediates broadcast to
+// both lanes at no register cost).  Each lane runs exactly the operation sequence of cues_from_u8, so the results are
+// bit-identical to the scalar form.  Used by the fused kernel family (fused.cu: process_group).
+// ------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 dup2(float c) { return pk2(c, c); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 abs2(f32x2 a) { return a & 0x7FFFFFFF7FFFFFFFull; }
+
+// byte ka of word wa and byte kb of word wb as an exact float pair (see byte_to_float): two PRMT, one FADD2
+__device__ __forceinline__ f32x2 bytes_to_float2(uint32_t wa, int ka, uint32_t wb, int kb) {
+    const f32x2 raw = pk2(__uint_as_float(__byte_perm(wa, 0x4B000000u, 0x7650 + ka)), __uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7650 + kb)));
+    return add2(raw, dup2(-8388608.0f));
+}
+// bytes k and k + 1 of one packed word
+__device__ __forceinline__ f32x2 bytes_to_float2(uint32_t w, int k) { return bytes_to_float2(w, k, w, k + 1); }
+
+// cues_from_u8 for two pixels at once (lane 0 -> a, lane 1 -> b).
+template <bool kTrig = true>
+__device__ __forceinline__ void cues2_from_u8(f32x2 i0, f32x2 i45, f32x2 i90, f32x2 i135, Cues& a, Cues& b) {
+    const f32x2 s1 = sub2(i0, i90), s2 = sub2(i45, i135), sum = add2(add2(i0, i90), add2(i45, i135));
+    float q0, q1;
+    unpk2(fma2(s1, s1, mul2(s2, s2)), q0, q1);
+    const f32x2 amp = pk2(sqrt_approx(q0), sqrt_approx(q1));
+    float d0, d1;
+    unpk2(add2(sum, dup2(1e-30f)), d0, d1);
+    const f32x2 rho = mul2(mul2(dup2(2.0f), amp), pk2(rcp_approx(d0), rcp_approx(d1)));
+    const f32x2 as1 = abs2(s1), as2 = abs2(s2);
+    float e0, e1;
+    unpk2(add2(add2(amp, as1), dup2(1e-30f)), e0, e1);
+    const f32x2 u = mul2(as2, pk2(rcp_approx(e0), rcp_approx(e1)));
+    const f32x2 t = mul2(u, u);
+    f32x2 pl = dup2(0.004059889819473028f);
+    pl = fma2(pl, t, dup2(-0.020706569775938988f));
+    pl = fma2(pl, t, dup2(0.049855392426252365f));
+    pl = fma2(pl, t, dup2(-0.08074377477169037f));
+    pl = fma2(pl, t, dup2(0.10888639092445374f));
+    pl = fma2(pl, t, dup2(-0.142609104514122f));
+    pl = fma2(pl, t, dup2(0.19998927414417267f));
+    pl = fma2(pl, t, dup2(-0.33333325386047363f));
+    const f32x2 half = fma2(mul2(u, t), pl, u);
+    const f32x2 other = sub2(dup2(kHalfPi), half);
+    float s1a, s1b, s2a, s2b, ha, hb, oa, ob;
+    unpk2(s1, s1a, s1b);
+    unpk2(s2, s2a, s2b);
+    unpk2(half, ha, hb);
+    unpk2(other, oa, ob);
+    const bool fa = s1a < 0.0f, fb = s1b < 0.0f;
+    unpk2(mul2(dup2(0.25f), sum), a.iun, b.iun);
+    unpk2(rho, a.rho, b.rho);
+    a.phi = copysignf(fa ? oa : ha, s2a);
+    b.phi = copysignf(fb ? ob : hb, s2b);
+    if constexpr (kTrig) {
+        float t0, t1, u0, u1;
+        unpk2(add2(dup2(1.0f), t), t0, t1);
+        unpk2(u, u0, u1);
+        const f32x2 cq = pk2(rsqrt_approx(t0), rsqrt_approx(t1));
+        float ca, cb, sa, sb;
+        unpk2(cq, ca, cb);
+        unpk2(mul2(u, cq), sa, sb);
+        a.cos_phi = fa ? sa : ca;
+        a.sin_phi = copysignf(fa ? ca : sa, s2a);
+        b.cos_phi = fb ? sb : cb;
+        b.sin_phi = copysignf(fb ? cb : sb, s2b);
+        (void)u0; (void)u1;
+    } else {
+        a.cos_phi = a.sin_phi = b.cos_phi = b.sin_phi = 0.0f;
+    }
+}
+
 // Three normal candidates in the channel order of get_normals (pre_encoders.py:99-113):
 //   N_diff = (cos phi sin td, sin phi sin td, cos td)
 //   N_spec = (cos(phi+pi/2) sin ts, sin(phi+pi/2) sin ts, cos ts) = (-sin phi sin ts, cos phi sin ts, cos ts)
