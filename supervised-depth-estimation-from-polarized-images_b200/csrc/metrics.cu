@@ -224,7 +224,7 @@ struct ImageParams {
 
 // EXT = false: the plain loop (one material id, no scaling): this kernel is bound by instruction issue, so the extras
 // of the full evaluation loops (id range, batch-level clamp, median scaling) are compiled in only when asked for.
-template <bool EXT>
+template <bool EXT, bool INST = true>   // INST = false: no material filter at all (object == "all")
 __device__ __forceinline__ void acc_masked(Acc& a, const ImageParams& p, int want_id, float g, float q, int id, float scale) {
     // trainer.py:1380 mask, :1410-1411 material filter, :1413-1414 median scaling, :1417-1418 clamp of the prediction
     bool keep = (g > p.min_d) & (g < p.max_d);
@@ -232,7 +232,7 @@ __device__ __forceinline__ void acc_masked(Acc& a, const ImageParams& p, int wan
         keep &= (want_id < 0) | ((id >= want_id) & (id <= p.want_hi));
         if (p.clamp_first) q = fminf(fmaxf(q, p.min_d), p.max_d);
         q = __fmul_rn(q, scale);
-    } else {
+    } else if constexpr (INST) {
         keep &= (want_id < 0) | (id == want_id);
     }
     acc_add(a, keep ? g : 1.0f, keep ? fminf(fmaxf(q, p.min_d), p.max_d) : 1.0f);   // rejected -> the neutral pair (1, 1)
@@ -240,7 +240,7 @@ __device__ __forceinline__ void acc_masked(Acc& a, const ImageParams& p, int wan
     a.seen += 1;
 }
 
-template <bool EXT>
+template <bool EXT, bool INST>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThreads)
     depth_errors_images_kernel(const ImageParams p) {
     __shared__ double warp_rows[kMetricThreads / 32][8];
@@ -264,10 +264,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
             const float4 g = ld_stream_f32x4(gt + 4 * i), q = ld_stream_f32x4(pred + 4 * i);
             uint32_t ids = 0;
             if (inst) ids = ld_stream_u32(inst + 4 * i);
-            acc_masked<EXT>(a, p, want_id, g.x, q.x, ids & 0xff, scale);
-            acc_masked<EXT>(a, p, want_id, g.y, q.y, (ids >> 8) & 0xff, scale);
-            acc_masked<EXT>(a, p, want_id, g.z, q.z, (ids >> 16) & 0xff, scale);
-            acc_masked<EXT>(a, p, want_id, g.w, q.w, ids >> 24, scale);
+            acc_masked<EXT, INST>(a, p, want_id, g.x, q.x, ids & 0xff, scale);
+            acc_masked<EXT, INST>(a, p, want_id, g.y, q.y, (ids >> 8) & 0xff, scale);
+            acc_masked<EXT, INST>(a, p, want_id, g.z, q.z, (ids >> 16) & 0xff, scale);
+            acc_masked<EXT, INST>(a, p, want_id, g.w, q.w, ids >> 24, scale);
             if (++since == 16) {
                 flush(s, a);
                 since = 0;
@@ -275,7 +275,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
         }
     } else {
         for (size_t i = tid; i < p.px; i += stride) {
-            acc_masked<EXT>(a, p, want_id, gt[i], pred[i], inst ? inst[i] : 0, scale);
+            acc_masked<EXT, INST>(a, p, want_id, gt[i], pred[i], inst ? inst[i] : 0, scale);
             if (++since == 64) {
                 flush(s, a);
                 since = 0;
@@ -643,8 +643,10 @@ static int launch_images(const float* gt, const float* pred, const uint8_t* inst
     p.vec4 = (px % 4 == 0) && (((reinterpret_cast<uintptr_t>(gt) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(inst) & 3) == 0);
     const bool ext = pred_scale || clamp_first || (inst && p.want_hi != p.group_ids[0]);
-    if (ext) depth_errors_images_kernel<true><<<dim3(kCluster, B, 1), kMetricThreads, 0, (cudaStream_t)stream>>>(p);
-    else depth_errors_images_kernel<false><<<dim3(kCluster, B, 1), kMetricThreads, 0, (cudaStream_t)stream>>>(p);
+    const dim3 grid(kCluster, B, 1);
+    if (ext) depth_errors_images_kernel<true, true><<<grid, kMetricThreads, 0, (cudaStream_t)stream>>>(p);
+    else if (inst && p.group_ids[0] >= 0) depth_errors_images_kernel<false, true><<<grid, kMetricThreads, 0, (cudaStream_t)stream>>>(p);
+    else depth_errors_images_kernel<false, false><<<grid, kMetricThreads, 0, (cudaStream_t)stream>>>(p);
     return launch_status();
 }
 
