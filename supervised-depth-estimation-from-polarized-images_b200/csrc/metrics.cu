@@ -329,74 +329,112 @@ __device__ __forceinline__ float key_value(uint32_t k) {
 __global__ void __launch_bounds__(kMedianThreads) masked_median_kernel(const MedianParams p) {
     __shared__ unsigned hist[2048];
     __shared__ unsigned warp_tot[kMedianThreads / 32];
-    __shared__ unsigned sel_bin, sel_rank, total;
+    __shared__ unsigned sel_bin, sel_rank, total, next_key;
     const size_t b = blockIdx.y;
     const float* gt = p.gt + b * p.px;
     const float* key_src = (blockIdx.x == 0 ? p.gt : p.pred) + b * p.px;
     const uint8_t* inst = (p.inst && p.want_id >= 0) ? p.inst + b * p.px : nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float middle[2] = {0.0f, 0.0f};
-    unsigned n = 0;
-    for (int which = 0; which < 2; ++which) {             // lower and upper middle element
-        uint32_t prefix = 0;
-        unsigned rank = 0;
-        for (int pass = 0; pass < 3; ++pass) {
-            const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
-            const int bits = pass == 2 ? 10 : 11;
-            for (int i = threadIdx.x; i < 2048; i += kMedianThreads) hist[i] = 0;
-            __syncthreads();
-            for (size_t i = threadIdx.x; i < p.px; i += kMedianThreads) {
-                const float g = gt[i];
-                const bool keep = (g > p.min_d) & (g < p.max_d) & (!inst || ((int)inst[i] >= p.want_id) & ((int)inst[i] <= p.want_hi));
-                if (!keep) continue;
-                float v = key_src[i];
-                if (p.clamp_first && blockIdx.x == 1) v = fminf(fmaxf(v, p.min_d), p.max_d);
-                const uint32_t k = order_key(v);
-                if (pass > 0 && (k >> (shift + bits)) != prefix) continue;
-                atomicAdd(&hist[(k >> shift) & ((1u << bits) - 1)], 1u);
-            }
-            __syncthreads();
-            // exclusive scan over the 2048 bins (two per thread) to find the bin that holds `rank`
-            const unsigned h0 = hist[2 * threadIdx.x], h1 = hist[2 * threadIdx.x + 1];
-            unsigned incl = h0 + h1;
+    const bool clamp_key = p.clamp_first && blockIdx.x == 1;
+
+    // One sweep over the image: `visit(key)` for every pixel under the mask, `skip(lane-unique)` otherwise; every lane of a
+    // warp takes part in every call (warp-uniform trip count), four pixels' loads are in flight per thread.
+    auto sweep = [&](auto&& visit) {
+        constexpr int kBatch = 4;
+        for (size_t base = 0; base < p.px; base += (size_t)kBatch * kMedianThreads) {
+            float g[kBatch], v[kBatch];
+            int id[kBatch];
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= off) incl += v;
+            for (int j = 0; j < kBatch; ++j) {
+                const size_t i = base + (size_t)j * kMedianThreads + threadIdx.x;
+                g[j] = 0.0f;                    // outside [min_d, max_d]: never kept
+                v[j] = 0.0f;
+                id[j] = p.want_id;
+                if (i < p.px) {
+                    g[j] = gt[i];
+                    v[j] = key_src[i];
+                    if (inst) id[j] = inst[i];
+                }
             }
-            if (lane == 31) warp_tot[warp] = incl;
-            __syncthreads();
-            unsigned base = 0;
-            for (int w = 0; w < warp; ++w) base += warp_tot[w];
-            if (pass == 0 && which == 0 && threadIdx.x == kMedianThreads - 1) total = base + incl;
-            __syncthreads();
-            if (pass == 0) {
-                n = total;
-                if (n == 0) break;
-                rank = which == 0 ? (n - 1) / 2 : n / 2;
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+                const bool keep = (g[j] > p.min_d) & (g[j] < p.max_d) & (!inst || ((id[j] >= p.want_id) & (id[j] <= p.want_hi)));
+                const float val = clamp_key ? fminf(fmaxf(v[j], p.min_d), p.max_d) : v[j];
+                visit(keep, order_key(val));
             }
-            const unsigned before = base + incl - (h0 + h1);
-            if (rank >= before && rank < before + h0) {
-                sel_bin = 2 * threadIdx.x;
-                sel_rank = rank - before;
-            } else if (rank >= before + h0 && rank < before + h0 + h1) {
-                sel_bin = 2 * threadIdx.x + 1;
-                sel_rank = rank - before - h0;
-            }
-            __syncthreads();
-            prefix = (prefix << bits) | sel_bin;
-            rank = sel_rank;
-            __syncthreads();
         }
-        if (n == 0) break;
-        middle[which] = key_value(prefix);
-        if ((n & 1) && which == 0) {      // odd count: one middle element
-            middle[1] = middle[0];
-            break;
+    };
+
+    // lower middle element: three-pass radix select
+    uint32_t prefix = 0;
+    unsigned rank = 0, n = 0, dup = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+        const int bits = pass == 2 ? 10 : 11;
+        for (int i = threadIdx.x; i < 2048; i += kMedianThreads) hist[i] = 0;
+        __syncthreads();
+        // lanes that fall into the same bin are counted by ONE shared-memory atomic (the depths of an image share a
+        // handful of exponents: the first pass would otherwise serialise 32-fold)
+        sweep([&](bool keep, uint32_t k) {
+            if (pass > 0 && (k >> (shift + bits)) != prefix) keep = false;
+            const uint32_t bin = (k >> shift) & ((1u << bits) - 1);
+            const unsigned peers = __match_any_sync(0xffffffffu, keep ? bin : (0x80000000u | (unsigned)lane));
+            if (keep && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+        });
+        __syncthreads();
+        // exclusive scan over the 2048 bins (two per thread) to find the bin that holds `rank`
+        const unsigned h0 = hist[2 * threadIdx.x], h1 = hist[2 * threadIdx.x + 1];
+        unsigned incl = h0 + h1;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned before = incl - (h0 + h1);
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        if (pass == 0 && threadIdx.x == kMedianThreads - 1) total = before + h0 + h1;
+        __syncthreads();
+        if (pass == 0) {
+            n = total;
+            if (n == 0) break;
+            rank = (n - 1) / 2;
+        }
+        if (rank >= before && rank < before + h0) {
+            sel_bin = 2 * threadIdx.x;
+            sel_rank = rank - before;
+        } else if (rank >= before + h0 && rank < before + h0 + h1) {
+            sel_bin = 2 * threadIdx.x + 1;
+            sel_rank = rank - before - h0;
+        }
+        __syncthreads();
+        prefix = (prefix << bits) | sel_bin;
+        rank = sel_rank;
+        dup = hist[sel_bin];          // after the last pass: how many masked values equal the selected one
+        __syncthreads();
+    }
+    float lower = 0.0f, upper = 0.0f;
+    if (n) {
+        lower = upper = key_value(prefix);
+        // even count: the upper middle element is the next one in sorted order -- the same value if it occurs again
+        // beyond the selected rank, else the smallest masked value above it (one more sweep)
+        if (!(n & 1) && rank + 1 >= dup) {
+            if (threadIdx.x == 0) next_key = 0xFFFFFFFFu;
+            __syncthreads();
+            unsigned best = 0xFFFFFFFFu;
+            sweep([&](bool keep, uint32_t k) {
+                if (keep && k > prefix) best = min(best, k);
+            });
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+            if (lane == 0) atomicMin(&next_key, best);
+            __syncthreads();
+            upper = key_value(next_key);
         }
     }
     if (threadIdx.x == 0)
-        p.medians[b * 2 + blockIdx.x] = n ? __fmul_rn(__fadd_rn(middle[0], middle[1]), 0.5f) : __int_as_float(0x7fc00000);
+        p.medians[b * 2 + blockIdx.x] = n ? __fmul_rn(__fadd_rn(lower, upper), 0.5f) : __int_as_float(0x7fc00000);
 }
 
 __global__ void median_ratio_kernel(const float* medians, int B, float* scale) {
