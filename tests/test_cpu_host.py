@@ -253,6 +253,37 @@ def test_install_patches_the_imported_reference_modules():
     assert "PATCHED" in out.stdout and int(out.stdout.split()[-1]) >= 10, out.stderr[-1500:]
 
 
+def test_install_patches_the_trainer_and_evaluation_classes():
+    """manydepth.trainer / manydepth.evaluation cannot be imported here (kornia, skimage ... are absent), so stand-in
+    modules with the reference's class and method names check the patch list of `install()`."""
+    import types
+    import polcue.compat as c
+    from polcue.compat import trainer as c_tr
+    fakes = {}
+    for mod_name, cls_name, methods in (("manydepth.trainer", "Trainer", ("compute_supervised_normals_losses", "compute_depth_losses_from_list")),
+                                        ("manydepth.evaluation", "Evaluation", ("compute_depth_losses_from_list",))):
+        mod = types.ModuleType(mod_name)
+        cls = type(cls_name, (), {m: (lambda self, *a, **k: "reference") for m in methods})
+        setattr(mod, cls_name, cls)
+        mod.compute_depth_errors = lambda gt, pred: "reference"
+        fakes[mod_name] = mod
+    saved = {k: sys.modules.get(k) for k in fakes}
+    sys.modules.update(fakes)
+    try:
+        done = c.install()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    assert "manydepth.trainer.Trainer.compute_depth_losses_from_list" in done
+    assert "manydepth.evaluation.Evaluation.compute_depth_losses_from_list" in done
+    assert "manydepth.trainer.Trainer.compute_supervised_normals_losses" in done and "manydepth.trainer.compute_depth_errors" in done
+    assert fakes["manydepth.trainer"].Trainer.compute_depth_losses_from_list is c_tr.compute_depth_losses_from_list
+    assert fakes["manydepth.evaluation"].Evaluation.compute_depth_losses_from_list is c_tr.compute_depth_losses_from_list
+
+
 def test_synthetic_generators_are_seeded_per_frame():
     from polcue import synth
     a = synth.gen_batch("P", 3, 2, 32, 48)
