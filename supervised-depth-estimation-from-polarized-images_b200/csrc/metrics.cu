@@ -337,8 +337,7 @@ __global__ void __launch_bounds__(kMedianThreads) masked_median_kernel(const Med
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool clamp_key = p.clamp_first && blockIdx.x == 1;
 
-    // One sweep over the image: `visit(key)` for every pixel under the mask, `skip(lane-unique)` otherwise; every lane of a
-    // warp takes part in every call (warp-uniform trip count), four pixels' loads are in flight per thread.
+    // One sweep over the image: `visit(keep, key)` for every pixel; four pixels' loads are in flight per thread.
     auto sweep = [&](auto&& visit) {
         constexpr int kBatch = 4;
         for (size_t base = 0; base < p.px; base += (size_t)kBatch * kMedianThreads) {
@@ -373,14 +372,23 @@ __global__ void __launch_bounds__(kMedianThreads) masked_median_kernel(const Med
         const int bits = pass == 2 ? 10 : 11;
         for (int i = threadIdx.x; i < 2048; i += kMedianThreads) hist[i] = 0;
         __syncthreads();
-        // lanes that fall into the same bin are counted by ONE shared-memory atomic (the depths of an image share a
-        // handful of exponents: the first pass would otherwise serialise 32-fold)
+        // a thread counts runs of the same bin in a register and issues one shared-memory atomic per run (the depths of
+        // an image share a handful of exponents: the first pass would otherwise hammer a few addresses)
+        uint32_t run_bin = 0xFFFFFFFFu;
+        unsigned run_len = 0;
         sweep([&](bool keep, uint32_t k) {
             if (pass > 0 && (k >> (shift + bits)) != prefix) keep = false;
+            if (!keep) return;
             const uint32_t bin = (k >> shift) & ((1u << bits) - 1);
-            const unsigned peers = __match_any_sync(0xffffffffu, keep ? bin : (0x80000000u | (unsigned)lane));
-            if (keep && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+            if (bin == run_bin) {
+                ++run_len;
+            } else {
+                if (run_len) atomicAdd(&hist[run_bin], run_len);
+                run_bin = bin;
+                run_len = 1;
+            }
         });
+        if (run_len) atomicAdd(&hist[run_bin], run_len);
         __syncthreads();
         // exclusive scan over the 2048 bins (two per thread) to find the bin that holds `rank`
         const unsigned h0 = hist[2 * threadIdx.x], h1 = hist[2 * threadIdx.x + 1];
