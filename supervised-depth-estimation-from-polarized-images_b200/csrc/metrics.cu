@@ -528,6 +528,7 @@ struct GroupParams {
     bool vec4;
 };
 
+template <bool ALL>   // ALL: the "all" group (range mask only) is among the requested groups
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThreads)
     depth_errors_groups_kernel(const __grid_constant__ GroupParams p) {
     extern __shared__ __align__(16) float table[];          // [n_groups][kGroupRows][kMetricThreads], see run_flush
@@ -541,20 +542,23 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     for (int i = threadIdx.x; i < p.n_groups * kGroupRows * kMetricThreads; i += kMetricThreads) table[i] = 0.0f;   // 0.0f == 0u
     // (each thread only ever touches its own column, no barrier needed before use)
 
-    Run all, mat;
-    run_clear(all);
+    // Every pixel is routed to exactly ONE slot: its material's, or -- when "all" is requested -- the slot of "all", which
+    // collects the pixels of no requested material; "all" itself is the sum of every slot, formed after the cluster fold.
+    // (One accumulate per pixel instead of two.)
+    Run mat;
     run_clear(mat);
     int cur = 0xFF;
+    const int other = ALL ? p.all_slot : 0xFF;
     auto pixel = [&](float g, float q, int id) {
         const bool keep = (g > p.min_d) & (g < p.max_d);
         const Contrib c = make_contrib(g, fminf(fmaxf(q, p.min_d), p.max_d), keep);
-        run_add(all, c, true);
-        const int slot = inst ? p.slot_of[id] : 0xFF;
+        int slot = inst ? p.slot_of[id] : 0xFF;
+        slot = (slot == 0xFF) ? other : slot;
         if (slot != cur) {                                   // the material under this thread's pixels changed
             if (cur != 0xFF) run_flush(table, cur, mat);
             cur = slot;
         }
-        run_add(mat, c, slot != 0xFF);
+        run_add(mat, c, ALL ? true : slot != 0xFF);
     };
     const size_t tid = (size_t)rank * kMetricThreads + threadIdx.x, stride = (size_t)kCluster * kMetricThreads;
     if (p.vec4) {
@@ -590,7 +594,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
         for (size_t i = tid; i < p.px; i += stride) pixel(gt[i], pred[i], inst ? inst[i] : 0);
     }
     if (cur != 0xFF) run_flush(table, cur, mat);
-    if (p.all_slot >= 0) run_flush(table, p.all_slot, all);
     __syncthreads();
     // CTA fold over threads in a fixed order: a warp takes (slot, row) pairs warp, warp + 8, ...; each lane adds its
     // eight columns (bank-conflict free), then a fixed shuffle tree.  Count rows are summed as exact integers.
@@ -632,8 +635,19 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
         const int slot = threadIdx.x >> 3, k = threadIdx.x & 7;
         double v = 0.0;
         for (unsigned r = 0; r < kCluster; ++r) v += cluster.map_shared_rank(&cta_tot[0][0], r)[slot * 8 + k];
-        p.sums[(b * p.n_groups + slot) * 8 + k] = v;
+        if (!ALL || slot != p.all_slot) p.sums[(b * p.n_groups + slot) * 8 + k] = v;
         cta_tot[slot][k] = v;       // rank 0's own copy has been read by this same thread already
+    }
+    __syncthreads();
+    if constexpr (ALL) {            // "all" = the pixels of no requested material + every material, in slot order
+        double total = 0.0;
+        if (rank == 0 && threadIdx.x < 8)
+            for (int g = 0; g < p.n_groups; ++g) total += cta_tot[g][threadIdx.x];
+        __syncthreads();
+        if (rank == 0 && threadIdx.x < 8) {
+            cta_tot[p.all_slot][threadIdx.x] = total;
+            p.sums[(b * p.n_groups + p.all_slot) * 8 + threadIdx.x] = total;
+        }
     }
     cluster.sync();
     if (rank == 0 && p.metrics && threadIdx.x < p.n_groups) finalize(cta_tot[threadIdx.x], p.metrics + (b * p.n_groups + threadIdx.x) * 7);
@@ -768,9 +782,10 @@ int polcue_depth_errors_groups_f32(const float* gt, const float* pred, const uin
              ((reinterpret_cast<uintptr_t>(inst) & 3) == 0);
     if (px / ((size_t)kCluster * kMetricThreads) + 8 > 65535) return POLCUE_E2BIG;   // 16-bit per-thread counts (run_flush)
     const size_t smem = (size_t)n_groups * kGroupRows * kMetricThreads * sizeof(float);
-    const cudaError_t e = cudaFuncSetAttribute(depth_errors_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = p.all_slot >= 0 ? depth_errors_groups_kernel<true> : depth_errors_groups_kernel<false>;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    depth_errors_groups_kernel<<<dim3(kCluster, B, 1), kMetricThreads, smem, (cudaStream_t)stream>>>(p);
+    kern<<<dim3(kCluster, B, 1), kMetricThreads, smem, (cudaStream_t)stream>>>(p);
     return launch_status();
 }
 
