@@ -14,7 +14,9 @@
  *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and never synchronise.
  *   - Return value: 0 on success; a NEGATIVE errno-style code for a rejected argument (nothing was
  *     launched); a POSITIVE value is the cudaError_t reported by the launch.
- *   - Re-entrant for distinct streams/outputs.  Not for use from forked DataLoader workers.
+ *   - Re-entrant for distinct streams/outputs; no process-global state changes numerics.  The `_host` entry points
+ *     cache their device rings per (device, geometry): calls for different devices or geometries run concurrently,
+ *     two threads using the same (device, geometry) serialise on that ring.  Not for use from forked DataLoader workers.
  *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef POLCUE_H_
@@ -44,8 +46,6 @@ typedef struct polcue_lut polcue_lut; /* opaque: zenith-angle lookup tables for 
 
 POLCUE_API const char* polcue_version(void);
 POLCUE_API const char* polcue_error_string(int code);
-/* Tuning knob for the zenith-angle sincos: 1 = MUFU sin/cos (3.6e-7 abs, default), 0 = polynomial (1.4e-7 abs). */
-POLCUE_API int polcue_debug_set_trig(int mufu);
 /* How many depth->normals launches took the TMA-staged kernel (the rest used the manually staged one). */
 POLCUE_API unsigned long long polcue_debug_stencil_tma_launches(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
@@ -62,6 +62,10 @@ POLCUE_API unsigned long long polcue_launch_count(void);
  * ------------------------------------------------------------------------------------------- */
 POLCUE_API int polcue_lut_create(double n, polcue_lut** out);
 POLCUE_API void polcue_lut_destroy(polcue_lut* lut);
+/* Zenith-angle sincos used by every later launch that is given THIS handle: 1 = MUFU sin/cos (3.6e-7 abs, the default of
+ * a new handle), 0 = polynomial (1.4e-7 abs).  A property of the handle, not of the process: callers that want both keep
+ * two handles.  Not to be changed while a call using the handle is being issued from another thread. */
+POLCUE_API int polcue_lut_set_trig(polcue_lut* lut, int mufu);
 /* Host-side introspection (no GPU needed): cell counts / knot counts of table t (0 diffuse, 1 spec1, 2 spec2). */
 POLCUE_API int polcue_lut_host_build(double n, polcue_lut** out); /* same tables, no device copy (CPU tests) */
 POLCUE_API int polcue_lut_cells(const polcue_lut* lut, int table);
@@ -166,9 +170,14 @@ POLCUE_API int polcue_loader_front_end_u8_host(int in_h, int in_w, int out_h, in
  * `chunk_frames` <= 0 picks a default.  This is the call bench.py's `e2e` figure times. */
 POLCUE_API int polcue_fused_mosaic_u8_host(const uint8_t* h_mosaic, int B, int H, int W, const polcue_lut* lut,
                                 float* h_iun, float* h_xolp, float* h_normals, int chunk_frames);
-/* Pinned host memory helpers for the callers of the *_host entry point. */
+/* Pinned host memory for the callers of the *_host entry points, placed on the NUMA node of the GPU that will DMA into it
+ * (read from /sys/bus/pci/devices/<bus id>/numa_node; anonymous mapping bound to that node, populated, registered with the
+ * driver as portable pinned memory; plain cudaHostAlloc when the node is unknown).  `device` < 0: the current device.
+ * polcue_host_alloc = polcue_host_alloc_on(.., -1).  polcue_host_numa_node: the node found for `device`, or -1. */
 POLCUE_API int polcue_host_alloc(void** ptr, size_t bytes);
+POLCUE_API int polcue_host_alloc_on(void** ptr, size_t bytes, int device);
 POLCUE_API int polcue_host_free(void* ptr);
+POLCUE_API int polcue_host_numa_node(int device);
 
 /* ---------------------------------------------------------------------------------------------
  * XOLP only.   polarisation/xolp.py:8-34   Iun_and_xolp(images[H,W,4], angles[4]) -> Iun, rho, phi

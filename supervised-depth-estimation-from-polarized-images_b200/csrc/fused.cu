@@ -345,12 +345,12 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) fused_mosaic_k
     }
 }
 
-int g_trig_mufu = 1;  // zenith-angle sincos: 1 = MUFU sin/cos (3.6e-7 abs, default), 0 = polynomial (1.4e-7).  DESIGN.md 5.
-
+// `mufu`: zenith-angle sincos of this launch, a property of the caller's table handle (polcue_lut_set_trig): MUFU sin/cos
+// (3.6e-7 abs, default) or the polynomial (1.4e-7).  DESIGN.md 5.
 template <int VEC>
-int launch_fused(const FusedParams& p, size_t smem, cudaStream_t stream) {
+int launch_fused(const FusedParams& p, size_t smem, cudaStream_t stream, bool mufu) {
     auto kern = !p.normals ? fused_mosaic_kernel<VEC, true, false>
-                           : (g_trig_mufu ? fused_mosaic_kernel<VEC, true, true> : fused_mosaic_kernel<VEC, false, true>);
+                           : (mufu ? fused_mosaic_kernel<VEC, true, true> : fused_mosaic_kernel<VEC, false, true>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
@@ -693,11 +693,6 @@ using namespace polcue;
 
 extern "C" {
 
-int polcue_debug_set_trig(int mufu) {
-    g_trig_mufu = mufu ? 1 : 0;
-    return POLCUE_OK;
-}
-
 static int fused_mosaic_common(const uint8_t* mosaic, int B, int H, int W, bool layout_superpixel, const int* angle_at,
                                const polcue_lut* lut, uint8_t* planes, float* iun, float* xolp, float* normals,
                                polcue_stream_t stream) {
@@ -753,10 +748,11 @@ static int fused_mosaic_common(const uint8_t* mosaic, int B, int H, int W, bool 
     p.plane_bytes = 4u * p.plane;
     const size_t smem = normals ? lut->bytes() : 0;
     cudaStream_t s = (cudaStream_t)stream;
+    const bool mufu = !lut || lut->trig_mufu != 0;
     switch (vec) {
-        case 4: return launch_fused<4>(p, smem, s);
-        case 2: return launch_fused<2>(p, smem, s);
-        default: return launch_fused<1>(p, smem, s);
+        case 4: return launch_fused<4>(p, smem, s, mufu);
+        case 2: return launch_fused<2>(p, smem, s, mufu);
+        default: return launch_fused<1>(p, smem, s, mufu);
     }
 }
 
@@ -812,10 +808,11 @@ static int fused_planes_common(const uint8_t* i0, long long off45, long long off
     p.plane_bytes = 4u * p.plane;
     const size_t smem = normals ? lut->bytes() : 0;
     cudaStream_t s = (cudaStream_t)stream;
+    const bool mufu = !lut || lut->trig_mufu != 0;
     switch (vec) {
-        case 4: return launch_fused<4>(p, smem, s);
-        case 2: return launch_fused<2>(p, smem, s);
-        default: return launch_fused<1>(p, smem, s);
+        case 4: return launch_fused<4>(p, smem, s, mufu);
+        case 2: return launch_fused<2>(p, smem, s, mufu);
+        default: return launch_fused<1>(p, smem, s, mufu);
     }
 }
 
@@ -913,8 +910,8 @@ int polcue_normals_from_xolp_f32(const float* xolp, int B, int H, int W, const p
         kern<<<tiles, kFusedThreads, smem, (cudaStream_t)stream>>>(p);
         return launch_status();
     };
-    if (vec == 4) return g_trig_mufu ? launch(normals_from_xolp_kernel<4, true>) : launch(normals_from_xolp_kernel<4, false>);
-    return g_trig_mufu ? launch(normals_from_xolp_kernel<1, true>) : launch(normals_from_xolp_kernel<1, false>);
+    if (vec == 4) return lut->trig_mufu ? launch(normals_from_xolp_kernel<4, true>) : launch(normals_from_xolp_kernel<4, false>);
+    return lut->trig_mufu ? launch(normals_from_xolp_kernel<1, true>) : launch(normals_from_xolp_kernel<1, false>);
 }
 
 int polcue_rho_diffuse_f32(const float* rho, size_t count, const polcue_lut* lut, float* theta, polcue_stream_t stream) {

@@ -243,6 +243,12 @@ void polcue_lut_destroy(polcue_lut* lut) {
     delete lut;
 }
 
+int polcue_lut_set_trig(polcue_lut* lut, int mufu) {
+    if (!lut) return POLCUE_EINVAL;
+    lut->trig_mufu = mufu ? 1 : 0;
+    return POLCUE_OK;
+}
+
 int polcue_lut_cells(const polcue_lut* lut, int table) {
     if (!lut || table < 0 || table > 2) return POLCUE_EINVAL;
     return lut->cells[table];

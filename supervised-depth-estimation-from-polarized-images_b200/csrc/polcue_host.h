@@ -22,6 +22,7 @@ struct polcue_lut {
     double steep_y[3] = {0, 0, 0};
     double steep_slope[3] = {0, 0, 0};
     float4* d_blob = nullptr;      // device copy (null for host-only builds)
+    int trig_mufu = 1;             // zenith-angle sincos of launches that use this handle: 1 = MUFU sin/cos (3.6e-7 abs), 0 = polynomial (1.4e-7)
     int device = -1;
     size_t bytes() const { return blob.size() * sizeof(float4); }
 };

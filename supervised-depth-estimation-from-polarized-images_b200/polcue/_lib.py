@@ -27,11 +27,11 @@ _SIGNATURES = {
     # name: (restype, argtypes)
     "polcue_version": (C.c_char_p, []),
     "polcue_error_string": (C.c_char_p, [C.c_int]),
-    "polcue_debug_set_trig": (C.c_int, [C.c_int]),
     "polcue_launch_count": (C.c_ulonglong, []),
     "polcue_debug_stencil_tma_launches": (C.c_ulonglong, []),
     "polcue_lut_create": (C.c_int, [C.c_double, C.POINTER(C.c_void_p)]),
     "polcue_lut_destroy": (None, [C.c_void_p]),
+    "polcue_lut_set_trig": (C.c_int, [C.c_void_p, C.c_int]),
     "polcue_lut_host_build": (C.c_int, [C.c_double, C.POINTER(C.c_void_p)]),
     "polcue_lut_cells": (C.c_int, [C.c_void_p, C.c_int]),
     "polcue_lut_steep": (C.c_int, [C.c_void_p, C.c_int, _f64p]),
@@ -55,6 +55,8 @@ _SIGNATURES = {
                                                  _f32p, _f32p, C.POINTER(C.c_float), _f32p, C.c_int]),
     "polcue_fused_mosaic_u8_host": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _f32p, _f32p, _f32p, C.c_int]),
     "polcue_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "polcue_host_alloc_on": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]),
+    "polcue_host_numa_node": (C.c_int, [C.c_int]),
     "polcue_host_free": (C.c_int, [C.c_void_p]),
     "polcue_xolp_stack_u8": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), _f32p, _f32p, _vp]),
     "polcue_xolp_stack_f32": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), _f32p, _f32p, _vp]),

@@ -36,8 +36,15 @@ def to_device(array, dtype=None):
     return t.to(default_device(), non_blocking=False)
 
 
-def install(verbose=False):
+def install(verbose=False, patch_loader=False):
     """Replace, in place, the hot-path functions of the reference modules that are ALREADY imported (`sys.modules`).
+
+    `patch_loader` (default False): also replace `manydepth.datasets.indoor_dataset.Iun_and_xolp`.  That function runs
+    inside `__getitem__`, i.e. in the DataLoader's FORKED worker processes (num_workers = 12 by default,
+    options.py:299-302), where CUDA cannot be (re-)initialised; the CUDA-backed mirror is only valid there with
+    `num_workers=0` or a `spawn` start method, so it is opt-in.  The recommended integration keeps the loader's uint8
+    planes and runs `polcue.ops.fused_planes` / `loader_front_end` on the collated batch in the main process
+    (INTEGRATION.md).  The mirror itself refuses to run in a forked worker with a clear error.
 
     For the `manydepth` package, of which only a few functions are on the path:
       manydepth.normals_vec.{rho_diffuse, rho_spec, calc_normals}
@@ -69,7 +76,8 @@ def install(verbose=False):
     for mod_name in ("manydepth.layers", "manydepth.trainer", "manydepth.evaluation"):
         patch(mod_name, "compute_depth_errors", layers.compute_depth_errors)
         patch(mod_name, "compute_depth_errors_numpy", layers.compute_depth_errors_numpy)
-    for mod_name in ("manydepth.trainer", "manydepth.datasets.indoor_dataset", "polarisation.xolp", "polarisation.xolp_and_normals"):
+    for mod_name in ("manydepth.trainer", "polarisation.xolp", "polarisation.xolp_and_normals") + (
+            ("manydepth.datasets.indoor_dataset",) if patch_loader else ()):
         patch(mod_name, "Iun_and_xolp", xolp.Iun_and_xolp)
     patch("manydepth.trainer", "compute_supervised_normals_losses",
           lambda self, depth_gt, depth_pred, intrinsics, mask: trainer.compute_supervised_normals_losses(depth_gt, depth_pred, intrinsics, mask),

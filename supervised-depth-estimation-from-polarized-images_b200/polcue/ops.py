@@ -37,18 +37,87 @@ def _need_cuda(t, name, dtype=None):
     return t.contiguous()
 
 
-def lut_for(n, device):
-    """Zenith-angle tables for refractive index `n` on `device` (cached; built once per pair)."""
+_trig = threading.local()
+
+
+class trig:
+    """``with ops.trig("poly"):`` -- the zenith-angle sincos variant of the calls issued by this thread inside the block:
+    "mufu" (MUFU sin/cos, 3.6e-7 abs, the default) or "poly" (polynomial, 1.4e-7 abs).  It only selects WHICH table handle
+    `lut_for` hands to the library (the mode is a property of the handle, polcue_lut_set_trig); nothing process-global."""
+
+    def __init__(self, mode):
+        if mode not in ("mufu", "poly"):
+            raise ValueError("trig mode must be 'mufu' or 'poly'")
+        self.mode = mode
+
+    def __enter__(self):
+        self.saved = getattr(_trig, "mode", "mufu")
+        _trig.mode = self.mode
+        return self
+
+    def __exit__(self, *exc):
+        _trig.mode = self.saved
+        return False
+
+
+def lut_for(n, device, mode=None):
+    """Zenith-angle tables for refractive index `n` on `device` (cached; built once per (n, device, trig mode))."""
     device = torch.device(device)
-    key = (float(n), device.index if device.index is not None else torch.cuda.current_device())
+    mode = mode or getattr(_trig, "mode", "mufu")
+    key = (float(n), device.index if device.index is not None else torch.cuda.current_device(), mode)
     with _lut_lock:
         h = _lut_cache.get(key)
         if h is None:
             with torch.cuda.device(key[1]):
                 out = C.c_void_p()
                 _lib.check(_lib.lib().polcue_lut_create(float(n), C.byref(out)), f"polcue_lut_create(n={n})")
+                _lib.check(_lib.lib().polcue_lut_set_trig(out, 1 if mode == "mufu" else 0), "polcue_lut_set_trig")
             h = _lut_cache[key] = out
     return h
+
+
+# ------------------------------------------------------------------------------------------
+# pinned host buffers on the GPU's NUMA node (for the *_host entry points)
+# ------------------------------------------------------------------------------------------
+class _HostBlock:
+    """Owns one polcue_host_alloc_on block; freed when the last tensor viewing it is gone."""
+
+    def __init__(self, nbytes, device_index):
+        self.ptr = C.c_void_p()
+        _lib.check(_lib.lib().polcue_host_alloc_on(C.byref(self.ptr), max(int(nbytes), 1), int(device_index)), "polcue_host_alloc_on")
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.lib().polcue_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def host_empty(shape, dtype=torch.float32, device=None):
+    """Zero-filled pinned CPU tensor whose pages live on the NUMA node of `device` (default: the
+    current CUDA device) -- the buffers to hand to `fused_mosaic_host` / `loader_front_end_host`."""
+    index = torch.cuda.current_device() if device is None else torch.device(device).index
+    numel = 1
+    for d in shape:
+        numel *= int(d)
+    nbytes = numel * torch.empty((), dtype=dtype).element_size()
+    block = _HostBlock(nbytes, index if index is not None else torch.cuda.current_device())
+    raw = (C.c_uint8 * max(nbytes, 1)).from_address(block.ptr.value)
+    raw._owner = block               # torch.frombuffer keeps `raw` alive as long as the storage lives (views included)
+    return torch.frombuffer(raw, dtype=dtype, count=numel).reshape(tuple(int(d) for d in shape))
+
+
+def _host_out(out, key, shape, dtype):
+    """A caller-supplied host output buffer, validated (shape, dtype, contiguity, CPU), or a new pinned one."""
+    t = out.get(key)
+    if t is None:
+        t = out[key] = host_empty(shape, dtype)
+    elif (not isinstance(t, torch.Tensor) or t.is_cuda or tuple(t.shape) != tuple(shape) or t.dtype != dtype
+          or not t.is_contiguous()):
+        raise ValueError(f"preallocated host `{key}` must be a contiguous CPU {dtype} tensor of shape {tuple(shape)}")
+    return t
 
 
 # ------------------------------------------------------------------------------------------
@@ -273,16 +342,13 @@ def fused_mosaic_host(mosaic, n=1.5, want_iun=False, want_normals=True, out=None
     hs, ws = h // 2, w // 2
     out = dict(out or {})
 
-    def buf(key, shape):
-        t = out.get(key)
-        if t is None:
-            t = out[key] = torch.empty(shape, dtype=torch.float32, pin_memory=True)
-        return t
-
-    xolp = buf("xolp", (b, 2, hs, ws))
-    normals = buf("normals", (b, 9, hs, ws)) if want_normals else None
-    iun = buf("iun", (b, hs, ws)) if want_iun else None
+    if h % 2 or w % 2:
+        raise ValueError("mosaic height and width must be even")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        xolp = _host_out(out, "xolp", (b, 2, hs, ws), torch.float32)
+        normals = _host_out(out, "normals", (b, 9, hs, ws), torch.float32) if want_normals else None
+        iun = _host_out(out, "iun", (b, hs, ws), torch.float32) if want_iun else None
     lut = lut_for(n, dev) if want_normals else C.c_void_p(0)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().polcue_fused_mosaic_u8_host(_ptr(mosaic), b, h, w, lut, _ptr(iun), _ptr(xolp), _ptr(normals),
@@ -306,23 +372,18 @@ def loader_front_end_host(i0, i45, i90, i135, out_hw, n=1.5, flip=None, want_pla
     oh, ow = int(out_hw[0]), int(out_hw[1])
     out = dict(out or {})
 
-    def buf(key, shp, dtype=torch.float32):
-        t = out.get(key)
-        if t is None:
-            t = out[key] = torch.empty(shp, dtype=dtype, pin_memory=True)
-        return t
-
-    xolp = buf("xolp", (b, 2, oh, ow))
-    planes = buf("planes", (b, 4, oh, ow), torch.uint8) if want_planes else None
-    normals = buf("normals", (b, 9, oh, ow)) if want_normals else None
-    xnorm = buf("xolp_norm", (b, 2, oh, ow)) if normalize_xolp is not None else None
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        xolp = _host_out(out, "xolp", (b, 2, oh, ow), torch.float32)
+        planes = _host_out(out, "planes", (b, 4, oh, ow), torch.uint8) if want_planes else None
+        normals = _host_out(out, "normals", (b, 9, oh, ow), torch.float32) if want_normals else None
+        xnorm = _host_out(out, "xolp_norm", (b, 2, oh, ow), torch.float32) if normalize_xolp is not None else None
     mean_std = (C.c_float * 2)(*[float(v) for v in normalize_xolp]) if normalize_xolp is not None else None
     flags = None
     if flip is not None:
         flags = torch.as_tensor([flip] * b if isinstance(flip, bool) else flip).to(torch.uint8).contiguous()
         if flags.numel() != b:
             raise ValueError(f"flip needs one flag per sample ({b})")
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     lut = lut_for(n, dev) if want_normals else C.c_void_p(0)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().polcue_loader_front_end_u8_host(h, w, oh, ow, *(_ptr(t) for t in imgs), b, _ptr(flags), lut, _ptr(planes),

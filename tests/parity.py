@@ -24,10 +24,13 @@ def aolp_error(got, ref):
 
 
 def assert_aolp_close(got, ref, exclude=None, tol=AOLP_TOL):
+    """A NaN (or inf) AoLP outside `exclude` fails: ~(err <= tol) is true for NaN errors."""
     err = aolp_error(got, ref)
     if exclude is not None:
         err = np.where(exclude, 0.0, err)
-    assert np.nanmax(err) <= tol, f"AoLP worst {np.nanmax(err):.3e} rad at {np.unravel_index(np.nanargmax(err), err.shape)}"
+    bad = ~(err <= tol)
+    assert not bad.any(), (f"AoLP: {int(bad.sum())} px out of tolerance (NaN counted), first at "
+                           f"{np.unravel_index(np.argmax(bad), bad.shape)}, worst finite {np.nanmax(err):.3e} rad")
 
 
 def angular_error(a, b, axis):
@@ -46,5 +49,7 @@ def assert_normals_close(got, ref, axis, twin_ok=None, skip=None, tol=NORMAL_TOL
         err = np.where(twin_ok, np.minimum(err, angular_error(got, np.asarray(ref) * sign, axis)), err)
     if skip is not None:
         err = np.where(skip, 0.0, err)
-    assert np.nanmax(err) <= tol, f"{what}: worst angular error {np.nanmax(err):.3e} rad"
-    return float(np.nanmax(err))
+    bad = ~(err <= tol)                     # NaN normals (bad table index, 0 * inf, unwritten tail) count as failures
+    assert not bad.any(), (f"{what}: {int(bad.sum())} px out of tolerance (NaN counted), first at "
+                           f"{np.unravel_index(np.argmax(bad), bad.shape)}, worst finite {np.nanmax(err):.3e} rad")
+    return float(err.max()) if err.size else 0.0

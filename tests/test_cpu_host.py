@@ -267,10 +267,17 @@ def test_install_patches_the_trainer_and_evaluation_classes():
         setattr(mod, cls_name, cls)
         mod.compute_depth_errors = lambda gt, pred: "reference"
         fakes[mod_name] = mod
+    loader = types.ModuleType("manydepth.datasets.indoor_dataset")
+    loader.Iun_and_xolp = lambda images, angles: "reference"
+    fakes["manydepth.datasets.indoor_dataset"] = loader
     saved = {k: sys.modules.get(k) for k in fakes}
     sys.modules.update(fakes)
     try:
         done = c.install()
+        # the loader-side function runs in forked DataLoader workers: left alone unless asked for
+        assert loader.Iun_and_xolp(None, None) == "reference" and not any("indoor_dataset" in d for d in done)
+        assert "manydepth.datasets.indoor_dataset.Iun_and_xolp" in c.install(patch_loader=True)
+        assert loader.Iun_and_xolp.__module__ == "polcue.compat.xolp"
     finally:
         for k, v in saved.items():
             if v is None:

@@ -25,12 +25,9 @@ def dev(a, dtype=None):
 
 def check_fused(mosaics, n=1.5, mufu=False):
     """mosaics: B x H x W uint8 numpy.  Full protocol of SURVEY 8c against the closed-form oracle."""
-    _lib.lib().polcue_debug_set_trig(1 if mufu else 0)
-    try:
+    with ops.trig("mufu" if mufu else "poly"):
         out = ops.fused_mosaic(dev(mosaics), n, want_iun=True, want_planes=True)
         torch.cuda.synchronize()
-    finally:
-        _lib.lib().polcue_debug_set_trig(1)   # library default
     worst = 0.0
     for b in range(mosaics.shape[0]):
         stack = O.stack_quadrants(mosaics[b])
@@ -296,8 +293,7 @@ def test_steep_end_segment_is_evaluated_in_float64(mufu):
     n = 1.8
     xk, yk = O.sorted_knots(n)["spec2"]
     rng = np.random.default_rng(18)
-    _lib.lib().polcue_debug_set_trig(1 if mufu else 0)
-    try:
+    with ops.trig("mufu" if mufu else "poly"):
         for shape in ((2, 16, 64), (1, 7, 13)):
             rho = np.concatenate((rng.uniform(0.99999, 1.00001, 500), rng.uniform(1.0, 2.5, 500), rng.uniform(0, 1, 1000),
                                   np.float32(xk[-3:]).astype(np.float64), np.nextafter(np.float32(xk[-2:]), np.float32(2)).astype(np.float64)))
@@ -323,8 +319,6 @@ def test_steep_end_segment_is_evaluated_in_float64(mufu):
         planes = [np.ascontiguousarray(O.stack_quadrants(mosaics[0])[..., k]) for k in range(4)]
         assert torch.equal(ops.fused_planes(*(dev(p)[None] for p in planes), n=n)["normals"],
                            ops.fused_mosaic(dev(mosaics[:1]), n)["normals"])
-    finally:
-        _lib.lib().polcue_debug_set_trig(1)
 
 
 def test_get_normals_random_refractive_indices():
@@ -336,11 +330,8 @@ def test_get_normals_random_refractive_indices():
         rho = np.where(rng.random(shape) < 0.5, rng.uniform(0, 1, shape) ** 2, rng.uniform(0, 2.2, shape))
         rho = np.where(rng.random(shape) < 0.1, 1 - rng.uniform(0, 1, shape) ** 3 * 1e-3, rho).astype(np.float32)
         x = np.stack((rho, rng.uniform(-np.pi / 2, np.pi / 2, shape).astype(np.float32)), axis=1)
-        _lib.lib().polcue_debug_set_trig(i & 1)
-        try:
+        with ops.trig("mufu" if i & 1 else "poly"):
             got = ops.get_normals(dev(x), float(n)).cpu().numpy()
-        finally:
-            _lib.lib().polcue_debug_set_trig(1)
         ref = O.get_normals(x, float(n))
         b, h, w = shape
         P.assert_normals_close(got.reshape(b, 3, 3, h, w), ref.reshape(b, 3, 3, h, w), axis=2, what=f"n={n:.4f}")

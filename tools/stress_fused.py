@@ -37,34 +37,33 @@ def main():
             mosaics = np.stack([synth.tile_mosaic(synth.gen_p_planes(case * 7 + f, hs, ws)) for f in range(b)])
         else:       # few grey levels: many ties and degenerate pixels
             mosaics = (rng.integers(0, 4, (b, 2 * hs, 2 * ws)) * 85).astype(np.uint8)
-        _lib.lib().polcue_debug_set_trig(case & 1)
-        out = ops.fused_mosaic(torch.from_numpy(mosaics).cuda(), n, want_iun=True, want_planes=True)
-        for f in range(b):
-            stack = O.stack_quadrants(mosaics[f])
-            assert np.array_equal(out["planes"][f].cpu().numpy(), stack.transpose(2, 0, 1)), case
-            iun, rho, phi = O.iun_and_xolp_closed(stack)
-            g_rho, g_phi = out["xolp"][f, 0].cpu().numpy(), out["xolp"][f, 1].cpu().numpy()
-            P.assert_dolp_close(out["iun"][f].cpu().numpy(), iun, "Iun")
-            P.assert_dolp_close(g_rho, rho, "rho")
-            P.assert_aolp_close(g_phi, phi)
-            ref = O.get_normals(np.stack((rho, phi))[None], n).reshape(3, 3, hs, ws)
-            got = out["normals"][f].cpu().numpy().reshape(3, 3, hs, ws)
-            worst["normals"] = max(worst["normals"], P.assert_normals_close(got, ref, axis=1, what=f"case {case} n={n:.4f}"))
-            worst["rho"] = max(worst["rho"], float(np.max(np.abs(g_rho - rho) / (np.abs(rho) + 1e-2))))
-            worst["phi"] = max(worst["phi"], float(np.max(P.aolp_error(g_phi, phi))))
-        # the other entry points give the same bits
-        planes = [out["planes"][:, k].contiguous() for k in range(4)]
-        fp = ops.fused_planes(*planes, n=n)
-        gn = ops.get_normals(out["xolp"], n)
-        raw = torch.zeros_like(torch.from_numpy(mosaics)).cuda()
-        pattern = [int(v) for v in rng.permutation(4)]
-        for pos, angle in enumerate(pattern):
-            raw[:, pos // 2::2, pos % 2::2] = planes[angle]
-        sp = ops.fused_mosaic(raw, n, superpixel=pattern)
-        assert torch.equal(fp["normals"], out["normals"]) and torch.equal(sp["normals"], out["normals"]) and torch.equal(sp["xolp"], out["xolp"]), case
-        ref_x = O.get_normals(out["xolp"].cpu().numpy(), n)          # get_normals sees the float32 XOLP, as in the reference
-        P.assert_normals_close(gn.cpu().numpy().reshape(b, 3, 3, hs, ws), ref_x.reshape(b, 3, 3, hs, ws), axis=2, what=f"get_normals case {case}")
-        _lib.lib().polcue_debug_set_trig(1)
+        with ops.trig("mufu" if case & 1 else "poly"):
+            out = ops.fused_mosaic(torch.from_numpy(mosaics).cuda(), n, want_iun=True, want_planes=True)
+            for f in range(b):
+                stack = O.stack_quadrants(mosaics[f])
+                assert np.array_equal(out["planes"][f].cpu().numpy(), stack.transpose(2, 0, 1)), case
+                iun, rho, phi = O.iun_and_xolp_closed(stack)
+                g_rho, g_phi = out["xolp"][f, 0].cpu().numpy(), out["xolp"][f, 1].cpu().numpy()
+                P.assert_dolp_close(out["iun"][f].cpu().numpy(), iun, "Iun")
+                P.assert_dolp_close(g_rho, rho, "rho")
+                P.assert_aolp_close(g_phi, phi)
+                ref = O.get_normals(np.stack((rho, phi))[None], n).reshape(3, 3, hs, ws)
+                got = out["normals"][f].cpu().numpy().reshape(3, 3, hs, ws)
+                worst["normals"] = max(worst["normals"], P.assert_normals_close(got, ref, axis=1, what=f"case {case} n={n:.4f}"))
+                worst["rho"] = max(worst["rho"], float(np.max(np.abs(g_rho - rho) / (np.abs(rho) + 1e-2))))
+                worst["phi"] = max(worst["phi"], float(np.max(P.aolp_error(g_phi, phi))))
+            # the other entry points give the same bits
+            planes = [out["planes"][:, k].contiguous() for k in range(4)]
+            fp = ops.fused_planes(*planes, n=n)
+            gn = ops.get_normals(out["xolp"], n)
+            raw = torch.zeros_like(torch.from_numpy(mosaics)).cuda()
+            pattern = [int(v) for v in rng.permutation(4)]
+            for pos, angle in enumerate(pattern):
+                raw[:, pos // 2::2, pos % 2::2] = planes[angle]
+            sp = ops.fused_mosaic(raw, n, superpixel=pattern)
+            assert torch.equal(fp["normals"], out["normals"]) and torch.equal(sp["normals"], out["normals"]) and torch.equal(sp["xolp"], out["xolp"]), case
+            ref_x = O.get_normals(out["xolp"].cpu().numpy(), n)          # get_normals sees the float32 XOLP, as in the reference
+            P.assert_normals_close(gn.cpu().numpy().reshape(b, 3, 3, hs, ws), ref_x.reshape(b, 3, 3, hs, ws), axis=2, what=f"get_normals case {case}")
     print(f"{args.cases} cases ok; worst errors: {worst}")
 
 
