@@ -226,6 +226,41 @@ def run_reference_arm(args, rank, world):
 # --------------------------------------------------------------------------------------------------
 # GPU leg
 # --------------------------------------------------------------------------------------------------
+def pcie_probe(dev, h_in, d_in, h_out, d_out, D, reps=3):
+    """The roofline of `e2e`: plain cudaMemcpyAsync copies (torch `copy_` from / to pinned memory) of exactly the bytes one
+    e2e step moves -- the mosaics host->device and XOLP + normals device->host -- alone and then both directions at once
+    on two streams (PCIe is full duplex), on all ranks at the same time.  Wall-clock around a device synchronise (each
+    copy is tens of milliseconds), max over ranks.  Returns GB/s per GPU and the duplex time of one step's bytes."""
+    import torch
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    d2h_bytes = sum(t.numel() * t.element_size() for t in h_out.values())
+    h2d_bytes = h_in.numel() * h_in.element_size()
+
+    def run(do_in, do_out):
+        torch.cuda.synchronize()
+        D.barrier()
+        best = float("inf")
+        for _ in range(reps):
+            D.barrier()
+            t0 = time.perf_counter()
+            if do_in:
+                with torch.cuda.stream(s_in):
+                    d_in.copy_(h_in, non_blocking=True)
+            if do_out:
+                with torch.cuda.stream(s_out):
+                    for key, t in h_out.items():
+                        t.copy_(d_out[key], non_blocking=True)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        return D.max_over_ranks(best, dev)
+
+    run(True, True)                                             # warm-up
+    t_in, t_out, t_both = run(True, False), run(False, True), run(True, True)
+    return {"h2d_gbs_alone": h2d_bytes / t_in / 1e9, "d2h_gbs_alone": d2h_bytes / t_out / 1e9,
+            "duplex_ms_for_one_step": t_both * 1e3, "d2h_gbs_duplex": d2h_bytes / t_both / 1e9,
+            "h2d_bytes": h2d_bytes, "d2h_bytes": d2h_bytes}
+
+
 def run_polcue_arm(args, rank, local_rank, world):
     import torch
     from polcue import _lib, dist as D, ops, synth
@@ -311,9 +346,10 @@ def run_polcue_arm(args, rank, local_rank, world):
 
     # ---- e2e: host buffers through the public host entry point -------------------------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    h_mosaic = mosaic.cpu().pin_memory()
-    h_out = {"xolp": torch.empty((B, 2, hs, ws), dtype=torch.float32).pin_memory(),
-             "normals": torch.empty((B, 9, hs, ws), dtype=torch.float32).pin_memory()}
+    h_mosaic = ops.host_empty((B, H, W), torch.uint8, dev)       # pinned, on the NUMA node of this rank's GPU (polcue_host_alloc_on)
+    h_mosaic.copy_(mosaic)
+    h_out = {"xolp": ops.host_empty((B, 2, hs, ws), torch.float32, dev),
+             "normals": ops.host_empty((B, 9, hs, ws), torch.float32, dev)}
     ops.fused_mosaic_host(h_mosaic, 1.5, out=h_out)             # warm-up: allocates the device ring
     torch.cuda.synchronize()
     D.barrier()
@@ -321,7 +357,12 @@ def run_polcue_arm(args, rank, local_rank, world):
     for _ in range(e2e_steps):
         ops.fused_mosaic_host(h_mosaic, 1.5, out=h_out)         # blocks until the results are in host memory
     e2e_ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps, dev)
-    same = bool(torch.equal(h_out["normals"][0], out["normals"][0].cpu()))
+    same = True
+    for key in ("xolp", "normals"):                             # EVERY frame of the host path equals the device path, bit for bit
+        back = h_out[key].to(dev)
+        same = same and bool(torch.equal(back, out[key]))
+        del back
+    pcie = pcie_probe(dev, h_mosaic, mosaic, h_out, out, D)     # plain cudaMemcpyAsync of the step's bytes: the e2e roofline
 
     # ---- informational: the training-loader usage -- host mosaics in, outputs stay in HBM for the encoders, the host
     #      reads back only the per-plane float64 checksums (11 doubles) ---------------------------------------------
@@ -355,8 +396,15 @@ def run_polcue_arm(args, rank, local_rank, world):
                      "launch_ms": mean_launch_ms},
         "e2e": {"value": world * B * MPIX_PER_FRAME / (e2e_ms * 1e-3), "unit": "Mpix/s", "ms_per_step": e2e_ms,
                 "steps": e2e_steps, "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": 44 * out_px,
-                "api": "polcue.ops.fused_mosaic_host -> polcue_fused_mosaic_u8_host (pinned host buffers)",
-                "matches_device_path": same},
+                "api": "polcue.ops.fused_mosaic_host -> polcue_fused_mosaic_u8_host (pinned host buffers from polcue_host_alloc_on)",
+                "matches_device_path": same, "matches_device_path_frames_compared": B,
+                "roofline": {"bound": "pcie", "achieved": 44 * out_px / (e2e_ms * 1e-3) / 1e9, "peak": pcie["d2h_gbs_alone"],
+                             "unit": "GB/s per GPU, device->host (the dominant direction: 3.53 of the step's 3.85 GB)",
+                             "frac": 44 * out_px / (e2e_ms * 1e-3) / 1e9 / pcie["d2h_gbs_alone"],
+                             "probe": pcie, "ranks_copying_concurrently": world,
+                             "host_numa_node_of_gpu": int(_lib.lib().polcue_host_numa_node(local_rank)),
+                             "note": "peak = best plain cudaMemcpyAsync of the step's device->host bytes with nothing else running on "
+                                     "this GPU's link, all ranks copying concurrently; the probe also times both directions at once"}},
         "e2e_device_resident_outputs": {
             "value": world * B * MPIX_PER_FRAME / (res_ms * 1e-3), "unit": "Mpix/s", "ms_per_step": res_ms, "steps": e2e_steps,
             "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": 11 * 8,

@@ -294,6 +294,49 @@ def depth_to_normals(depth, camera_matrix, dtype=np.float64):
     return nrm / np.maximum(length, dtype(1e-12))
 
 
+def depth_to_normals_conditioning(depth, camera_matrix):
+    """Float64 forward-error model of a float32 evaluation of `depth_to_normals` (any association order), per pixel.
+
+    Returns (n, bound, dead): n = the UN-normalised cross product gu x gv (B x 3 x H x W); dead (B x H x W) = both
+    gradients are exactly the zero vector (all eight neighbours invalid: the normal is the exact zero vector in ANY
+    arithmetic); bound (B x H x W) = the first-order angular error, in radians per unit round-off, of the normalised cross
+    product when every input of the Sobel sums carries a relative error of one unit round-off (inf where n vanishes
+    although the gradients do not, i.e. they are exactly parallel -- one isolated valid neighbour -- where the result is
+    0 or a round-off direction depending on FMA contraction, in the reference's CUDA ops as well):
+        |d gu| <= A_u = sum |w_u| |xyz| / 8,   |d gv| <= A_v,
+        |d n|  <= |A_u| |gv| + |gu| |A_v| + |gu| |gv|,        bound = |d n| / |n|.
+    A float32 implementation with k roundings per term stays below k * 2^-24 * bound; tests use it to tell the pixels
+    where 1e-3 rad is attainable in float32 (nearly all) from those where the cross product cancels (gradients nearly
+    parallel next to zero-depth holes), and to bound the error there as well.  Test infrastructure only.
+    """
+    depth = np.asarray(depth, dtype=np.float64)
+    km = np.asarray(camera_matrix, dtype=np.float64)
+    b, _, h, w = depth.shape
+    u = np.arange(w, dtype=np.float64)[None, None, :]
+    v = np.arange(h, dtype=np.float64)[None, :, None]
+    fx, fy = km[:, 0, 0][:, None, None], km[:, 1, 1][:, None, None]
+    cx, cy = km[:, 0, 2][:, None, None], km[:, 1, 2][:, None, None]
+    z = depth[:, 0]
+    xyz = np.stack((((u - cx) / fx) * z, ((v - cy) / fy) * z, z), axis=1)
+    pad = np.pad(xyz, ((0, 0), (0, 0), (1, 1), (1, 1)), mode="edge")
+    apad = np.abs(pad)
+
+    def win(a, dy, dx):
+        return a[:, :, 1 + dy:1 + dy + h, 1 + dx:1 + dx + w]
+
+    gu = ((win(pad, -1, 1) - win(pad, -1, -1)) + 2 * (win(pad, 0, 1) - win(pad, 0, -1)) + (win(pad, 1, 1) - win(pad, 1, -1))) / 8
+    gv = ((win(pad, 1, -1) - win(pad, -1, -1)) + 2 * (win(pad, 1, 0) - win(pad, -1, 0)) + (win(pad, 1, 1) - win(pad, -1, 1))) / 8
+    au = (win(apad, -1, 1) + win(apad, -1, -1) + 2 * (win(apad, 0, 1) + win(apad, 0, -1)) + win(apad, 1, 1) + win(apad, 1, -1)) / 8
+    av = (win(apad, 1, -1) + win(apad, -1, -1) + 2 * (win(apad, 1, 0) + win(apad, -1, 0)) + win(apad, 1, 1) + win(apad, -1, 1)) / 8
+    n = np.cross(gu, gv, axis=1)
+    length = lambda a: np.sqrt((a * a).sum(axis=1))
+    dn = length(au) * length(gv) + length(gu) * length(av) + length(gu) * length(gv)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        bound = np.where(length(n) > 0, dn / length(n), np.inf)
+    dead = (gu == 0).all(axis=1) & (gv == 0).all(axis=1)
+    return n, bound, dead
+
+
 def normals_loss_torch(depth_gt, depth_pred, camera_matrix, mask):
     """Trainer.compute_supervised_normals_losses, manydepth/trainer.py:1298-1309, as a float64 torch graph (CPU) so that
     autograd supplies the reference gradient w.r.t. depth_pred.

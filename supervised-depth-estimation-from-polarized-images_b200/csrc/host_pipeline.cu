@@ -19,6 +19,7 @@
 
 #include <cctype>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <list>
 #include <map>
@@ -233,18 +234,23 @@ int polcue_host_alloc_on(void** ptr, size_t bytes, int device) {
         if (e != cudaSuccess) return (int)e;
     }
     const int node = gpu_numa_node(dev);
-    if (node >= 0 && node < 1024) {
-        // anonymous mapping bound to the GPU's node, populated, then registered with the driver (page-locked + DMA-mapped)
+    const char* mode = std::getenv("POLCUE_HOST_ALLOC");       // A/B probing only: "cuda" forces plain cudaHostAlloc
+    if (!(mode && std::strcmp(mode, "cuda") == 0)) {
+        // Anonymous mapping backed by transparent huge pages (2 MB pages keep the IOMMU's translation cache effective
+        // when several GPUs stream results into host memory at once), bound to the GPU's NUMA node when the platform
+        // exposes one, populated here, then registered with the driver (page-locked + DMA-mapped, portable).
         const size_t page = 2u << 20;
         const size_t len = (bytes + page - 1) / page * page;
         void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         if (p != MAP_FAILED) {
             madvise(p, len, MADV_HUGEPAGE);
-            unsigned long mask[16] = {0};
-            mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
-            // MPOL_PREFERRED (1): the node if it has room, another one rather than failing; a refusal (seccomp, no NUMA) is not an error
-            (void)syscall(SYS_mbind, p, len, 1, mask, (unsigned long)(8 * sizeof(mask)), 0u);
-            std::memset(p, 0, len);                          // first touch: pages are allocated here, on the bound node
+            if (node >= 0 && node < 1024) {
+                unsigned long mask[16] = {0};
+                mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+                // MPOL_PREFERRED (1): the node if it has room, another one rather than failing; a refusal (seccomp) is not an error
+                (void)syscall(SYS_mbind, p, len, 1, mask, (unsigned long)(8 * sizeof(mask)), 0u);
+            }
+            std::memset(p, 0, len);                          // first touch: pages are allocated here
             if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
                 std::lock_guard<std::mutex> guard(g_host_mutex);
                 g_host_blocks[p] = HostBlock{len, true};

@@ -99,6 +99,32 @@ def gen_depth_batch(first, count, h=TRAIN_H, w=TRAIN_W):
     return tuple(np.stack([it[k] for it in items]) for k in range(4))
 
 
+def add_hole_regions(gt, seed=0):
+    """HAMMER-like missing regions on top of the 10 % random invalid pixels of `gen_depth_sample`: per image a few
+    elliptic blobs (depth sensor drop-outs on glossy / transparent objects), a strip along one image border and one
+    isolated valid pixel inside a blob (its eight neighbours are all invalid).  gt: B x H x W float32; returns a copy."""
+    gt = np.array(gt, dtype=np.float32, copy=True)
+    b, h, w = gt.shape
+    v, u = np.mgrid[0:h, 0:w]
+    for i in range(b):
+        rng = np.random.default_rng(977 + int(seed) + i)
+        for _ in range(4):
+            cy, cx = rng.uniform(0, h), rng.uniform(0, w)
+            ry, rx = rng.uniform(2, max(3, h / 6)), rng.uniform(2, max(3, w / 6))
+            gt[i][((v - cy) / ry) ** 2 + ((u - cx) / rx) ** 2 < 1.0] = 0.0
+        side = int(rng.integers(0, 4))
+        width = int(rng.integers(1, max(2, min(h, w) // 10 + 1)))
+        if side == 0: gt[i, :width] = 0.0
+        elif side == 1: gt[i, -width:] = 0.0
+        elif side == 2: gt[i, :, :width] = 0.0
+        else: gt[i, :, -width:] = 0.0
+        if h >= 5 and w >= 5:
+            y, x = int(rng.integers(2, h - 2)), int(rng.integers(2, w - 2))
+            gt[i, y - 2:y + 3, x - 2:x + 3] = 0.0
+            gt[i, y, x] = 0.8                                   # lonely valid pixel
+    return gt
+
+
 # --------------------------------------------------------------------------------------
 # torch variant of Gen-P for large resident batches (bench only; same formulas, torch RNG)
 # --------------------------------------------------------------------------------------

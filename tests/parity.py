@@ -53,3 +53,36 @@ def assert_normals_close(got, ref, axis, twin_ok=None, skip=None, tol=NORMAL_TOL
     assert not bad.any(), (f"{what}: {int(bad.sum())} px out of tolerance (NaN counted), first at "
                            f"{np.unravel_index(np.argmax(bad), bad.shape)}, worst finite {np.nanmax(err):.3e} rad")
     return float(err.max()) if err.size else 0.0
+
+
+STENCIL_ROUNDINGS = 4.0          # float32 evaluations of the stencil stay below this many unit round-offs of the model
+
+
+def assert_stencil_normals_close(got, depth, camera_matrix, oracle, what="depth_to_normals", max_ill_fraction=2e-3):
+    """Parity of a float32 depth->normals result with the float64 oracle on depth maps WITH zero-depth holes.
+
+    Every pixel is checked, none is skipped:
+      * where both Sobel gradients are exactly zero (all eight neighbours invalid: hole interiors) the result must be the
+        exact zero vector, as F.normalize gives it in any arithmetic;
+      * elsewhere the angular error must be <= max(1e-3 rad, STENCIL_ROUNDINGS * 2^-24 * bound), `bound` being the
+        oracle's float64 conditioning model (oracle.depth_to_normals_conditioning), and the normal must have unit length;
+      * the pixels whose model bound exceeds 1e-3 rad (the cross product cancels: exactly or nearly parallel gradients,
+        e.g. one isolated valid neighbour; float32 cannot reach 1e-3 there, in the reference's float32 torch ops either)
+        are counted and must stay below `max_ill_fraction` of the image; they must still be finite and of length <= 1.
+    Returns (worst error over the well-conditioned pixels, number of ill-conditioned pixels)."""
+    got = np.asarray(got, np.float64)
+    assert np.isfinite(got).all(), f"{what}: non-finite normals"
+    ref = oracle.depth_to_normals(depth, camera_matrix)
+    _, bound, dead = oracle.depth_to_normals_conditioning(depth, camera_matrix)
+    assert (got[np.broadcast_to(dead[:, None], got.shape)] == 0).all(), f"{what}: non-zero normal inside a zero-depth hole"
+    lim = np.maximum(NORMAL_TOL, STENCIL_ROUNDINGS * 2.0 ** -24 * bound)
+    ill = (lim > NORMAL_TOL) & ~dead
+    err = np.where(dead | ~np.isfinite(lim), 0.0, angular_error(got, ref, axis=1))
+    bad = ~(err <= lim)
+    assert not bad.any(), (f"{what}: {int(bad.sum())} px beyond max(1e-3, model bound), worst {np.nanmax(err - lim):.3e} rad over, first at "
+                           f"{np.unravel_index(np.argmax(bad), bad.shape)}")
+    assert ill.mean() <= max_ill_fraction, f"{what}: {int(ill.sum())} ill-conditioned px ({ill.mean():.2e} of the image)"
+    length = np.sqrt((got * got).sum(axis=1))
+    assert (length < 1 + 1e-5).all() and ((np.abs(length - 1) < 1e-5) | dead | ill).all(), f"{what}: normals are not unit length"
+    well = ~ill & ~dead
+    return (float(err[well].max()) if well.any() else 0.0), int(ill.sum())

@@ -134,6 +134,53 @@ def test_fused_full_frame_properties():
     P.assert_normals_close(nrm[0, :, 480:544].cpu().numpy().reshape(3, 3, 64, ws), ref, axis=1)
 
 
+@pytest.mark.parametrize("kind", ["P", "U"])
+def test_fused_benchmarked_configuration_64_full_frames(kind):
+    """BASELINE configs[1] exactly as bench.py launches it: B = 64 mosaics of 2448 x 2048 in ONE launch (78 336 tiles handed
+    out through cluster launch control).  (a) frames 0, 31, 63 against the oracle on three row strips each (first rows,
+    middle, last rows); (b) EVERY frame bit-equal to its own single-frame launch; (c) the host entry point
+    (polcue_fused_mosaic_u8_host, what `e2e` times) bit-equal on all frames."""
+    B, H, W = 64, synth.FRAME_H, synth.FRAME_W
+    hs, ws = H // 2, W // 2
+    if kind == "P":
+        mosaic = synth.gen_p_batch_torch(0, B, H, W, device="cuda")           # bench.py's generator
+    else:
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(64)
+        mosaic = torch.randint(0, 256, (B, H, W), dtype=torch.uint8, device="cuda", generator=gen)
+    out = ops.fused_mosaic(mosaic, 1.5)
+    torch.cuda.synchronize()
+    # (a) oracle strips
+    for f in (0, 31, 63):
+        frame = mosaic[f].cpu().numpy()
+        stack = O.stack_quadrants(frame)
+        for r0 in (0, 480, hs - 48):
+            rows = slice(r0, r0 + 48)
+            _, rho, phi = O.iun_and_xolp_closed(stack[rows])
+            P.assert_dolp_close(out["xolp"][f, 0, rows].cpu().numpy(), rho, f"rho frame {f} rows {r0}")
+            P.assert_aolp_close(out["xolp"][f, 1, rows].cpu().numpy(), phi)
+            ref = O.get_normals(np.stack((rho, phi))[None], 1.5).reshape(3, 3, 48, ws)
+            P.assert_normals_close(out["normals"][f, :, rows].cpu().numpy().reshape(3, 3, 48, ws), ref, axis=1,
+                                   what=f"normals frame {f} rows {r0}")
+    # (b) every frame == its single-frame launch
+    one = {}
+    for f in range(B):
+        one = ops.fused_mosaic(mosaic[f:f + 1], 1.5, out=one)
+        assert torch.equal(one["xolp"][0], out["xolp"][f]) and torch.equal(one["normals"][0], out["normals"][f]), f
+    # (c) host entry point on all frames (NUMA-local pinned buffers from the library)
+    h_mosaic = ops.host_empty((B, H, W), torch.uint8)
+    h_mosaic.copy_(mosaic)
+    host = ops.fused_mosaic_host(h_mosaic, 1.5)
+    for key in ("xolp", "normals"):
+        assert torch.equal(host[key].cuda(), out[key]), key
+    # unit length everywhere, AoLP in range
+    norms = out["normals"].view(B, 3, 3, hs, ws).norm(dim=2)
+    assert float((norms - 1).abs().max()) < 3e-6
+    assert float(out["xolp"][:, 1].abs().max()) <= np.pi / 2 + 1e-6
+    del host, h_mosaic, out, norms, mosaic
+    torch.cuda.empty_cache()
+
+
 def test_fused_without_optional_outputs_and_bad_args():
     mosaic = dev(synth.gen_u_mosaic(1, 64, 96))[None]
     full = ops.fused_mosaic(mosaic, 1.5, want_iun=True)
@@ -408,29 +455,39 @@ def torch_sobel_restatement(depth, K):
     return F.normalize(torch.cross(g[:, :, 0], g[:, :, 1], dim=1), dim=1, p=2, eps=1e-12)
 
 
-@pytest.mark.parametrize("shape", [(320, 480), (64, 96), (37, 131), (5, 3), (1, 1), (9, 260)])
+def holey_depth(first, batch, h, w):
+    """GT depth as the reference feeds it (HAMMER: 0 = invalid): 10 % random invalid pixels, a depth step, plus -- on images
+    large enough -- contiguous missing regions, an invalid border strip and an isolated valid pixel."""
+    gt, pred, inst, k = synth.gen_depth_batch(first, batch, h, w)
+    if min(h, w) >= 8:
+        gt = synth.add_hole_regions(gt, first)
+    return gt, pred, inst, k
+
+
+@pytest.mark.parametrize("shape", [(320, 480), (64, 96), (37, 131), (5, 3), (1, 1), (9, 260), (832, 1088)])
 def test_depth_to_normals(shape):
+    """Hole-free surface: 1e-3 rad on every pixel.  GT with zero-depth holes (the data trainer.py:1305 actually passes):
+    every pixel checked by the conditioning-aware protocol of parity.assert_stencil_normals_close -- 1e-3 rad wherever the
+    float64 model says float32 can reach it, exact zero vectors inside holes, an explicit count bound on the rest."""
     h, w = shape
-    gt, _, _, k = synth.gen_depth_batch(3, 3, h, w)
+    batch = 3 if h * w < 500_000 else 1
+    gt, _, _, k = holey_depth(3, batch, h, w)
     valid_only = np.where(gt > 0, gt, 0.7).astype(np.float32)          # smooth surface, no invalid holes
-    for depth, tol in ((valid_only, 1e-3), (gt, None)):
+    torch.backends.cudnn.allow_tf32 = False                             # the float32 restatement below must not use TF32 convolutions
+    got = c_depth.depth_to_normals(dev(valid_only)[:, None], dev(k)).cpu().numpy()
+    ref = O.depth_to_normals(valid_only[:, None], k)
+    P.assert_normals_close(got, ref, axis=1, tol=1e-3)
+    assert np.abs(np.linalg.norm(got, axis=1) - np.linalg.norm(ref, axis=1)).max() < 1e-5     # unit length (zero on one-pixel-wide images)
+    for depth in (gt, synth.gen_depth_batch(3, batch, h, w)[0]):        # with region holes, and with the random 10 % only
         got = c_depth.depth_to_normals(dev(depth)[:, None], dev(k)).cpu().numpy()
-        ref64 = O.depth_to_normals(depth[:, None], k)
-        if tol is not None:
-            P.assert_normals_close(got, ref64, axis=1, tol=tol)
-        else:
-            # with zero-depth holes the cross product cancels catastrophically at a few pixels in float32:
-            # compare where the float64 normal is well conditioned, and require finite unit-or-zero output everywhere
-            err = P.angular_error(got, ref64, axis=1)
-            assert np.isfinite(got).all()
-            assert np.quantile(err, 0.999) < 2e-3
+        worst, ill = P.assert_stencil_normals_close(got, depth[:, None], k, O, max_ill_fraction=3e-3 if h * w > 100_000 else 4e-2)
+        # the float32 torch restatement of kornia's op sequence agrees too wherever float32 can reach the bound
         ref32 = torch_sobel_restatement(dev(depth)[:, None], dev(k)).cpu().numpy()
+        _, bound, dead = O.depth_to_normals_conditioning(depth[:, None], k)
+        well = (P.STENCIL_ROUNDINGS * 2.0 ** -24 * bound <= P.NORMAL_TOL) & ~dead
         err32 = P.angular_error(got, ref32, axis=1)
-        assert np.quantile(err32, 0.999) < 2e-3
-    nrm = np.linalg.norm(got, axis=1)
-    # unit length, except where the float32 cross product underflows next to zero-depth holes (kornia divides by
-    # max(norm, 1e-12) there too and returns a short vector)
-    assert ((np.abs(nrm - 1) < 1e-5) | (nrm < 1e-5)).all()
+        assert (err32[well] <= 1e-3).all(), float(err32[well].max())
+        assert (ref32[np.broadcast_to(dead[:, None], ref32.shape)] == 0).all()
 
 
 def test_stencil_metrics_and_loss_randomized_shapes_and_cameras():
@@ -448,7 +505,7 @@ def test_stencil_metrics_and_loss_randomized_shapes_and_cameras():
         k = np.stack([np.array([[rng.uniform(200, 900), 0, rng.uniform(0, w)], [0, rng.uniform(200, 900), rng.uniform(0, h)], [0, 0, 1]])
                       for _ in range(b)]).astype(np.float32)
         got = ops.depth_to_normals(dev(depth)[:, None], dev(k)).cpu().numpy()
-        P.assert_normals_close(got, O.depth_to_normals(depth[:, None], k), axis=1, tol=2e-3, what=f"stencil case {case}")
+        P.assert_normals_close(got, O.depth_to_normals(depth[:, None], k), axis=1, tol=1e-3, what=f"stencil case {case}")
         # metrics: prediction = noisy depth, 15 % invalid ground truth, random range and material
         pred = (depth * (1 + 0.1 * rng.standard_normal(depth.shape))).clip(0.05, 4).astype(np.float32)
         gt = np.where(rng.random(depth.shape) < 0.15, 0, depth).astype(np.float32)
@@ -570,6 +627,73 @@ def test_supervised_depth_and_normals_losses_fused(shape):
     ops.supervised_losses(dev(gt)[:, None], d4, dev(k), lo, hi)[0].backward()
     expect = torch.sign(d4.detach() - dev(gt)[:, None]) * mask / mask.sum()
     assert torch.allclose(d4.grad, expect, rtol=1e-6, atol=0)
+
+
+def _ill_conditioned_neighbourhood(gt, k):
+    """Pixels whose GT normal is a round-off direction in ANY float32 evaluation (parallel gradients next to holes), and
+    the pixels within one step of them (whose gradient gathers from them)."""
+    _, bound, dead = O.depth_to_normals_conditioning(gt[:, None], k)
+    ill = (P.STENCIL_ROUNDINGS * 2.0 ** -24 * bound > P.NORMAL_TOL) & ~dead
+    near = ill.copy()
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            near |= np.roll(np.roll(ill, dy, axis=1), dx, axis=2)
+    return ill, near
+
+
+@pytest.mark.parametrize("shape", [(320, 480), (64, 96), (37, 131), (16, 128), (9, 260)])
+def test_losses_on_ground_truth_with_zero_depth_holes(shape):
+    """The normal HAMMER case (trainer.py:1242-1243, :1298-1309): depth_gt == 0 marks invalid pixels, next to valid ones.
+    Forward and backward of the stand-alone normals loss (range mask passed as a tensor) and of the supervised block
+    (mask derived from the staged GT tile) against float64 torch autograd.  Where the GT normal is a pure round-off
+    direction (exactly parallel gradients: a handful of pixels, counted) the loss may differ by at most 2 / sum(mask) per
+    such pixel and the gradient is compared outside their 3 x 3 neighbourhoods; everything else is held to the usual bounds."""
+    h, w = shape
+    gt, _, _, k = holey_depth(11, 3, h, w)
+    assert 0.1 < (gt == 0).mean() < 0.6
+    vv, uu = np.mgrid[0:h, 0:w].astype(np.float32)
+    smooth = np.where(gt > 0, gt, 0.7).astype(np.float32)
+    pred = (smooth * (1.0 + 0.05 * np.sin(uu / 23.0 + np.arange(3)[:, None, None]) * np.cos(vv / 17.0))).astype(np.float32)
+    lo, hi = 0.1, 2.0
+    mask = ((gt >= lo) & (gt <= hi)).astype(np.float32)
+    ill, near = _ill_conditioned_neighbourhood(gt, k)
+    n_ill = int((ill & (mask > 0)).sum())
+    assert n_ill <= max(32, 2e-4 * mask.size), n_ill
+    t64 = lambda a: torch.from_numpy(a.astype(np.float64))
+    g64, m64 = t64(gt)[:, None], t64(mask)[:, None]
+    p64 = t64(pred)[:, None].requires_grad_(True)
+    ref_normals = O.normals_loss_torch(g64, p64, t64(k), m64)
+    ref_depth = ((g64 - p64).abs() * m64).sum() / m64.sum()
+    (1.3 * ref_normals + 0.7 * ref_depth).backward()
+    ref_grad = p64.grad[:, 0].numpy()
+    slack = 2.0 * n_ill / mask.sum()
+
+    def check_grad(got, ref):
+        scale = np.abs(ref).max() + 1e-30
+        err = np.abs(got - ref) / scale
+        assert np.isfinite(got).all()
+        assert err[~near].max() < 2e-3 and np.sqrt((err[~near] ** 2).mean()) < 2e-4, (float(err[~near].max()), scale)
+        assert np.abs(got[near]).max(initial=0.0) <= 4.0 * scale + 1e-30           # bounded next to the round-off normals too
+
+    # stand-alone normals loss, mask tensor
+    d1 = dev(pred)[:, None].requires_grad_(True)
+    loss = ops.normals_loss(dev(gt)[:, None], d1, dev(k), dev(mask)[:, None])
+    assert abs(float(loss.detach()) - float(ref_normals.detach())) <= 2e-5 * abs(float(ref_normals.detach())) + slack
+    loss.backward()
+    p2 = t64(pred)[:, None].requires_grad_(True)
+    O.normals_loss_torch(g64, p2, t64(k), m64).backward()
+    check_grad(d1.grad[:, 0].cpu().numpy().astype(np.float64), p2.grad[:, 0].numpy())
+    # supervised block: range mask from the GT tile, L1 + normals
+    d2 = dev(pred)[:, None].requires_grad_(True)
+    depth_loss, normals_loss = ops.supervised_losses(dev(gt)[:, None], d2, dev(k), lo, hi)
+    assert torch.equal(normals_loss.detach(), loss.detach())                     # same kernel arithmetic, same mask
+    assert abs(float(depth_loss.detach()) - float(ref_depth.detach())) < 2e-6 * max(1.0, abs(float(ref_depth.detach())))
+    (1.3 * normals_loss + 0.7 * depth_loss).backward()
+    check_grad(d2.grad[:, 0].cpu().numpy().astype(np.float64), ref_grad)
+    # invalid GT pixels get no L1 gradient and pull no normals gradient through their own mask
+    only_l1 = dev(pred)[:, None].requires_grad_(True)
+    ops.supervised_losses(dev(gt)[:, None], only_l1, dev(k), lo, hi)[0].backward()
+    assert float(only_l1.grad[:, 0][dev(gt) == 0].abs().max()) == 0.0
 
 
 def test_normals_loss_matches_composition_of_public_ops_and_is_deterministic():
