@@ -103,6 +103,21 @@ POLCUE_API int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W
                            uint8_t* planes, float* iun, float* xolp, float* normals,
                            polcue_stream_t stream);
 
+/* The fused pipeline with the dataset statistics / output checksum as a BY-PRODUCT of the same launch:
+ *   polarisation/xolp_mean_and_std_dev.py:26-32  mean / std of DoLP and AoLP over a set of frames (the constants of
+ *   manydepth/networks/pre_encoders.py:79); per-plane float64 output checksums of the sequence benchmark.
+ * stats13 (13 device doubles): sum rho, sum phi, the sums of the nine normal channels, sum rho^2, sum phi^2 over the batch.
+ * The sums follow the library's canonical order (group of 4 pixels -> tile of 256 groups -> segment of 1024 tiles -> total,
+ * polcue_device.cuh): bitwise reproducible under the kernel's dynamic tile scheduling, and bit-identical to
+ * polcue_channel_stats_f32 of the stored xolp / normals.  The outputs are not read again (one extra launch folds the
+ * 64-byte tile records).  Shapes without 4-pixel groups (Ws % 4 != 0) and tables with a steep end segment take the
+ * separate statistics pass internally -- same results, two more reads of the outputs.
+ * workspace: polcue_fused_stats_workspace_bytes(B, H, W) bytes, 64-byte aligned, first 8 bytes zero before the first use. */
+POLCUE_API size_t polcue_fused_stats_workspace_bytes(int B, int H, int W);
+POLCUE_API int polcue_fused_mosaic_stats_u8(const uint8_t* mosaic, int B, int H, int W, const polcue_lut* lut,
+                                 uint8_t* planes, float* iun, float* xolp, float* normals,
+                                 void* workspace, double* stats13, polcue_stream_t stream);
+
 /* The same pipeline for the RAW sensor layout (not used by the reference, whose HAMMER images are stored pre-tiled):
  * an interleaved 2x2 super-pixel mosaic, output pixel (y, x) owning mosaic pixels (2y, 2x), (2y, 2x+1), (2y+1, 2x),
  * (2y+1, 2x+1).  angle_at: 4 HOST ints, the angle index (0, 1, 2, 3 = 0, 45, 90, 135 deg) found at those four
@@ -289,7 +304,8 @@ POLCUE_API int polcue_depth_errors_images_f32(const float* gt, const float* pred
  * Per-channel sum and sum of squares (float64) of a planar float32 tensor x[B, C, hw].
  *   polarisation/xolp_mean_and_std_dev.py:26-32 (mean / std of DoLP and AoLP over a set of frames; the constants
  *   of manydepth/networks/pre_encoders.py:79); also the output checksum of the sequence benchmark.
- * stats: C x 2 doubles (device): sum, sum of squares per channel; additive across frames and ranks.
+ * stats: C x 2 doubles (device): sum, sum of squares per channel; additive across frames and ranks.  Canonical order
+ * (see polcue_fused_mosaic_stats_u8): float32 inside a tile of 1024 elements, float64 above; bitwise reproducible.
  * workspace: polcue_channel_stats_workspace_bytes(B, C, hw) bytes, first 8 bytes zero before the first use.
  * ------------------------------------------------------------------------------------------- */
 POLCUE_API size_t polcue_channel_stats_workspace_bytes(int B, int C, size_t hw);
@@ -322,6 +338,17 @@ POLCUE_API int polcue_depth_errors_images_scaled_f32(const float* gt, const floa
 POLCUE_API int polcue_depth_errors_groups_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px,
                                    float min_d, float max_d, const int* group_ids, int n_groups, double* sums,
                                    float* metrics, polcue_stream_t stream);
+
+/* One evaluation pass over a shard of the test split with no host work between the launches (BASELINE configs[4]):
+ *   normals (B x 3 x H x W, or NULL to skip) = depth_to_normals(gt, K)                 manydepth/trainer.py:1484 (GT normals)
+ *   sums / metrics = polcue_depth_errors_groups_f32(..)                                  trainer.py:1356-1430, evaluation.py:215-288
+ *   mean_acc (1 + n_groups * 7 device doubles) = {B, sum over images of every group's seven per-image metrics}: the
+ *   accumulators of the reference's mean over images (np.array(errors).mean(0), trainer.py:1426), additive across
+ *   ranks -- one all-reduce of this vector and a division finish the evaluation.
+ * Three launches on `stream`; capturable in a CUDA graph. */
+POLCUE_API int polcue_eval_pass_f32(const float* gt, const float* pred, const uint8_t* inst, const float* K, int B, int H, int W,
+                         float min_d, float max_d, const int* group_ids, int n_groups, float* normals, double* sums,
+                         float* metrics, double* mean_acc, polcue_stream_t stream);
 
 #ifdef __cplusplus
 }

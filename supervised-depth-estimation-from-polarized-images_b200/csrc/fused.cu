@@ -122,6 +122,7 @@ struct FusedParams {
     uint32_t frame_bytes;    // input frame stride in bytes                 (all strides < 2^32, checked on the host)
     uint32_t plane;          // Hs * Ws
     uint32_t plane_bytes;    // 4 * Hs * Ws
+    float* tile_records;     // STATS kernels only: [tiles][kSumRecord] per-tile sums (rho, phi, 9 normal channels, rho^2, phi^2)
 };
 
 template <int VEC>
@@ -234,8 +235,10 @@ __device__ __noinline__ void steep_redo(const FusedParams& p, uint32_t b, uint32
     }
 }
 
-template <int VEC, bool MUFU, bool NORMALS>
-__device__ __forceinline__ void process_group(const FusedParams& p, const LutShared& lut, const GroupIn<VEC>& g) {
+constexpr int kStatValues = 13;   // sums of rho, phi and the nine normal channels, then the squares of rho and phi
+
+template <int VEC, bool MUFU, bool NORMALS, bool STATS = false>
+__device__ __forceinline__ void process_group(const FusedParams& p, const LutShared& lut, const GroupIn<VEC>& g, float* part = nullptr) {
     using PK = Packed<VEC>;
     const uint32_t b = g.b;
     const uint32_t pix = g.rem * VEC;   // first pixel inside the Hs x Ws plane (Ws = groups_per_row * VEC)
@@ -306,17 +309,57 @@ __device__ __forceinline__ void process_group(const FusedParams& p, const LutSha
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
             st_stream_vec<VEC>(no, nrm[c]);
+            if constexpr (STATS && VEC == 4) part[2 + c] = group_sum4(nrm[c][0], nrm[c][1], nrm[c][2], nrm[c][3]);
             no += p.plane;
         }
-        if (steep_bits) steep_redo(p, b, pix, steep_bits);   // rare: float64 evaluation of a steep end segment
+        if (steep_bits) steep_redo(p, b, pix, steep_bits);   // rare: float64 evaluation of a steep end segment (never with STATS)
+    }
+    if constexpr (STATS && VEC == 4) {      // group partials in the canonical order (polcue_device.cuh)
+        part[0] = group_sum4(rho[0], rho[1], rho[2], rho[3]);
+        part[1] = group_sum4(phi[0], phi[1], phi[2], phi[3]);
+        part[11] = group_squares4(rho[0], rho[1], rho[2], rho[3]);
+        part[12] = group_squares4(phi[0], phi[1], phi[2], phi[3]);
+    }
+}
+
+// Statistics by-product: the 13 group partials of this thread -> the tile record, canonical order.  Per warp one
+// butterfly level in registers (xor 16), the 16 surviving lane sums of every value go through a 832-byte shared slab,
+// lane v finishes the tree of value v; the eight warp sums are added in order by the first 13 threads.
+__device__ __forceinline__ void tile_record_store(float (&part)[kStatValues], float (*slab)[kStatValues][16], float (*warp_sums)[16],
+                                                  float* record) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int v = 0; v < kStatValues; ++v) part[v] = __fadd_rn(part[v], __shfl_xor_sync(0xffffffffu, part[v], 16));
+    if (lane < 16) {
+#pragma unroll
+        for (int v = 0; v < kStatValues; ++v) slab[warp][v][lane] = part[v];
+    }
+    __syncwarp();
+    if (lane < kStatValues) {
+        const float4* row = reinterpret_cast<const float4*>(&slab[warp][lane][0]);
+        const float4 a = row[0], b = row[1], c = row[2], d = row[3];
+        // xor 8: l + (l ^ 8); xor 4; xor 2; xor 1
+        const float e0 = __fadd_rn(a.x, c.x), e1 = __fadd_rn(a.y, c.y), e2 = __fadd_rn(a.z, c.z), e3 = __fadd_rn(a.w, c.w);
+        const float e4 = __fadd_rn(b.x, d.x), e5 = __fadd_rn(b.y, d.y), e6 = __fadd_rn(b.z, d.z), e7 = __fadd_rn(b.w, d.w);
+        const float f0 = __fadd_rn(e0, e4), f1 = __fadd_rn(e1, e5), f2 = __fadd_rn(e2, e6), f3 = __fadd_rn(e3, e7);
+        const float g0 = __fadd_rn(f0, f2), g1 = __fadd_rn(f1, f3);
+        warp_sums[warp][lane] = __fadd_rn(g0, g1);
+    }
+    __syncthreads();
+    if (threadIdx.x < kStatValues) {
+        float t = warp_sums[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t = __fadd_rn(t, warp_sums[w][threadIdx.x]);
+        record[threadIdx.x] = t;
     }
 }
 
 // One tile = one group of VEC pixels per thread (512 groups per CTA).  Tiles arrive in order through cluster launch
 // control; the loop is software-pipelined two deep: while tile k is computed and stored, the quadrant words of tile
 // k+1 are already in flight and the query for tile k+2 is outstanding, so no warp waits on DRAM latency.
-template <int VEC, bool MUFU, bool NORMALS>
+template <int VEC, bool MUFU, bool NORMALS, bool STATS = false>
 __global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) fused_mosaic_kernel(const __grid_constant__ FusedParams p) {
+    static_assert(!STATS || (VEC == 4 && NORMALS && kFusedThreads == kSumTileGroups), "the statistics by-product needs 4-pixel groups, 256 per tile");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t bar;
     __shared__ __align__(16) uint4 clc_resp;
@@ -325,7 +368,8 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) fused_mosaic_k
     ClcTiles clc;
     clc.init(&clc_resp, &clc_bar);
     clc.prefetch();                                      // query for the tile after blockIdx.x
-    GroupIn<VEC> cur = load_group<VEC>(p, blockIdx.x);
+    uint32_t cur_tile = blockIdx.x;
+    GroupIn<VEC> cur = load_group<VEC>(p, cur_tile);
     if constexpr (NORMALS) lut_stage_wait(&bar);
     const LutShared lut = lut_shared(smem_raw, p.lut);
 
@@ -339,9 +383,20 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) fused_mosaic_k
             clc.prefetch();
             nxt = load_group<VEC>(p, next_tile);         // in flight while `cur` is processed
         }
-        if (cur.valid) process_group<VEC, MUFU, NORMALS>(p, lut, cur);
+        if constexpr (STATS) {
+            __shared__ __align__(16) float slab[kFusedThreads / 32][kStatValues][16];
+            __shared__ float warp_sums[kFusedThreads / 32][16];
+            float part[kStatValues];
+#pragma unroll
+            for (int v = 0; v < kStatValues; ++v) part[v] = 0.0f;       // threads past the end of the batch add +0
+            if (cur.valid) process_group<VEC, MUFU, NORMALS, true>(p, lut, cur, part);
+            tile_record_store(part, slab, warp_sums, p.tile_records + (size_t)cur_tile * kSumRecord);
+        } else {
+            if (cur.valid) process_group<VEC, MUFU, NORMALS>(p, lut, cur);
+        }
         if (!more) break;
         cur = nxt;
+        cur_tile = next_tile;
     }
 }
 
@@ -351,6 +406,9 @@ template <int VEC>
 int launch_fused(const FusedParams& p, size_t smem, cudaStream_t stream, bool mufu) {
     auto kern = !p.normals ? fused_mosaic_kernel<VEC, true, false>
                            : (mufu ? fused_mosaic_kernel<VEC, true, true> : fused_mosaic_kernel<VEC, false, true>);
+    if constexpr (VEC == 4) {
+        if (p.tile_records) kern = mufu ? fused_mosaic_kernel<4, true, true, true> : fused_mosaic_kernel<4, false, true, true>;
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
@@ -695,7 +753,7 @@ extern "C" {
 
 static int fused_mosaic_common(const uint8_t* mosaic, int B, int H, int W, bool layout_superpixel, const int* angle_at,
                                const polcue_lut* lut, uint8_t* planes, float* iun, float* xolp, float* normals,
-                               polcue_stream_t stream) {
+                               polcue_stream_t stream, void* stats_workspace = nullptr, bool* stats_fused = nullptr) {
     if (!mosaic || !xolp || B < 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return POLCUE_EINVAL;
     if (layout_superpixel) {
         if (!angle_at) return POLCUE_EINVAL;
@@ -746,6 +804,13 @@ static int fused_mosaic_common(const uint8_t* mosaic, int B, int H, int W, bool 
     for (int k = 0; k < 4; ++k) p.angle_at[k] = layout_superpixel ? angle_at[k] : k;
     p.plane = (uint32_t)Hs * (uint32_t)Ws;
     p.plane_bytes = 4u * p.plane;
+    p.tile_records = nullptr;
+    // statistics by-product: 4-pixel groups, normals present, no steep table (its float64 redo overwrites stored values)
+    const uint32_t tiles = (p.groups_total + kFusedThreads - 1) / kFusedThreads;
+    if (stats_workspace && vec == 4 && normals && !lut->steep_mask) {
+        p.tile_records = fold_records(stats_workspace, tiles);
+        if (stats_fused) *stats_fused = true;
+    }
     const size_t smem = normals ? lut->bytes() : 0;
     cudaStream_t s = (cudaStream_t)stream;
     const bool mufu = !lut || lut->trig_mufu != 0;
@@ -754,6 +819,50 @@ static int fused_mosaic_common(const uint8_t* mosaic, int B, int H, int W, bool 
         case 2: return launch_fused<2>(p, smem, s, mufu);
         default: return launch_fused<1>(p, smem, s, mufu);
     }
+}
+
+static size_t stats_scratch_offset(int B, int H, int W) {
+    const size_t hw = (size_t)(H / 2) * (W / 2);
+    // the by-product's tile records, or (fallback) the workspace of the separate statistics pass over the 9 normal channels
+    const unsigned long long tiles = ((unsigned long long)B * (hw / 4) + kFusedThreads - 1) / kFusedThreads + 1;
+    const size_t fused = tiles < (1ull << 31) ? fold_workspace_bytes((uint32_t)tiles, kSumRecord) : 64;
+    const size_t separate = polcue_channel_stats_workspace_bytes(B, 9, hw);
+    return ((fused > separate ? fused : separate) + 63) / 64 * 64;
+}
+
+size_t polcue_fused_stats_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 64;
+    return stats_scratch_offset(B, H, W) + 22 * sizeof(double) + 64;
+}
+
+__global__ void pack_stats13_kernel(const double* __restrict__ xolp4, const double* __restrict__ normals18, double* __restrict__ out) {
+    const int i = threadIdx.x;
+    if (i < 2) out[i] = xolp4[2 * i];                   // sum rho, sum phi
+    else if (i < 11) out[i] = normals18[2 * (i - 2)];   // sums of the nine normal channels
+    else if (i < 13) out[i] = xolp4[2 * (i - 11) + 1];  // squares of rho, phi
+}
+
+int polcue_fused_mosaic_stats_u8(const uint8_t* mosaic, int B, int H, int W, const polcue_lut* lut, uint8_t* planes, float* iun,
+                                 float* xolp, float* normals, void* workspace, double* stats13, polcue_stream_t stream) {
+    if (!workspace || !stats13 || !normals || B <= 0) return POLCUE_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 63) || (reinterpret_cast<uintptr_t>(stats13) & 7)) return POLCUE_EINVAL;
+    bool fused = false;
+    int rc = fused_mosaic_common(mosaic, B, H, W, false, nullptr, lut, planes, iun, xolp, normals, stream, workspace, &fused);
+    if (rc != POLCUE_OK) return rc;
+    const size_t hw = (size_t)(H / 2) * (W / 2);
+    if (fused) {
+        const uint32_t tiles = (uint32_t)(((unsigned long long)B * (hw / 4) + kFusedThreads - 1) / kFusedThreads);
+        return launch_fold_tiles(workspace, tiles, kSumRecord, kStatValues, stats13, (cudaStream_t)stream);
+    }
+    // Shapes / tables the by-product does not cover (widths that are not multiples of 8, steep end segments): the separate
+    // statistics pass over the stored outputs, which adds in the same canonical order.
+    double* tmp = reinterpret_cast<double*>(static_cast<char*>(workspace) + stats_scratch_offset(B, H, W));
+    rc = polcue_channel_stats_f32(xolp, B, 2, hw, workspace, tmp, stream);
+    if (rc != POLCUE_OK) return rc;
+    rc = polcue_channel_stats_f32(normals, B, 9, hw, workspace, tmp + 4, stream);
+    if (rc != POLCUE_OK) return rc;
+    pack_stats13_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(tmp, tmp + 4, stats13);
+    return launch_status();
 }
 
 int polcue_fused_mosaic_u8(const uint8_t* mosaic, int B, int H, int W, const polcue_lut* lut, uint8_t* planes, float* iun,
@@ -806,6 +915,7 @@ static int fused_planes_common(const uint8_t* i0, long long off45, long long off
     p.frame_bytes = (uint32_t)frame_stride;
     p.plane = (uint32_t)H * (uint32_t)W;
     p.plane_bytes = 4u * p.plane;
+    p.tile_records = nullptr;
     const size_t smem = normals ? lut->bytes() : 0;
     cudaStream_t s = (cudaStream_t)stream;
     const bool mufu = !lut || lut->trig_mufu != 0;

@@ -653,6 +653,19 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     if (rank == 0 && p.metrics && threadIdx.x < p.n_groups) finalize(cta_tot[threadIdx.x], p.metrics + (b * p.n_groups + threadIdx.x) * 7);
 }
 
+// {n_images, sum over images of the per-image metric rows} -- the accumulators of the reference's mean over images
+// (np.array(errors).mean(0), trainer.py:1426; evaluation.py:283-285), additive across ranks.  One thread per
+// (group, metric) adds the images in index order, so the result is bitwise reproducible.  NaN rows (empty masks)
+// poison the mean exactly as they do in the reference.
+__global__ void __launch_bounds__(128) image_mean_acc_kernel(const float* __restrict__ metrics, int B, int n_values, double* __restrict__ acc) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == 0) acc[0] = (double)B;
+    if (v >= n_values) return;
+    double t = 0.0;
+    for (int b = 0; b < B; ++b) t += (double)__ldg(metrics + (size_t)b * n_values + v);
+    acc[1 + v] = t;
+}
+
 }  // namespace
 }  // namespace polcue
 
@@ -786,6 +799,24 @@ int polcue_depth_errors_groups_f32(const float* gt, const float* pred, const uin
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<dim3(kCluster, B, 1), kMetricThreads, smem, (cudaStream_t)stream>>>(p);
+    return launch_status();
+}
+
+int polcue_eval_pass_f32(const float* gt, const float* pred, const uint8_t* inst, const float* K, int B, int H, int W, float min_d,
+                         float max_d, const int* group_ids, int n_groups, float* normals, double* sums, float* metrics,
+                         double* mean_acc, polcue_stream_t stream) {
+    if (!metrics || !mean_acc || H <= 0 || W <= 0 || B <= 0) return POLCUE_EINVAL;
+    if (reinterpret_cast<uintptr_t>(mean_acc) & 7) return POLCUE_EINVAL;
+    int rc = POLCUE_OK;
+    if (normals) {
+        if (!K) return POLCUE_EINVAL;
+        rc = polcue_depth_to_normals_f32(gt, K, B, H, W, normals, stream);
+        if (rc != POLCUE_OK) return rc;
+    }
+    rc = polcue_depth_errors_groups_f32(gt, pred, inst, B, (size_t)H * W, min_d, max_d, group_ids, n_groups, sums, metrics, stream);
+    if (rc != POLCUE_OK) return rc;
+    const int n_values = n_groups * 7;
+    image_mean_acc_kernel<<<(n_values + 127) / 128, 128, 0, (cudaStream_t)stream>>>(metrics, B, n_values, mean_acc);
     return launch_status();
 }
 

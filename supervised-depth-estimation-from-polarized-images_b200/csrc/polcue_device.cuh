@@ -532,6 +532,45 @@ struct ClcTiles {
     }
 };
 
+// ------------------------------------------------------------------------------------------
+// Deterministic sums ("canonical order"), shared by the statistics kernel (stats.cu) and the statistics by-product of
+// the fused kernel (fused.cu) so that both give the SAME BITS for the same data under any CTA scheduling:
+//   group   4 consecutive elements of a channel's batch-flattened sequence (1 element when hw % 4 != 0):
+//           sum  = (x + y) + (z + w),   squares = fma(x, x, fma(y, y, fma(z, z, w * w)))            float32
+//   tile    256 consecutive groups = 8 "warps" of 32: per warp the xor butterfly 16, 8, 4, 2, 1 (float add commutes, so
+//           the lane that evaluates a node does not matter), then the 8 warp sums added in order 0..7          float32
+//   segment 1024 consecutive tiles: thread j adds tiles j, j + 256, j + 512, j + 768 in float64, block_sum_f64
+//   total   thread j adds segments j, j + 256, ... in float64, block_sum_f64
+// Missing groups / tiles (ragged ends) contribute +0.
+// ------------------------------------------------------------------------------------------
+constexpr int kSumTileGroups = 256;
+constexpr int kSumSegmentTiles = 1024;
+constexpr int kSumRecord = 16;          // floats per tile record of the fused by-product (13 used)
+
+__device__ __forceinline__ float group_sum4(float x, float y, float z, float w) { return __fadd_rn(__fadd_rn(x, y), __fadd_rn(z, w)); }
+__device__ __forceinline__ float group_squares4(float x, float y, float z, float w) {
+    return fmaf(x, x, fmaf(y, y, fmaf(z, z, __fmul_rn(w, w))));
+}
+__device__ __forceinline__ float warp_tree_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+// float64 sum over the 256 threads of a CTA in a fixed order (shuffle-down tree, then the 8 warp sums in order); the
+// result is valid in thread 0.  scratch: 8 doubles of shared memory.
+__device__ __forceinline__ double block_sum_f64(double v, double* scratch) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();                      // scratch may still be read from a previous call
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; ++w) t += scratch[w];
+    return t;
+}
+
 // Exact unsigned division by a runtime constant (d >= 1, n < 2^31): q = (n * mul) >> 32 >> shift.
 struct FastDiv {
     uint32_t mul, shift, div;

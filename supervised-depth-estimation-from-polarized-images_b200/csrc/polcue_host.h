@@ -47,6 +47,13 @@ int fused_planes_strided(const uint8_t* planes, int B, int H, int W, const polcu
                          float* normals, cudaStream_t stream, float* xolp_norm = nullptr, float norm_mean = 0.0f,
                          float norm_std = 1.0f);
 
+// stats.cu: canonical float64 fold of per-tile float records (polcue_device.cuh, "Deterministic sums").  The workspace
+// holds a ticket word (first 8 bytes, zero before the first use; the kernel re-zeroes it), the segment partials and the
+// tile records [n_tiles][stride]; out receives n_values (<= stride, <= 32) doubles.
+size_t fold_workspace_bytes(uint32_t n_tiles, int stride);
+float* fold_records(void* workspace, uint32_t n_tiles);
+int launch_fold_tiles(void* workspace, uint32_t n_tiles, int stride, int n_values, double* out, cudaStream_t stream);
+
 // magic numbers for polcue::FastDiv (exact for numerators < 2^31)
 inline void make_fastdiv(uint32_t d, uint32_t& mul, uint32_t& shift) {
     if (d <= 1) {

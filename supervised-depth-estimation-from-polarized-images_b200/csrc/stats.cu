@@ -5,115 +5,158 @@
 // checksum of the sequence benchmark.  The two sums are additive across frames and ranks
 // (one all-reduce of 2 C doubles).
 //
-// Roofline: HBM, 4 B per element.  One CTA per 64 KB slab of one (b, c) plane: float4 streaming loads, float32
-// partial sums over 64 elements per thread, float64 from there on; warp shuffles -> shared -> one partial per CTA;
-// the last CTA to finish folds the partials of every channel in a fixed order, so results are bitwise reproducible.
+// Roofline: HBM, 4 B per element.  The sums follow the library's canonical order (polcue_device.cuh: group -> tile ->
+// segment -> total), the same order the statistics by-product of the fused kernel uses, so
+// polcue_fused_mosaic_stats_u8 and this function return the same bits for the same data, and every run does.
+// One WARP per tile of 256 groups: lane l loads groups l, l + 32, ... (eight 16-byte loads in flight), the eight
+// butterfly trees of the tile run in registers, lane 0 writes the tile record; fold_tiles_kernel then adds the
+// records in float64 (one CTA per segment of 1024 tiles, the last CTA to finish adds the segments).
 #include "polcue_device.cuh"
 #include "polcue_host.h"
 
 namespace polcue {
 namespace {
 
-constexpr int kStatThreads = 256, kStatVecPerThread = 16;               // 16 float4 per thread
-constexpr int kStatSlab = kStatThreads * kStatVecPerThread * 4;         // 16384 floats = 64 KB per CTA
+constexpr int kStatThreads = 256;
+constexpr int kFoldValues = 32;          // values per tile record the fold kernel can carry
 
 struct StatParams {
     const float* x;
     size_t hw;
-    int planes;          // B * C
-    int channels;        // C
-    unsigned chunks;     // slabs per plane
-    bool vec4;
-    unsigned long long* ticket;
-    double* partials;    // [planes * chunks][2]
-    double* stats;       // [C][2]
+    int channels;              // C of the tensor
+    int c0;                    // first channel of this launch (records hold channels c0 .. c0 + gridDim.y - 1)
+    int vec;                   // elements per group: 4 (hw % 4 == 0) or 1
+    unsigned long long groups; // B * hw / vec, per channel
+    uint32_t groups_per_image; // hw / vec
+    uint32_t n_tiles;
+    int stride;                // floats per tile record
+    bool aligned16;
+    float* records;            // [n_tiles][stride]: (sum, squares) of channel c at [2 (c - c0)], [2 (c - c0) + 1]
 };
 
-__device__ __forceinline__ double block_sum(double v, double* scratch) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+__global__ void __launch_bounds__(kStatThreads) channel_tiles_kernel(const StatParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();                      // scratch may still be read from a previous call
-    if (lane == 0) scratch[warp] = v;
-    __syncthreads();
-    double t = 0.0;
-    if (threadIdx.x == 0)
-        for (int w = 0; w < kStatThreads / 32; ++w) t += scratch[w];
-    return t;                             // valid in thread 0
-}
-
-__global__ void __launch_bounds__(kStatThreads) channel_stats_kernel(const StatParams p) {
-    __shared__ double scratch[kStatThreads / 32];
-    __shared__ bool last;
-    const int plane = blockIdx.y;
-    const float* src = p.x + (size_t)plane * p.hw;
-    const size_t lo = (size_t)blockIdx.x * kStatSlab;
-    const size_t hi = lo + kStatSlab < p.hw ? lo + kStatSlab : p.hw;
-    double s = 0.0, q = 0.0;
-    if (p.vec4) {
-        float fs = 0.0f, fq = 0.0f;
-#pragma unroll 4
-        for (int k = 0; k < kStatVecPerThread; ++k) {
-            const size_t i = lo + ((size_t)k * kStatThreads + threadIdx.x) * 4;
-            if (i < hi) {                       // hw % 4 == 0: a vector never straddles the end
-                const float4 v = ld_stream_f32x4(src + i);
-                fs += (v.x + v.y) + (v.z + v.w);
-                fq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, fq))));
+    const uint32_t tile = blockIdx.x * 8 + warp;
+    if (tile >= p.n_tiles) return;
+    const int c = p.c0 + blockIdx.y;
+    float gs[8], gq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const unsigned long long g = (unsigned long long)tile * kSumTileGroups + 32 * j + lane;
+        gs[j] = gq[j] = 0.0f;
+        if (g < p.groups) {
+            const unsigned long long b = g / p.groups_per_image, r = g - b * p.groups_per_image;
+            const float* src = p.x + ((size_t)(b * p.channels + c) * p.hw + (size_t)r * p.vec);
+            if (p.vec == 4) {
+                float4 v;
+                if (p.aligned16) v = ld_stream_f32x4(src);
+                else v = make_float4(ld_stream_f32(src), ld_stream_f32(src + 1), ld_stream_f32(src + 2), ld_stream_f32(src + 3));
+                gs[j] = group_sum4(v.x, v.y, v.z, v.w);
+                gq[j] = group_squares4(v.x, v.y, v.z, v.w);
+            } else {
+                const float v = ld_stream_f32(src);
+                gs[j] = v;
+                gq[j] = __fmul_rn(v, v);
             }
         }
-        s = fs;
-        q = fq;
-    } else {
-        for (size_t i = lo + threadIdx.x; i < hi; i += kStatThreads) {
-            const float v = ld_stream_f32(src + i);
-            s += v;
-            q += (double)v * v;
+    }
+    float ts = 0.0f, tq = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {       // "warp" j of the canonical tile
+        const float ws = warp_tree_sum(gs[j]), wq = warp_tree_sum(gq[j]);
+        ts = j ? __fadd_rn(ts, ws) : ws;
+        tq = j ? __fadd_rn(tq, wq) : wq;
+    }
+    if (lane == 0) {
+        float* rec = p.records + (size_t)tile * p.stride + 2 * blockIdx.y;
+        rec[0] = ts;
+        rec[1] = tq;
+    }
+}
+
+// records [n_tiles][stride] (float) -> out[n_values] (double), canonical segment / total order.
+__global__ void __launch_bounds__(kStatThreads) fold_tiles_kernel(const float* __restrict__ records, uint32_t n_tiles, int stride,
+                                                                  int n_values, double* __restrict__ seg_part,
+                                                                  unsigned long long* ticket, double* __restrict__ out) {
+    __shared__ double scratch[8];
+    __shared__ bool last;
+    const uint32_t seg = blockIdx.x;
+    double acc[kFoldValues];
+#pragma unroll
+    for (int v = 0; v < kFoldValues; ++v) acc[v] = 0.0;
+    for (int m = 0; m < kSumSegmentTiles / kStatThreads; ++m) {
+        const uint32_t t = seg * kSumSegmentTiles + m * kStatThreads + threadIdx.x;
+        if (t < n_tiles) {
+            const float* rec = records + (size_t)t * stride;
+#pragma unroll
+            for (int v = 0; v < kFoldValues; ++v)
+                if (v < n_values) acc[v] += (double)__ldcg(rec + v);
         }
     }
-    const double ts = block_sum(s, scratch);
-    const double tq = block_sum(q, scratch);
+#pragma unroll
+    for (int v = 0; v < kFoldValues; ++v) {
+        if (v < n_values) {                                  // uniform
+            const double s = block_sum_f64(acc[v], scratch);
+            if (threadIdx.x == 0) seg_part[(size_t)seg * kFoldValues + v] = s;
+        }
+    }
     if (threadIdx.x == 0) {
-        const size_t slot = ((size_t)plane * p.chunks + blockIdx.x) * 2;
-        p.partials[slot] = ts;
-        p.partials[slot + 1] = tq;
         __threadfence();
-        last = atomicAdd(p.ticket, 1ull) == (unsigned long long)gridDim.x * gridDim.y - 1;
+        last = atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1;
     }
     __syncthreads();
     if (!last) return;
     __threadfence();
-    // fixed-order fold: channel c gathers planes c, c + C, c + 2C, ... and all their slabs
-    const int batches = p.planes / p.channels;
-    for (int c = 0; c < p.channels; ++c) {
-        double fs = 0.0, fq = 0.0;
-        const size_t per_channel = (size_t)batches * p.chunks;
-        for (size_t j = threadIdx.x; j < per_channel; j += kStatThreads) {
-            const size_t b = j / p.chunks, ch = j - b * p.chunks;
-            const size_t slot = ((b * p.channels + c) * p.chunks + ch) * 2;
-            fs += __ldcg(p.partials + slot);
-            fq += __ldcg(p.partials + slot + 1);
-        }
-        const double a = block_sum(fs, scratch);
-        const double b2 = block_sum(fq, scratch);
-        if (threadIdx.x == 0) {
-            p.stats[2 * c] = a;
-            p.stats[2 * c + 1] = b2;
-        }
+    for (int v = 0; v < n_values; ++v) {
+        double a = 0.0;
+        for (uint32_t s = threadIdx.x; s < gridDim.x; s += kStatThreads) a += __ldcg(seg_part + (size_t)s * kFoldValues + v);
+        const double t = block_sum_f64(a, scratch);
+        if (threadIdx.x == 0) out[v] = t;
     }
-    if (threadIdx.x == 0) *p.ticket = 0ull;
+    if (threadIdx.x == 0) *ticket = 0ull;
 }
 
 }  // namespace
+
+size_t fold_workspace_bytes(uint32_t n_tiles, int stride) {
+    const size_t segs = ((size_t)n_tiles + kSumSegmentTiles - 1) / kSumSegmentTiles;
+    return 64 + segs * kFoldValues * sizeof(double) + (size_t)n_tiles * stride * sizeof(float);
+}
+
+float* fold_records(void* workspace, uint32_t n_tiles) {
+    const size_t segs = ((size_t)n_tiles + kSumSegmentTiles - 1) / kSumSegmentTiles;
+    return reinterpret_cast<float*>(static_cast<char*>(workspace) + 64 + segs * kFoldValues * sizeof(double));
+}
+
+int launch_fold_tiles(void* workspace, uint32_t n_tiles, int stride, int n_values, double* out, cudaStream_t stream) {
+    if (n_values > kFoldValues || n_values > stride) return POLCUE_EINVAL;
+    const uint32_t segs = (n_tiles + kSumSegmentTiles - 1) / kSumSegmentTiles;
+    fold_tiles_kernel<<<segs ? segs : 1, kStatThreads, 0, stream>>>(fold_records(workspace, n_tiles), n_tiles, stride, n_values,
+                                                                    reinterpret_cast<double*>(static_cast<char*>(workspace) + 64),
+                                                                    static_cast<unsigned long long*>(workspace), out);
+    return launch_status();
+}
+
 }  // namespace polcue
 
 using namespace polcue;
 
+namespace {
+constexpr int kChannelsPerPass = 16;     // 32 values per tile record
+unsigned long long tiles_of(int B, size_t hw) {
+    const int vec = hw % 4 == 0 ? 4 : 1;
+    const unsigned long long groups = (unsigned long long)B * (hw / vec);
+    return (groups + kSumTileGroups - 1) / kSumTileGroups;
+}
+}  // namespace
+
 extern "C" {
 
 size_t polcue_channel_stats_workspace_bytes(int B, int C, size_t hw) {
-    if (B <= 0 || C <= 0) return 64;
-    const size_t chunks = (hw + kStatSlab - 1) / kStatSlab;
-    return 64 + (size_t)B * C * chunks * 2 * sizeof(double);
+    if (B <= 0 || C <= 0 || hw == 0) return 64;
+    const unsigned long long tiles = tiles_of(B, hw);
+    if (tiles >= (1ull << 31)) return 64;
+    return fold_workspace_bytes((uint32_t)tiles, 2 * (C < kChannelsPerPass ? C : kChannelsPerPass));
 }
 
 int polcue_channel_stats_f32(const float* x, int B, int C, size_t hw, void* workspace, double* stats, polcue_stream_t stream) {
@@ -121,20 +164,29 @@ int polcue_channel_stats_f32(const float* x, int B, int C, size_t hw, void* work
     if ((reinterpret_cast<uintptr_t>(workspace) & 63) || (reinterpret_cast<uintptr_t>(stats) & 7) ||
         (reinterpret_cast<uintptr_t>(x) & 3))
         return POLCUE_EINVAL;
-    const size_t chunks = (hw + kStatSlab - 1) / kStatSlab;
-    if ((size_t)B * C > 65535 || chunks >= (1ull << 31)) return POLCUE_E2BIG;
+    const unsigned long long tiles = tiles_of(B, hw);
+    if (tiles >= (1ull << 31) - 8 || hw >= (1ull << 32)) return POLCUE_E2BIG;
     StatParams p;
     p.x = x;
     p.hw = hw;
-    p.planes = B * C;
     p.channels = C;
-    p.chunks = (unsigned)chunks;
-    p.vec4 = hw % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-    p.ticket = static_cast<unsigned long long*>(workspace);
-    p.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 64);
-    p.stats = stats;
-    channel_stats_kernel<<<dim3((unsigned)chunks, (unsigned)(B * C)), kStatThreads, 0, (cudaStream_t)stream>>>(p);
-    return launch_status();
+    p.vec = hw % 4 == 0 ? 4 : 1;
+    p.groups = (unsigned long long)B * (hw / p.vec);
+    p.groups_per_image = (uint32_t)(hw / p.vec);
+    p.n_tiles = (uint32_t)tiles;
+    p.aligned16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    p.records = fold_records(workspace, p.n_tiles);
+    for (int c0 = 0; c0 < C; c0 += kChannelsPerPass) {       // 16 channels per pass share the workspace (stream order)
+        const int nc = C - c0 < kChannelsPerPass ? C - c0 : kChannelsPerPass;
+        p.c0 = c0;
+        p.stride = 2 * (C < kChannelsPerPass ? C : kChannelsPerPass);
+        channel_tiles_kernel<<<dim3((p.n_tiles + 7) / 8, (unsigned)nc), kStatThreads, 0, (cudaStream_t)stream>>>(p);
+        int rc = launch_status();
+        if (rc != POLCUE_OK) return rc;
+        rc = launch_fold_tiles(workspace, p.n_tiles, p.stride, 2 * nc, stats + 2 * c0, (cudaStream_t)stream);
+        if (rc != POLCUE_OK) return rc;
+    }
+    return POLCUE_OK;
 }
 
 }  // extern "C"

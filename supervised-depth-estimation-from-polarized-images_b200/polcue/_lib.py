@@ -39,6 +39,8 @@ _SIGNATURES = {
     "polcue_lut_eval_host": (C.c_int, [C.c_void_p, C.c_int, _f32p, C.c_size_t, _f32p]),
     "polcue_split_pol": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "polcue_fused_mosaic_u8": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _u8p, _f32p, _f32p, _f32p, _vp]),
+    "polcue_fused_stats_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "polcue_fused_mosaic_stats_u8": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _u8p, _f32p, _f32p, _f32p, _vp, _f64p, _vp]),
     "polcue_fused_superpixel_u8": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, _u8p, _f32p, _f32p, _f32p, _vp]),
     "polcue_fused_planes_u8": (C.c_int, [_u8p, _u8p, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, _f32p, _f32p, _f32p, _vp]),
     "polcue_resize_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
@@ -84,6 +86,8 @@ _SIGNATURES = {
                                                        C.c_int, _f32p, _f64p, _f32p, _vp]),
     "polcue_depth_errors_groups_f32": (C.c_int, [_f32p, _f32p, _u8p, C.c_int, C.c_size_t, C.c_float, C.c_float, C.POINTER(C.c_int),
                                                   C.c_int, _f64p, _f32p, _vp]),
+    "polcue_eval_pass_f32": (C.c_int, [_f32p, _f32p, _u8p, _f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_int),
+                                      C.c_int, _f32p, _f64p, _f32p, _f64p, _vp]),
     "polcue_channel_stats_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_size_t]),
     "polcue_channel_stats_f32": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_size_t, _vp, _f64p, _vp]),
 }

@@ -156,10 +156,14 @@ def split_pol_batch(imgs):
 # ------------------------------------------------------------------------------------------
 # fused pipeline
 # ------------------------------------------------------------------------------------------
-def fused_mosaic(mosaic, n=1.5, want_iun=False, want_planes=False, want_normals=True, out=None, superpixel=None):
+def fused_mosaic(mosaic, n=1.5, want_iun=False, want_planes=False, want_normals=True, out=None, superpixel=None, want_stats=False):
     """B x H x W uint8 mosaics -> dict(xolp [B,2,Hs,Ws], normals [B,9,Hs,Ws], iun, planes).
 
     `out` may hold preallocated tensors under the same keys (steady-state loops reuse them).
+    `want_stats`: adds `stats13` (float64 [13] on device: sum rho, sum phi, the sums of the nine normal channels, sum rho^2,
+    sum phi^2 over the batch) as a by-product of the same launch -- the dataset statistics of xolp_mean_and_std_dev.py and
+    the output checksums of the sequence benchmark without reading the outputs again; bit-identical to `channel_stats` of
+    the stored tensors (`stats_from_stats13` splits it the same way).
     `superpixel`: None for the reference's quadrant-tiled images; for a raw interleaved 2x2 polarizer mosaic the four
     angle indices (0..3 = 0/45/90/135 deg) at positions (0,0), (0,1), (1,0), (1,1), e.g. (2, 1, 3, 0).
     """
@@ -186,8 +190,22 @@ def fused_mosaic(mosaic, n=1.5, want_iun=False, want_planes=False, want_normals=
     iun = buf("iun", (b, hs, ws), torch.float32) if want_iun else None
     planes = buf("planes", (b, 4, hs, ws), torch.uint8) if want_planes else None
     lut = lut_for(n, dev) if want_normals else C.c_void_p(0)
+    if want_stats and (superpixel is not None or not want_normals):
+        raise ValueError("want_stats needs the quadrant layout and the normals output")
     with torch.cuda.device(dev):
-        if superpixel is None:
+        if want_stats:
+            need = int(_lib.lib().polcue_fused_stats_workspace_bytes(b, h, w))
+            key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+            ws_t = _fused_stat_workspaces.get(key)
+            if ws_t is None or ws_t.numel() < need:
+                ws_t = _fused_stat_workspaces[key] = torch.zeros(need, dtype=torch.uint8, device=dev)
+            stats = out.get("stats13")
+            if stats is None or stats.dtype != torch.float64 or tuple(stats.shape) != (13,) or stats.device != dev:
+                stats = out["stats13"] = torch.empty(13, dtype=torch.float64, device=dev)
+            _lib.check(_lib.lib().polcue_fused_mosaic_stats_u8(_ptr(mosaic), b, h, w, lut, _ptr(planes), _ptr(iun), _ptr(xolp),
+                                                               _ptr(normals), _ptr(ws_t), _ptr(stats), _stream(mosaic)),
+                       "polcue_fused_mosaic_stats_u8")
+        elif superpixel is None:
             _lib.check(_lib.lib().polcue_fused_mosaic_u8(_ptr(mosaic), b, h, w, lut, _ptr(planes), _ptr(iun), _ptr(xolp),
                                                          _ptr(normals), _stream(mosaic)), "polcue_fused_mosaic_u8")
         else:
@@ -197,6 +215,14 @@ def fused_mosaic(mosaic, n=1.5, want_iun=False, want_planes=False, want_normals=
             _lib.check(_lib.lib().polcue_fused_superpixel_u8(_ptr(mosaic), b, h, w, arr, lut, _ptr(planes), _ptr(iun), _ptr(xolp),
                                                              _ptr(normals), _stream(mosaic)), "polcue_fused_superpixel_u8")
     return out
+
+
+_fused_stat_workspaces = {}
+
+
+def stats_from_stats13(stats13):
+    """(xolp_stats [2, 2] = (sum, sum of squares) of rho and phi, normal_sums [9]) from the by-product vector."""
+    return torch.stack((stats13[:2], stats13[11:13]), dim=1), stats13[2:11]
 
 
 def fused_planes(i0, i45, i90, i135, n=1.5, want_iun=False, want_normals=True, out=None):
@@ -673,6 +699,55 @@ def depth_errors_groups(gt, pred, inst, min_depth, max_depth, group_ids):
     return sums, metrics
 
 
+def eval_pass(gt, pred, inst, camera_matrix, min_depth, max_depth, group_ids, want_normals=True, out=None):
+    """One evaluation pass over this rank's images with no host work between the launches (BASELINE configs[4]): the GT
+    depth->normals stencil, every mask group's per-image metrics, and `mean_acc` = {n_images, sum over images of the
+    per-image metrics} (float64 [1 + G * 7]) -- all-reduce it and divide for the reference's mean over images
+    (trainer.py:1426).  gt / pred: B x H x W float32, inst: uint8, camera_matrix: B x 3 x 3.
+    `out` may hold the tensors of a previous call (a fixed set of buffers makes the pass CUDA-graph capturable).
+    Returns dict(normals [B,3,H,W] or None, sums [B,G,8], metrics [B,G,7], mean_acc [1 + 7 G])."""
+    gt = _need_cuda(gt, "gt", torch.float32)
+    pred = _need_cuda(pred, "pred", torch.float32)
+    if gt.dim() != 3 or pred.shape != gt.shape:
+        raise ValueError("gt and pred must share one B x H x W shape")
+    ids = [(-1 if g is None else int(g)) for g in group_ids]
+    if not 1 <= len(ids) <= 16:
+        raise ValueError("between 1 and 16 groups per launch")
+    if any(g >= 0 for g in ids):
+        inst = _need_cuda(inst, "inst", torch.uint8)
+        if inst.shape != gt.shape:
+            raise ValueError("inst must have the same shape as gt")
+    else:
+        inst = None
+    b, h, w = gt.shape
+    dev, g = gt.device, len(ids)
+    k = None
+    if want_normals:
+        k = _need_cuda(camera_matrix, "camera_matrix", torch.float32)
+        if k.shape != (b, 3, 3):
+            raise ValueError("camera_matrix must be B x 3 x 3")
+    out = dict(out or {})
+
+    def buf(key, shape, dtype):
+        t = out.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != dev or not t.is_contiguous():
+            t = out[key] = torch.empty(shape, dtype=dtype, device=dev)
+        return t
+
+    normals = buf("normals", (b, 3, h, w), torch.float32) if want_normals else None
+    sums = buf("sums", (b, g, 8), torch.float64)
+    metrics = buf("metrics", (b, g, 7), torch.float32)
+    acc = buf("mean_acc", (1 + 7 * g,), torch.float64)
+    arr = (C.c_int * g)(*ids)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().polcue_eval_pass_f32(_ptr(gt), _ptr(pred), _ptr(inst), _ptr(k), b, h, w, float(min_depth), float(max_depth),
+                                                   arr, g, _ptr(normals), _ptr(sums), _ptr(metrics), _ptr(acc), _stream(gt)),
+                   "polcue_eval_pass_f32")
+    if not want_normals:
+        out["normals"] = None
+    return out
+
+
 def metrics_from_sums(sums):
     """8 additive accumulators (any leading shape) -> 7 metrics in the reference order (float64 tensor/array)."""
     n = sums[..., 0]
@@ -707,12 +782,14 @@ def channel_stats(x):
     return stats
 
 
-def xolp_statistics(xolp, reduce_over_ranks=True):
+def xolp_statistics(xolp, reduce_over_ranks=True, stats13=None):
     """DoLP / AoLP mean and (population) std over a set of frames, as polarisation/xolp_mean_and_std_dev.py:26-32 prints
-    them.  xolp: B x 2 x H x W.  With torch.distributed initialised the sums are all-reduced first."""
+    them.  xolp: B x 2 x H x W.  With torch.distributed initialised the sums are all-reduced first.
+    `stats13`: the by-product of `fused_mosaic(.., want_stats=True)` for the same frames -- the outputs are then not read."""
     from . import dist as D
     b = xolp.shape[0]
-    acc = torch.cat((channel_stats(xolp).reshape(-1),
+    per_channel = channel_stats(xolp) if stats13 is None else stats_from_stats13(stats13)[0]
+    acc = torch.cat((per_channel.reshape(-1),
                      torch.tensor([float(xolp.numel() // 2)], dtype=torch.float64, device=xolp.device)))
     if reduce_over_ranks:
         D.all_reduce_sums(acc)

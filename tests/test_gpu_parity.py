@@ -1,5 +1,7 @@
 """GPU parity tests: every CUDA entry point (through the C ABI) against the CPU oracle and the golden
 reference outputs, with BASELINE.json's tolerances (tests/parity.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -490,6 +492,25 @@ def test_depth_to_normals(shape):
         assert (ref32[np.broadcast_to(dead[:, None], ref32.shape)] == 0).all()
 
 
+KORNIA_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kornia_outputs.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(KORNIA_GOLDEN), reason="tests/golden/kornia_outputs.npz absent: run tools/pin_kornia.py where kornia 0.5.11 is installed")
+def test_depth_to_normals_against_kornia_outputs():
+    """The CUDA stencil against outputs of kornia 0.5.11 itself (fixture written by tools/pin_kornia.py), every pixel, under
+    the conditioning-aware protocol; the reference's own float32 result must lie inside the same bounds."""
+    data = np.load(KORNIA_GOLDEN)
+    for name in sorted({k.split("/")[0] for k in data.files if "/" in k}):
+        depth, km = data[name + "/depth"], data[name + "/K"]
+        got = ops.depth_to_normals(dev(depth), dev(km)).cpu().numpy()
+        _, bound, dead = O.depth_to_normals_conditioning(depth, km)
+        lim = np.maximum(P.NORMAL_TOL, P.STENCIL_ROUNDINGS * 2.0 ** -24 * bound)
+        for ref, slack in ((data[name + "/normals_f64"], 1.0), (data[name + "/normals_f32"], 2.0)):   # float32 vs float32: both carry round-off
+            err = np.where(dead | ~np.isfinite(lim), 0.0, P.angular_error(got, ref, axis=1))
+            assert not (~(err <= slack * lim)).any(), (name, float(np.nanmax(err)))
+        assert (got.transpose(0, 2, 3, 1)[dead] == 0).all(), name
+
+
 def test_stencil_metrics_and_loss_randomized_shapes_and_cameras():
     """Differential sweep: 16 random (batch, shape, camera, depth range, mask) cases through the stencil, the per-image
     metrics (range + material filter), the flat metric sums and the normals loss with its gradient."""
@@ -899,14 +920,41 @@ def test_channel_stats_and_xolp_statistics(shape):
     x = (rng.normal(0.3, 0.8, shape)).astype(np.float32)
     got = ops.channel_stats(dev(x)).cpu().numpy()
     x64 = x.astype(np.float64)
-    assert np.allclose(got[:, 0], x64.sum(axis=(0, 2, 3)), rtol=1e-7, atol=1e-6)
-    assert np.allclose(got[:, 1], (x64 ** 2).sum(axis=(0, 2, 3)), rtol=1e-7)
+    # float32 inside a tile of 1024 elements (the canonical order shared with the fused kernel's by-product), float64 above
+    assert np.allclose(got[:, 0], x64.sum(axis=(0, 2, 3)), rtol=0, atol=2e-7 * np.abs(x64).sum(axis=(0, 2, 3)).max() + 1e-12)
+    assert np.allclose(got[:, 1], (x64 ** 2).sum(axis=(0, 2, 3)), rtol=2e-7)
     assert torch.equal(ops.channel_stats(dev(x)), ops.channel_stats(dev(x)))          # fixed reduction order
     if shape[1] == 2:
         st = ops.xolp_statistics(dev(x))
         ref = O.xolp_statistics(x[:, 0], x[:, 1])
         for key, val in ref.items():
             assert abs(st[key] - val) < 1e-6 * max(1.0, abs(val)), key
+
+
+@pytest.mark.parametrize("case", [("P", 3, 128, 192, 1.5), ("U", 2, 64, 264, 1.5), ("P", 5, 250, 328, 1.33), ("U", 1, 2048, 2448, 1.5),
+                                  ("U", 2, 34, 66, 1.5), ("U", 2, 60, 144, 1.8)])
+def test_statistics_by_product_of_the_fused_kernel_equals_the_statistics_pass_bit_for_bit(case):
+    """per-plane sums (and the squares of DoLP / AoLP) come out of the fused launch itself.  They equal
+    polcue_channel_stats_f32 of the stored outputs BIT FOR BIT (one canonical summation order, polcue_device.cuh), are
+    identical from run to run although tiles are handed out dynamically, and match float64 numpy sums.  The last two cases
+    take the internal fallback (Ws = 33: no 4-pixel groups; n = 1.8: steep table) and must give the same."""
+    kind, b, h, w, n = case
+    mosaic = dev(synth.gen_batch(kind, 17, b, h, w))
+    out = ops.fused_mosaic(mosaic, n, want_stats=True)
+    plain = ops.fused_mosaic(mosaic, n)
+    assert torch.equal(out["xolp"], plain["xolp"]) and torch.equal(out["normals"], plain["normals"])
+    xs, ns = ops.stats_from_stats13(out["stats13"])
+    assert torch.equal(xs, ops.channel_stats(out["xolp"]))
+    assert torch.equal(ns, ops.channel_stats(out["normals"])[:, 0])
+    for _ in range(3):
+        again = ops.fused_mosaic(mosaic, n, want_stats=True, out={})
+        assert torch.equal(again["stats13"], out["stats13"])
+    x64, n64 = out["xolp"].double(), out["normals"].double()
+    ref = torch.cat((x64.sum(dim=(0, 2, 3)), n64.sum(dim=(0, 2, 3)), (x64 ** 2).sum(dim=(0, 2, 3))))
+    scale = torch.cat((x64.abs().sum(dim=(0, 2, 3)), n64.abs().sum(dim=(0, 2, 3)), (x64 ** 2).sum(dim=(0, 2, 3))))
+    assert float(((out["stats13"] - ref).abs() / scale).max()) < 2e-7
+    st = ops.xolp_statistics(out["xolp"], reduce_over_ranks=False, stats13=out["stats13"])
+    assert st == ops.xolp_statistics(out["xolp"], reduce_over_ranks=False)
 
 
 def test_xolp_statistics_of_fused_output_match_the_reference_script():

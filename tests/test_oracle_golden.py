@@ -1,4 +1,6 @@
 """CPU: the oracle restatements against outputs of the reference itself (tests/golden)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -205,3 +207,23 @@ def test_loader_front_end_oracle_composition():
     assert small.shape == (4, 20, 30) and xolp.shape == (2, 20, 30) and normals.shape == (9, 20, 30)
     assert np.array_equal(small[2], O.resize_lanczos_u8(np.ascontiguousarray(planes[2][:, ::-1]), (20, 30)))
     assert np.allclose(np.linalg.norm(normals.reshape(3, 3, 20, 30), axis=1), 1.0)
+
+
+KORNIA_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kornia_outputs.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(KORNIA_GOLDEN), reason="tests/golden/kornia_outputs.npz absent: run tools/pin_kornia.py where kornia 0.5.11 is installed")
+def test_depth_to_normals_oracle_against_kornia_outputs():
+    """Pins a10 (kornia.geometry.depth.depth_to_normals, trainer.py:1305-1306) on outputs of kornia itself when the fixture
+    exists: float64 oracle == kornia float64 to 1e-12 wherever the cross product does not vanish, zero vectors where kornia
+    gives zero vectors."""
+    data = np.load(KORNIA_GOLDEN)
+    names = sorted({k.split("/")[0] for k in data.files if "/" in k})
+    assert names
+    for name in names:
+        depth, km, ref = data[name + "/depth"], data[name + "/K"], data[name + "/normals_f64"]
+        got = O.depth_to_normals(depth, km)
+        _, bound, dead = O.depth_to_normals_conditioning(depth, km)
+        well = np.isfinite(bound) & (bound < 1e6) & ~dead
+        assert np.abs(got - ref).transpose(0, 2, 3, 1)[well].max(initial=0.0) < 1e-12 * max(1.0, float(bound[well].max(initial=1.0))), name
+        assert (ref.transpose(0, 2, 3, 1)[dead] == 0).all() and (got.transpose(0, 2, 3, 1)[dead] == 0).all(), name

@@ -5,78 +5,39 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29517 \
       tools/run_eval_split.py [--images 120] [--check]
 
-Per rank: its contiguous shard of the images -> GT depth->normals stencil + per-image masked compute_depth_errors
-(range mask and every material level of trainer.py:1389-1411, all 11 groups in one launch) -> mean over ALL images
-with one NCCL all-reduce of 1 + 11 x 7 float64.  --check recomputes everything unsharded on rank 0 with
-the CPU oracle and asserts equality (test infrastructure use of oracle/).
+Per rank: its contiguous shard of the images -> polcue_eval_pass_f32 (GT depth->normals stencil, per-image masked
+compute_depth_errors for the range mask and every material level of trainer.py:1389-1411, accumulators of the mean over
+images: three launches, no host work in between) -> one NCCL all-reduce of 1 + 11 x 7 float64.  --check recomputes
+everything unsharded on rank 0 with the CPU oracle and asserts equality (test infrastructure use of oracle/).
+The runner is tools/workloads.py::cfg5_eval, which bench.py runs as well.
 """
 import argparse
 import json
 import os
 import sys
-import time
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 sys.path.insert(0, ROOT)
-from polcue import dist as D, ops, synth  # noqa: E402
+from polcue import dist as D  # noqa: E402
+import workloads  # noqa: E402
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=120)        # 10 batches x 12, trainer.py:915-916
     ap.add_argument("--check", action="store_true")
-    ap.add_argument("--reps", type=int, default=100)
+    ap.add_argument("--reps", type=int, default=200)
     args = ap.parse_args()
     rank, local_rank, world = D.init()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    lo, hi = D.shard_range(args.images, rank, world)
-    gt, pred, inst, k = (torch.from_numpy(a).to(dev) for a in synth.gen_depth_batch(lo, hi - lo))
-    groups = [None] + list(synth.MATERIAL_LEVELS)
-
-    def evaluate():
-        normals = ops.depth_to_normals(gt[:, None], k)
-        _, per_image = ops.depth_errors_groups(gt, pred, inst, 0.1, 2.0, groups)        # [B, 11, 7] in one launch
-        rows = per_image.to(torch.float64)
-        acc = torch.cat((torch.full((1,), float(rows.shape[0]), dtype=torch.float64, device=dev), rows.sum(dim=0).reshape(-1)))
-        D.all_reduce_sums(acc)                                                         # one all-reduce: 1 + 11 x 7 float64
-        return normals, (acc[1:] / acc[0]).reshape(len(groups), 7)
-
-    for _ in range(5):                      # warm-up: clocks, allocator, TMA descriptor encoder
-        normals, means = evaluate()
-    torch.cuda.synchronize()
-    D.barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.reps):
-        evaluate()
-    b.record()
-    torch.cuda.synchronize()
-    ms = D.max_over_ranks(a.elapsed_time(b) / args.reps, dev)
-    chk = normals.double().sum().reshape(1)
-    D.all_reduce_sums(chk)
+    res = workloads.cfg5_eval(rank, world, dev, images=args.images, reps=args.reps, check=args.check)
     if rank == 0:
-        out = {"config": "cfg5: GT depth->normals + per-image masked depth errors, 11 mask groups, mean over images",
-               "images": args.images, "n_gpus": world, "ms_per_pass": ms, "images_per_s": args.images / (ms * 1e-3),
-               "abs_rel_all": float(means[0, 0]), "a1_all": float(means[0, 4]), "normals_checksum": float(chk[0])}
-        if args.check:
-            from oracle import polcue_oracle as O
-            g, p, i, kk = synth.gen_depth_batch(0, args.images)
-            t0 = time.perf_counter()
-            for gi, level in enumerate(groups):
-                _, mean = O.depth_errors_per_image(g, p, 0.1, 2.0, i if level is not None else None, level)
-                got = means[gi].cpu().numpy()
-                assert np.array_equal(np.isnan(got), np.isnan(mean)), (level, got, mean)
-                assert np.allclose(got, mean, rtol=5e-6, equal_nan=True), (level, got, mean)
-            ref = O.depth_to_normals(g[:, None], kk)
-            # float32 kernel vs float64 oracle over ~55 M components, a few of them ill-conditioned next to depth holes
-            assert abs(ref.sum() - float(chk[0])) < 1e-5 * abs(ref.sum()), (ref.sum(), float(chk[0]))
-            out["check"] = f"sharded == unsharded oracle for {len(groups)} mask groups ({time.perf_counter() - t0:.1f} s on the CPU)"
-        print(json.dumps(out), flush=True)
+        print(json.dumps(res), flush=True)
     D.barrier()
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -2,14 +2,14 @@
 """BASELINE.json configs[2] and configs[3].
 
   --mode sequence (configs[2]): a 10k-frame synthetic HAMMER-shaped sequence (2448x2048 mosaics) sharded across the
-      ranks in contiguous blocks, processed in resident chunks of 64 frames into double-buffered outputs, only
-      per-plane float64 checksums kept (the outputs would be 551 GB); one all-reduce of the checksums at the end.
+      ranks in contiguous blocks, processed in resident chunks of 64 frames, only per-plane float64 checksums kept -- a
+      by-product of the fused launch itself, the outputs (551 GB in all) are never read back; one all-reduce at the end.
       Frames come from a pool of distinct Gen-P frames resident on the device and addressed by global frame index,
       so any sharding sees the same sequence.
   --mode loader (configs[3]): the manydepth train-loader path at training resolution: four uint8 planes
       [32, 320, 480] (indoor_dataset.py:435-438) -> XOLP [32,2,320,480] -> get_normals [32,9,320,480], i.e. what
-      feeds ShallowEncoder / ShallowNormalsEncoder (pre_encoders.py:49-113); kernels only (the convolutional
-      encoders are outside the path).
+      feeds ShallowEncoder / ShallowNormalsEncoder (pre_encoders.py:49-113), timed alone and followed by torch stand-ins
+      of the encoders (tools/encoder_standins.py).  Both modes live in tools/workloads.py, which bench.py runs too.
 
   --mode loader_full (configs[3] from the stored images): the four FULL-resolution gray images of every sample (HAMMER
       quadrants, 832x1088) in pinned host memory -> H2D -> loader front end (Pillow-exact Lanczos resize to 320x480,
@@ -28,84 +28,22 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 from polcue import _lib, dist as D, ops, synth  # noqa: E402
 
 
 def run_sequence(args, rank, world, dev):
-    chunk, pool_n = 64, 64
-    pool = synth.gen_p_batch_torch(0, pool_n, device=dev)                 # frame f of the sequence = pool[f % pool_n]
-    lo, hi = D.shard_range(args.frames, rank, world)
-    hs, ws = synth.FRAME_H // 2, synth.FRAME_W // 2
-    bufs = [{"xolp": torch.empty((chunk, 2, hs, ws), dtype=torch.float32, device=dev),
-             "normals": torch.empty((chunk, 9, hs, ws), dtype=torch.float32, device=dev)} for _ in range(2)]
-    sums = torch.zeros(11, dtype=torch.float64, device=dev)
-    side = torch.cuda.Stream(dev)
-    done = [torch.cuda.Event(), torch.cuda.Event()]
-    idx = torch.arange(chunk, device=dev)
-    ops.lut_for(1.5, dev)
-    torch.cuda.synchronize()
-    D.barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = _lib.launch_count()
-    a.record()
-    k = 0
-    for first in range(lo, hi, chunk):
-        n = min(chunk, hi - first)
-        frames = pool[(first + idx[:n]) % pool_n] if (first % pool_n or n != chunk) else pool   # gather only when ragged
-        out = bufs[k & 1]
-        torch.cuda.current_stream().wait_event(done[k & 1])               # the checksum pass has released this buffer
-        ops.fused_mosaic(frames, 1.5, out={"xolp": out["xolp"][:n], "normals": out["normals"][:n]})
-        ready = torch.cuda.Event()
-        ready.record()
-        with torch.cuda.stream(side):                                     # checksums overlap the next chunk's kernel
-            side.wait_event(ready)
-            sums[:2] += ops.channel_stats(out["xolp"][:n])[:, 0]          # polcue_channel_stats_f32 (per-plane float64 sums)
-            sums[2:] += ops.channel_stats(out["normals"][:n])[:, 0]
-            done[k & 1].record(side)
-        k += 1
-    torch.cuda.current_stream().wait_stream(side)
-    b.record()
-    torch.cuda.synchronize()
-    ms = D.max_over_ranks(a.elapsed_time(b), dev)
-    D.all_reduce_sums(sums)
+    import workloads
+    res = workloads.cfg3_sequence(rank, world, dev, frames=args.frames)
     if rank == 0:
-        print(json.dumps({"config": "cfg3: 10k-frame synthetic sequence, contiguous shards, chunks of 64, checksums only",
-                          "frames": args.frames, "n_gpus": world, "seconds": ms / 1e3, "frames_per_s": args.frames / (ms / 1e3),
-                          "mosaic_mpix_per_s": args.frames * synth.FRAME_H * synth.FRAME_W / 1e6 / (ms / 1e3),
-                          "fused_launches_rank0": _lib.launch_count() - launches0,
-                          "checksums": [float(v) for v in sums.cpu()],
-                          "note": "wall time includes the checksum kernels (a second full read of the 44 B/px outputs, on a side stream)"}), flush=True)
+        print(json.dumps(res), flush=True)
 
 
 def run_loader(args, rank, world, dev):
-    b, h, w = 32, synth.TRAIN_H, synth.TRAIN_W
-    planes = [torch.stack([torch.from_numpy(synth.gen_p_planes(rank * b + i, h, w)[k]) for i in range(b)]).to(dev) for k in range(4)]
-    ops.lut_for(1.5, dev)
-
-    out = {}
-
-    def step():
-        nonlocal out
-        out = ops.fused_planes(*planes, n=1.5, out=out)          # XOLP + normals from the four planes in ONE launch
-        return out
-
-    for _ in range(5):
-        step()
-    torch.cuda.synchronize()
-    D.barrier()
-    a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.reps):
-        step()
-    e.record()
-    torch.cuda.synchronize()
-    ms = D.max_over_ranks(a.elapsed_time(e) / args.reps, dev)
+    import workloads
+    res = workloads.cfg4_loader(rank, world, dev, reps=args.reps)
     if rank == 0:
-        px = b * h * w
-        print(json.dumps({"config": "cfg4: loader path at training resolution, planes u8 [32,4,320,480] -> xolp + normals (1 fused launch)",
-                          "n_gpus": world, "us_per_batch": ms * 1e3, "batches_per_s": world / (ms * 1e-3),
-                          "achieved_gbs": 48 * px / (ms * 1e-3) / 1e9,
-                          "note": "48 B/px in one launch of 4.9 Mpx"}), flush=True)
+        print(json.dumps(res), flush=True)
 
 
 def _cpu_loader_sample(seed):

@@ -1,0 +1,236 @@
+"""The measured workloads of BASELINE.json configs[2..4], shared by bench.py (driver-run) and the tools/run_*.py CLIs.
+
+Each function runs on every rank of a torchrun job (one process per GPU), times on the device with CUDA events, takes
+the max over ranks and returns a small dict on every rank (rank 0 prints it).  Nothing here touches oracle/ except the
+explicitly named `check` helpers, which are test infrastructure (the checker, never the thing measured).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+from polcue import _lib, dist as D, ops, synth  # noqa: E402
+
+HBM_FALLBACK_GBS = 6650.0
+
+
+def hbm_peak():
+    try:
+        import json
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return HBM_FALLBACK_GBS
+
+
+# --------------------------------------------------------------------------------------------------
+# cfg3: the 10k-frame sequence, sharded, chunks of 64, checksums as a by-product of the fused launch
+# --------------------------------------------------------------------------------------------------
+def cfg3_sequence(rank, world, dev, frames=10000, chunk=64, pool=None):
+    """BASELINE configs[2]: frames [lo, hi) of a `frames`-frame synthetic HAMMER-shaped sequence per rank (contiguous
+    shards, strong scaling), resident chunks of 64 mosaics -> fused kernel with the statistics by-product (13 float64
+    sums per launch, accumulated on the device; the 551 GB of outputs are overwritten chunk after chunk and never read
+    back), one all-reduce of the sums at the end.  Frame f of the sequence is pool[f % 64] (64 distinct Gen-P frames
+    resident on every rank), so any sharding sees the same sequence."""
+    pool_n = 64
+    if pool is None:
+        pool = synth.gen_p_batch_torch(0, pool_n, device=dev)
+    lo, hi = D.shard_range(frames, rank, world)
+    hs, ws = synth.FRAME_H // 2, synth.FRAME_W // 2
+    out = {"xolp": torch.empty((chunk, 2, hs, ws), dtype=torch.float32, device=dev),
+           "normals": torch.empty((chunk, 9, hs, ws), dtype=torch.float32, device=dev)}
+    sums = torch.zeros(13, dtype=torch.float64, device=dev)
+    idx = torch.arange(chunk, device=dev)
+    ops.lut_for(1.5, dev)
+
+    def run_chunk(first, n, acc):
+        frames_in = pool[(first + idx[:n]) % pool_n] if (first % pool_n or n != chunk) else pool   # gather only when ragged
+        res = ops.fused_mosaic(frames_in, 1.5, out={"xolp": out["xolp"][:n], "normals": out["normals"][:n], "stats13": out.get("stats13")},
+                               want_stats=True)
+        out["stats13"] = res["stats13"]
+        acc += res["stats13"]
+
+    scratch = torch.zeros_like(sums)
+    for _ in range(3):                                    # warm-up: clocks, table upload, workspace allocation
+        run_chunk(0, chunk, scratch)
+    torch.cuda.synchronize()
+    D.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    a.record()
+    for first in range(lo, hi, chunk):
+        run_chunk(first, min(chunk, hi - first), sums)
+    b.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - launches0
+    ms = D.max_over_ranks(a.elapsed_time(b), dev)
+    D.all_reduce_sums(sums)
+    # size-independent parity property: the sequence repeats the 64-frame pool, so its checksum is frames/64 x the pool's
+    one = torch.zeros_like(sums)
+    run_chunk(0, chunk, one)
+    whole, rest = divmod(frames, pool_n)
+    expect = one * whole
+    if rest:
+        part = torch.zeros_like(sums)
+        run_chunk(whole * pool_n, rest, part)
+        expect = expect + part
+    rel = float(((sums - expect).abs() / expect.abs().clamp_min(1e-300)).max())
+    mpix = frames * synth.FRAME_H * synth.FRAME_W / 1e6
+    return {"workload": f"cfg3: {frames}-frame synthetic sequence of 2448x2048 mosaics, contiguous shards over {world} GPU(s), chunks of "
+                        f"{chunk}, per-plane float64 checksums as a by-product of the fused launch (outputs never re-read)",
+            "frames": frames, "n_gpus": world, "scaling": "strong", "seconds": ms / 1e3, "frames_per_s": frames / (ms / 1e3),
+            "value": mpix / (ms / 1e3), "unit": "Mpix/s", "launches_rank0": launches,
+            "roofline_frac": 48.0 * (hi - lo) * hs * ws / (ms * 1e-3) / 1e9 / hbm_peak(),
+            "checksums": [float(v) for v in sums.cpu()],
+            "parity": f"checksum == frames/64 x the 64-frame pool's checksum: max relative difference {rel:.1e}",
+            "parity_ok": bool(rel < 1e-12)}
+
+
+# --------------------------------------------------------------------------------------------------
+# cfg4: the train-loader path at training resolution feeding the encoders, batch 32
+# --------------------------------------------------------------------------------------------------
+def cfg4_loader(rank, world, dev, reps=200, with_encoders=True):
+    """BASELINE configs[3]: four uint8 planes [32, 320, 480] (indoor_dataset.py:435-438) -> XOLP [32,2,320,480] +
+    get_normals [32,9,320,480] in ONE launch (`polcue_fused_planes_u8`), alone and followed by the forward passes of
+    the encoders they feed (pre_encoders.py:49-97, resnet_encoder.py:783-822; torch stand-ins with the reference's layer
+    geometry, random weights, eval mode -- their time is measured, they are not part of the path)."""
+    b, h, w = 32, synth.TRAIN_H, synth.TRAIN_W
+    planes = [torch.stack([torch.from_numpy(synth.gen_p_planes(rank * b + i, h, w)[k]) for i in range(b)]).to(dev) for k in range(4)]
+    ops.lut_for(1.5, dev)
+    out = {}
+
+    def kernel():
+        nonlocal out
+        out = ops.fused_planes(*planes, n=1.5, out=out)
+        return out
+
+    def timed(fn, n):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        D.barrier()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return D.max_over_ranks(a.elapsed_time(e) / n, dev)
+
+    ms_kernel = timed(kernel, reps)
+    px = b * h * w
+    res = {"workload": "cfg4: train-loader path at training resolution, planes u8 [32,4,320,480] -> xolp [32,2,320,480] + normals "
+                       "[32,9,320,480] (1 fused launch) -> ShallowEncoder / ShallowNormalsEncoder / ShallowResnetEncoder forward",
+           "n_gpus": world, "scaling": "weak", "kernel_us": ms_kernel * 1e3, "value": world * b / (ms_kernel * 1e-3), "unit": "samples/s",
+           "roofline_frac": 48.0 * px / (ms_kernel * 1e-3) / 1e9 / hbm_peak(),
+           "note": "4.9 Mpx per launch: 236 MB, launch-latency sized"}
+    if with_encoders:
+        from encoder_standins import PolarEncoders
+        enc = PolarEncoders().to(dev).eval()
+        rgb = torch.rand((b, 3, h, w), device=dev)
+
+        @torch.no_grad()
+        def encoders_only():
+            return enc(out["xolp"], out["normals"], rgb)
+
+        @torch.no_grad()
+        def both():
+            o = kernel()
+            return enc(o["xolp"], o["normals"], rgb)
+
+        n = max(10, reps // 10)
+        ms_enc = timed(encoders_only, n)
+        ms_both = timed(both, n)
+        res.update({"encoders_ms": ms_enc, "kernel_plus_encoders_ms": ms_both, "kernel_share_of_step": ms_kernel / ms_both,
+                    "samples_per_s_with_encoders": world * b / (ms_both * 1e-3)})
+    return res
+
+
+# --------------------------------------------------------------------------------------------------
+# cfg5: the evaluation path over a HAMMER-test-sized split
+# --------------------------------------------------------------------------------------------------
+def cfg5_eval(rank, world, dev, images=120, reps=200, check=False, graph=True):
+    """BASELINE configs[4]: per rank its contiguous shard of `images` 320x480 images -> GT depth->normals stencil +
+    per-image masked compute_depth_errors for the range mask and every material level (11 groups, one launch) ->
+    accumulators of the mean over images; one all-reduce of 1 + 11 x 7 float64.  `polcue_eval_pass_f32`: three launches,
+    no host work in between; timed eagerly and replayed from a CUDA graph (the 120-image pass is launch-latency sized)."""
+    lo, hi = D.shard_range(images, rank, world)
+    n_local = hi - lo
+    groups = [None] + list(synth.MATERIAL_LEVELS)
+    if n_local > 0:
+        gt, pred, inst, k = (torch.from_numpy(a).to(dev) for a in synth.gen_depth_batch(lo, n_local))
+    bufs = {}
+
+    def local_pass():
+        nonlocal bufs
+        if n_local > 0:
+            bufs = ops.eval_pass(gt, pred, inst, k, 0.1, 2.0, groups, out=bufs)
+            return bufs["mean_acc"]
+        return torch.zeros(1 + 7 * len(groups), dtype=torch.float64, device=dev)
+
+    def evaluate():
+        acc = local_pass().clone()
+        D.all_reduce_sums(acc)                                # the one collective: 78 float64
+        return acc
+
+    def timed(fn, n):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        D.barrier()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return D.max_over_ranks(a.elapsed_time(e) / n, dev)
+
+    acc = evaluate()
+    means = (acc[1:] / acc[0]).reshape(len(groups), 7)
+    ms_eager = timed(evaluate, reps)
+    ms_local = timed(local_pass, reps)
+    ms_graph = None
+    if graph and n_local > 0:
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            local_pass()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                local_pass()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        ms_graph = timed(g.replay, reps)
+        assert torch.equal(bufs["mean_acc"], local_pass())     # the replay wrote the same accumulators
+    px = n_local * synth.TRAIN_H * synth.TRAIN_W
+    bytes_alg = px * (16 + 9)                                  # stencil 4 R + 12 W, metrics 4 + 4 + 1 R (gt is read by both kernels)
+    chk = (bufs["normals"].double().sum().reshape(1) if n_local > 0 else torch.zeros(1, dtype=torch.float64, device=dev))
+    D.all_reduce_sums(chk)
+    res = {"workload": f"cfg5: evaluation path, {images} synthetic 320x480 images over {world} GPU(s): GT depth->normals + per-image "
+                       "masked depth errors for 11 mask groups + mean over images (polcue_eval_pass_f32, 3 launches) + 1 all-reduce",
+           "images": images, "n_gpus": world, "scaling": "strong", "ms_per_pass": ms_eager, "value": images / (ms_eager * 1e-3),
+           "unit": "images/s", "ms_local_launches_only": ms_local, "ms_local_cuda_graph_replay": ms_graph,
+           "roofline_frac_of_local_pass": bytes_alg / ((ms_graph or ms_local) * 1e-3) / 1e9 / hbm_peak(),
+           "abs_rel_all": float(means[0, 0]), "a1_all": float(means[0, 4]), "normals_checksum": float(chk[0])}
+    if check and rank == 0:
+        from oracle import polcue_oracle as O                  # the checker (test infrastructure), never timed
+        g_, p_, i_, kk = synth.gen_depth_batch(0, images)
+        t0 = time.perf_counter()
+        worst = 0.0
+        for gi, level in enumerate(groups):
+            _, mean = O.depth_errors_per_image(g_, p_, 0.1, 2.0, i_ if level is not None else None, level)
+            got = means[gi].cpu().numpy()
+            assert np.array_equal(np.isnan(got), np.isnan(mean)), (level, got, mean)
+            assert np.allclose(got, mean, rtol=5e-6, equal_nan=True), (level, got, mean)
+            worst = max(worst, float(np.nanmax(np.abs(got / mean - 1))))
+        res["parity"] = (f"sharded mean over images == unsharded oracle for {len(groups)} mask groups, worst relative difference "
+                         f"{worst:.1e} ({time.perf_counter() - t0:.1f} s on the CPU)")
+        res["parity_ok"] = True
+    return res
