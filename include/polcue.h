@@ -185,10 +185,9 @@ POLCUE_API int polcue_loader_front_end_u8_host(int in_h, int in_w, int out_h, in
  * `chunk_frames` <= 0 picks a default.  This is the call bench.py's `e2e` figure times. */
 POLCUE_API int polcue_fused_mosaic_u8_host(const uint8_t* h_mosaic, int B, int H, int W, const polcue_lut* lut,
                                 float* h_iun, float* h_xolp, float* h_normals, int chunk_frames);
-/* Pinned host memory for the callers of the *_host entry points: an anonymous mapping backed by transparent huge pages,
- * bound to the NUMA node of the GPU that will DMA into it when the platform exposes one
- * (/sys/bus/pci/devices/<bus id>/numa_node), populated, and registered with the driver as portable pinned memory; plain
- * cudaHostAlloc if the mapping cannot be registered.  `device` < 0: the current device.
+/* Pinned host memory for the callers of the *_host entry points: driver-allocated portable pinned memory (cudaHostAlloc),
+ * zero-filled, allocated while the calling thread prefers the NUMA node of the GPU that will DMA into it when the platform
+ * exposes one (/sys/bus/pci/devices/<bus id>/numa_node).  `device` < 0: the current device.
  * polcue_host_alloc = polcue_host_alloc_on(.., -1).  polcue_host_numa_node: the node found for `device`, or -1. */
 POLCUE_API int polcue_host_alloc(void** ptr, size_t bytes);
 POLCUE_API int polcue_host_alloc_on(void** ptr, size_t bytes, int device);

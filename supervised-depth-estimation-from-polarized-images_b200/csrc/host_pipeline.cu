@@ -234,23 +234,23 @@ int polcue_host_alloc_on(void** ptr, size_t bytes, int device) {
         if (e != cudaSuccess) return (int)e;
     }
     const int node = gpu_numa_node(dev);
-    const char* mode = std::getenv("POLCUE_HOST_ALLOC");       // A/B probing only: "cuda" forces plain cudaHostAlloc
-    if (!(mode && std::strcmp(mode, "cuda") == 0)) {
-        // Anonymous mapping backed by transparent huge pages (2 MB pages keep the IOMMU's translation cache effective
-        // when several GPUs stream results into host memory at once), bound to the GPU's NUMA node when the platform
-        // exposes one, populated here, then registered with the driver (page-locked + DMA-mapped, portable).
+    const bool bind = node >= 0 && node < 1024;
+    const char* mode = std::getenv("POLCUE_HOST_ALLOC");       // A/B probing only: "mapped" = huge-page mapping + cudaHostRegister
+    if (mode && std::strcmp(mode, "mapped") == 0) {
+        // Anonymous mapping backed by transparent huge pages, bound to the GPU's node, populated, then registered with the
+        // driver.  Measured on B200 / PCIe 5 (profiles/pcie_probe_r02*.json, bench e2e): device->host copies into such a
+        // registered mapping reach 39 GB/s where driver-allocated pinned memory reaches 57 GB/s, so this is NOT the default.
         const size_t page = 2u << 20;
         const size_t len = (bytes + page - 1) / page * page;
         void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         if (p != MAP_FAILED) {
             madvise(p, len, MADV_HUGEPAGE);
-            if (node >= 0 && node < 1024) {
+            if (bind) {
                 unsigned long mask[16] = {0};
                 mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
-                // MPOL_PREFERRED (1): the node if it has room, another one rather than failing; a refusal (seccomp) is not an error
                 (void)syscall(SYS_mbind, p, len, 1, mask, (unsigned long)(8 * sizeof(mask)), 0u);
             }
-            std::memset(p, 0, len);                          // first touch: pages are allocated here
+            std::memset(p, 0, len);
             if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
                 std::lock_guard<std::mutex> guard(g_host_mutex);
                 g_host_blocks[p] = HostBlock{len, true};
@@ -261,7 +261,17 @@ int polcue_host_alloc_on(void** ptr, size_t bytes, int device) {
             munmap(p, len);
         }
     }
+    // Driver-allocated pinned memory; while it is allocated (and first touched) the calling thread PREFERS the GPU's NUMA
+    // node (set_mempolicy MPOL_PREFERRED = 1), so on a two-socket box the pages land next to the GPU that will DMA into
+    // them.  A refused syscall (seccomp, single-node VM) changes nothing.
+    unsigned long mask[16] = {0};
+    if (bind) {
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        (void)syscall(SYS_set_mempolicy, 1, mask, (unsigned long)(8 * sizeof(mask)));
+    }
     const cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+    if (e == cudaSuccess) std::memset(*ptr, 0, bytes);
+    if (bind) (void)syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
     if (e != cudaSuccess) return as_code(e);
     std::lock_guard<std::mutex> guard(g_host_mutex);
     g_host_blocks[*ptr] = HostBlock{bytes, false};

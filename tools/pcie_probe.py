@@ -4,9 +4,9 @@
   python tools/pcie_probe.py                                         # 1 GPU
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29531 tools/pcie_probe.py
 
-Per rank: a `--mb` MB device buffer and pinned host buffers of two kinds -- torch's `pin_memory()` (cudaHostAlloc) and
-`polcue.ops.host_empty` (polcue_host_alloc_on: huge-page mapping, NUMA-bound when the platform says where the GPU sits,
-registered).  Device->host and host->device copies (cudaMemcpyAsync via `copy_`), each direction alone and both at once,
+Per rank: a `--mb` MB device buffer and pinned host buffers of three kinds -- torch's `pin_memory()` (cudaHostAlloc),
+`polcue.ops.host_empty` (polcue_host_alloc_on: cudaHostAlloc under a NUMA preference for the GPU's node) and the same with
+POLCUE_HOST_ALLOC=mapped (huge-page anonymous mapping + cudaHostRegister).  Device->host and host->device copies (cudaMemcpyAsync via `copy_`), each direction alone and both at once,
 first with ONE rank copying (the others idle), then with ALL ranks copying at the same time.  One JSON line: GB/s per
 GPU and aggregate.  This is the roofline `bench.py` reports for `e2e` and the evidence for its multi-GPU scaling.
 """
@@ -43,8 +43,16 @@ def main():
     n = args.mb << 20
     d_buf = torch.empty(n, dtype=torch.uint8, device=dev)
     d_src = torch.randint(0, 255, (n,), dtype=torch.uint8, device=dev)
+    def mapped():
+        os.environ["POLCUE_HOST_ALLOC"] = "mapped"
+        try:
+            return ops.host_empty((n,), torch.uint8, dev)
+        finally:
+            os.environ.pop("POLCUE_HOST_ALLOC", None)
+
     kinds = {"torch_pin_memory": lambda: torch.empty(n, dtype=torch.uint8).pin_memory(),
-             "polcue_host_alloc": lambda: ops.host_empty((n,), torch.uint8, dev)}
+             "polcue_host_alloc": lambda: ops.host_empty((n,), torch.uint8, dev),
+             "polcue_host_alloc_mapped_hugepages": mapped}
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     step = (args.chunk_mb << 20) or n
 
