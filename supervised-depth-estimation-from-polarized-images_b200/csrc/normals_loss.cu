@@ -19,11 +19,8 @@
 // where the per-axis weights fold the replicate padding back onto border pixels:
 //     S[-1] = S[+1] = 1, D[-1] = +1, D[+1] = -1, S[0] = 2 + [q == 0] + [q == last], D[0] = [q == last] - [q == 0].
 // Phase 1 of the backward kernel writes gu_bar, gv_bar of the tile + 1-pixel ring to shared memory, phase 2 gathers.
-// Depth tiles (halo 2) are staged by TMA tensor copies when rows are 16-byte multiples, else by hand.
-#include <cuda.h>
-
-#include <mutex>
-
+// Two kernel families: packed (rows that are 16-byte multiples: GT and prediction in the two lanes of packed FP32
+// instructions, interleaved shared tile) and scalar (any width / alignment); both stage their tiles by hand.
 #include "polcue_device.cuh"
 #include "polcue_host.h"
 
@@ -41,7 +38,7 @@ __host__ __device__ constexpr uint32_t tile_bytes(int th) { return kLBoxW * box_
 constexpr int kGH = kBwdH + 2, kGPitch = kLW + 8;                // adjoint fields of the tile + 1-pixel ring
 constexpr int kGCol = 4;                                          // G column of tile column 0 (16-byte aligned rows)
 constexpr int kMaxLossBlocks = 1 << 18;
-constexpr uint32_t kLTilePad = (tile_bytes(kBwdH) + 127) / 128 * 128;           // TMA destinations are 128-byte aligned
+constexpr uint32_t kLTilePad = (tile_bytes(kBwdH) + 127) / 128 * 128;
 constexpr size_t kBwdSmem = 2 * kLTilePad + 6 * kGH * kGPitch * sizeof(float);
 
 struct LossParams {
@@ -63,49 +60,15 @@ struct LossParams {
     float* grad_pred;
 };
 
-// Stage a halo'd depth tile: TMA (zero-filled outside the image) or manual with clamped coordinates.
-template <bool TMA, int TH>
-__device__ __forceinline__ void stage_begin(float (*tile)[kLBoxW], const CUtensorMap* tmap, const float* plane, int H, int W, int x0,
-                                            int y0, int b, uint64_t* bar) {
-    if constexpr (TMA) {
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(tile_bytes(TH)) : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                    smem_u32(&tile[0][0])),
-                "l"(tmap), "r"(x0 - kLCol), "r"(y0 - kLRow), "r"(b), "r"(smem_u32(bar))
-                : "memory");
-        }
-    } else {
-        for (int i = threadIdx.x; i < box_rows(TH) * (kLW + 2 * kHalo); i += kLossThreads) {
-            const int r = i / (kLW + 2 * kHalo), c = i - r * (kLW + 2 * kHalo);
-            const int yy = min(max(y0 + r - kLRow, 0), H - 1);
-            const int xx = min(max(x0 + c - kHalo, 0), W - 1);
-            tile[r][kLCol - kHalo + c] = __ldg(plane + (size_t)yy * W + xx);
-        }
-    }
-}
-
-// After a TMA load: replicate the image border into the first ring outside the image (the only out-of-image cells
-// any in-image pixel's window touches).
+// Stage a halo'd depth tile by hand with clamped coordinates (replicate padding).
 template <int TH>
-__device__ __forceinline__ void patch_replicate(float (*tile)[kLBoxW], int H, int W, int x0, int y0) {
-    const int last_x = W - 1 - x0, last_y = H - 1 - y0;
-    const bool left = x0 == 0, right = last_x < kLW + 1, top = y0 == 0, bottom = last_y < TH + 1;
-    if (left | right) {
-        for (int r = threadIdx.x; r < box_rows(TH); r += kLossThreads) {
-            if (left) tile[r][kLCol - 1] = tile[r][kLCol];
-            if (right && last_x >= -1) tile[r][kLCol + last_x + 1] = tile[r][kLCol + last_x];
-        }
+__device__ __forceinline__ void stage_tile(float (*tile)[kLBoxW], const float* plane, int H, int W, int x0, int y0) {
+    for (int i = threadIdx.x; i < box_rows(TH) * (kLW + 2 * kHalo); i += kLossThreads) {
+        const int r = i / (kLW + 2 * kHalo), c = i - r * (kLW + 2 * kHalo);
+        const int yy = min(max(y0 + r - kLRow, 0), H - 1);
+        const int xx = min(max(x0 + c - kHalo, 0), W - 1);
+        tile[r][kLCol - kHalo + c] = __ldg(plane + (size_t)yy * W + xx);
     }
-    __syncthreads();
-    if (top | bottom) {
-        for (int c = threadIdx.x; c < kLBoxW; c += kLossThreads) {
-            if (top) tile[kLRow - 1][c] = tile[kLRow][c];
-            if (bottom && last_y >= -1) tile[kLRow + last_y + 1][c] = tile[kLRow + last_y][c];
-        }
-    }
-    __syncthreads();
 }
 
 struct Cam {
@@ -258,77 +221,11 @@ __device__ __forceinline__ float mask_value(const LossParams& p, size_t idx, flo
     else return __ldg(p.mask + idx);
 }
 
-// L1 = true adds the supervised depth loss of the same block of the trainer (trainer.py:1246):
-//     supervised_depth_loss = (|gt - pred| * mask).sum() / mask.sum()
-template <bool TMA, bool L1>
-__global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const __grid_constant__ CUtensorMap tm_gt,
-                                                                        const __grid_constant__ CUtensorMap tm_pred, const LossParams p) {
-    __shared__ __align__(128) float tg[box_rows(kFwdH)][kLBoxW];
-    __shared__ __align__(128) float tp[box_rows(kFwdH)][kLBoxW];
-    __shared__ uint64_t bar;
-    __shared__ double red[kLossThreads / 32][3];
-    __shared__ bool last;
-    const int b = blockIdx.z, x0 = blockIdx.x * kLW, y0 = blockIdx.y * kFwdH;
-    const size_t hw = (size_t)p.H * p.W;
-    if (TMA && threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_u32(&bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (TMA) __syncthreads();
-    stage_begin<TMA, kFwdH>(tg, &tm_gt, p.gt + b * hw, p.H, p.W, x0, y0, b, &bar);
-    stage_begin<TMA, kFwdH>(tp, &tm_pred, p.pred + b * hw, p.H, p.W, x0, y0, b, &bar);
-    if constexpr (TMA) {
-        lut_stage_wait(&bar);
-        patch_replicate<kFwdH>(tg, p.H, p.W, x0, y0);
-        patch_replicate<kFwdH>(tp, p.H, p.W, x0, y0);
-    } else {
-        __syncthreads();
-    }
-    const Cam cam = load_cam(p.K, b);
-    float s = 0.0f, m = 0.0f, l1 = 0.0f;   // at most 16 pixels per thread: float32 partials, float64 from the warp level on
-    for (int i = threadIdx.x; i < (kLW / 4) * kFwdH; i += kLossThreads) {
-        const int ty = i / (kLW / 4), tx0 = 4 * (i - ty * (kLW / 4));
-        const int x = x0 + tx0, y = y0 + ty;
-        if (x >= p.W || y >= p.H) continue;
-        float gu[3][4], gv[3][4], a4[3][4], b4[3][4];
-        gradients4(tg, ty, tx0, x, y, p.H, p.W, cam, gu, gv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float u[3] = {gu[0][j], gu[1][j], gu[2][j]}, v[3] = {gv[0][j], gv[1][j], gv[2][j]};
-            float n[3], un[3];
-            cross_rn(u, v, n);
-            normalize3(n, un);
-            a4[0][j] = un[0]; a4[1][j] = un[1]; a4[2][j] = un[2];
-        }
-        gradients4(tp, ty, tx0, x, y, p.H, p.W, cam, gu, gv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float u[3] = {gu[0][j], gu[1][j], gu[2][j]}, v[3] = {gv[0][j], gv[1][j], gv[2][j]};
-            float n[3], un[3];
-            cross_rn(u, v, n);
-            normalize3(n, un);
-            b4[0][j] = un[0]; b4[1][j] = un[1]; b4[2][j] = un[2];
-        }
-        float fs = 0.0f, fm = 0.0f, fl = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (x + j < p.W) {
-                const float zg = tg[kLRow + ty][kLCol + tx0 + j];
-                const float mk = mask_value<L1>(p, b * hw + (size_t)y * p.W + x + j, zg);
-                if constexpr (L1) fl = fmaf(fabsf(zg - tp[kLRow + ty][kLCol + tx0 + j]), mk, fl);
-                const float a[3] = {a4[0][j], a4[1][j], a4[2][j]}, bb3[3] = {b4[0][j], b4[1][j], b4[2][j]};
-                float inv_den, ab, bb;
-                bool clamped;
-                const float c = cosine(a, bb3, inv_den, ab, bb, clamped);
-                fs = fmaf(2.0f - c, mk, fs);
-                fm += mk;
-            }
-        }
-        s += fs;
-        m += fm;
-        l1 += fl;
-    }
-    // deterministic reduction: warp shuffle -> shared -> per-CTA partial -> last CTA folds in fixed order
+// Deterministic reduction shared by the forward kernels: warp shuffle -> shared -> per-CTA partial -> the last CTA to
+// finish folds the partials in a fixed order (bitwise reproducible) and writes sums / losses.
+template <bool L1>
+__device__ __forceinline__ void loss_block_reduce(const LossParams& p, float s, float m, float l1, double (*red)[3], bool* last_flag) {
+    bool& last = *last_flag;
     double sd = s, md = m, ld = l1;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -397,32 +294,480 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const
     }
 }
 
+
+// L1 = true adds the supervised depth loss of the same block of the trainer (trainer.py:1246):
+//     supervised_depth_loss = (|gt - pred| * mask).sum() / mask.sum()
+// Scalar kernel: any width / alignment (the packed kernel below serves rows that are 16-byte multiples).
+template <bool L1>
+__global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const LossParams p) {
+    __shared__ __align__(16) float tg[box_rows(kFwdH)][kLBoxW];
+    __shared__ __align__(16) float tp[box_rows(kFwdH)][kLBoxW];
+    __shared__ double red[kLossThreads / 32][3];
+    __shared__ bool last;
+    const int b = blockIdx.z, x0 = blockIdx.x * kLW, y0 = blockIdx.y * kFwdH;
+    const size_t hw = (size_t)p.H * p.W;
+    stage_tile<kFwdH>(tg, p.gt + b * hw, p.H, p.W, x0, y0);
+    stage_tile<kFwdH>(tp, p.pred + b * hw, p.H, p.W, x0, y0);
+    __syncthreads();
+    const Cam cam = load_cam(p.K, b);
+    float s = 0.0f, m = 0.0f, l1 = 0.0f;   // at most 16 pixels per thread: float32 partials, float64 from the warp level on
+    for (int i = threadIdx.x; i < (kLW / 4) * kFwdH; i += kLossThreads) {
+        const int ty = i / (kLW / 4), tx0 = 4 * (i - ty * (kLW / 4));
+        const int x = x0 + tx0, y = y0 + ty;
+        if (x >= p.W || y >= p.H) continue;
+        float gu[3][4], gv[3][4], a4[3][4], b4[3][4];
+        gradients4(tg, ty, tx0, x, y, p.H, p.W, cam, gu, gv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float u[3] = {gu[0][j], gu[1][j], gu[2][j]}, v[3] = {gv[0][j], gv[1][j], gv[2][j]};
+            float n[3], un[3];
+            cross_rn(u, v, n);
+            normalize3(n, un);
+            a4[0][j] = un[0]; a4[1][j] = un[1]; a4[2][j] = un[2];
+        }
+        gradients4(tp, ty, tx0, x, y, p.H, p.W, cam, gu, gv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float u[3] = {gu[0][j], gu[1][j], gu[2][j]}, v[3] = {gv[0][j], gv[1][j], gv[2][j]};
+            float n[3], un[3];
+            cross_rn(u, v, n);
+            normalize3(n, un);
+            b4[0][j] = un[0]; b4[1][j] = un[1]; b4[2][j] = un[2];
+        }
+        float fs = 0.0f, fm = 0.0f, fl = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (x + j < p.W) {
+                const float zg = tg[kLRow + ty][kLCol + tx0 + j];
+                const float mk = mask_value<L1>(p, b * hw + (size_t)y * p.W + x + j, zg);
+                if constexpr (L1) fl = fmaf(fabsf(zg - tp[kLRow + ty][kLCol + tx0 + j]), mk, fl);
+                const float a[3] = {a4[0][j], a4[1][j], a4[2][j]}, bb3[3] = {b4[0][j], b4[1][j], b4[2][j]};
+                float inv_den, ab, bb;
+                bool clamped;
+                const float c = cosine(a, bb3, inv_den, ab, bb, clamped);
+                fs = fmaf(2.0f - c, mk, fs);
+                fm += mk;
+            }
+        }
+        s += fs;
+        m += fm;
+        l1 += fl;
+    }
+    loss_block_reduce<L1>(p, s, m, l1, red, &last);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Packed forward (rows that are 16-byte multiples).  The GT and the predicted depth go through the IDENTICAL stencil,
+// so they ride in the two lanes of Blackwell's packed FP32 instructions (FFMA2 / FADD2 / FMUL2: the scalar FLOP rate
+// in half the issue slots, tools/probes/int_pipe_probe.cu): every lane runs exactly the operation sequence of
+// gradients4 / cross_rn / normalize3 above, so losses are bit-identical to the scalar kernel's.  The tile is staged
+// INTERLEAVED -- shared element = (gt, pred) of one pixel -- so one LDS.128 delivers two ready-made lane pairs and a
+// thread's 3 x 6 window of both fields costs 9 loads (18 in the planar layout).  Staging is by hand (coalesced
+// 16-byte global loads, replicate padding by clamped coordinates); TMA cannot interleave two tensors.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPW = 128, kPH = 32;                    // tile
+constexpr int kPPitch = kPW + 4;                      // (gt, pred) pairs per shared row: column 0 = image column x0 - 1, 129 = x0 + 128
+
+// Stage rows y0 - 1 .. y0 + TH of both fields, interleaved.  T has TH + 2 rows of kPPitch pairs.
+template <int TH>
+__device__ __forceinline__ void stage_pairs(float2 (*T)[kPPitch], const float* __restrict__ G, const float* __restrict__ P, int H, int W,
+                                            int x0, int y0) {
+    for (int i = threadIdx.x; i < (TH + 2) * (kPW / 4); i += kLossThreads) {
+        const int r = i / (kPW / 4), q = i - r * (kPW / 4);
+        const int x = x0 + 4 * q;
+        if (x < W) {
+            const int yy = min(max(y0 + r - 1, 0), H - 1);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(G + (size_t)yy * W + x));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(P + (size_t)yy * W + x));
+            float2* dst = &T[r][1 + 4 * q];
+            dst[0] = make_float2(g.x, d.x);
+            dst[1] = make_float2(g.y, d.y);
+            dst[2] = make_float2(g.z, d.z);
+            dst[3] = make_float2(g.w, d.w);
+        }
+    }
+    // the column left of the tile and the first column right of it (or of the image): replicate padding by clamping
+    const int cr = min(W - x0, kPW);                  // tile-relative index of the first column beyond the tile / image
+    for (int i = threadIdx.x; i < (TH + 2) * 2; i += kLossThreads) {
+        const int r = i >> 1, right = i & 1;
+        const int yy = min(max(y0 + r - 1, 0), H - 1);
+        const int xx = right ? min(x0 + cr, W - 1) : max(x0 - 1, 0);
+        T[r][right ? 1 + cr : 0] = make_float2(__ldg(G + (size_t)yy * W + xx), __ldg(P + (size_t)yy * W + xx));
+    }
+}
+
+// 8 x gradients of xyz of both fields for the four pixels starting at tile column tx0 of tile row ty (shared row ty + 1):
+// lane 0 = GT, lane 1 = prediction.  Same arithmetic, per lane, as gradients4.
+// `win` = the shared pair of the window's top-left pixel (row y - 1, column x - 1; 16-byte aligned), `pitch` pairs per row.
+__device__ __forceinline__ void gradients4_pairs(const float2* win, int pitch, const f32x2 (&fx6)[6], const f32x2 (&fy3)[3],
+                                                 f32x2 (&gu)[3][4], f32x2 (&gv)[3][4], f32x2 (&centre)[4]) {
+    f32x2 Z[3][6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const ulonglong2* row = reinterpret_cast<const ulonglong2*>(win + r * pitch);   // pairs of columns x - 1 .. x + 4
+        const ulonglong2 a = row[0], b = row[1], c = row[2];
+        Z[r][0] = a.x; Z[r][1] = a.y; Z[r][2] = b.x; Z[r][3] = b.y; Z[r][4] = c.x; Z[r][5] = c.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) centre[j] = Z[1][1 + j];
+    f32x2 Su[3][6], Dv[3][6];
+    const f32x2 two = dup2(2.0f);
+    const f32x2 fy1x2 = mul2(two, fy3[1]);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        Su[2][c] = fma2(two, Z[1][c], add2(Z[0][c], Z[2][c]));
+        Dv[2][c] = sub2(Z[2][c], Z[0][c]);
+        Su[0][c] = mul2(fx6[c], Su[2][c]);
+        Dv[0][c] = mul2(fx6[c], Dv[2][c]);
+        const f32x2 lo = mul2(fy3[0], Z[0][c]);
+        Su[1][c] = fma2(fy3[2], Z[2][c], fma2(fy1x2, Z[1][c], lo));
+        Dv[1][c] = sub2(mul2(fy3[2], Z[2][c]), lo);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int comp = 0; comp < 3; ++comp) {
+            gu[comp][j] = sub2(Su[comp][j + 2], Su[comp][j]);
+            gv[comp][j] = fma2(two, Dv[comp][j + 1], add2(Dv[comp][j], Dv[comp][j + 2]));
+        }
+}
+
+// cross_rn + normalize3 on both lanes; returns the scale factors (inv) of both lanes.
+__device__ __forceinline__ f32x2 unit_normals_pairs(const f32x2 (&u)[3], const f32x2 (&v)[3], f32x2 (&n)[3]) {
+    f32x2 c[3];
+    c[0] = sub2(mul2(u[1], v[2]), mul2(u[2], v[1]));
+    c[1] = sub2(mul2(u[2], v[0]), mul2(u[0], v[2]));
+    c[2] = sub2(mul2(u[0], v[1]), mul2(u[1], v[0]));
+    float qa, qb;
+    unpk2(fma2(c[0], c[0], fma2(c[1], c[1], mul2(c[2], c[2]))), qa, qb);
+    const f32x2 inv = pk2(fminf(rsqrt_approx(qa), kInvCap), fminf(rsqrt_approx(qb), kInvCap));
+    n[0] = mul2(c[0], inv);
+    n[1] = mul2(c[1], inv);
+    n[2] = mul2(c[2], inv);
+    return inv;
+}
+
+template <bool L1>
+__global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel(const LossParams p) {
+    __shared__ __align__(16) float2 T[kPH + 2][kPPitch];
+    __shared__ double red[kLossThreads / 32][3];
+    __shared__ bool last;
+    const int b = blockIdx.z, x0 = blockIdx.x * kPW, y0 = blockIdx.y * kPH;
+    const size_t hw = (size_t)p.H * p.W;
+    stage_pairs<kPH>(T, p.gt + b * hw, p.pred + b * hw, p.H, p.W, x0, y0);
+    __syncthreads();
+    const Cam cam = load_cam(p.K, b);
+    const int tx0 = 4 * (threadIdx.x & 31), x = x0 + tx0;
+    f32x2 fx6[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) fx6[c] = dup2(((float)min(max(x + c - 1, 0), p.W - 1) - cam.cx) * cam.inv_fx);
+    float s = 0.0f, m = 0.0f, l1 = 0.0f;   // at most 16 pixels per thread: float32 partials, float64 from the warp level on
+    if (x < p.W) {
+#pragma unroll 1
+        for (int ty = threadIdx.x >> 5; ty < kPH; ty += kLossThreads / 32) {
+            const int y = y0 + ty;
+            if (y >= p.H) break;
+            f32x2 fy3[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) fy3[r] = dup2(((float)min(max(y + r - 1, 0), p.H - 1) - cam.cy) * cam.inv_fy);
+            f32x2 gu[3][4], gv[3][4], centre[4];
+            gradients4_pairs(&T[ty][tx0], kPPitch, fx6, fy3, gu, gv, centre);
+            float mk4[4];
+            if constexpr (!L1) {
+                const float4 mv = __ldg(reinterpret_cast<const float4*>(p.mask + b * hw + (size_t)y * p.W + x));
+                mk4[0] = mv.x; mk4[1] = mv.y; mk4[2] = mv.z; mk4[3] = mv.w;
+            }
+            float fs = 0.0f, fm = 0.0f, fl = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const f32x2 u[3] = {gu[0][j], gu[1][j], gu[2][j]}, v[3] = {gv[0][j], gv[1][j], gv[2][j]};
+                f32x2 n[3];
+                unit_normals_pairs(u, v, n);
+                float a[3], bb3[3];
+                unpk2(n[0], a[0], bb3[0]);
+                unpk2(n[1], a[1], bb3[1]);
+                unpk2(n[2], a[2], bb3[2]);
+                float zg, zp;
+                unpk2(centre[j], zg, zp);
+                float mk;
+                if constexpr (L1) mk = (zg >= p.min_d && zg <= p.max_d) ? 1.0f : 0.0f;
+                else mk = mk4[j];
+                if constexpr (L1) fl = fmaf(fabsf(zg - zp), mk, fl);
+                float inv_den, ab, bb;
+                bool clamped;
+                const float c = cosine(a, bb3, inv_den, ab, bb, clamped);
+                fs = fmaf(2.0f - c, mk, fs);
+                fm += mk;
+            }
+            s += fs;
+            m += fm;
+            l1 += fl;
+        }
+    }
+    loss_block_reduce<L1>(p, s, m, l1, red, &last);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Packed backward (rows that are 16-byte multiples).  Phase 1 runs the two stencils of every pixel of the tile + ring
+// in the two lanes of packed FP32 instructions (as the packed forward does) and stores the six adjoint fields as three
+// PAIR fields A = (gu_bar_x, gu_bar_y), B = (gv_bar_x, gv_bar_y), C = (gu_bar_z, gv_bar_z); phase 2 gathers them with
+// packed instructions too: the vertical combinations of A / B / C are independent chains per lane, and the horizontal
+// chain  acc = fma(Dh, VU, fma(Sh, VV, acc))  of components x and y runs in the two lanes of one register pair.  Every
+// lane performs exactly the operation sequence of the scalar kernel below: gradients are bit-identical to it.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBPitch = 136;                          // pairs per shared row; tile column c lives at index c + 3 (c = -2 .. 129)
+constexpr int kBTileRows = kBwdH + 4;                 // rows y0 - 2 .. y0 + kBwdH + 1
+constexpr size_t kBwdPairsSmem = (size_t)(kBTileRows + 3 * kGH) * kBPitch * sizeof(float2);
+
+// 3 x 3 window, one pixel (the two ring columns): same arithmetic as `gradients`, both fields in the two lanes.
+__device__ __forceinline__ void gradients1_pairs(const float2* win, int pitch, int x, int y, int H, int W, const Cam& cam, f32x2 (&gu)[3],
+                                                 f32x2 (&gv)[3], f32x2& centre) {
+    f32x2 fx3[3], fy3[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        fx3[k] = dup2(((float)min(max(x + k - 1, 0), W - 1) - cam.cx) * cam.inv_fx);
+        fy3[k] = dup2(((float)min(max(y + k - 1, 0), H - 1) - cam.cy) * cam.inv_fy);
+    }
+    f32x2 Z[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Z[r][c] = *reinterpret_cast<const f32x2*>(win + r * pitch + c);
+    centre = Z[1][1];
+    f32x2 Su[3][3], Dv[3][3];
+    const f32x2 two = dup2(2.0f);
+    const f32x2 fy1x2 = mul2(two, fy3[1]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Su[2][c] = fma2(two, Z[1][c], add2(Z[0][c], Z[2][c]));
+        Dv[2][c] = sub2(Z[2][c], Z[0][c]);
+        Su[0][c] = mul2(fx3[c], Su[2][c]);
+        Dv[0][c] = mul2(fx3[c], Dv[2][c]);
+        const f32x2 lo = mul2(fy3[0], Z[0][c]);
+        Su[1][c] = fma2(fy3[2], Z[2][c], fma2(fy1x2, Z[1][c], lo));
+        Dv[1][c] = sub2(mul2(fy3[2], Z[2][c]), lo);
+    }
+#pragma unroll
+    for (int comp = 0; comp < 3; ++comp) {
+        gu[comp] = sub2(Su[comp][2], Su[comp][0]);
+        gv[comp] = fma2(two, Dv[comp][1], add2(Dv[comp][0], Dv[comp][2]));
+    }
+}
+
+// adjoint_px from the packed gradients of one pixel (lane 0 = GT, lane 1 = prediction).
+__device__ __forceinline__ void adjoint_pairs(const f32x2 (&gu)[3], const f32x2 (&gv)[3], float k, f32x2& A, f32x2& B, f32x2& C) {
+    A = B = C = 0ull;
+    if (k == 0.0f) return;
+    f32x2 n[3];
+    const f32x2 inv2 = unit_normals_pairs(gu, gv, n);
+    float a[3], bn[3], up[3], vp[3], tmp, inv;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        unpk2(n[c], a[c], bn[c]);
+        unpk2(gu[c], tmp, up[c]);
+        unpk2(gv[c], tmp, vp[c]);
+    }
+    unpk2(inv2, tmp, inv);
+    float inv_den, ab, bb;
+    bool clamped;
+    cosine(a, bn, inv_den, ab, bb, clamped);
+    const float w_b = clamped ? 0.0f : ab * inv_den / fmaxf(bb, 1e-30f);
+    float g[3], nb[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = a[c] * inv_den - w_b * bn[c];
+    const float gb = (inv >= kInvCap) ? 0.0f : fmaf(g[0], bn[0], fmaf(g[1], bn[1], g[2] * bn[2]));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) nb[c] = k * inv * (g[c] - gb * bn[c]);
+    A = pk2(vp[1] * nb[2] - vp[2] * nb[1], vp[2] * nb[0] - vp[0] * nb[2]);
+    B = pk2(nb[1] * up[2] - nb[2] * up[1], nb[2] * up[0] - nb[0] * up[2]);
+    C = pk2(vp[0] * nb[1] - vp[1] * nb[0], nb[0] * up[1] - nb[1] * up[0]);
+}
+
+template <bool L1>
+__global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_pairs_kernel(const LossParams p) {
+    extern __shared__ __align__(128) unsigned char bwd_smem[];
+    float2 (*T)[kBPitch] = reinterpret_cast<float2 (*)[kBPitch]>(bwd_smem);                                     // (gt, pred) tile, halo 2
+    float2 (*G)[kGH][kBPitch] = reinterpret_cast<float2 (*)[kGH][kBPitch]>(bwd_smem + sizeof(float2) * kBTileRows * kBPitch);   // A, B, C
+    const int b = blockIdx.z, x0 = blockIdx.x * kLW, y0 = blockIdx.y * kBwdH;
+    const size_t hw = (size_t)p.H * p.W;
+    const float* Gt = p.gt + b * hw;
+    const float* Pr = p.pred + b * hw;
+    // ---- stage rows y0 - 2 .. y0 + kBwdH + 1, columns x0 - 2 .. x0 + 129 (replicate padding by clamping) ----
+    for (int i = threadIdx.x; i < kBTileRows * (kLW / 4); i += kLossThreads) {
+        const int r = i / (kLW / 4), q = i - r * (kLW / 4);
+        const int x = x0 + 4 * q;
+        if (x < p.W) {
+            const int yy = min(max(y0 + r - 2, 0), p.H - 1);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(Gt + (size_t)yy * p.W + x));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(Pr + (size_t)yy * p.W + x));
+            float2* dst = &T[r][3 + 4 * q];
+            dst[0] = make_float2(g.x, d.x);
+            dst[1] = make_float2(g.y, d.y);
+            dst[2] = make_float2(g.z, d.z);
+            dst[3] = make_float2(g.w, d.w);
+        }
+    }
+    const int cr = min(p.W - x0, kLW);                 // first tile column beyond the tile / the image
+    for (int i = threadIdx.x; i < kBTileRows * 4; i += kLossThreads) {
+        const int r = i >> 2, k4 = i & 3;
+        const int c = (k4 < 2) ? k4 - 2 : cr + (k4 - 2);   // -2, -1, cr, cr + 1
+        const int yy = min(max(y0 + r - 2, 0), p.H - 1);
+        const int xx = min(max(x0 + c, 0), p.W - 1);
+        T[r][3 + c] = make_float2(__ldg(Gt + (size_t)yy * p.W + xx), __ldg(Pr + (size_t)yy * p.W + xx));
+    }
+    __syncthreads();
+    const Cam cam = load_cam(p.K, b);
+    const float scale = -__ldg(p.grad_out) / (float)p.sums2[1];    // -grad_out / sum(mask)
+    const float l1_scale = (L1 && p.grad_l1) ? __ldg(p.grad_l1) / (float)p.sums2[1] : 0.0f;
+
+    // ---- phase 1: adjoints of the two gradients at every pixel of the tile and its 1-pixel ring ----
+    {
+        const int tx0 = 4 * (threadIdx.x & 31), x = x0 + tx0;
+        f32x2 fx6[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) fx6[c] = dup2(((float)min(max(x + c - 1, 0), p.W - 1) - cam.cx) * cam.inv_fx);
+#pragma unroll 1
+        for (int gy = threadIdx.x >> 5; gy < kGH; gy += kLossThreads / 32) {
+            const int ty = gy - 1, y = y0 + ty;
+            f32x2 oa[4] = {0ull, 0ull, 0ull, 0ull}, ob[4] = {0ull, 0ull, 0ull, 0ull}, oc[4] = {0ull, 0ull, 0ull, 0ull};
+            if (y >= 0 && y < p.H && x < p.W) {
+                f32x2 fy3[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) fy3[r] = dup2(((float)min(max(y + r - 1, 0), p.H - 1) - cam.cy) * cam.inv_fy);
+                f32x2 gu[3][4], gv[3][4], centre[4];
+                gradients4_pairs(&T[ty + 1][tx0 + 2], kBPitch, fx6, fy3, gu, gv, centre);
+                float mk4[4];
+                if constexpr (!L1) {
+                    const float4 mv = __ldg(reinterpret_cast<const float4*>(p.mask + b * hw + (size_t)y * p.W + x));
+                    mk4[0] = mv.x; mk4[1] = mv.y; mk4[2] = mv.z; mk4[3] = mv.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float mk;
+                    if constexpr (L1) {
+                        float zg, zp;
+                        unpk2(centre[j], zg, zp);
+                        mk = (zg >= p.min_d && zg <= p.max_d) ? 1.0f : 0.0f;
+                    } else {
+                        mk = mk4[j];
+                    }
+                    const f32x2 u[3] = {gu[0][j], gu[1][j], gu[2][j]}, v[3] = {gv[0][j], gv[1][j], gv[2][j]};
+                    adjoint_pairs(u, v, scale * mk, oa[j], ob[j], oc[j]);
+                }
+            }
+            // index 3 + tx0 is 8 mod 16 bytes: 64-bit stores
+            f32x2* sa = reinterpret_cast<f32x2*>(&G[0][gy][3 + tx0]);
+            f32x2* sb = reinterpret_cast<f32x2*>(&G[1][gy][3 + tx0]);
+            f32x2* sc = reinterpret_cast<f32x2*>(&G[2][gy][3 + tx0]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sa[j] = oa[j];
+                sb[j] = ob[j];
+                sc[j] = oc[j];
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < kGH * 2; i += kLossThreads) {     // the two ring columns, one pixel at a time
+        const int gy = i >> 1, tx = (i & 1) ? kLW : -1;
+        const int ty = gy - 1;
+        const int x = x0 + tx, y = y0 + ty;
+        f32x2 A = 0ull, B = 0ull, C = 0ull;
+        if (x >= 0 && x < p.W && y >= 0 && y < p.H) {
+            f32x2 gu[3], gv[3], centre;
+            gradients1_pairs(&T[ty + 1][tx + 2], kBPitch, x, y, p.H, p.W, cam, gu, gv, centre);
+            float zg, zp;
+            unpk2(centre, zg, zp);
+            const float mk = mask_value<L1>(p, b * hw + (size_t)y * p.W + x, zg);
+            adjoint_pairs(gu, gv, scale * mk, A, B, C);
+        }
+        *reinterpret_cast<f32x2*>(&G[0][gy][3 + tx]) = A;
+        *reinterpret_cast<f32x2*>(&G[1][gy][3 + tx]) = B;
+        *reinterpret_cast<f32x2*>(&G[2][gy][3 + tx]) = C;
+    }
+    __syncthreads();
+
+    // ---- phase 2: gather, four pixels at a time ----
+    {
+        const int tx0 = 4 * (threadIdx.x & 31), x = x0 + tx0;
+        if (x >= p.W) return;
+#pragma unroll 1
+        for (int ty = threadIdx.x >> 5; ty < kBwdH; ty += kLossThreads / 32) {
+            const int y = y0 + ty;
+            if (y >= p.H) break;
+            const float Sv[3] = {1.0f, 2.0f + (y == 0) + (y == p.H - 1), 1.0f};
+            const float Dv[3] = {1.0f, (float)(y == p.H - 1) - (float)(y == 0), -1.0f};
+            f32x2 VA[6], VB[6], VC[6];      // vertical combinations: (VU_x, VU_y), (VV_x, VV_y), (VU_z, VV_z) of the six window columns
+#pragma unroll
+            for (int k6 = 0; k6 < 6; ++k6) VA[k6] = VB[k6] = VC[k6] = 0ull;
+#pragma unroll
+            for (int di = 0; di < 3; ++di) {
+                const f32x2 ws = dup2(Sv[di]), wd = dup2(Dv[di]), wsd = pk2(Sv[di], Dv[di]);
+                const ulonglong2* ra = reinterpret_cast<const ulonglong2*>(&G[0][ty + di][tx0 + 2]);   // columns x - 1 .. x + 4
+                const ulonglong2* rb = reinterpret_cast<const ulonglong2*>(&G[1][ty + di][tx0 + 2]);
+                const ulonglong2* rc = reinterpret_cast<const ulonglong2*>(&G[2][ty + di][tx0 + 2]);
+#pragma unroll
+                for (int h = 0; h < 3; ++h) {
+                    const ulonglong2 a = ra[h], bq = rb[h], c = rc[h];
+                    VA[2 * h] = fma2(ws, a.x, VA[2 * h]);
+                    VA[2 * h + 1] = fma2(ws, a.y, VA[2 * h + 1]);
+                    VB[2 * h] = fma2(wd, bq.x, VB[2 * h]);
+                    VB[2 * h + 1] = fma2(wd, bq.y, VB[2 * h + 1]);
+                    VC[2 * h] = fma2(wsd, c.x, VC[2 * h]);
+                    VC[2 * h + 1] = fma2(wsd, c.y, VC[2 * h + 1]);
+                }
+            }
+            const float fyq = ((float)y - cam.cy) * cam.inv_fy;
+            float res[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int xj = x + j;
+                const float Sh[3] = {1.0f, 2.0f + (xj == 0) + (xj == p.W - 1), 1.0f};
+                const float Dh[3] = {1.0f, (float)(xj == p.W - 1) - (float)(xj == 0), -1.0f};
+                f32x2 acc01 = 0ull;
+                float acc2 = 0.0f;
+#pragma unroll
+                for (int dj = 0; dj < 3; ++dj) {
+                    acc01 = fma2(dup2(Dh[dj]), VA[j + dj], fma2(dup2(Sh[dj]), VB[j + dj], acc01));
+                    float vu2, vv2;
+                    unpk2(VC[j + dj], vu2, vv2);
+                    acc2 = fmaf(Dh[dj], vu2, fmaf(Sh[dj], vv2, acc2));
+                }
+                float a0, a1;
+                unpk2(acc01, a0, a1);
+                const float fxq = ((float)xj - cam.cx) * cam.inv_fx;
+                res[j] = fmaf(fxq, a0, fmaf(fyq, a1, acc2));
+                if constexpr (L1) {
+                    float zg, zp;
+                    unpk2(*reinterpret_cast<const f32x2*>(&T[ty + 2][3 + tx0 + j]), zg, zp);
+                    const float mk = (zg >= p.min_d && zg <= p.max_d) ? 1.0f : 0.0f;
+                    const float sgn = (zp > zg) ? 1.0f : ((zp < zg) ? -1.0f : 0.0f);
+                    res[j] = fmaf(l1_scale * mk, sgn, res[j]);
+                }
+            }
+            float* o = p.grad_pred + b * hw + (size_t)y * p.W + x;
+            if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                *reinterpret_cast<float4*>(o) = make_float4(res[0], res[1], res[2], res[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = res[j];
+            }
+        }
+    }
+}
+
 // 72 KB of shared memory per CTA: three CTAs per SM, so up to 85 registers per thread (no spills)
-template <bool TMA, bool L1>
-__global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_kernel(const __grid_constant__ CUtensorMap tm_gt,
-                                                                        const __grid_constant__ CUtensorMap tm_pred, const LossParams p) {
+template <bool L1>
+__global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_kernel(const LossParams p) {
     // dynamic shared memory: two halo'd depth tiles and the six adjoint fields of the tile + 1-pixel ring (46 KB)
     extern __shared__ __align__(128) unsigned char bwd_smem[];
     float (*tg)[kLBoxW] = reinterpret_cast<float (*)[kLBoxW]>(bwd_smem);
     float (*tp)[kLBoxW] = reinterpret_cast<float (*)[kLBoxW]>(bwd_smem + kLTilePad);
     float (*G)[kGH][kGPitch] = reinterpret_cast<float (*)[kGH][kGPitch]>(bwd_smem + 2 * kLTilePad);   // gu_bar xyz, gv_bar xyz
-    __shared__ uint64_t bar;
     const int b = blockIdx.z, x0 = blockIdx.x * kLW, y0 = blockIdx.y * kBwdH;
     const size_t hw = (size_t)p.H * p.W;
-    if (TMA && threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(smem_u32(&bar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (TMA) __syncthreads();
-    stage_begin<TMA, kBwdH>(tg, &tm_gt, p.gt + b * hw, p.H, p.W, x0, y0, b, &bar);
-    stage_begin<TMA, kBwdH>(tp, &tm_pred, p.pred + b * hw, p.H, p.W, x0, y0, b, &bar);
-    if constexpr (TMA) {
-        lut_stage_wait(&bar);
-        patch_replicate<kBwdH>(tg, p.H, p.W, x0, y0);
-        patch_replicate<kBwdH>(tp, p.H, p.W, x0, y0);
-    } else {
-        __syncthreads();
-    }
+    stage_tile<kBwdH>(tg, p.gt + b * hw, p.H, p.W, x0, y0);
+    stage_tile<kBwdH>(tp, p.pred + b * hw, p.H, p.W, x0, y0);
+    __syncthreads();
     const Cam cam = load_cam(p.K, b);
     const float scale = -__ldg(p.grad_out) / (float)p.sums2[1];    // -grad_out / sum(mask)
     const float l1_scale = (L1 && p.grad_l1) ? __ldg(p.grad_l1) / (float)p.sums2[1] : 0.0f;
@@ -547,35 +892,6 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_kernel(const
     }
 }
 
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn loss_encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    });
-    return fn;
-}
-
-bool make_map(CUtensorMap* tmap, const float* base, int B, int H, int W, int tile_h) {
-    EncodeTiledFn encode = loss_encode_tiled();
-    if (!encode || W % 4 != 0 || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
-    const cuuint32_t box[3] = {kLBoxW, (cuuint32_t)box_rows(tile_h), 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 int check_common(const float* gt, const float* pred, const float* K, const float* mask, int B, int H, int W, int tile_h, bool cap,
                  dim3& grid) {
     if (!gt || !pred || !K || !mask || B < 0 || H <= 0 || W <= 0 || B > 65535) return POLCUE_EINVAL;
@@ -620,15 +936,17 @@ static int loss_forward(const float* depth_gt, const float* depth_pred, const fl
     p.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 64);
     p.sums2 = sums;
     p.loss = loss;
-    CUtensorMap mg, mp;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool tma = make_map(&mg, depth_gt, B, H, W, kFwdH) && make_map(&mp, depth_pred, B, H, W, kFwdH);
+    // rows that are 16-byte multiples: the packed (GT, prediction) kernel; anything else: the scalar kernel with a hand-staged tile
+    const bool pairs = W % 4 == 0 && ((reinterpret_cast<uintptr_t>(depth_gt) | reinterpret_cast<uintptr_t>(depth_pred) |
+                                       (range_mask ? 0 : reinterpret_cast<uintptr_t>(mask))) & 15) == 0;
+    static_assert(kPW == kLW && kPH == kFwdH, "both forward kernels must tile alike: one partial per CTA, same fold order");
     if (with_l1) {
-        if (tma) normals_loss_fwd_kernel<true, true><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
-        else normals_loss_fwd_kernel<false, true><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
+        if (pairs) normals_loss_fwd_pairs_kernel<true><<<grid, kLossThreads, 0, s>>>(p);
+        else normals_loss_fwd_kernel<true><<<grid, kLossThreads, 0, s>>>(p);
     } else {
-        if (tma) normals_loss_fwd_kernel<true, false><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
-        else normals_loss_fwd_kernel<false, false><<<grid, kLossThreads, 0, s>>>(mg, mp, p);
+        if (pairs) normals_loss_fwd_pairs_kernel<false><<<grid, kLossThreads, 0, s>>>(p);
+        else normals_loss_fwd_kernel<false><<<grid, kLossThreads, 0, s>>>(p);
     }
     return launch_status();
 }
@@ -655,14 +973,20 @@ static int loss_backward(const float* depth_gt, const float* depth_pred, const f
     p.grad_out = grad_out;
     p.grad_l1 = grad_l1;
     p.grad_pred = grad_pred;
-    CUtensorMap mg, mp;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool tma = make_map(&mg, depth_gt, B, H, W, kBwdH) && make_map(&mp, depth_pred, B, H, W, kBwdH);
-    auto kern = with_l1 ? (tma ? normals_loss_bwd_kernel<true, true> : normals_loss_bwd_kernel<false, true>)
-                        : (tma ? normals_loss_bwd_kernel<true, false> : normals_loss_bwd_kernel<false, false>);
+    const bool pairs = W % 4 == 0 && ((reinterpret_cast<uintptr_t>(depth_gt) | reinterpret_cast<uintptr_t>(depth_pred) |
+                                       (range_mask ? 0 : reinterpret_cast<uintptr_t>(mask))) & 15) == 0;
+    if (pairs) {
+        auto kern = with_l1 ? normals_loss_bwd_pairs_kernel<true> : normals_loss_bwd_pairs_kernel<false>;
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdPairsSmem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, kLossThreads, kBwdPairsSmem, s>>>(p);
+        return launch_status();
+    }
+    auto kern = with_l1 ? normals_loss_bwd_kernel<true> : normals_loss_bwd_kernel<false>;
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, kLossThreads, kBwdSmem, s>>>(mg, mp, p);
+    kern<<<grid, kLossThreads, kBwdSmem, s>>>(p);
     return launch_status();
 }
 

@@ -717,6 +717,42 @@ def test_losses_on_ground_truth_with_zero_depth_holes(shape):
     assert float(only_l1.grad[:, 0][dev(gt) == 0].abs().max()) == 0.0
 
 
+def _misaligned(t):
+    """The same values at an address that is 4 mod 16 bytes: forces the scalar (hand-staged, unpacked) kernels."""
+    flat = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)
+    view = flat[1:].view(t.shape)
+    view.copy_(t)
+    assert view.data_ptr() % 16 == 4
+    return view
+
+
+@pytest.mark.parametrize("shape", [(320, 480), (64, 96), (36, 132), (16, 128), (2, 260), (45, 4)])
+def test_packed_loss_kernels_are_bit_identical_to_the_scalar_kernels(shape):
+    """Rows that are 16-byte multiples take the packed-FP32 kernels (GT and prediction in the two lanes of FFMA2 / FADD2 /
+    FMUL2, interleaved shared tile); every lane runs the scalar kernels' operation sequence, so loss, sums and gradients must
+    be BIT-IDENTICAL to the scalar kernels (reached here through 16-byte-misaligned views of the same data).  GT with holes."""
+    h, w = shape
+    gt, _, _, k = holey_depth(21, 3, h, w)
+    vv, uu = np.mgrid[0:h, 0:w].astype(np.float32)
+    pred = (np.where(gt > 0, gt, 0.7) * (1.0 + 0.05 * np.sin(uu / 23.0 + np.arange(3)[:, None, None]) * np.cos(vv / 17.0))).astype(np.float32)
+    rng = np.random.default_rng(5)
+    mask = (rng.random(gt.shape) < 0.8).astype(np.float32)
+    g, pr, m, kk = dev(gt)[:, None], dev(pred)[:, None], dev(mask)[:, None], dev(k)
+    results = []
+    for variant in ("packed", "scalar"):
+        gg = g if variant == "packed" else _misaligned(g)
+        d1 = pr.clone().requires_grad_(True)
+        loss = ops.normals_loss(gg, d1, kk, m)
+        (1.7 * loss).backward()
+        d2 = pr.clone().requires_grad_(True)
+        dl, nl = ops.supervised_losses(gg, d2, kk, 0.1, 1.6)
+        (0.7 * dl + 1.3 * nl).backward()
+        results.append((loss.detach(), d1.grad, dl.detach(), nl.detach(), d2.grad))
+    for a, b in zip(*results):
+        assert torch.equal(a, b)
+    assert float(results[0][1].abs().max()) > 0
+
+
 def test_normals_loss_matches_composition_of_public_ops_and_is_deterministic():
     gt, pred, mask, k = _loss_case((64, 96))
     args = (dev(gt)[:, None], dev(pred)[:, None], dev(k), dev(mask)[:, None])
