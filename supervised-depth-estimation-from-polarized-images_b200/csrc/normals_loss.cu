@@ -98,22 +98,33 @@ __device__ __forceinline__ void gradients(const float (*tile)[kLBoxW], int ty, i
     for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int c = 0; c < 3; ++c) Z[r][c] = tile[kLRow + ty + r - 1][kLCol + tx + c - 1];
-    float Su[3][3], Dv[3][3];
+    // The stencil arithmetic is DEFINED here, rounding by rounding (no compiler-chosen contraction), and repeated verbatim by
+    // gradients4, the packed twins below and stencil.cu, so every kernel gives the same bits:
+    //   S2 = fma(2, Z1, Z0 + Z2), D2 = Z2 - Z0                     vertical smoothing / difference of Z per column
+    //   X: P = fl(fx S2), Q = fl(fx D2);  gu_x = P[+1] - P[-1];  gv_x = fma(2, Q[0], Q[-1] + Q[+1])
+    //   Y: lo = fl(fy[-1] Z0), hi = fl(fy[+1] Z2), S1 = fma(fy[+1], Z2, fma(2 fy[0], Z1, lo)), D1 = hi - lo;
+    //      gu_y = S1[+1] - S1[-1];  gv_y = fma(2, D1[0], D1[-1] + D1[+1])
+    //   Z: gu_z = S2[+1] - S2[-1];  gv_z = fma(2, D2[0], D2[-1] + D2[+1])
+    // Products that feed a difference are rounded separately, so replicated rows / columns (image borders, one-pixel-wide
+    // images) and parallel gradients cancel to exact zeros.
+    float S2[3], D2[3], S1[3], D1[3], P[3], Q[3];
     const float fy1x2 = 2.0f * fy3[1];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        Su[2][c] = fmaf(2.0f, Z[1][c], Z[0][c] + Z[2][c]);
-        Dv[2][c] = Z[2][c] - Z[0][c];
-        Su[0][c] = fx3[c] * Su[2][c];
-        Dv[0][c] = fx3[c] * Dv[2][c];
-        Su[1][c] = fmaf(fy3[2], Z[2][c], fmaf(fy1x2, Z[1][c], fy3[0] * Z[0][c]));
-        Dv[1][c] = __fsub_rn(__fmul_rn(fy3[2], Z[2][c]), __fmul_rn(fy3[0], Z[0][c]));
+        S2[c] = fmaf(2.0f, Z[1][c], __fadd_rn(Z[0][c], Z[2][c]));
+        D2[c] = __fsub_rn(Z[2][c], Z[0][c]);
+        P[c] = __fmul_rn(fx3[c], S2[c]);
+        Q[c] = __fmul_rn(fx3[c], D2[c]);
+        const float lo = __fmul_rn(fy3[0], Z[0][c]);
+        S1[c] = fmaf(fy3[2], Z[2][c], fmaf(fy1x2, Z[1][c], lo));
+        D1[c] = __fsub_rn(__fmul_rn(fy3[2], Z[2][c]), lo);
     }
-#pragma unroll
-    for (int comp = 0; comp < 3; ++comp) {
-        gu[comp] = Su[comp][2] - Su[comp][0];
-        gv[comp] = fmaf(2.0f, Dv[comp][1], Dv[comp][0] + Dv[comp][2]);
-    }
+    gu[0] = __fsub_rn(P[2], P[0]);
+    gv[0] = fmaf(2.0f, Q[1], __fadd_rn(Q[0], Q[2]));
+    gu[1] = __fsub_rn(S1[2], S1[0]);
+    gv[1] = fmaf(2.0f, D1[1], __fadd_rn(D1[0], D1[2]));
+    gu[2] = __fsub_rn(S2[2], S2[0]);
+    gv[2] = fmaf(2.0f, D2[1], __fadd_rn(D2[0], D2[2]));
 }
 
 // The same for four consecutive pixels starting at tile-local column tx0 (a multiple of 4): the 3 x 6 window is read
@@ -134,26 +145,30 @@ __device__ __forceinline__ void gradients4(const float (*tile)[kLBoxW], int ty, 
         Z[r][1] = mid.x; Z[r][2] = mid.y; Z[r][3] = mid.z; Z[r][4] = mid.w;
         Z[r][5] = row[4];
     }
-    float Su[3][6], Dv[3][6];
+    float S2[6], D2[6], S1[6], D1[6], P[6], Q[6];
     const float fy1x2 = 2.0f * fy3[1];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-        Su[2][c] = fmaf(2.0f, Z[1][c], Z[0][c] + Z[2][c]);
-        Dv[2][c] = Z[2][c] - Z[0][c];
-        Su[0][c] = fx6[c] * Su[2][c];
-        Dv[0][c] = fx6[c] * Dv[2][c];
-        Su[1][c] = fmaf(fy3[2], Z[2][c], fmaf(fy1x2, Z[1][c], fy3[0] * Z[0][c]));
-        Dv[1][c] = __fsub_rn(__fmul_rn(fy3[2], Z[2][c]), __fmul_rn(fy3[0], Z[0][c]));
+        S2[c] = fmaf(2.0f, Z[1][c], __fadd_rn(Z[0][c], Z[2][c]));
+        D2[c] = __fsub_rn(Z[2][c], Z[0][c]);
+        P[c] = __fmul_rn(fx6[c], S2[c]);
+        Q[c] = __fmul_rn(fx6[c], D2[c]);
+        const float lo = __fmul_rn(fy3[0], Z[0][c]);
+        S1[c] = fmaf(fy3[2], Z[2][c], fmaf(fy1x2, Z[1][c], lo));
+        D1[c] = __fsub_rn(__fmul_rn(fy3[2], Z[2][c]), lo);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int comp = 0; comp < 3; ++comp) {
-            gu[comp][j] = Su[comp][j + 2] - Su[comp][j];
-            gv[comp][j] = fmaf(2.0f, Dv[comp][j + 1], Dv[comp][j] + Dv[comp][j + 2]);
-        }
+    for (int j = 0; j < 4; ++j) {
+        gu[0][j] = __fsub_rn(P[j + 2], P[j]);
+        gv[0][j] = fmaf(2.0f, Q[j + 1], __fadd_rn(Q[j], Q[j + 2]));
+        gu[1][j] = __fsub_rn(S1[j + 2], S1[j]);
+        gv[1][j] = fmaf(2.0f, D1[j + 1], __fadd_rn(D1[j], D1[j + 2]));
+        gu[2][j] = __fsub_rn(S2[j + 2], S2[j]);
+        gv[2][j] = fmaf(2.0f, D2[j + 1], __fadd_rn(D2[j], D2[j + 2]));
+    }
 }
 
+// products rounded separately (never contracted): parallel vectors cancel to an exact zero vector
 __device__ __forceinline__ void cross_rn(const float (&a)[3], const float (&b)[3], float (&n)[3]) {
     n[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
     n[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
@@ -164,22 +179,45 @@ constexpr float kInvCap = 1.0f / (64.0f * 1e-12f);   // n here is 64 x the refer
 
 // unit (or capped) normal and the factor it was scaled by
 __device__ __forceinline__ float normalize3(const float (&n)[3], float (&u)[3]) {
-    const float inv = fminf(rsqrt_approx(fmaf(n[0], n[0], fmaf(n[1], n[1], n[2] * n[2]))), kInvCap);
-    u[0] = n[0] * inv;
-    u[1] = n[1] * inv;
-    u[2] = n[2] * inv;
+    const float inv = fminf(rsqrt_approx(fmaf(n[0], n[0], fmaf(n[1], n[1], __fmul_rn(n[2], n[2])))), kInvCap);
+    u[0] = __fmul_rn(n[0], inv);
+    u[1] = __fmul_rn(n[1], inv);
+    u[2] = __fmul_rn(n[2], inv);
     return inv;
 }
 
 // cos = <a,b> / max(|a||b|, 1e-8)   (torch 1.7.1 F.cosine_similarity: w12 * rsqrt(clamp_min(w1 w2, eps^2)))
 __device__ __forceinline__ float cosine(const float (&a)[3], const float (&b)[3], float& inv_den, float& ab, float& bb,
                                         bool& clamped) {
-    ab = fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2]));
-    const float aa = fmaf(a[0], a[0], fmaf(a[1], a[1], a[2] * a[2]));
-    bb = fmaf(b[0], b[0], fmaf(b[1], b[1], b[2] * b[2]));
-    clamped = aa * bb <= 1e-16f;
-    inv_den = clamped ? 1e8f : rsqrtf(aa * bb);
-    return ab * inv_den;
+    ab = fmaf(a[0], b[0], fmaf(a[1], b[1], __fmul_rn(a[2], b[2])));
+    const float aa = fmaf(a[0], a[0], fmaf(a[1], a[1], __fmul_rn(a[2], a[2])));
+    bb = fmaf(b[0], b[0], fmaf(b[1], b[1], __fmul_rn(b[2], b[2])));
+    const float den2 = __fmul_rn(aa, bb);
+    clamped = den2 <= 1e-16f;
+    inv_den = clamped ? 1e8f : rsqrtf(den2);
+    return __fmul_rn(ab, inv_den);
+}
+
+// The adjoint arithmetic after the cosine, with every rounding spelled out (no compiler-chosen contraction) so that the
+// scalar and the packed kernel produce the same bits:
+//   g = dcos/db: above the eps clamp a/D - <a,b> b / (D |b|^2), inside it a / eps;   b = n * inv: the capped normalisation is
+//   linear, otherwise project out b and divide by |n| (= multiply by inv);   n = gu x gv  =>  gu_bar = gv x n_bar, gv_bar = n_bar x gu.
+__device__ __forceinline__ void adjoint_tail(const float (&a)[3], const float (&bn)[3], float inv, const float (&up)[3], const float (&vp)[3],
+                                             float k, float inv_den, float ab, float bb, bool clamped, float (&gub)[3], float (&gvb)[3]) {
+    const float w_b = clamped ? 0.0f : __fdiv_rn(__fmul_rn(ab, inv_den), fmaxf(bb, 1e-30f));
+    float g[3], nb[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = fmaf(-w_b, bn[c], __fmul_rn(a[c], inv_den));
+    const float gb = (inv >= kInvCap) ? 0.0f : fmaf(g[0], bn[0], fmaf(g[1], bn[1], __fmul_rn(g[2], bn[2])));
+    const float ki = __fmul_rn(k, inv);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) nb[c] = __fmul_rn(ki, fmaf(-gb, bn[c], g[c]));
+    gub[0] = fmaf(vp[1], nb[2], -__fmul_rn(vp[2], nb[1]));
+    gub[1] = fmaf(vp[2], nb[0], -__fmul_rn(vp[0], nb[2]));
+    gub[2] = fmaf(vp[0], nb[1], -__fmul_rn(vp[1], nb[0]));
+    gvb[0] = fmaf(nb[1], up[2], -__fmul_rn(nb[2], up[1]));
+    gvb[1] = fmaf(nb[2], up[0], -__fmul_rn(nb[0], up[2]));
+    gvb[2] = fmaf(nb[0], up[1], -__fmul_rn(nb[1], up[0]));
 }
 
 // Adjoints of the predicted-depth gradients of one pixel: (gu, gv) of the GT tile -> a; of the prediction -> b, n;
@@ -196,22 +234,7 @@ __device__ __forceinline__ void adjoint_px(const float (&ug)[3], const float (&v
     float inv_den, ab, bb;
     bool clamped;
     cosine(a, bn, inv_den, ab, bb, clamped);
-    // g = dcos/db: above the eps clamp a/D - <a,b> b / (D |b|^2), inside it a / eps
-    const float w_b = clamped ? 0.0f : ab * inv_den / fmaxf(bb, 1e-30f);
-    float g[3], nb[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) g[c] = a[c] * inv_den - w_b * bn[c];
-    // b = n * inv: capped normalisation is linear, otherwise project out b and divide by |n| (= multiply by inv)
-    const float gb = (inv >= kInvCap) ? 0.0f : fmaf(g[0], bn[0], fmaf(g[1], bn[1], g[2] * bn[2]));
-#pragma unroll
-    for (int c = 0; c < 3; ++c) nb[c] = k * inv * (g[c] - gb * bn[c]);
-    // n = gu x gv  =>  gu_bar = gv x n_bar, gv_bar = n_bar x gu
-    gub[0] = vp[1] * nb[2] - vp[2] * nb[1];
-    gub[1] = vp[2] * nb[0] - vp[0] * nb[2];
-    gub[2] = vp[0] * nb[1] - vp[1] * nb[0];
-    gvb[0] = nb[1] * up[2] - nb[2] * up[1];
-    gvb[1] = nb[2] * up[0] - nb[0] * up[2];
-    gvb[2] = nb[0] * up[1] - nb[1] * up[0];
+    adjoint_tail(a, bn, inv, up, vp, k, inv_den, ab, bb, clamped, gub, gvb);
 }
 
 // mask of one pixel: the caller's float mask, or the supervised range test on the GT depth (trainer.py:1241-1242)
@@ -340,12 +363,12 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const
             if (x + j < p.W) {
                 const float zg = tg[kLRow + ty][kLCol + tx0 + j];
                 const float mk = mask_value<L1>(p, b * hw + (size_t)y * p.W + x + j, zg);
-                if constexpr (L1) fl = fmaf(fabsf(zg - tp[kLRow + ty][kLCol + tx0 + j]), mk, fl);
+                if constexpr (L1) fl = fmaf(fabsf(__fsub_rn(zg, tp[kLRow + ty][kLCol + tx0 + j])), mk, fl);
                 const float a[3] = {a4[0][j], a4[1][j], a4[2][j]}, bb3[3] = {b4[0][j], b4[1][j], b4[2][j]};
                 float inv_den, ab, bb;
                 bool clamped;
                 const float c = cosine(a, bb3, inv_den, ab, bb, clamped);
-                fs = fmaf(2.0f - c, mk, fs);
+                fs = fmaf(__fsub_rn(2.0f, c), mk, fs);
                 fm += mk;
             }
         }
@@ -410,34 +433,36 @@ __device__ __forceinline__ void gradients4_pairs(const float2* win, int pitch, c
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) centre[j] = Z[1][1 + j];
-    f32x2 Su[3][6], Dv[3][6];
+    f32x2 S2[6], D2[6], S1[6], D1[6], P[6], Q[6];
     const f32x2 two = dup2(2.0f);
     const f32x2 fy1x2 = mul2(two, fy3[1]);
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-        Su[2][c] = fma2(two, Z[1][c], add2(Z[0][c], Z[2][c]));
-        Dv[2][c] = sub2(Z[2][c], Z[0][c]);
-        Su[0][c] = mul2(fx6[c], Su[2][c]);
-        Dv[0][c] = mul2(fx6[c], Dv[2][c]);
+        S2[c] = fma2(two, Z[1][c], add2(Z[0][c], Z[2][c]));
+        D2[c] = sub2(Z[2][c], Z[0][c]);
+        P[c] = mul2(fx6[c], S2[c]);
+        Q[c] = mul2(fx6[c], D2[c]);
         const f32x2 lo = mul2(fy3[0], Z[0][c]);
-        Su[1][c] = fma2(fy3[2], Z[2][c], fma2(fy1x2, Z[1][c], lo));
-        Dv[1][c] = sub2(mul2(fy3[2], Z[2][c]), lo);
+        S1[c] = fma2(fy3[2], Z[2][c], fma2(fy1x2, Z[1][c], lo));
+        D1[c] = sub2_unfused(mul2(fy3[2], Z[2][c]), lo);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int comp = 0; comp < 3; ++comp) {
-            gu[comp][j] = sub2(Su[comp][j + 2], Su[comp][j]);
-            gv[comp][j] = fma2(two, Dv[comp][j + 1], add2(Dv[comp][j], Dv[comp][j + 2]));
-        }
+    for (int j = 0; j < 4; ++j) {
+        gu[0][j] = sub2_unfused(P[j + 2], P[j]);
+        gv[0][j] = fma2(two, Q[j + 1], add2_unfused(Q[j], Q[j + 2]));
+        gu[1][j] = sub2(S1[j + 2], S1[j]);
+        gv[1][j] = fma2(two, D1[j + 1], add2(D1[j], D1[j + 2]));
+        gu[2][j] = sub2(S2[j + 2], S2[j]);
+        gv[2][j] = fma2(two, D2[j + 1], add2(D2[j], D2[j + 2]));
+    }
 }
 
 // cross_rn + normalize3 on both lanes; returns the scale factors (inv) of both lanes.
 __device__ __forceinline__ f32x2 unit_normals_pairs(const f32x2 (&u)[3], const f32x2 (&v)[3], f32x2 (&n)[3]) {
     f32x2 c[3];
-    c[0] = sub2(mul2(u[1], v[2]), mul2(u[2], v[1]));
-    c[1] = sub2(mul2(u[2], v[0]), mul2(u[0], v[2]));
-    c[2] = sub2(mul2(u[0], v[1]), mul2(u[1], v[0]));
+    c[0] = sub2_unfused(mul2(u[1], v[2]), mul2(u[2], v[1]));
+    c[1] = sub2_unfused(mul2(u[2], v[0]), mul2(u[0], v[2]));
+    c[2] = sub2_unfused(mul2(u[0], v[1]), mul2(u[1], v[0]));
     float qa, qb;
     unpk2(fma2(c[0], c[0], fma2(c[1], c[1], mul2(c[2], c[2]))), qa, qb);
     const f32x2 inv = pk2(fminf(rsqrt_approx(qa), kInvCap), fminf(rsqrt_approx(qb), kInvCap));
@@ -492,11 +517,11 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel
                 float mk;
                 if constexpr (L1) mk = (zg >= p.min_d && zg <= p.max_d) ? 1.0f : 0.0f;
                 else mk = mk4[j];
-                if constexpr (L1) fl = fmaf(fabsf(zg - zp), mk, fl);
+                if constexpr (L1) fl = fmaf(fabsf(__fsub_rn(zg, zp)), mk, fl);
                 float inv_den, ab, bb;
                 bool clamped;
                 const float c = cosine(a, bb3, inv_den, ab, bb, clamped);
-                fs = fmaf(2.0f - c, mk, fs);
+                fs = fmaf(__fsub_rn(2.0f, c), mk, fs);
                 fm += mk;
             }
             s += fs;
@@ -534,24 +559,23 @@ __device__ __forceinline__ void gradients1_pairs(const float2* win, int pitch, i
 #pragma unroll
         for (int c = 0; c < 3; ++c) Z[r][c] = *reinterpret_cast<const f32x2*>(win + r * pitch + c);
     centre = Z[1][1];
-    f32x2 Su[3][3], Dv[3][3];
+    f32x2 S2[3], D2[3], S1[3], D1[3];
     const f32x2 two = dup2(2.0f);
     const f32x2 fy1x2 = mul2(two, fy3[1]);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        Su[2][c] = fma2(two, Z[1][c], add2(Z[0][c], Z[2][c]));
-        Dv[2][c] = sub2(Z[2][c], Z[0][c]);
-        Su[0][c] = mul2(fx3[c], Su[2][c]);
-        Dv[0][c] = mul2(fx3[c], Dv[2][c]);
+        S2[c] = fma2(two, Z[1][c], add2(Z[0][c], Z[2][c]));
+        D2[c] = sub2(Z[2][c], Z[0][c]);
         const f32x2 lo = mul2(fy3[0], Z[0][c]);
-        Su[1][c] = fma2(fy3[2], Z[2][c], fma2(fy1x2, Z[1][c], lo));
-        Dv[1][c] = sub2(mul2(fy3[2], Z[2][c]), lo);
+        S1[c] = fma2(fy3[2], Z[2][c], fma2(fy1x2, Z[1][c], lo));
+        D1[c] = sub2_unfused(mul2(fy3[2], Z[2][c]), lo);
     }
-#pragma unroll
-    for (int comp = 0; comp < 3; ++comp) {
-        gu[comp] = sub2(Su[comp][2], Su[comp][0]);
-        gv[comp] = fma2(two, Dv[comp][1], add2(Dv[comp][0], Dv[comp][2]));
-    }
+    gu[0] = sub2_unfused(mul2(fx3[2], S2[2]), mul2(fx3[0], S2[0]));
+    gv[0] = fma2(two, mul2(fx3[1], D2[1]), add2_unfused(mul2(fx3[0], D2[0]), mul2(fx3[2], D2[2])));
+    gu[1] = sub2(S1[2], S1[0]);
+    gv[1] = fma2(two, D1[1], add2(D1[0], D1[2]));
+    gu[2] = sub2(S2[2], S2[0]);
+    gv[2] = fma2(two, D2[1], add2(D2[0], D2[2]));
 }
 
 // adjoint_px from the packed gradients of one pixel (lane 0 = GT, lane 1 = prediction).
@@ -571,16 +595,11 @@ __device__ __forceinline__ void adjoint_pairs(const f32x2 (&gu)[3], const f32x2 
     float inv_den, ab, bb;
     bool clamped;
     cosine(a, bn, inv_den, ab, bb, clamped);
-    const float w_b = clamped ? 0.0f : ab * inv_den / fmaxf(bb, 1e-30f);
-    float g[3], nb[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) g[c] = a[c] * inv_den - w_b * bn[c];
-    const float gb = (inv >= kInvCap) ? 0.0f : fmaf(g[0], bn[0], fmaf(g[1], bn[1], g[2] * bn[2]));
-#pragma unroll
-    for (int c = 0; c < 3; ++c) nb[c] = k * inv * (g[c] - gb * bn[c]);
-    A = pk2(vp[1] * nb[2] - vp[2] * nb[1], vp[2] * nb[0] - vp[0] * nb[2]);
-    B = pk2(nb[1] * up[2] - nb[2] * up[1], nb[2] * up[0] - nb[0] * up[2]);
-    C = pk2(vp[0] * nb[1] - vp[1] * nb[0], nb[0] * up[1] - nb[1] * up[0]);
+    float gub[3], gvb[3];
+    adjoint_tail(a, bn, inv, up, vp, k, inv_den, ab, bb, clamped, gub, gvb);
+    A = pk2(gub[0], gub[1]);
+    B = pk2(gvb[0], gvb[1]);
+    C = pk2(gub[2], gvb[2]);
 }
 
 template <bool L1>

@@ -343,6 +343,24 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
     return d;
 }
 __device__ __forceinline__ f32x2 abs2(f32x2 a) { return a & 0x7FFFFFFF7FFFFFFFull; }
+__device__ __forceinline__ f32x2 neg2(f32x2 a) { return a ^ 0x8000000080000000ull; }   // folds into the consumer's operand modifier
+// NOTE (measured, ptxas 12.9): a mul.rn.f32x2 whose result feeds an add.rn.f32x2 / sub.rn.f32x2 IS contracted into FFMA2
+// by ptxas, .rn qualifier and -fmad=false notwithstanding (the scalar mul.rn.f32 / add.rn.f32 pair is not).  Code that
+// must agree bit for bit with a scalar twin, or that relies on separately rounded products cancelling exactly, therefore
+// never feeds a packed product into a packed add / sub: it subtracts the two lanes with scalar instructions
+// (sub2_unfused below: two FADD instead of one FADD2).
+__device__ __forceinline__ f32x2 sub2_unfused(f32x2 a, f32x2 b) {
+    float a0, a1, b0, b1;
+    unpk2(a, a0, a1);
+    unpk2(b, b0, b1);
+    return pk2(__fsub_rn(a0, b0), __fsub_rn(a1, b1));
+}
+__device__ __forceinline__ f32x2 add2_unfused(f32x2 a, f32x2 b) {
+    float a0, a1, b0, b1;
+    unpk2(a, a0, a1);
+    unpk2(b, b0, b1);
+    return pk2(__fadd_rn(a0, b0), __fadd_rn(a1, b1));
+}
 
 // byte ka of word wa and byte kb of word wb as an exact float pair (see byte_to_float): two PRMT, one FADD2
 __device__ __forceinline__ f32x2 bytes_to_float2(uint32_t wa, int ka, uint32_t wb, int kb) {

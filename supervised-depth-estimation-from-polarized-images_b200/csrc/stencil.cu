@@ -77,37 +77,47 @@ __device__ __forceinline__ void stencil_rows(const StencilParams& p, const float
         // and the vertical difference D = bottom - top; then d/du = S[c+2] - S[c], d/dv = D[c] + 2 D[c+1] + D[c+2].
         // The column factor fx[c] is common to a column's three rows, so X needs one multiply per column.  The common
         // factor 1/8 of both gradients only scales the cross product by 1/64; it is folded into the guard below.
-        float Su[3][6], Dv[3][6];
+        // The arithmetic below is the library's DEFINITION of the stencil, rounding by rounding (normals_loss.cu repeats it in
+        // its scalar and packed kernels, so the normals inside the loss are these, bit for bit):
+        //   S2 = fma(2, Z1, Z0 + Z2), D2 = Z2 - Z0                     vertical smoothing / difference of Z per column
+        //   X: P = fl(fx S2), Q = fl(fx D2);  gu_x = P[+1] - P[-1];  gv_x = fma(2, Q[0], Q[-1] + Q[+1])
+        //   Y: lo = fl(fy[-1] Z0), hi = fl(fy[+1] Z2), S1 = fma(fy[+1], Z2, fma(2 fy[0], Z1, lo)), D1 = hi - lo;
+        //      gu_y = S1[+1] - S1[-1];  gv_y = fma(2, D1[0], D1[-1] + D1[+1])
+        //   Z: gu_z = S2[+1] - S2[-1];  gv_z = fma(2, D2[0], D2[-1] + D2[+1])
+        //   n = gu x gv with n_0 = fl(gu_1 gv_2) - fl(gu_2 gv_1), ...;  unit = fl(n * min(rsqrt(|n|^2), 1 / (64 eps)))
+        // Products that feed a difference are rounded separately: replicated rows / columns and parallel gradients (next to
+        // zero-depth holes) cancel to exact zeros, as they do in the float64 oracle.
+        // The common factor 1/8 of both gradients only scales the cross product by 1/64; it is folded into the guard.
+        float S2[6], D2[6], S1[6], D1[6], P[6], Q[6];
         const float fy1x2 = 2.0f * fy3[1];
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-            Su[2][c] = fmaf(2.0f, Z[1][c], Z[0][c] + Z[2][c]);
-            Dv[2][c] = Z[2][c] - Z[0][c];
-            Su[0][c] = fx6[c] * Su[2][c];
-            Dv[0][c] = fx6[c] * Dv[2][c];
-            Su[1][c] = fmaf(fy3[2], Z[2][c], fmaf(fy1x2, Z[1][c], fy3[0] * Z[0][c]));
-            // separately rounded products: equal rows (replicated borders, flat regions) must cancel to exactly 0
-            Dv[1][c] = __fsub_rn(__fmul_rn(fy3[2], Z[2][c]), __fmul_rn(fy3[0], Z[0][c]));
+            S2[c] = fmaf(2.0f, Z[1][c], __fadd_rn(Z[0][c], Z[2][c]));
+            D2[c] = __fsub_rn(Z[2][c], Z[0][c]);
+            P[c] = __fmul_rn(fx6[c], S2[c]);
+            Q[c] = __fmul_rn(fx6[c], D2[c]);
+            const float lo = __fmul_rn(fy3[0], Z[0][c]);
+            S1[c] = fmaf(fy3[2], Z[2][c], fmaf(fy1x2, Z[1][c], lo));
+            D1[c] = __fsub_rn(__fmul_rn(fy3[2], Z[2][c]), lo);
         }
         float out[3][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float gu[3], gv[3];  // 8 * d/du, 8 * d/dv of (X, Y, Z)
-#pragma unroll
-            for (int comp = 0; comp < 3; ++comp) {
-                gu[comp] = Su[comp][j + 2] - Su[comp][j];
-                gv[comp] = fmaf(2.0f, Dv[comp][j + 1], Dv[comp][j] + Dv[comp][j + 2]);
-            }
-            // products rounded separately (no FMA contraction): parallel gradients next to zero-depth holes then
-            // cancel to an exact zero vector, as they do in the reference's torch.cross, instead of leaving round-off
+            gu[0] = __fsub_rn(P[j + 2], P[j]);
+            gv[0] = fmaf(2.0f, Q[j + 1], __fadd_rn(Q[j], Q[j + 2]));
+            gu[1] = __fsub_rn(S1[j + 2], S1[j]);
+            gv[1] = fmaf(2.0f, D1[j + 1], __fadd_rn(D1[j], D1[j + 2]));
+            gu[2] = __fsub_rn(S2[j + 2], S2[j]);
+            gv[2] = fmaf(2.0f, D2[j + 1], __fadd_rn(D2[j], D2[j + 2]));
             const float nx = __fsub_rn(__fmul_rn(gu[1], gv[2]), __fmul_rn(gu[2], gv[1]));
             const float ny = __fsub_rn(__fmul_rn(gu[2], gv[0]), __fmul_rn(gu[0], gv[2]));
             const float nz = __fsub_rn(__fmul_rn(gu[0], gv[1]), __fmul_rn(gu[1], gv[0]));
             // n / max(|n|, eps) with n = 64 x the reference's cross product: 1 / max(|n|, 64 eps) = min(rsqrt(|n|^2), 1 / (64 eps))
-            const float inv = fminf(rsqrt_approx(fmaf(nx, nx, fmaf(ny, ny, nz * nz))), 1.0f / (64.0f * 1e-12f));
-            out[0][j] = nx * inv;
-            out[1][j] = ny * inv;
-            out[2][j] = nz * inv;
+            const float inv = fminf(rsqrt_approx(fmaf(nx, nx, fmaf(ny, ny, __fmul_rn(nz, nz)))), 1.0f / (64.0f * 1e-12f));
+            out[0][j] = __fmul_rn(nx, inv);
+            out[1][j] = __fmul_rn(ny, inv);
+            out[2][j] = __fmul_rn(nz, inv);
         }
         float* o = p.normals + (size_t)b * 3 * hw + (size_t)y * p.W + xb;
         if (p.vec4 && xb + 3 < p.W) {
