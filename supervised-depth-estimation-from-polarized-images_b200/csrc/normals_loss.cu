@@ -244,76 +244,59 @@ __device__ __forceinline__ float mask_value(const LossParams& p, size_t idx, flo
     else return __ldg(p.mask + idx);
 }
 
-// Deterministic reduction shared by the forward kernels: warp shuffle -> shared -> per-CTA partial -> the last CTA to
-// finish folds the partials in a fixed order (bitwise reproducible) and writes sums / losses.
+// Deterministic reduction shared by the forward kernels: float32 inside a warp (512 pixels; the mask sum is an exact
+// integer), the eight warp sums added in order in float64 -> one partial per CTA.  loss_fold_kernel (a second, tiny
+// launch) adds the partials in a fixed order -- bitwise reproducible, and no CTA of the main kernel waits on a ticket.
 template <bool L1>
-__device__ __forceinline__ void loss_block_reduce(const LossParams& p, float s, float m, float l1, double (*red)[3], bool* last_flag) {
-    bool& last = *last_flag;
-    double sd = s, md = m, ld = l1;
+__device__ __forceinline__ void loss_block_reduce(const LossParams& p, float s, float m, float l1, double (*red)[3]) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        sd += __shfl_down_sync(0xffffffffu, sd, off);
-        md += __shfl_down_sync(0xffffffffu, md, off);
-        if constexpr (L1) ld += __shfl_down_sync(0xffffffffu, ld, off);
+        s = __fadd_rn(s, __shfl_down_sync(0xffffffffu, s, off));
+        m = __fadd_rn(m, __shfl_down_sync(0xffffffffu, m, off));
+        if constexpr (L1) l1 = __fadd_rn(l1, __shfl_down_sync(0xffffffffu, l1, off));
     }
     if ((threadIdx.x & 31) == 0) {
-        red[threadIdx.x >> 5][0] = sd;
-        red[threadIdx.x >> 5][1] = md;
-        red[threadIdx.x >> 5][2] = ld;
+        red[threadIdx.x >> 5][0] = (double)s;
+        red[threadIdx.x >> 5][1] = (double)m;
+        red[threadIdx.x >> 5][2] = (double)l1;
     }
     __syncthreads();
-    const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    const unsigned ctas = gridDim.x * gridDim.y * gridDim.z;
-    if (threadIdx.x == 0) {
-        double ts = 0.0, tmk = 0.0, tl = 0.0;
-        for (int w = 0; w < kLossThreads / 32; ++w) {
-            ts += red[w][0];
-            tmk += red[w][1];
-            tl += red[w][2];
-        }
-        p.partials[3 * (size_t)cta] = ts;
-        p.partials[3 * (size_t)cta + 1] = tmk;
-        p.partials[3 * (size_t)cta + 2] = tl;
-        __threadfence();
-        last = atomicAdd(p.ticket, 1ull) == ctas - 1;
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int w = 0; w < kLossThreads / 32; ++w) t += red[w][threadIdx.x];
+        const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        p.partials[3 * (size_t)cta + threadIdx.x] = t;
     }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    double fs = 0.0, fm = 0.0, fl1 = 0.0;
-    for (unsigned j = threadIdx.x; j < ctas; j += kLossThreads) {
-        fs += __ldcg(p.partials + 3 * (size_t)j);
-        fm += __ldcg(p.partials + 3 * (size_t)j + 1);
-        if constexpr (L1) fl1 += __ldcg(p.partials + 3 * (size_t)j + 2);
+}
+
+constexpr int kFoldThreads = 1024;
+__global__ void __launch_bounds__(kFoldThreads) loss_fold_kernel(const double* __restrict__ partials, unsigned ctas, int with_l1,
+                                                                 double* __restrict__ sums, float* __restrict__ loss) {
+    __shared__ double red[kFoldThreads / 32][3];
+    double f[3] = {0.0, 0.0, 0.0};
+    for (unsigned j = threadIdx.x; j < ctas; j += kFoldThreads) {
+        f[0] += partials[3 * (size_t)j];
+        f[1] += partials[3 * (size_t)j + 1];
+        f[2] += partials[3 * (size_t)j + 2];
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        fs += __shfl_down_sync(0xffffffffu, fs, off);
-        fm += __shfl_down_sync(0xffffffffu, fm, off);
-        if constexpr (L1) fl1 += __shfl_down_sync(0xffffffffu, fl1, off);
-    }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) {
-        red[threadIdx.x >> 5][0] = fs;
-        red[threadIdx.x >> 5][1] = fm;
-        red[threadIdx.x >> 5][2] = fl1;
-    }
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) f[k] += __shfl_down_sync(0xffffffffu, f[k], off);
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 3; ++k) red[threadIdx.x >> 5][k] = f[k];
     __syncthreads();
     if (threadIdx.x == 0) {
-        double ts = 0.0, tmk = 0.0, tl = 0.0;
-        for (int w = 0; w < kLossThreads / 32; ++w) {
-            ts += red[w][0];
-            tmk += red[w][1];
-            tl += red[w][2];
+        double t[3] = {0.0, 0.0, 0.0};
+        for (int w = 0; w < kFoldThreads / 32; ++w)
+            for (int k = 0; k < 3; ++k) t[k] += red[w][k];
+        sums[0] = t[0];
+        sums[1] = t[1];
+        if (with_l1) sums[2] = t[2];
+        if (loss) {
+            loss[0] = (float)(t[0] / t[1]);
+            if (with_l1) loss[1] = (float)(t[2] / t[1]);
         }
-        p.sums2[0] = ts;
-        p.sums2[1] = tmk;
-        if constexpr (L1) p.sums2[2] = tl;
-        if (p.loss) {
-            p.loss[0] = (float)(ts / tmk);
-            if constexpr (L1) p.loss[1] = (float)(tl / tmk);
-        }
-        *p.ticket = 0ull;
     }
 }
 
@@ -326,7 +309,6 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const
     __shared__ __align__(16) float tg[box_rows(kFwdH)][kLBoxW];
     __shared__ __align__(16) float tp[box_rows(kFwdH)][kLBoxW];
     __shared__ double red[kLossThreads / 32][3];
-    __shared__ bool last;
     const int b = blockIdx.z, x0 = blockIdx.x * kLW, y0 = blockIdx.y * kFwdH;
     const size_t hw = (size_t)p.H * p.W;
     stage_tile<kFwdH>(tg, p.gt + b * hw, p.H, p.W, x0, y0);
@@ -376,7 +358,7 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const
         m += fm;
         l1 += fl;
     }
-    loss_block_reduce<L1>(p, s, m, l1, red, &last);
+    loss_block_reduce<L1>(p, s, m, l1, red);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -390,32 +372,61 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kPW = 128, kPH = 32;                    // tile
 constexpr int kPPitch = kPW + 4;                      // (gt, pred) pairs per shared row: column 0 = image column x0 - 1, 129 = x0 + 128
+constexpr size_t kFwdPairsTileBytes = (size_t)(kPH + 2) * kPPitch * sizeof(float2);
+constexpr size_t kFwdPairsMaskBytes = (size_t)kPH * kPW * sizeof(float);
 
-// Stage rows y0 - 1 .. y0 + TH of both fields, interleaved.  T has TH + 2 rows of kPPitch pairs.
-template <int TH>
-__device__ __forceinline__ void stage_pairs(float2 (*T)[kPPitch], const float* __restrict__ G, const float* __restrict__ P, int H, int W,
+// Stage rows y0 - HALO .. y0 + TH + HALO - 1 of both fields, interleaved; tile column c lives at pair index c + OFF.
+// All global loads of a thread are issued before the first shared store (the loop is fully unrolled), so a tile costs
+// one memory round trip, not one per row.  Replicate padding by clamped coordinates.
+template <int TH, int HALO, int OFF, int PITCH>
+__device__ __forceinline__ void stage_pairs(float2 (*T)[PITCH], const float* __restrict__ G, const float* __restrict__ P, int H, int W,
                                             int x0, int y0) {
-    for (int i = threadIdx.x; i < (TH + 2) * (kPW / 4); i += kLossThreads) {
-        const int r = i / (kPW / 4), q = i - r * (kPW / 4);
-        const int x = x0 + 4 * q;
-        if (x < W) {
-            const int yy = min(max(y0 + r - 1, 0), H - 1);
-            const float4 g = __ldg(reinterpret_cast<const float4*>(G + (size_t)yy * W + x));
-            const float4 d = __ldg(reinterpret_cast<const float4*>(P + (size_t)yy * W + x));
-            float2* dst = &T[r][1 + 4 * q];
-            dst[0] = make_float2(g.x, d.x);
-            dst[1] = make_float2(g.y, d.y);
-            dst[2] = make_float2(g.z, d.z);
-            dst[3] = make_float2(g.w, d.w);
+    constexpr int kRows = TH + 2 * HALO, kIter = (kRows + 7) / 8;
+    const int q = threadIdx.x & 31, r0 = threadIdx.x >> 5;
+    const int x = x0 + 4 * q;
+    float4 g[kIter], d[kIter];
+#pragma unroll
+    for (int k = 0; k < kIter; ++k) {
+        const int r = r0 + 8 * k;
+        if (r < kRows && x < W) {
+            const int yy = min(max(y0 + r - HALO, 0), H - 1);
+            g[k] = __ldg(reinterpret_cast<const float4*>(G + (size_t)yy * W + x));
+            d[k] = __ldg(reinterpret_cast<const float4*>(P + (size_t)yy * W + x));
         }
     }
-    // the column left of the tile and the first column right of it (or of the image): replicate padding by clamping
+    // the HALO columns left of the tile and the first HALO columns right of it (or of the image)
     const int cr = min(W - x0, kPW);                  // tile-relative index of the first column beyond the tile / image
-    for (int i = threadIdx.x; i < (TH + 2) * 2; i += kLossThreads) {
-        const int r = i >> 1, right = i & 1;
-        const int yy = min(max(y0 + r - 1, 0), H - 1);
-        const int xx = right ? min(x0 + cr, W - 1) : max(x0 - 1, 0);
-        T[r][right ? 1 + cr : 0] = make_float2(__ldg(G + (size_t)yy * W + xx), __ldg(P + (size_t)yy * W + xx));
+    float2 edge[(kRows * 2 * HALO + kLossThreads - 1) / kLossThreads];
+#pragma unroll
+    for (int k = 0; k < (kRows * 2 * HALO + kLossThreads - 1) / kLossThreads; ++k) {
+        const int i = threadIdx.x + k * kLossThreads;
+        if (i < kRows * 2 * HALO) {
+            const int r = i / (2 * HALO), e = i - r * (2 * HALO);
+            const int c = (e < HALO) ? e - HALO : cr + (e - HALO);
+            const int yy = min(max(y0 + r - HALO, 0), H - 1);
+            const int xx = min(max(x0 + c, 0), W - 1);
+            edge[k] = make_float2(__ldg(G + (size_t)yy * W + xx), __ldg(P + (size_t)yy * W + xx));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kIter; ++k) {
+        const int r = r0 + 8 * k;
+        if (r < kRows && x < W) {
+            float2* dst = &T[r][OFF + 4 * q];
+            dst[0] = make_float2(g[k].x, d[k].x);
+            dst[1] = make_float2(g[k].y, d[k].y);
+            dst[2] = make_float2(g[k].z, d[k].z);
+            dst[3] = make_float2(g[k].w, d[k].w);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < (kRows * 2 * HALO + kLossThreads - 1) / kLossThreads; ++k) {
+        const int i = threadIdx.x + k * kLossThreads;
+        if (i < kRows * 2 * HALO) {
+            const int r = i / (2 * HALO), e = i - r * (2 * HALO);
+            const int c = (e < HALO) ? e - HALO : cr + (e - HALO);
+            T[r][OFF + c] = edge[k];
+        }
     }
 }
 
@@ -474,34 +485,50 @@ __device__ __forceinline__ f32x2 unit_normals_pairs(const f32x2 (&u)[3], const f
 
 template <bool L1>
 __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel(const LossParams p) {
-    __shared__ __align__(16) float2 T[kPH + 2][kPPitch];
+    extern __shared__ __align__(128) unsigned char fwd_smem[];          // the (gt, pred) tile, then the mask tile (plain variant)
+    float2 (*T)[kPPitch] = reinterpret_cast<float2 (*)[kPPitch]>(fwd_smem);
+    float (*M)[kPW] = reinterpret_cast<float (*)[kPW]>(fwd_smem + kFwdPairsTileBytes);
     __shared__ double red[kLossThreads / 32][3];
-    __shared__ bool last;
     const int b = blockIdx.z, x0 = blockIdx.x * kPW, y0 = blockIdx.y * kPH;
     const size_t hw = (size_t)p.H * p.W;
-    stage_pairs<kPH>(T, p.gt + b * hw, p.pred + b * hw, p.H, p.W, x0, y0);
+    // the caller's mask of the tile rides along with the depth tile (requested before the tile's loads are consumed), so
+    // no global load is left inside the arithmetic loop
+    float4 mreg[kPH / 8];
+    if constexpr (!L1) {
+#pragma unroll
+        for (int k = 0; k < kPH / 8; ++k) {
+            const int yy = y0 + (int)(threadIdx.x >> 5) + 8 * k, xx = x0 + 4 * (int)(threadIdx.x & 31);
+            mreg[k] = (yy < p.H && xx < p.W) ? __ldg(reinterpret_cast<const float4*>(p.mask + b * hw + (size_t)yy * p.W + xx))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    stage_pairs<kPH, 1, 1, kPPitch>(T, p.gt + b * hw, p.pred + b * hw, p.H, p.W, x0, y0);
+    if constexpr (!L1) {
+#pragma unroll
+        for (int k = 0; k < kPH / 8; ++k) *reinterpret_cast<float4*>(&M[(threadIdx.x >> 5) + 8 * k][4 * (threadIdx.x & 31)]) = mreg[k];
+    }
     __syncthreads();
     const Cam cam = load_cam(p.K, b);
     const int tx0 = 4 * (threadIdx.x & 31), x = x0 + tx0;
     f32x2 fx6[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) fx6[c] = dup2(((float)min(max(x + c - 1, 0), p.W - 1) - cam.cx) * cam.inv_fx);
-    float s = 0.0f, m = 0.0f, l1 = 0.0f;   // at most 16 pixels per thread: float32 partials, float64 from the warp level on
+    float s = 0.0f, m = 0.0f, l1 = 0.0f;   // at most 16 pixels per thread
     if (x < p.W) {
 #pragma unroll 1
         for (int ty = threadIdx.x >> 5; ty < kPH; ty += kLossThreads / 32) {
             const int y = y0 + ty;
             if (y >= p.H) break;
+            float mk4[4] = {0.f, 0.f, 0.f, 0.f};
+            if constexpr (!L1) {
+                const float4 mv = *reinterpret_cast<const float4*>(&M[ty][tx0]);
+                mk4[0] = mv.x; mk4[1] = mv.y; mk4[2] = mv.z; mk4[3] = mv.w;
+            }
             f32x2 fy3[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) fy3[r] = dup2(((float)min(max(y + r - 1, 0), p.H - 1) - cam.cy) * cam.inv_fy);
             f32x2 gu[3][4], gv[3][4], centre[4];
             gradients4_pairs(&T[ty][tx0], kPPitch, fx6, fy3, gu, gv, centre);
-            float mk4[4];
-            if constexpr (!L1) {
-                const float4 mv = __ldg(reinterpret_cast<const float4*>(p.mask + b * hw + (size_t)y * p.W + x));
-                mk4[0] = mv.x; mk4[1] = mv.y; mk4[2] = mv.z; mk4[3] = mv.w;
-            }
             float fs = 0.0f, fm = 0.0f, fl = 0.0f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -529,7 +556,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel
             l1 += fl;
         }
     }
-    loss_block_reduce<L1>(p, s, m, l1, red, &last);
+    loss_block_reduce<L1>(p, s, m, l1, red);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -612,28 +639,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_pairs_kernel
     const float* Gt = p.gt + b * hw;
     const float* Pr = p.pred + b * hw;
     // ---- stage rows y0 - 2 .. y0 + kBwdH + 1, columns x0 - 2 .. x0 + 129 (replicate padding by clamping) ----
-    for (int i = threadIdx.x; i < kBTileRows * (kLW / 4); i += kLossThreads) {
-        const int r = i / (kLW / 4), q = i - r * (kLW / 4);
-        const int x = x0 + 4 * q;
-        if (x < p.W) {
-            const int yy = min(max(y0 + r - 2, 0), p.H - 1);
-            const float4 g = __ldg(reinterpret_cast<const float4*>(Gt + (size_t)yy * p.W + x));
-            const float4 d = __ldg(reinterpret_cast<const float4*>(Pr + (size_t)yy * p.W + x));
-            float2* dst = &T[r][3 + 4 * q];
-            dst[0] = make_float2(g.x, d.x);
-            dst[1] = make_float2(g.y, d.y);
-            dst[2] = make_float2(g.z, d.z);
-            dst[3] = make_float2(g.w, d.w);
-        }
-    }
-    const int cr = min(p.W - x0, kLW);                 // first tile column beyond the tile / the image
-    for (int i = threadIdx.x; i < kBTileRows * 4; i += kLossThreads) {
-        const int r = i >> 2, k4 = i & 3;
-        const int c = (k4 < 2) ? k4 - 2 : cr + (k4 - 2);   // -2, -1, cr, cr + 1
-        const int yy = min(max(y0 + r - 2, 0), p.H - 1);
-        const int xx = min(max(x0 + c, 0), p.W - 1);
-        T[r][3 + c] = make_float2(__ldg(Gt + (size_t)yy * p.W + xx), __ldg(Pr + (size_t)yy * p.W + xx));
-    }
+    stage_pairs<kBwdH, 2, 3, kBPitch>(T, Gt, Pr, p.H, p.W, x0, y0);
     __syncthreads();
     const Cam cam = load_cam(p.K, b);
     const float scale = -__ldg(p.grad_out) / (float)p.sums2[1];    // -grad_out / sum(mask)
@@ -960,13 +966,20 @@ static int loss_forward(const float* depth_gt, const float* depth_pred, const fl
     const bool pairs = W % 4 == 0 && ((reinterpret_cast<uintptr_t>(depth_gt) | reinterpret_cast<uintptr_t>(depth_pred) |
                                        (range_mask ? 0 : reinterpret_cast<uintptr_t>(mask))) & 15) == 0;
     static_assert(kPW == kLW && kPH == kFwdH, "both forward kernels must tile alike: one partial per CTA, same fold order");
-    if (with_l1) {
-        if (pairs) normals_loss_fwd_pairs_kernel<true><<<grid, kLossThreads, 0, s>>>(p);
-        else normals_loss_fwd_kernel<true><<<grid, kLossThreads, 0, s>>>(p);
+    if (pairs) {
+        auto kern = with_l1 ? normals_loss_fwd_pairs_kernel<true> : normals_loss_fwd_pairs_kernel<false>;
+        const size_t smem = kFwdPairsTileBytes + (with_l1 ? 0 : kFwdPairsMaskBytes);
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<grid, kLossThreads, smem, s>>>(p);
+    } else if (with_l1) {
+        normals_loss_fwd_kernel<true><<<grid, kLossThreads, 0, s>>>(p);
     } else {
-        if (pairs) normals_loss_fwd_pairs_kernel<false><<<grid, kLossThreads, 0, s>>>(p);
-        else normals_loss_fwd_kernel<false><<<grid, kLossThreads, 0, s>>>(p);
+        normals_loss_fwd_kernel<false><<<grid, kLossThreads, 0, s>>>(p);
     }
+    const int rc1 = launch_status();
+    if (rc1 != POLCUE_OK) return rc1;
+    loss_fold_kernel<<<1, kFoldThreads, 0, s>>>(p.partials, grid.x * grid.y * grid.z, with_l1 ? 1 : 0, sums, loss);
     return launch_status();
 }
 

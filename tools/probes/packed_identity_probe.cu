@@ -14,7 +14,7 @@ __global__ void probe(const float* g, const float* pr, int* bad, float* dump) {
     const int H = 64, W = 256;
     stage_tile<8>(tg, g, H, W, 0, 0);
     stage_tile<8>(tp, pr, H, W, 0, 0);
-    stage_pairs<8>(T, g, pr, H, W, 0, 0);
+    stage_pairs<8, 1, 1, kPPitch>(T, g, pr, H, W, 0, 0);
     __syncthreads();
     Cam cam{1.0f / 706.7f, 127.3f, 1.0f / 707.5f, 31.9f};
     const int tx0 = 4 * (threadIdx.x & 31), ty = threadIdx.x >> 5, x = tx0, y = ty;
