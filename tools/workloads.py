@@ -46,15 +46,20 @@ def cfg3_sequence(rank, world, dev, frames=10000, chunk=64, pool=None):
     out = {"xolp": torch.empty((chunk, 2, hs, ws), dtype=torch.float32, device=dev),
            "normals": torch.empty((chunk, 9, hs, ws), dtype=torch.float32, device=dev)}
     sums = torch.zeros(13, dtype=torch.float64, device=dev)
-    idx = torch.arange(chunk, device=dev)
     ops.lut_for(1.5, dev)
 
     def run_chunk(first, n, acc):
-        frames_in = pool[(first + idx[:n]) % pool_n] if (first % pool_n or n != chunk) else pool   # gather only when ragged
-        res = ops.fused_mosaic(frames_in, 1.5, out={"xolp": out["xolp"][:n], "normals": out["normals"][:n], "stats13": out.get("stats13")},
-                               want_stats=True)
-        out["stats13"] = res["stats13"]
-        acc += res["stats13"]
+        """Frames [first, first + n) of the sequence.  The sequence cycles through the resident pool, so a chunk is one or
+        two contiguous VIEWS of it (no gather copy): pool[o : o + n] and, when it wraps, the head of the pool."""
+        done = 0
+        while done < n:
+            o = (first + done) % pool_n
+            m = min(n - done, pool_n - o)
+            res = ops.fused_mosaic(pool[o:o + m], 1.5, want_stats=True,
+                                   out={"xolp": out["xolp"][done:done + m], "normals": out["normals"][done:done + m], "stats13": out.get("stats13")})
+            out["stats13"] = res["stats13"]
+            acc += res["stats13"]
+            done += m
 
     scratch = torch.zeros_like(sums)
     for _ in range(3):                                    # warm-up: clocks, table upload, workspace allocation
