@@ -26,8 +26,8 @@ struct StatParams {
     int channels;              // C of the tensor
     int c0;                    // first channel of this launch (records hold channels c0 .. c0 + gridDim.y - 1)
     int vec;                   // elements per group: 4 (hw % 4 == 0) or 1
-    unsigned long long groups; // B * hw / vec, per channel
-    uint32_t groups_per_image; // hw / vec
+    uint32_t groups;           // B * hw / vec, per channel (< 2^31)
+    FastDiv groups_per_image;  // hw / vec
     uint32_t n_tiles;
     int stride;                // floats per tile record
     bool aligned16;
@@ -42,11 +42,11 @@ __global__ void __launch_bounds__(kStatThreads) channel_tiles_kernel(const StatP
     float gs[8], gq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const unsigned long long g = (unsigned long long)tile * kSumTileGroups + 32 * j + lane;
+        const uint32_t g = tile * kSumTileGroups + 32 * j + lane;
         gs[j] = gq[j] = 0.0f;
         if (g < p.groups) {
-            const unsigned long long b = g / p.groups_per_image, r = g - b * p.groups_per_image;
-            const float* src = p.x + ((size_t)(b * p.channels + c) * p.hw + (size_t)r * p.vec);
+            const uint32_t b = fastdiv(g, p.groups_per_image), r = g - b * p.groups_per_image.div;
+            const float* src = p.x + ((size_t)(b * (uint32_t)p.channels + c) * p.hw + (size_t)r * p.vec);
             if (p.vec == 4) {
                 float4 v;
                 if (p.aligned16) v = ld_stream_f32x4(src);
@@ -60,12 +60,50 @@ __global__ void __launch_bounds__(kStatThreads) channel_tiles_kernel(const StatP
             }
         }
     }
-    float ts = 0.0f, tq = 0.0f;
+    // The eight butterfly trees of the sums and the eight of the squares, all at once: at every level (xor 16, 8, 4, 2, 1)
+    // a lane keeps half of its values and hands the other half to its partner, so 16 values x 5 levels cost 16 shuffles
+    // instead of 80.  Each value still sees the canonical pairing order (float add commutes), so the bits are the canonical
+    // ones.  Afterwards lane l holds the warp-tree sum of (squares if l & 16 else sums) of "warp" j = bits 3, 2, 1 of l.
+    float v8[8];
+    {
+        const bool hi = lane & 16;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {       // "warp" j of the canonical tile
-        const float ws = warp_tree_sum(gs[j]), wq = warp_tree_sum(gq[j]);
-        ts = j ? __fadd_rn(ts, ws) : ws;
-        tq = j ? __fadd_rn(tq, wq) : wq;
+        for (int k = 0; k < 8; ++k) {
+            const float keep = hi ? gq[k] : gs[k], send = hi ? gs[k] : gq[k];
+            v8[k] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+        }
+    }
+    float v4[4];
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float keep = hi ? v8[4 + k] : v8[k], send = hi ? v8[k] : v8[4 + k];
+            v4[k] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+        }
+    }
+    float v2[2];
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float keep = hi ? v4[2 + k] : v4[k], send = hi ? v4[k] : v4[2 + k];
+            v2[k] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+        }
+    }
+    float v1;
+    {
+        const bool hi = lane & 2;
+        const float keep = hi ? v2[1] : v2[0], send = hi ? v2[0] : v2[1];
+        v1 = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+    }
+    v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, 1));
+    // the eight warp sums of the tile in order 0..7: "warp" j sits in lane 2 j (sums) and 16 + 2 j (squares)
+    float ts = __shfl_sync(0xffffffffu, v1, 0), tq = __shfl_sync(0xffffffffu, v1, 16);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+        ts = __fadd_rn(ts, __shfl_sync(0xffffffffu, v1, 2 * j));
+        tq = __fadd_rn(tq, __shfl_sync(0xffffffffu, v1, 16 + 2 * j));
     }
     if (lane == 0) {
         float* rec = p.records + (size_t)tile * p.stride + 2 * blockIdx.y;
@@ -171,8 +209,10 @@ int polcue_channel_stats_f32(const float* x, int B, int C, size_t hw, void* work
     p.hw = hw;
     p.channels = C;
     p.vec = hw % 4 == 0 ? 4 : 1;
-    p.groups = (unsigned long long)B * (hw / p.vec);
-    p.groups_per_image = (uint32_t)(hw / p.vec);
+    if ((unsigned long long)B * (hw / p.vec) >= (1ull << 31)) return POLCUE_E2BIG;
+    p.groups = (uint32_t)((unsigned long long)B * (hw / p.vec));
+    p.groups_per_image.div = (uint32_t)(hw / p.vec);
+    make_fastdiv(p.groups_per_image.div, p.groups_per_image.mul, p.groups_per_image.shift);
     p.n_tiles = (uint32_t)tiles;
     p.aligned16 = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     p.records = fold_records(workspace, p.n_tiles);
