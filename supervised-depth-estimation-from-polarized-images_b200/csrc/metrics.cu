@@ -654,16 +654,19 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
 }
 
 // {n_images, sum over images of the per-image metric rows} -- the accumulators of the reference's mean over images
-// (np.array(errors).mean(0), trainer.py:1426; evaluation.py:283-285), additive across ranks.  One thread per
-// (group, metric) adds the images in index order, so the result is bitwise reproducible.  NaN rows (empty masks)
+// (np.array(errors).mean(0), trainer.py:1426; evaluation.py:283-285), additive across ranks.  Fixed summation order,
+// so the result is bitwise reproducible.  NaN rows (empty masks)
 // poison the mean exactly as they do in the reference.
 __global__ void __launch_bounds__(128) image_mean_acc_kernel(const float* __restrict__ metrics, int B, int n_values, double* __restrict__ acc) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v == 0) acc[0] = (double)B;
+    // one warp per (group, metric): lane l adds images l, l + 32, ... in order, then a fixed shuffle tree
+    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (v == 0 && lane == 0) acc[0] = (double)B;
     if (v >= n_values) return;
     double t = 0.0;
-    for (int b = 0; b < B; ++b) t += (double)__ldg(metrics + (size_t)b * n_values + v);
-    acc[1 + v] = t;
+    for (int b = lane; b < B; b += 32) t += (double)__ldg(metrics + (size_t)b * n_values + v);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+    if (lane == 0) acc[1 + v] = t;
 }
 
 }  // namespace
@@ -816,7 +819,7 @@ int polcue_eval_pass_f32(const float* gt, const float* pred, const uint8_t* inst
     rc = polcue_depth_errors_groups_f32(gt, pred, inst, B, (size_t)H * W, min_d, max_d, group_ids, n_groups, sums, metrics, stream);
     if (rc != POLCUE_OK) return rc;
     const int n_values = n_groups * 7;
-    image_mean_acc_kernel<<<(n_values + 127) / 128, 128, 0, (cudaStream_t)stream>>>(metrics, B, n_values, mean_acc);
+    image_mean_acc_kernel<<<(n_values + 3) / 4, 128, 0, (cudaStream_t)stream>>>(metrics, B, n_values, mean_acc);
     return launch_status();
 }
 
