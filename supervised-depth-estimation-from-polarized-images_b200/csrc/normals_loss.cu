@@ -371,6 +371,12 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const
 // 16-byte global loads, replicate padding by clamped coordinates); TMA cannot interleave two tensors.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kPW = 128, kPH = 32;                    // tile
+
+// Shared rows of (gt, pred) pairs are swizzled in 16-byte units (two pairs): unit u lives at u ^ ((u >> 3) & 1).  A thread's
+// window is three consecutive units starting at an even or odd unit 2 * lane (+1); without the swizzle lanes l and l + 4 of
+// every quarter-warp hit the same banks (32-byte lane stride: two-way conflicts on every LDS.128, four-way on the 8-byte
+// stores); with it the eight lanes of a quarter-warp cover the eight bank groups exactly once for each of the three loads.
+__device__ __forceinline__ int swz_pair(int i) { return i ^ (((i >> 4) & 1) << 1); }
 constexpr int kPPitch = kPW + 4;                      // (gt, pred) pairs per shared row: column 0 = image column x0 - 1, 129 = x0 + 128
 constexpr size_t kFwdPairsTileBytes = (size_t)(kPH + 2) * kPPitch * sizeof(float2);
 constexpr size_t kFwdPairsMaskBytes = (size_t)kPH * kPW * sizeof(float);
@@ -412,11 +418,11 @@ __device__ __forceinline__ void stage_pairs(float2 (*T)[PITCH], const float* __r
     for (int k = 0; k < kIter; ++k) {
         const int r = r0 + 8 * k;
         if (r < kRows && x < W) {
-            float2* dst = &T[r][OFF + 4 * q];
-            dst[0] = make_float2(g[k].x, d[k].x);
-            dst[1] = make_float2(g[k].y, d[k].y);
-            dst[2] = make_float2(g[k].z, d[k].z);
-            dst[3] = make_float2(g[k].w, d[k].w);
+            static_assert(OFF % 2 == 1, "the four pairs of a group are: upper half of a unit, a whole unit, lower half of the next");
+            float2* row = &T[r][0];
+            row[swz_pair(OFF + 4 * q)] = make_float2(g[k].x, d[k].x);
+            *reinterpret_cast<float4*>(&row[swz_pair(OFF + 4 * q + 1)]) = make_float4(g[k].y, d[k].y, g[k].z, d[k].z);
+            row[swz_pair(OFF + 4 * q + 3)] = make_float2(g[k].w, d[k].w);
         }
     }
 #pragma unroll
@@ -425,21 +431,23 @@ __device__ __forceinline__ void stage_pairs(float2 (*T)[PITCH], const float* __r
         if (i < kRows * 2 * HALO) {
             const int r = i / (2 * HALO), e = i - r * (2 * HALO);
             const int c = (e < HALO) ? e - HALO : cr + (e - HALO);
-            T[r][OFF + c] = edge[k];
+            T[r][swz_pair(OFF + c)] = edge[k];
         }
     }
 }
 
 // 8 x gradients of xyz of both fields for the four pixels starting at tile column tx0 of tile row ty (shared row ty + 1):
 // lane 0 = GT, lane 1 = prediction.  Same arithmetic, per lane, as gradients4.
-// `win` = the shared pair of the window's top-left pixel (row y - 1, column x - 1; 16-byte aligned), `pitch` pairs per row.
-__device__ __forceinline__ void gradients4_pairs(const float2* win, int pitch, const f32x2 (&fx6)[6], const f32x2 (&fy3)[3],
+// `top` = the shared row of image row y - 1 (`pitch` pairs per row), `p0` = the (even) pair index of column x - 1 in it.
+__device__ __forceinline__ void gradients4_pairs(const float2* top, int p0, int pitch, const f32x2 (&fx6)[6], const f32x2 (&fy3)[3],
                                                  f32x2 (&gu)[3][4], f32x2 (&gv)[3][4], f32x2 (&centre)[4]) {
     f32x2 Z[3][6];
+    const int u0 = swz_pair(p0), u1 = swz_pair(p0 + 2), u2 = swz_pair(p0 + 4);    // the window's three 16-byte units
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const ulonglong2* row = reinterpret_cast<const ulonglong2*>(win + r * pitch);   // pairs of columns x - 1 .. x + 4
-        const ulonglong2 a = row[0], b = row[1], c = row[2];
+        const float2* row = top + r * pitch;                                          // pairs of columns x - 1 .. x + 4
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(row + u0), b = *reinterpret_cast<const ulonglong2*>(row + u1),
+                         c = *reinterpret_cast<const ulonglong2*>(row + u2);
         Z[r][0] = a.x; Z[r][1] = a.y; Z[r][2] = b.x; Z[r][3] = b.y; Z[r][4] = c.x; Z[r][5] = c.y;
     }
 #pragma unroll
@@ -528,7 +536,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel
 #pragma unroll
             for (int r = 0; r < 3; ++r) fy3[r] = dup2(((float)min(max(y + r - 1, 0), p.H - 1) - cam.cy) * cam.inv_fy);
             f32x2 gu[3][4], gv[3][4], centre[4];
-            gradients4_pairs(&T[ty][tx0], kPPitch, fx6, fy3, gu, gv, centre);
+            gradients4_pairs(&T[ty][0], tx0, kPPitch, fx6, fy3, gu, gv, centre);
             float fs = 0.0f, fm = 0.0f, fl = 0.0f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -572,8 +580,8 @@ constexpr int kBTileRows = kBwdH + 4;                 // rows y0 - 2 .. y0 + kBw
 constexpr size_t kBwdPairsSmem = (size_t)(kBTileRows + 3 * kGH) * kBPitch * sizeof(float2);
 
 // 3 x 3 window, one pixel (the two ring columns): same arithmetic as `gradients`, both fields in the two lanes.
-__device__ __forceinline__ void gradients1_pairs(const float2* win, int pitch, int x, int y, int H, int W, const Cam& cam, f32x2 (&gu)[3],
-                                                 f32x2 (&gv)[3], f32x2& centre) {
+__device__ __forceinline__ void gradients1_pairs(const float2* top, int p0, int pitch, int x, int y, int H, int W, const Cam& cam,
+                                                 f32x2 (&gu)[3], f32x2 (&gv)[3], f32x2& centre) {
     f32x2 fx3[3], fy3[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -584,7 +592,7 @@ __device__ __forceinline__ void gradients1_pairs(const float2* win, int pitch, i
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) Z[r][c] = *reinterpret_cast<const f32x2*>(win + r * pitch + c);
+        for (int c = 0; c < 3; ++c) Z[r][c] = *reinterpret_cast<const f32x2*>(top + r * pitch + swz_pair(p0 + c));
     centre = Z[1][1];
     f32x2 S2[3], D2[3], S1[3], D1[3];
     const f32x2 two = dup2(2.0f);
@@ -660,7 +668,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_pairs_kernel
 #pragma unroll
                 for (int r = 0; r < 3; ++r) fy3[r] = dup2(((float)min(max(y + r - 1, 0), p.H - 1) - cam.cy) * cam.inv_fy);
                 f32x2 gu[3][4], gv[3][4], centre[4];
-                gradients4_pairs(&T[ty + 1][tx0 + 2], kBPitch, fx6, fy3, gu, gv, centre);
+                gradients4_pairs(&T[ty + 1][0], tx0 + 2, kBPitch, fx6, fy3, gu, gv, centre);
                 float mk4[4];
                 if constexpr (!L1) {
                     const float4 mv = __ldg(reinterpret_cast<const float4*>(p.mask + b * hw + (size_t)y * p.W + x));
@@ -680,15 +688,15 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_pairs_kernel
                     adjoint_pairs(u, v, scale * mk, oa[j], ob[j], oc[j]);
                 }
             }
-            // index 3 + tx0 is 8 mod 16 bytes: 64-bit stores
-            f32x2* sa = reinterpret_cast<f32x2*>(&G[0][gy][3 + tx0]);
-            f32x2* sb = reinterpret_cast<f32x2*>(&G[1][gy][3 + tx0]);
-            f32x2* sc = reinterpret_cast<f32x2*>(&G[2][gy][3 + tx0]);
+            // pairs 3 + tx0 .. 6 + tx0 of the row: the upper half of a unit, a whole unit, the lower half of the next
+            const int pa = swz_pair(3 + tx0), pb = swz_pair(4 + tx0), pc = swz_pair(6 + tx0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                sa[j] = oa[j];
-                sb[j] = ob[j];
-                sc[j] = oc[j];
+            for (int f = 0; f < 3; ++f) {
+                const f32x2* o = f == 0 ? oa : (f == 1 ? ob : oc);
+                float2* row = &G[f][gy][0];
+                *reinterpret_cast<f32x2*>(row + pa) = o[0];
+                *reinterpret_cast<ulonglong2*>(row + pb) = make_ulonglong2(o[1], o[2]);
+                *reinterpret_cast<f32x2*>(row + pc) = o[3];
             }
         }
     }
@@ -699,15 +707,15 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_pairs_kernel
         f32x2 A = 0ull, B = 0ull, C = 0ull;
         if (x >= 0 && x < p.W && y >= 0 && y < p.H) {
             f32x2 gu[3], gv[3], centre;
-            gradients1_pairs(&T[ty + 1][tx + 2], kBPitch, x, y, p.H, p.W, cam, gu, gv, centre);
+            gradients1_pairs(&T[ty + 1][0], tx + 2, kBPitch, x, y, p.H, p.W, cam, gu, gv, centre);
             float zg, zp;
             unpk2(centre, zg, zp);
             const float mk = mask_value<L1>(p, b * hw + (size_t)y * p.W + x, zg);
             adjoint_pairs(gu, gv, scale * mk, A, B, C);
         }
-        *reinterpret_cast<f32x2*>(&G[0][gy][3 + tx]) = A;
-        *reinterpret_cast<f32x2*>(&G[1][gy][3 + tx]) = B;
-        *reinterpret_cast<f32x2*>(&G[2][gy][3 + tx]) = C;
+        *reinterpret_cast<f32x2*>(&G[0][gy][swz_pair(3 + tx)]) = A;
+        *reinterpret_cast<f32x2*>(&G[1][gy][swz_pair(3 + tx)]) = B;
+        *reinterpret_cast<f32x2*>(&G[2][gy][swz_pair(3 + tx)]) = C;
     }
     __syncthreads();
 
@@ -727,12 +735,14 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_pairs_kernel
 #pragma unroll
             for (int di = 0; di < 3; ++di) {
                 const f32x2 ws = dup2(Sv[di]), wd = dup2(Dv[di]), wsd = pk2(Sv[di], Dv[di]);
-                const ulonglong2* ra = reinterpret_cast<const ulonglong2*>(&G[0][ty + di][tx0 + 2]);   // columns x - 1 .. x + 4
-                const ulonglong2* rb = reinterpret_cast<const ulonglong2*>(&G[1][ty + di][tx0 + 2]);
-                const ulonglong2* rc = reinterpret_cast<const ulonglong2*>(&G[2][ty + di][tx0 + 2]);
+                const float2* ra = &G[0][ty + di][0];      // columns x - 1 .. x + 4 = pairs tx0 + 2 .. tx0 + 7 = three swizzled units
+                const float2* rb = &G[1][ty + di][0];
+                const float2* rc = &G[2][ty + di][0];
 #pragma unroll
                 for (int h = 0; h < 3; ++h) {
-                    const ulonglong2 a = ra[h], bq = rb[h], c = rc[h];
+                    const int u = swz_pair(tx0 + 2 + 2 * h);
+                    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(ra + u), bq = *reinterpret_cast<const ulonglong2*>(rb + u),
+                                     c = *reinterpret_cast<const ulonglong2*>(rc + u);
                     VA[2 * h] = fma2(ws, a.x, VA[2 * h]);
                     VA[2 * h + 1] = fma2(ws, a.y, VA[2 * h + 1]);
                     VB[2 * h] = fma2(wd, bq.x, VB[2 * h]);
@@ -763,7 +773,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_pairs_kernel
                 res[j] = fmaf(fxq, a0, fmaf(fyq, a1, acc2));
                 if constexpr (L1) {
                     float zg, zp;
-                    unpk2(*reinterpret_cast<const f32x2*>(&T[ty + 2][3 + tx0 + j]), zg, zp);
+                    unpk2(*reinterpret_cast<const f32x2*>(&T[ty + 2][swz_pair(3 + tx0 + j)]), zg, zp);
                     const float mk = (zg >= p.min_d && zg <= p.max_d) ? 1.0f : 0.0f;
                     const float sgn = (zp > zg) ? 1.0f : ((zp < zg) ? -1.0f : 0.0f);
                     res[j] = fmaf(l1_scale * mk, sgn, res[j]);

@@ -25,7 +25,7 @@ __global__ void probe(const float* g, const float* pr, int* bad, float* dump) {
     for (int c = 0; c < 6; ++c) fx6[c] = dup2(((float)min(max(x + c - 1, 0), W - 1) - cam.cx) * cam.inv_fx);
     for (int r = 0; r < 3; ++r) fy3[r] = dup2(((float)min(max(y + r - 1, 0), H - 1) - cam.cy) * cam.inv_fy);
     f32x2 gu[3][4], gv[3][4], centre[4];
-    gradients4_pairs(&T[ty][tx0], kPPitch, fx6, fy3, gu, gv, centre);
+    gradients4_pairs(&T[ty][0], tx0, kPPitch, fx6, fy3, gu, gv, centre);
     for (int j = 0; j < 4; ++j) {
         for (int c = 0; c < 3; ++c) {
             float a, b;
