@@ -361,3 +361,24 @@ def test_two_rank_gloo_reduction_matches_single_process(tmp_path):
         pooled += O.depth_error_sums(gt[b][m], np.clip(pred[b][m], 0.1, 2.0))
     assert np.allclose(got[7:15], pooled, rtol=1e-12)
     assert got[15] == 2.0
+
+
+def test_bench_reference_arm_prints_one_contract_line_with_blas_pinned():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm): one JSON line on stdout with the
+    contract's keys, the same workload label as the CUDA arm, the requested frames / steps honoured, and worker
+    processes whose BLAS really runs single-threaded (round 1 pinned the variables too late and measured 3x low)."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--frames", "2", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-1500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+                "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["config"]["frames_per_step"] == 2 and line["gpu_launches"] == 0
+    assert line["config"]["workload"].startswith("cfg2:") and line["unit"] == "Mpix/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 2
+    assert "observed with threadpoolctl: 1;" in line["cpu_baseline"]["sample"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
