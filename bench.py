@@ -270,7 +270,7 @@ def run_polcue_arm(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     D.init("nccl")
-    ops._trig.mode = args.trig                     # which table handle (sincos variant) this process hands to the library
+    ops.set_default_trig(args.trig)               # which table handle (sincos variant) this process hands to the library
 
     B, H, W = args.frames, FRAME_H, FRAME_W
     hs, ws = H // 2, W // 2

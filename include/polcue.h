@@ -253,7 +253,8 @@ POLCUE_API int polcue_depth_to_normals_f32(const float* depth, const float* K, i
  *     loss = sum((2 - cos(n_gt, n_pred)) * mask) / sum(mask),  n = depth_to_normals(depth, K)
  * depth_gt, depth_pred, mask: B x 1 x H x W float32; K: B x 3 x 3.
  * fwd: sums2 (device, 2 doubles) receives {sum((2-cos) m), sum(m)}; loss (device float, may be NULL) = their ratio.
- *      workspace: polcue_normals_loss_workspace_bytes() bytes, first 8 bytes zero before the first use.
+ *      workspace: polcue_normals_loss_workspace_bytes() bytes (per-CTA partials; a second tiny launch folds them in a
+ *      fixed order, so results are bitwise reproducible).
  * bwd: grad_pred (B x 1 x H x W) = d(loss)/d(depth_pred) * grad_out, with sums2 from the forward call and grad_out a
  *      DEVICE float scalar.  depth_gt and mask receive no gradient (they are data).
  * ------------------------------------------------------------------------------------------- */

@@ -387,17 +387,20 @@ constexpr size_t kFwdPairsMaskBytes = (size_t)kPH * kPW * sizeof(float);
 template <int TH, int HALO, int OFF, int PITCH>
 __device__ __forceinline__ void stage_pairs(float2 (*T)[PITCH], const float* __restrict__ G, const float* __restrict__ P, int H, int W,
                                             int x0, int y0) {
-    constexpr int kRows = TH + 2 * HALO, kIter = (kRows + 7) / 8;
+    constexpr int kRows = TH + 2 * HALO, kIter = (kRows + 7) / 8, kFull = kRows / 8;   // iterations whose row always exists
     const int q = threadIdx.x & 31, r0 = threadIdx.x >> 5;
     const int x = x0 + 4 * q;
+    const bool in_x = x < W;                           // W % 4 == 0: a group is inside the image or outside it
     float4 g[kIter], d[kIter];
+    if (in_x) {
 #pragma unroll
-    for (int k = 0; k < kIter; ++k) {
-        const int r = r0 + 8 * k;
-        if (r < kRows && x < W) {
-            const int yy = min(max(y0 + r - HALO, 0), H - 1);
-            g[k] = __ldg(reinterpret_cast<const float4*>(G + (size_t)yy * W + x));
-            d[k] = __ldg(reinterpret_cast<const float4*>(P + (size_t)yy * W + x));
+        for (int k = 0; k < kIter; ++k) {
+            const int r = r0 + 8 * k;
+            if (k < kFull || r < kRows) {
+                const unsigned off = (unsigned)min(max(y0 + r - HALO, 0), H - 1) * (unsigned)W + (unsigned)x;   // H * W < 2^31 (checked on the host)
+                g[k] = __ldg(reinterpret_cast<const float4*>(G + off));
+                d[k] = __ldg(reinterpret_cast<const float4*>(P + off));
+            }
         }
     }
     // the HALO columns left of the tile and the first HALO columns right of it (or of the image)
@@ -414,15 +417,18 @@ __device__ __forceinline__ void stage_pairs(float2 (*T)[PITCH], const float* __r
             edge[k] = make_float2(__ldg(G + (size_t)yy * W + xx), __ldg(P + (size_t)yy * W + xx));
         }
     }
+    if (in_x) {
+        static_assert(OFF % 2 == 1, "the four pairs of a group are: upper half of a unit, a whole unit, lower half of the next");
+        const int pa = swz_pair(OFF + 4 * q), pb = swz_pair(OFF + 4 * q + 1), pc = swz_pair(OFF + 4 * q + 3);
 #pragma unroll
-    for (int k = 0; k < kIter; ++k) {
-        const int r = r0 + 8 * k;
-        if (r < kRows && x < W) {
-            static_assert(OFF % 2 == 1, "the four pairs of a group are: upper half of a unit, a whole unit, lower half of the next");
-            float2* row = &T[r][0];
-            row[swz_pair(OFF + 4 * q)] = make_float2(g[k].x, d[k].x);
-            *reinterpret_cast<float4*>(&row[swz_pair(OFF + 4 * q + 1)]) = make_float4(g[k].y, d[k].y, g[k].z, d[k].z);
-            row[swz_pair(OFF + 4 * q + 3)] = make_float2(g[k].w, d[k].w);
+        for (int k = 0; k < kIter; ++k) {
+            const int r = r0 + 8 * k;
+            if (k < kFull || r < kRows) {
+                float2* row = &T[r][0];
+                row[pa] = make_float2(g[k].x, d[k].x);
+                *reinterpret_cast<float4*>(&row[pb]) = make_float4(g[k].y, d[k].y, g[k].z, d[k].z);
+                row[pc] = make_float2(g[k].w, d[k].w);
+            }
         }
     }
 #pragma unroll
@@ -934,7 +940,7 @@ int check_common(const float* gt, const float* pred, const float* K, const float
          reinterpret_cast<uintptr_t>(mask)) & 3)
         return POLCUE_EINVAL;
     grid = dim3((W + kLW - 1) / kLW, (H + tile_h - 1) / tile_h, B);
-    if (grid.y > 65535) return POLCUE_E2BIG;
+    if (grid.y > 65535 || (unsigned long long)H * W >= (1ull << 31)) return POLCUE_E2BIG;   // 32-bit pixel offsets inside an image
     if (cap && (unsigned long long)grid.x * grid.y * grid.z > (unsigned long long)kMaxLossBlocks) return POLCUE_E2BIG;   // one partial per CTA
     return POLCUE_OK;
 }

@@ -60,6 +60,13 @@ class trig:
         return False
 
 
+def set_default_trig(mode):
+    """The sincos variant of every later call of THIS thread outside a `with ops.trig(..)` block ("mufu" or "poly")."""
+    if mode not in ("mufu", "poly"):
+        raise ValueError("trig mode must be 'mufu' or 'poly'")
+    _trig.mode = mode
+
+
 def lut_for(n, device, mode=None):
     """Zenith-angle tables for refractive index `n` on `device` (cached; built once per (n, device, trig mode))."""
     device = torch.device(device)
