@@ -1052,6 +1052,76 @@ def _bands_intact(buf, pad, fill):
     return bool((buf[:pad] == fill).all()) and bool((buf[-pad:] == fill).all())
 
 
+def test_eval_pass_equals_the_separate_entry_points_and_replays_from_a_cuda_graph():
+    """polcue_eval_pass_f32 (BASELINE configs[4]): GT normals, every mask group's per-image metrics and the accumulators of
+    the mean over images in three launches -- bit-equal to the separate entry points, equal to the oracle's mean over
+    images, NaN rows (empty masks) poisoning the mean as np.array(errors).mean(0) does, and capturable in a CUDA graph."""
+    gt, pred, inst, k = synth.gen_depth_batch(40, 7, 64, 96)
+    inst[3] = 60                                     # image 3 holds a single material: every other group's mask is empty there
+    groups = [None] + list(synth.MATERIAL_LEVELS)
+    g, q, i, kk = dev(gt), dev(pred), dev(inst), dev(k)
+    out = ops.eval_pass(g, q, i, kk, 0.1, 2.0, groups)
+    assert torch.equal(out["normals"], ops.depth_to_normals(g[:, None], kk))
+    sums, metrics = ops.depth_errors_groups(g, q, i, 0.1, 2.0, groups)
+    assert torch.equal(out["sums"], sums) and torch.equal(out["metrics"].nan_to_num(-1.0), metrics.nan_to_num(-1.0))
+    acc = out["mean_acc"].cpu().numpy()
+    assert acc[0] == 7
+    rows = metrics.double().cpu().numpy()                          # [B, G, 7]
+    expect = rows.sum(axis=0).reshape(-1)                          # NaN where an image has an empty mask for the group
+    assert np.array_equal(np.isnan(acc[1:]), np.isnan(expect))
+    assert np.allclose(acc[1:], expect, rtol=1e-12, equal_nan=True)
+    for gi, level in enumerate(groups):
+        _, mean = O.depth_errors_per_image(gt, pred, 0.1, 2.0, inst if level is not None else None, level)
+        got = acc[1 + 7 * gi: 8 + 7 * gi] / acc[0]
+        assert np.array_equal(np.isnan(got), np.isnan(mean)) and np.allclose(got, mean, rtol=5e-6, equal_nan=True), level
+    # a fixed set of buffers: capture once, replay, same bits
+    bufs = ops.eval_pass(g, q, i, kk, 0.1, 2.0, groups)
+    graph, side = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            ops.eval_pass(g, q, i, kk, 0.1, 2.0, groups, out=bufs)
+    torch.cuda.current_stream().wait_stream(side)
+    bufs["mean_acc"].zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(bufs["mean_acc"].cpu().numpy(), acc, equal_nan=True)
+    # no normals requested, bad arguments
+    lean = ops.eval_pass(g, q, i, None, 0.1, 2.0, groups, want_normals=False)
+    assert lean["normals"] is None and torch.equal(lean["mean_acc"].nan_to_num(-1.0), out["mean_acc"].nan_to_num(-1.0))
+    with pytest.raises(ValueError):
+        ops.eval_pass(g, q[:, :32], i, kk, 0.1, 2.0, groups)
+
+
+def test_trig_mode_is_a_property_of_the_table_handle_and_host_buffers_are_pinned():
+    """No process-global state changes numerics: `ops.trig` only selects which table handle a call receives (the mode lives in
+    the handle, polcue_lut_set_trig), so two threads / two blocks cannot disturb each other; polcue_host_alloc_on hands out
+    pinned memory that the host entry points (and torch) treat as such, and rejects bad arguments."""
+    import ctypes as C
+    mosaic = dev(synth.gen_u_mosaic(3, 64, 96))[None]
+    with ops.trig("poly"):
+        poly = ops.fused_mosaic(mosaic, 1.5)["normals"].clone()
+        with ops.trig("mufu"):
+            inner = ops.fused_mosaic(mosaic, 1.5)["normals"].clone()
+        assert torch.equal(ops.fused_mosaic(mosaic, 1.5)["normals"], poly)          # restored after the inner block
+    mufu = ops.fused_mosaic(mosaic, 1.5)["normals"]
+    assert torch.equal(inner, mufu) and not torch.equal(poly, mufu) and float((poly - mufu).abs().max()) < 2e-6
+    assert ops.lut_for(1.5, mosaic.device, "poly").value != ops.lut_for(1.5, mosaic.device, "mufu").value
+    L = _lib.lib()
+    assert L.polcue_lut_set_trig(None, 1) == _lib.EINVAL
+    t = ops.host_empty((3, 5, 7), torch.float32)
+    assert t.is_pinned() and t.shape == (3, 5, 7) and float(t.abs().sum()) == 0.0
+    view = t[1]
+    del t
+    view.fill_(2.0)                                                                   # the block lives as long as any view of it
+    assert float(view.sum()) == 70.0
+    ptr = C.c_void_p()
+    assert L.polcue_host_alloc_on(C.byref(ptr), 0, -1) == _lib.EINVAL and L.polcue_host_alloc_on(None, 16, -1) == _lib.EINVAL
+    assert L.polcue_host_free(C.c_void_p(12345)) == _lib.EINVAL and L.polcue_host_free(None) == 0
+    with pytest.raises(ValueError):                                                  # a stale host buffer of another geometry is refused
+        ops.fused_mosaic_host(mosaic.cpu(), 1.5, out={"xolp": torch.empty((1, 2, 16, 24))})
+
+
 @pytest.mark.parametrize("shape", [(2, 2), (6, 10), (34, 66), (66, 128), (130, 250), (128, 192)])
 def test_kernels_never_write_outside_their_outputs(shape):
     import ctypes as C
