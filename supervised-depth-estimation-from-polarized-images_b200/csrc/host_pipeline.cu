@@ -264,14 +264,17 @@ int polcue_host_alloc_on(void** ptr, size_t bytes, int device) {
     // Driver-allocated pinned memory; while it is allocated (and first touched) the calling thread PREFERS the GPU's NUMA
     // node (set_mempolicy MPOL_PREFERRED = 1), so on a two-socket box the pages land next to the GPU that will DMA into
     // them.  A refused syscall (seccomp, single-node VM) changes nothing.
-    unsigned long mask[16] = {0};
-    if (bind) {
+    unsigned long mask[16] = {0}, saved_mask[16] = {0};
+    int saved_mode = 0;
+    bool switched = false;
+    if (bind && syscall(SYS_get_mempolicy, &saved_mode, saved_mask, (unsigned long)(8 * sizeof(saved_mask)), nullptr, 0ul) == 0) {
         mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
-        (void)syscall(SYS_set_mempolicy, 1, mask, (unsigned long)(8 * sizeof(mask)));
+        switched = syscall(SYS_set_mempolicy, 1, mask, (unsigned long)(8 * sizeof(mask))) == 0;
     }
     const cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
     if (e == cudaSuccess) std::memset(*ptr, 0, bytes);
-    if (bind) (void)syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+    if (switched)      // the caller's own policy comes back, whatever it was
+        (void)syscall(SYS_set_mempolicy, saved_mode, saved_mode == 0 ? nullptr : saved_mask, saved_mode == 0 ? 0ul : (unsigned long)(8 * sizeof(saved_mask)));
     if (e != cudaSuccess) return as_code(e);
     std::lock_guard<std::mutex> guard(g_host_mutex);
     g_host_blocks[*ptr] = HostBlock{bytes, false};
