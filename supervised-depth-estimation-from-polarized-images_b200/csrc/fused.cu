@@ -496,7 +496,7 @@ constexpr int kXolpItems = 4;   // pixel groups per thread: a CTA moves ~48 KB, 
 // plainly (no per-CTA setup to amortise, so the hardware's own CTA queue is the dynamic scheduler).
 template <typename T, bool GENERAL, int V>
 __global__ void __launch_bounds__(256) xolp_stack_kernel(const T* __restrict__ stack, size_t hw, size_t total, Pinv pv,
-                                                          float* __restrict__ iun, float* __restrict__ xolp) {
+                                                          float* __restrict__ iun, float* __restrict__ xolp, FastDiv hw_div) {
 #pragma unroll 2
     for (int item = 0; item < kXolpItems; ++item) {
     const size_t i = (((size_t)blockIdx.x * kXolpItems + item) * 256 + threadIdx.x) * V;
@@ -524,7 +524,8 @@ __global__ void __launch_bounds__(256) xolp_stack_kernel(const T* __restrict__ s
             rho[j] = q.rho; phi[j] = q.phi; un[j] = q.iun;
         }
     }
-    const size_t b = i / hw, r = i - b * hw;      // V divides hw when V > 1: a group never straddles two images
+    // image index: a 32-bit multiply-shift when the batch has < 2^31 pixels (hw_div.div != 0), else the 64-bit division
+    const size_t b = hw_div.div ? (size_t)fastdiv((uint32_t)i, hw_div) : i / hw, r = i - b * hw;      // V divides hw when V > 1
     float* xo = xolp + b * 2 * hw + r;
     st_stream_vec<V>(xo, rho);
     st_stream_vec<V>(xo + hw, phi);
@@ -536,7 +537,7 @@ template <int V>
 __global__ void __launch_bounds__(256) xolp_planes_kernel(const uint8_t* __restrict__ i0, const uint8_t* __restrict__ i45,
                                                            const uint8_t* __restrict__ i90, const uint8_t* __restrict__ i135,
                                                            size_t hw, size_t total, float* __restrict__ iun,
-                                                           float* __restrict__ xolp) {
+                                                           float* __restrict__ xolp, FastDiv hw_div) {
 #pragma unroll 2
     for (int item = 0; item < kXolpItems; ++item) {
     const size_t i = (((size_t)blockIdx.x * kXolpItems + item) * 256 + threadIdx.x) * V;
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(256) xolp_planes_kernel(const uint8_t* __restr
                                            (float)ld_stream_u8(i135 + i));
         rho[0] = q.rho; phi[0] = q.phi; un[0] = q.iun;
     }
-    const size_t b = i / hw, r = i - b * hw;
+    const size_t b = hw_div.div ? (size_t)fastdiv((uint32_t)i, hw_div) : i / hw, r = i - b * hw;
     float* xo = xolp + b * 2 * hw + r;
     st_stream_vec<V>(xo, rho);
     st_stream_vec<V>(xo + hw, phi);
@@ -962,10 +963,15 @@ static int xolp_stack_common(const void* stack, bool is_u8, int B, int H, int W,
     if (ctas >= (1ull << 31)) return POLCUE_E2BIG;
     const unsigned grid = (unsigned)ctas;
     cudaStream_t s = (cudaStream_t)stream;
-#define POLCUE_LAUNCH_STACK(T, G)                                                                              \
-    do {                                                                                                       \
-        if (v4) xolp_stack_kernel<T, G, 4><<<grid, 256, 0, s>>>((const T*)stack, hw, total, pv, iun, xolp);    \
-        else xolp_stack_kernel<T, G, 1><<<grid, 256, 0, s>>>((const T*)stack, hw, total, pv, iun, xolp);       \
+    FastDiv hw_div{0, 0, 0};
+    if (total < (1ull << 31) && hw < (1ull << 31)) {
+        hw_div.div = (uint32_t)hw;
+        make_fastdiv(hw_div.div, hw_div.mul, hw_div.shift);
+    }
+#define POLCUE_LAUNCH_STACK(T, G)                                                                                      \
+    do {                                                                                                               \
+        if (v4) xolp_stack_kernel<T, G, 4><<<grid, 256, 0, s>>>((const T*)stack, hw, total, pv, iun, xolp, hw_div);    \
+        else xolp_stack_kernel<T, G, 1><<<grid, 256, 0, s>>>((const T*)stack, hw, total, pv, iun, xolp, hw_div);       \
     } while (0)
     if (is_u8) {
         if (pinv) POLCUE_LAUNCH_STACK(uint8_t, true);
@@ -999,8 +1005,13 @@ int polcue_xolp_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t* 
     const size_t per_cta = 256 * kXolpItems * (v4 ? 4 : 1);
     const size_t ctas = (total + per_cta - 1) / per_cta;
     if (ctas >= (1ull << 31)) return POLCUE_E2BIG;
-    if (v4) xolp_planes_kernel<4><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(i0, i45, i90, i135, hw, total, iun, xolp);
-    else xolp_planes_kernel<1><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(i0, i45, i90, i135, hw, total, iun, xolp);
+    FastDiv hw_div{0, 0, 0};
+    if (total < (1ull << 31) && hw < (1ull << 31)) {
+        hw_div.div = (uint32_t)hw;
+        make_fastdiv(hw_div.div, hw_div.mul, hw_div.shift);
+    }
+    if (v4) xolp_planes_kernel<4><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(i0, i45, i90, i135, hw, total, iun, xolp, hw_div);
+    else xolp_planes_kernel<1><<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(i0, i45, i90, i135, hw, total, iun, xolp, hw_div);
     return launch_status();
 }
 
