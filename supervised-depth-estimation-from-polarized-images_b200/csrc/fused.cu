@@ -704,13 +704,13 @@ __global__ void __launch_bounds__(256) theta_kernel(const float* __restrict__ rh
 
 // calc_normals: (phi, theta)[B, HW] -> [B, 3, HW]   (normals_vec.py:53-60)
 __global__ void __launch_bounds__(256) calc_normals_kernel(const float* __restrict__ phi, const float* __restrict__ theta,
-                                                            size_t hw, size_t total, float* __restrict__ out) {
+                                                            size_t hw, size_t total, float* __restrict__ out, FastDiv hw_div) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         float sp, cp, st, ct;
         sincos_poly(ld_stream_f32(phi + i), sp, cp);
         sincos_poly(ld_stream_f32(theta + i), st, ct);
-        const size_t b = i / hw, r = i - b * hw;
+        const size_t b = hw_div.div ? (size_t)fastdiv((uint32_t)i, hw_div) : i / hw, r = i - b * hw;
         float* o = out + b * 3 * hw + r;
         st_stream_f32(o, cp * st);
         st_stream_f32(o + hw, sp * st);
@@ -1069,7 +1069,12 @@ int polcue_calc_normals_f32(const float* phi, const float* theta, int B, size_t 
     if (!phi || !theta || !normals || B < 0) return POLCUE_EINVAL;
     const size_t total = hw * (size_t)B;
     if (!total) return POLCUE_OK;
-    calc_normals_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(phi, theta, hw, total, normals);
+    FastDiv hw_div{0, 0, 0};
+    if (total < (1ull << 31) && hw && hw < (1ull << 31)) {
+        hw_div.div = (uint32_t)hw;
+        make_fastdiv(hw_div.div, hw_div.mul, hw_div.shift);
+    }
+    calc_normals_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(phi, theta, hw, total, normals, hw_div);
     return launch_status();
 }
 
