@@ -413,10 +413,30 @@ __global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks) fused_mosaic_k
     }
 }
 
+// XOLP only (no normals wanted): nothing to stage per CTA and a third of the arithmetic, so the tile machinery above costs
+// more than it hides (0.73 of the HBM peak).  A plain launch instead: four groups per thread, all sixteen quadrant words
+// requested before the first is used, the hardware's own CTA queue as the scheduler (as the XOLP kernels below).
+constexpr int kStreamItems = 4;
+template <int VEC>
+__global__ void __launch_bounds__(kFusedThreads) fused_xolp_stream_kernel(const __grid_constant__ FusedParams p) {
+    GroupIn<VEC> g[kStreamItems];
+#pragma unroll
+    for (int item = 0; item < kStreamItems; ++item) g[item] = load_group<VEC>(p, blockIdx.x * kStreamItems + item);
+    const LutShared none{};
+#pragma unroll
+    for (int item = 0; item < kStreamItems; ++item)
+        if (g[item].valid) process_group<VEC, true, false>(p, none, g[item]);
+}
+
 // `mufu`: zenith-angle sincos of this launch, a property of the caller's table handle (polcue_lut_set_trig): MUFU sin/cos
 // (3.6e-7 abs, default) or the polynomial (1.4e-7).  DESIGN.md 5.
 template <int VEC>
 int launch_fused(const FusedParams& p, size_t smem, cudaStream_t stream, bool mufu) {
+    if (!p.normals) {
+        const uint32_t tiles = (p.groups_total + kFusedThreads - 1) / kFusedThreads;
+        fused_xolp_stream_kernel<VEC><<<(tiles + kStreamItems - 1) / kStreamItems, kFusedThreads, 0, stream>>>(p);
+        return launch_status();
+    }
     auto kern = !p.normals ? fused_mosaic_kernel<VEC, true, false>
                            : (mufu ? fused_mosaic_kernel<VEC, true, true> : fused_mosaic_kernel<VEC, false, true>);
     if constexpr (VEC == 4) {
