@@ -1022,6 +1022,11 @@ int polcue_xolp_planes_u8(const uint8_t* i0, const uint8_t* i45, const uint8_t* 
     const size_t hw = (size_t)H * W, total = hw * B;
     const bool v4 = hw % 4 == 0 && aligned(i0, 4) && aligned(i45, 4) && aligned(i90, 4) && aligned(i135, 4) && aligned(xolp, 16) &&
                     aligned(iun, 16);
+    if (v4 && W % 4 == 0 && (unsigned long long)B * H * (W / 4) < (1ull << 31) && hw < (1ull << 30)) {
+        // rows of whole 4-pixel groups: the streaming member of the fused family (all loads of four groups first), measured faster
+        return fused_planes_common(i0, i45 - i0, i90 - i0, i135 - i0, (unsigned long long)hw, true, true, B, H, W, nullptr, iun, xolp,
+                                   nullptr, stream);
+    }
     const size_t per_cta = 256 * kXolpItems * (v4 ? 4 : 1);
     const size_t ctas = (total + per_cta - 1) / per_cta;
     if (ctas >= (1ull << 31)) return POLCUE_E2BIG;
