@@ -259,11 +259,26 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     const size_t tid = (size_t)rank * kMetricThreads + threadIdx.x, stride = (size_t)kCluster * kMetricThreads;
     int since = 0;
     if (p.vec4) {
+        // the loads of the next group are issued before the current one is reduced (the top stall of this kernel was the
+        // long scoreboard: nothing else in a thread overlaps its own loads)
         const size_t n4 = p.px >> 2;
-        for (size_t i = tid; i < n4; i += stride) {
-            const float4 g = ld_stream_f32x4(gt + 4 * i), q = ld_stream_f32x4(pred + 4 * i);
-            uint32_t ids = 0;
+        float4 g = make_float4(1.f, 1.f, 1.f, 1.f), q = g;
+        uint32_t ids = 0;
+        size_t i = tid;
+        if (i < n4) {
+            g = ld_stream_f32x4(gt + 4 * i);
+            q = ld_stream_f32x4(pred + 4 * i);
             if (inst) ids = ld_stream_u32(inst + 4 * i);
+        }
+        while (i < n4) {
+            const size_t nx = i + stride;
+            float4 g2 = g, q2 = q;
+            uint32_t ids2 = 0;
+            if (nx < n4) {
+                g2 = ld_stream_f32x4(gt + 4 * nx);
+                q2 = ld_stream_f32x4(pred + 4 * nx);
+                if (inst) ids2 = ld_stream_u32(inst + 4 * nx);
+            }
             acc_masked<EXT, INST>(a, p, want_id, g.x, q.x, ids & 0xff, scale);
             acc_masked<EXT, INST>(a, p, want_id, g.y, q.y, (ids >> 8) & 0xff, scale);
             acc_masked<EXT, INST>(a, p, want_id, g.z, q.z, (ids >> 16) & 0xff, scale);
@@ -272,6 +287,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
                 flush(s, a);
                 since = 0;
             }
+            g = g2; q = q2; ids = ids2;
+            i = nx;
         }
     } else {
         for (size_t i = tid; i < p.px; i += stride) {
