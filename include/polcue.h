@@ -345,7 +345,8 @@ POLCUE_API int polcue_depth_errors_groups_f32(const float* gt, const float* pred
  *   mean_acc (1 + n_groups * 7 device doubles) = {B, sum over images of every group's seven per-image metrics}: the
  *   accumulators of the reference's mean over images (np.array(errors).mean(0), trainer.py:1426), additive across
  *   ranks -- one all-reduce of this vector and a division finish the evaluation.
- * Three launches on `stream`; capturable in a CUDA graph. */
+ * Three launches; the stencil runs on an internal side stream forked from and joined back into `stream` (the two passes
+ * only share their input and overlap); capturable in a CUDA graph. */
 POLCUE_API int polcue_eval_pass_f32(const float* gt, const float* pred, const uint8_t* inst, const float* K, int B, int H, int W,
                          float min_d, float max_d, const int* group_ids, int n_groups, float* normals, double* sums,
                          float* metrics, double* mean_acc, polcue_stream_t stream);

@@ -16,6 +16,8 @@
 // Roofline: HBM, 8 B per element (+1 B with an instance-id filter).
 #include <cooperative_groups.h>
 
+#include <mutex>
+
 #include "polcue_device.cuh"
 #include "polcue_host.h"
 
@@ -822,22 +824,67 @@ int polcue_depth_errors_groups_f32(const float* gt, const float* pred, const uin
     return launch_status();
 }
 
+namespace {
+// A side stream and two events per device for the fork / join inside polcue_eval_pass_f32.  The mutex is held only while a
+// call ENQUEUES its work, which fixes the order of the event records; it is never held while the GPU runs.
+struct EvalLanes {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+std::mutex g_eval_mutex;
+EvalLanes g_eval_lanes[64];
+
+cudaError_t eval_lanes(int dev, EvalLanes*& out) {
+    EvalLanes& l = g_eval_lanes[dev];
+    if (!l.side) {
+        cudaError_t e = cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    out = &l;
+    return cudaSuccess;
+}
+}  // namespace
+
 int polcue_eval_pass_f32(const float* gt, const float* pred, const uint8_t* inst, const float* K, int B, int H, int W, float min_d,
                          float max_d, const int* group_ids, int n_groups, float* normals, double* sums, float* metrics,
                          double* mean_acc, polcue_stream_t stream) {
     if (!metrics || !mean_acc || H <= 0 || W <= 0 || B <= 0) return POLCUE_EINVAL;
     if (reinterpret_cast<uintptr_t>(mean_acc) & 7) return POLCUE_EINVAL;
+    if (normals && !K) return POLCUE_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
     int rc = POLCUE_OK;
+    // The stencil and the metric pass only share their INPUT, and at the evaluation split's size (120 images) neither
+    // fills the machine on its own (2-3 partial waves each): the stencil runs on a side stream, forked from and joined
+    // back into `stream` with events, so the two overlap.  (Works under stream capture: the side stream joins the capture.)
+    EvalLanes* lanes = nullptr;
+    std::unique_lock<std::mutex> guard(g_eval_mutex, std::defer_lock);
     if (normals) {
-        if (!K) return POLCUE_EINVAL;
-        rc = polcue_depth_to_normals_f32(gt, K, B, H, W, normals, stream);
-        if (rc != POLCUE_OK) return rc;
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess || dev < 0 || dev >= 64) return e != cudaSuccess ? (int)e : POLCUE_EINVAL;
+        guard.lock();
+        e = eval_lanes(dev, lanes);
+        if (e == cudaSuccess) e = cudaEventRecord(lanes->fork, s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(lanes->side, lanes->fork, 0);
+        if (e != cudaSuccess) return (int)e;
+        rc = polcue_depth_to_normals_f32(gt, K, B, H, W, normals, lanes->side);
+        e = cudaEventRecord(lanes->join, lanes->side);           // joined below even if the launch was refused
+        if (e != cudaSuccess) return (int)e;
     }
-    rc = polcue_depth_errors_groups_f32(gt, pred, inst, B, (size_t)H * W, min_d, max_d, group_ids, n_groups, sums, metrics, stream);
-    if (rc != POLCUE_OK) return rc;
-    const int n_values = n_groups * 7;
-    image_mean_acc_kernel<<<(n_values + 3) / 4, 128, 0, (cudaStream_t)stream>>>(metrics, B, n_values, mean_acc);
-    return launch_status();
+    int rc2 = POLCUE_OK;
+    if (rc == POLCUE_OK) rc2 = polcue_depth_errors_groups_f32(gt, pred, inst, B, (size_t)H * W, min_d, max_d, group_ids, n_groups, sums, metrics, s);
+    if (rc == POLCUE_OK && rc2 == POLCUE_OK) {
+        const int n_values = n_groups * 7;
+        image_mean_acc_kernel<<<(n_values + 3) / 4, 128, 0, s>>>(metrics, B, n_values, mean_acc);
+        rc2 = launch_status();
+    }
+    if (normals) {
+        const cudaError_t e = cudaStreamWaitEvent(s, lanes->join, 0);
+        if (e != cudaSuccess && rc == POLCUE_OK && rc2 == POLCUE_OK) return (int)e;
+    }
+    return rc != POLCUE_OK ? rc : rc2;
 }
 
 }  // extern "C"
