@@ -198,6 +198,29 @@ def test_fused_without_optional_outputs_and_bad_args():
     assert L.polcue_fused_mosaic_u8(mosaic.data_ptr(), 0, 64, 96, None, None, None, full["xolp"].data_ptr(), None, None) == 0
 
 
+@pytest.mark.parametrize("shape", [(2, 2), (2, 6), (10, 14), (34, 66), (130, 250), (64, 8200), (2048, 2448)])
+def test_xolp_only_streaming_kernel_equals_the_full_kernel(shape):
+    """`want_normals=False` takes the plain streaming member of the fused family (four groups per thread, no table, no tile
+    loop): its XOLP, Iun and planes must equal the full kernel's bit for bit on every vector width, ragged tails included,
+    for the quadrant layout, the raw super-pixel layout and four separate planes."""
+    h, w = shape
+    rng = np.random.default_rng(h * 7 + w)
+    b = 1 if h * w > 1_000_000 else 3
+    mosaic = dev(rng.integers(0, 256, (b, h, w), dtype=np.uint8))
+    full = ops.fused_mosaic(mosaic, 1.5, want_iun=True, want_planes=True)
+    lean = ops.fused_mosaic(mosaic, 1.5, want_iun=True, want_planes=True, want_normals=False)
+    assert set(lean) == {"xolp", "iun", "planes"}
+    for key in lean:
+        assert torch.equal(lean[key], full[key]), key
+    sp_full = ops.fused_mosaic(mosaic, 1.5, superpixel=(2, 1, 3, 0))
+    sp_lean = ops.fused_mosaic(mosaic, 1.5, superpixel=(2, 1, 3, 0), want_normals=False)
+    assert torch.equal(sp_lean["xolp"], sp_full["xolp"])
+    planes = [full["planes"][:, k].contiguous() for k in range(4)]
+    _, x = ops.xolp_from_planes(*planes)
+    assert torch.equal(x, full["xolp"])
+    assert torch.equal(ops.fused_planes(*planes, want_normals=False)["xolp"], full["xolp"])
+
+
 def test_fused_host_entry_point_matches_device_entry_point():
     mosaic = torch.from_numpy(synth.gen_batch("P", 9, 5, 128, 192)).pin_memory()
     host = ops.fused_mosaic_host(mosaic, 1.5, want_iun=True, chunk_frames=2)   # 3 chunks, ragged tail
