@@ -187,15 +187,27 @@ __device__ __forceinline__ float normalize3(const float (&n)[3], float (&u)[3]) 
 }
 
 // cos = <a,b> / max(|a||b|, 1e-8)   (torch 1.7.1 F.cosine_similarity: w12 * rsqrt(clamp_min(w1 w2, eps^2)))
+// the part of `cosine` after the three dot products (the packed kernels form aa and bb in the two lanes of one register pair)
+__device__ __forceinline__ float cosine_from_dots(float ab, float aa, float bb, float& inv_den, bool& clamped) {
+    const float den2 = __fmul_rn(aa, bb);
+    clamped = den2 <= 1e-16f;
+    inv_den = clamped ? 1e8f : rsqrtf(den2);
+    return __fmul_rn(ab, inv_den);
+}
 __device__ __forceinline__ float cosine(const float (&a)[3], const float (&b)[3], float& inv_den, float& ab, float& bb,
                                         bool& clamped) {
     ab = fmaf(a[0], b[0], fmaf(a[1], b[1], __fmul_rn(a[2], b[2])));
     const float aa = fmaf(a[0], a[0], fmaf(a[1], a[1], __fmul_rn(a[2], a[2])));
     bb = fmaf(b[0], b[0], fmaf(b[1], b[1], __fmul_rn(b[2], b[2])));
-    const float den2 = __fmul_rn(aa, bb);
-    clamped = den2 <= 1e-16f;
-    inv_den = clamped ? 1e8f : rsqrtf(den2);
-    return __fmul_rn(ab, inv_den);
+    return cosine_from_dots(ab, aa, bb, inv_den, clamped);
+}
+// the same from the packed unit normals n (lane 0 = a, lane 1 = b): (aa, bb) cost three packed instructions instead of six
+__device__ __forceinline__ float cosine_pairs(const f32x2 (&n)[3], const float (&a)[3], const float (&b)[3], float& inv_den, float& ab,
+                                              float& bb, bool& clamped) {
+    ab = fmaf(a[0], b[0], fmaf(a[1], b[1], __fmul_rn(a[2], b[2])));
+    float aa;
+    unpk2(fma2(n[0], n[0], fma2(n[1], n[1], mul2(n[2], n[2]))), aa, bb);
+    return cosine_from_dots(ab, aa, bb, inv_den, clamped);
 }
 
 // The adjoint arithmetic after the cosine, with every rounding spelled out (no compiler-chosen contraction) so that the
@@ -561,7 +573,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel
                 if constexpr (L1) fl = fmaf(fabsf(__fsub_rn(zg, zp)), mk, fl);
                 float inv_den, ab, bb;
                 bool clamped;
-                const float c = cosine(a, bb3, inv_den, ab, bb, clamped);
+                const float c = cosine_pairs(n, a, bb3, inv_den, ab, bb, clamped);
                 fs = fmaf(__fsub_rn(2.0f, c), mk, fs);
                 fm += mk;
             }
@@ -635,7 +647,7 @@ __device__ __forceinline__ void adjoint_pairs(const f32x2 (&gu)[3], const f32x2 
     unpk2(inv2, tmp, inv);
     float inv_den, ab, bb;
     bool clamped;
-    cosine(a, bn, inv_den, ab, bb, clamped);
+    cosine_pairs(n, a, bn, inv_den, ab, bb, clamped);
     float gub[3], gvb[3];
     adjoint_tail(a, bn, inv, up, vp, k, inv_den, ab, bb, clamped, gub, gvb);
     A = pk2(gub[0], gub[1]);
