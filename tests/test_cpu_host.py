@@ -382,3 +382,19 @@ def test_bench_reference_arm_prints_one_contract_line_with_blas_pinned():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 2
     assert "observed with threadpoolctl: 1;" in line["cpu_baseline"]["sample"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_bench_side_modules_import_and_encoder_standins_have_the_reference_geometry():
+    """bench.py's cfg3 / cfg4 / cfg5 blocks live in tools/workloads.py; the encoder stand-ins it times must keep the layer
+    geometry of pre_encoders.py:49-97 / resnet_encoder.py:783-822 (2 / 9 -> 64 channels at 1/8 resolution, resnet18 stem +
+    layer1 + layer2 -> 128 channels at 1/8)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import workloads                                   # noqa: F401  (imports polcue.ops; no GPU call at import time)
+    from encoder_standins import PolarEncoders
+    enc = PolarEncoders().eval()
+    with torch.no_grad():
+        fx, fn, fr = enc(torch.rand(2, 2, 64, 96), torch.rand(2, 9, 64, 96), torch.rand(2, 3, 64, 96))
+    assert fx.shape == (2, 64, 8, 12) and fn.shape == (2, 64, 8, 12) and fr.shape == (2, 128, 8, 12)
+    convs = [m for m in enc.xolp_branch.modules() if isinstance(m, torch.nn.Conv2d)]
+    assert [c.kernel_size[0] for c in convs] == [7, 3, 3, 5, 3, 3, 5, 3, 3] and convs[0].stride == (2, 2)
