@@ -36,6 +36,41 @@ def to_device(array, dtype=None):
     return t.to(default_device(), non_blocking=False)
 
 
+_SHADOWED = {   # reference module name -> mirror module (the two small top-level packages of the reference)
+    "polarisation.xolp": "xolp",
+    "polarisation.pol_split_and_save": "pol_split_and_save",
+    "polarisation.xolp_and_normals": "xolp_and_normals",
+    "ppp_code.physical_normals_channels": "physical_normals_channels",
+}
+
+
+def shadow():
+    """Serve `polarisation.{xolp, pol_split_and_save, xolp_and_normals}` and `ppp_code.physical_normals_channels` under the
+    reference's own module names: after `polcue.compat.shadow()`, `from polarisation.xolp import Iun_and_xolp` resolves to
+    the CUDA implementation without the reference checkout on `sys.path`.  Call it BEFORE anything imports those modules;
+    if the reference's own modules are already in `sys.modules` this raises (use `install()` to patch them in place).
+    Returns the list of module names now served."""
+    import importlib
+    import sys
+    import types
+
+    for name in _SHADOWED:
+        mod = sys.modules.get(name)
+        if mod is not None and not getattr(mod, "__name__", "").startswith(__name__ + "."):
+            raise RuntimeError(f"{name} is already imported from {getattr(mod, '__file__', '?')}: call polcue.compat.install() instead")
+    for name, mirror in _SHADOWED.items():
+        pkg_name, _, leaf = name.partition(".")
+        pkg = sys.modules.get(pkg_name)
+        if pkg is None:
+            pkg = types.ModuleType(pkg_name, f"polcue shadow of the reference's `{pkg_name}` package (hot-path modules only)")
+            pkg.__path__ = []          # a package with no files: only the modules registered here can be imported from it
+            sys.modules[pkg_name] = pkg
+        mod = importlib.import_module("." + mirror, __name__)
+        sys.modules[name] = mod
+        setattr(pkg, leaf, mod)
+    return sorted(_SHADOWED)
+
+
 def install(verbose=False, patch_loader=False):
     """Replace, in place, the hot-path functions of the reference modules that are ALREADY imported (`sys.modules`).
 

@@ -224,18 +224,26 @@ def test_product_package_never_imports_the_oracle():
                 assert "polcue_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
 
 
-def test_dropin_packages_shadow_the_reference_module_names():
-    """`polcue/dropin` on sys.path serves `polarisation.*` and `ppp_code.physical_normals_channels` under the reference's names."""
-    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+def test_shadow_serves_the_reference_module_names():
+    """`polcue.compat.shadow()` serves `polarisation.*` and `ppp_code.physical_normals_channels` under the reference's names,
+    and refuses when the reference's own modules are already imported (that case is `install()`'s)."""
+    pkg = os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200")
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import polcue.compat as c; served = c.shadow()\n"
             "from polarisation.xolp import Iun_and_xolp\n"
             "from polarisation.pol_split_and_save import split_pol\n"
             "from polarisation.xolp_and_normals import rho_spec, rho_diffuse, calc_normals\n"
             "from ppp_code.physical_normals_channels import PolarisationImage_channel, calc_normals_channel\n"
-            "import polcue.compat.xolp as c; print('OK', Iun_and_xolp is c.Iun_and_xolp, split_pol.__module__)\n") % (
-        os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200"),
-        os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200", "polcue", "dropin"))
+            "import polarisation, polcue.compat.xolp as cx\n"
+            "print('OK', Iun_and_xolp is cx.Iun_and_xolp, split_pol.__module__, len(served), polarisation.xolp is cx)\n") % pkg
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
-    assert "OK True polcue.compat.pol_split_and_save" in out.stdout, out.stderr[-1500:]
+    assert "OK True polcue.compat.pol_split_and_save 4 True" in out.stdout, out.stderr[-1500:]
+    if os.path.isdir("/root/reference/polarisation"):
+        code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, '/root/reference')\n"
+                "import polarisation.xolp, polcue.compat as c\n"
+                "try:\n    c.shadow()\nexcept RuntimeError as e:\n    print('REFUSED', 'install()' in str(e))\n") % pkg
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+        assert "REFUSED True" in out.stdout, out.stderr[-1500:]
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/manydepth"), reason="reference checkout not present on this box")
