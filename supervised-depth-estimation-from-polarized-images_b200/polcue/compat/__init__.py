@@ -9,9 +9,9 @@ module it replaces, so a call site changes only its import line (INTEGRATION.md 
   polarisation/xolp_and_normals.py               polcue.compat.xolp_and_normals
   ppp_code/physical_normals_channels.py          polcue.compat.physical_normals_channels
   manydepth/normals_vec.py                       polcue.compat.normals_vec
-  manydepth/networks/pre_encoders.py (get_normals)  polcue.compat.pre_encoders
+  manydepth/networks/pre_encoders.py (get_normals)  polcue.compat.normals_vec.get_normals
   manydepth/layers.py (compute_depth_errors*)    polcue.compat.layers
-  kornia.geometry.depth (depth_to_normals)       polcue.compat.depth
+  kornia.geometry.depth (depth_to_normals)       polcue.compat.trainer.depth_to_normals
   manydepth/datasets/indoor_dataset.py (resize_pol, get_xolp)  polcue.compat.indoor_dataset
   manydepth/trainer.py, manydepth/evaluation.py (compute_depth_losses_from_list)  polcue.compat.trainer
 
@@ -93,7 +93,7 @@ def install(verbose=False, patch_loader=False):
     """
     import sys
 
-    from . import layers, normals_vec, physical_normals_channels, pol_split_and_save, pre_encoders, trainer, xolp, xolp_and_normals
+    from . import layers, normals_vec, physical_normals_channels, pol_split_and_save, trainer, xolp, xolp_and_normals
 
     done = []
 
@@ -107,7 +107,7 @@ def install(verbose=False, patch_loader=False):
     for name in ("rho_diffuse", "rho_spec", "calc_normals"):
         patch("manydepth.normals_vec", name, getattr(normals_vec, name))
         patch("manydepth.networks.pre_encoders", name, getattr(normals_vec, name))
-    patch("manydepth.networks.pre_encoders", "get_normals", staticmethod(pre_encoders.get_normals), owner="ShallowNormalsEncoder")
+    patch("manydepth.networks.pre_encoders", "get_normals", staticmethod(normals_vec.get_normals), owner="ShallowNormalsEncoder")
     for mod_name in ("manydepth.layers", "manydepth.trainer", "manydepth.evaluation"):
         patch(mod_name, "compute_depth_errors", layers.compute_depth_errors)
         patch(mod_name, "compute_depth_errors_numpy", layers.compute_depth_errors_numpy)

@@ -1,5 +1,15 @@
-"""Mirror of the hot-path member of manydepth/trainer.py: Trainer.compute_supervised_normals_losses (:1298-1309)."""
+"""Mirror of the hot-path members of manydepth/trainer.py: `depth_to_normals` as imported at :37 (kornia.geometry.depth),
+Trainer.compute_supervised_normals_losses (:1298-1309), the supervised block of compute_losses (:1240-1251) and
+compute_depth_losses_from_list (:1356-1435, also evaluation.py:215-288)."""
 from .. import ops
+
+
+def depth_to_normals(depth, camera_matrix, normalize_points=False):
+    """kornia.geometry.depth.depth_to_normals (kornia 0.5.11), forward only: the GT branch (:1305, :1477).  The predicted
+    branch of the loss has its own backward inside compute_supervised_normals_losses; a tensor that requires grad raises."""
+    if normalize_points:
+        raise NotImplementedError("normalize_points=True is never used by the reference (trainer.py:1305-1306)")
+    return ops.depth_to_normals(depth, camera_matrix)
 
 
 def compute_supervised_normals_losses(depth_gt, depth_pred, intrinsics, mask):

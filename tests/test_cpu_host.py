@@ -254,7 +254,7 @@ def test_install_patches_the_imported_reference_modules():
             "import polcue.compat as c, polcue.compat.normals_vec as cnv, polcue.compat.layers as cly\n"
             "done = c.install()\n"
             "assert nv.rho_diffuse is cnv.rho_diffuse and pe.rho_spec is cnv.rho_spec and ly.compute_depth_errors is cly.compute_depth_errors\n"
-            "assert pe.ShallowNormalsEncoder.get_normals.__module__ == 'polcue.compat.pre_encoders'\n"
+            "assert pe.ShallowNormalsEncoder.get_normals.__module__ == 'polcue.compat.normals_vec'\n"
             "assert px.Iun_and_xolp.__module__ == 'polcue.compat.xolp'\n"
             "print('PATCHED', len(done))\n") % os.path.join(ROOT, "supervised-depth-estimation-from-polarized-images_b200")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)

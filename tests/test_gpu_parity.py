@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 
 from polcue import ops, synth  # noqa: E402
 from polcue import _lib  # noqa: E402
-from polcue.compat import (depth as c_depth, layers as c_layers, normals_vec as c_nv,  # noqa: E402
-                           physical_normals_channels as c_ppp, pol_split_and_save as c_split, pre_encoders as c_pre,
+from polcue.compat import (trainer as c_depth, layers as c_layers, normals_vec as c_nv,  # noqa: E402
+                           physical_normals_channels as c_ppp, pol_split_and_save as c_split,
                            xolp as c_xolp, xolp_and_normals as c_xn)
 
 
@@ -338,7 +338,7 @@ def test_table_inversions_vs_golden(golden, n):
 def test_get_normals_vs_golden(golden):
     for tag in ("u", "p"):
         x = dev(golden[f"getn_{tag}_x32"])
-        got = c_pre.get_normals(x, 1.5)
+        got = c_nv.get_normals(x, 1.5)
         assert got.shape == (1, 9, 64, 96) and got.dtype == torch.float32
         ref = golden[f"getn_{tag}_n"]
         P.assert_normals_close(got.cpu().numpy().reshape(3, 3, 64, 96), ref.reshape(3, 3, 64, 96), axis=1)
