@@ -351,6 +351,40 @@ POLCUE_API int polcue_eval_pass_f32(const float* gt, const float* pred, const ui
                          float min_d, float max_d, const int* group_ids, int n_groups, float* normals, double* sums,
                          float* metrics, double* mean_acc, polcue_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The one collective of the path, over NVLink peer memory.  The reference evaluates on one device and has no
+ * collective; a sharded evaluation ends in a sum over ranks of {n_images, per-group sums of the per-image metrics}
+ * (manydepth/trainer.py:1426-1428: np.array(errors).mean(0)) -- at most 1 + 16 x 7 doubles.  One process per GPU, all on
+ * ONE node: every rank owns a small exchange block in its HBM, shared with the other ranks through CUDA IPC; an exchange
+ * is one CTA per rank that stores its values into every rank's block through NVLink and adds what arrived in RANK ORDER
+ * (all ranks get the identical, bitwise reproducible sum).  polcue_eval_pass_peer_f32 does it inside the last kernel of
+ * the evaluation pass, so a sharded pass costs no extra launch and no library round trip.
+ *   polcue_peer_create   allocates this rank's block on the CURRENT device; ipc_handle receives POLCUE_PEER_HANDLE_BYTES
+ *                        bytes to hand to the other ranks (any transport: torch.distributed, MPI, a file).  world == 1
+ *                        needs no handle and no connect.
+ *   polcue_peer_connect  ipc_handles = the world handles in rank order; maps the other ranks' blocks.  All ranks must have
+ *                        connected before the first exchange and must make the same sequence of exchanges; the calls of
+ *                        one rank must be stream-ordered.  Capturable in a CUDA graph (the call counter lives on the device).
+ *   polcue_peer_status   synchronising read of the number of exchanges made and of the first one whose wait for a peer
+ *                        timed out (~4 s; its results are NaN), 0 = none.
+ *   polcue_peer_destroy  after a barrier of the caller's: no peer may still be exchanging.
+ * ------------------------------------------------------------------------------------------- */
+#define POLCUE_PEER_HANDLE_BYTES 64
+#define POLCUE_PEER_MAX_RANKS 16
+#define POLCUE_PEER_MAX_VALUES 128
+typedef struct polcue_peer polcue_peer;
+POLCUE_API int polcue_peer_create(int world, int rank, polcue_peer** out, void* ipc_handle);
+POLCUE_API int polcue_peer_connect(polcue_peer* peer, const void* ipc_handles);
+POLCUE_API int polcue_peer_allreduce_f64(polcue_peer* peer, const double* in, int n, double* out, polcue_stream_t stream);
+POLCUE_API int polcue_peer_status(polcue_peer* peer, unsigned long long* calls, unsigned long long* failed_call);
+POLCUE_API int polcue_peer_destroy(polcue_peer* peer);
+/* polcue_eval_pass_f32 whose last kernel also exchanges the accumulators: mean_acc receives this rank's own
+ * {B, sums} as before, mean_acc_all (1 + n_groups * 7 device doubles) the sum over all ranks.  Three launches. */
+POLCUE_API int polcue_eval_pass_peer_f32(const float* gt, const float* pred, const uint8_t* inst, const float* K, int B, int H, int W,
+                              float min_d, float max_d, const int* group_ids, int n_groups, float* normals, double* sums,
+                              float* metrics, double* mean_acc, polcue_peer* peer, double* mean_acc_all,
+                              polcue_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

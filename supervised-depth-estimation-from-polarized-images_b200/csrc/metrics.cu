@@ -19,6 +19,7 @@
 #include <mutex>
 
 #include "polcue_device.cuh"
+#include "peer.cuh"
 #include "polcue_host.h"
 
 namespace cg = cooperative_groups;
@@ -688,6 +689,30 @@ __global__ void __launch_bounds__(128) image_mean_acc_kernel(const float* __rest
     if (lane == 0) acc[1 + v] = t;
 }
 
+// image_mean_acc_kernel and the sum over ranks in ONE CTA (peer.cuh): warp w adds the images of values w, w + 32, ..., the
+// accumulators go to shared memory, thread k publishes the k-th one to every rank and adds what the ranks sent, in rank order.
+static_assert(1 + 16 * 7 <= kPeerMaxValues, "accumulators of the largest group list fit one exchange");
+__global__ void __launch_bounds__(1024) image_mean_acc_peer_kernel(const __grid_constant__ PeerParams pp, const float* __restrict__ metrics,
+                                                                   int B, int n_values, double* __restrict__ acc,
+                                                                   double* __restrict__ acc_all) {
+    __shared__ double local[kPeerMaxValues];
+    const int lane = threadIdx.x & 31;
+    for (int v = threadIdx.x >> 5; v < n_values; v += blockDim.x >> 5) {
+        double t = 0.0;
+        for (int b = lane; b < B; b += 32) t += (double)__ldg(metrics + (size_t)b * n_values + v);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+        if (lane == 0) local[1 + v] = t;
+    }
+    if (threadIdx.x == 0) local[0] = (double)B;
+    __syncthreads();
+    const int n = 1 + n_values, k = threadIdx.x;
+    const double mine = k < n ? local[k] : 0.0;
+    if (k < n) acc[k] = mine;
+    const double total = peer_allreduce_cta(pp, mine, n);
+    if (k < n) acc_all[k] = total;
+}
+
 }  // namespace
 }  // namespace polcue
 
@@ -847,11 +872,13 @@ cudaError_t eval_lanes(int dev, EvalLanes*& out) {
 }
 }  // namespace
 
-int polcue_eval_pass_f32(const float* gt, const float* pred, const uint8_t* inst, const float* K, int B, int H, int W, float min_d,
-                         float max_d, const int* group_ids, int n_groups, float* normals, double* sums, float* metrics,
-                         double* mean_acc, polcue_stream_t stream) {
+static int eval_pass(const float* gt, const float* pred, const uint8_t* inst, const float* K, int B, int H, int W, float min_d,
+                     float max_d, const int* group_ids, int n_groups, float* normals, double* sums, float* metrics,
+                     double* mean_acc, polcue_peer* peer, double* mean_acc_all, polcue_stream_t stream) {
     if (!metrics || !mean_acc || H <= 0 || W <= 0 || B <= 0) return POLCUE_EINVAL;
     if (reinterpret_cast<uintptr_t>(mean_acc) & 7) return POLCUE_EINVAL;
+    PeerParams pp;
+    if (peer && (!peer_params(peer, pp) || !mean_acc_all || (reinterpret_cast<uintptr_t>(mean_acc_all) & 7))) return POLCUE_EINVAL;
     if (normals && !K) return POLCUE_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = POLCUE_OK;
@@ -877,7 +904,8 @@ int polcue_eval_pass_f32(const float* gt, const float* pred, const uint8_t* inst
     if (rc == POLCUE_OK) rc2 = polcue_depth_errors_groups_f32(gt, pred, inst, B, (size_t)H * W, min_d, max_d, group_ids, n_groups, sums, metrics, s);
     if (rc == POLCUE_OK && rc2 == POLCUE_OK) {
         const int n_values = n_groups * 7;
-        image_mean_acc_kernel<<<(n_values + 3) / 4, 128, 0, s>>>(metrics, B, n_values, mean_acc);
+        if (peer) image_mean_acc_peer_kernel<<<1, 1024, 0, s>>>(pp, metrics, B, n_values, mean_acc, mean_acc_all);
+        else image_mean_acc_kernel<<<(n_values + 3) / 4, 128, 0, s>>>(metrics, B, n_values, mean_acc);
         rc2 = launch_status();
     }
     if (normals) {
@@ -885,6 +913,19 @@ int polcue_eval_pass_f32(const float* gt, const float* pred, const uint8_t* inst
         if (e != cudaSuccess && rc == POLCUE_OK && rc2 == POLCUE_OK) return (int)e;
     }
     return rc != POLCUE_OK ? rc : rc2;
+}
+
+int polcue_eval_pass_f32(const float* gt, const float* pred, const uint8_t* inst, const float* K, int B, int H, int W, float min_d,
+                         float max_d, const int* group_ids, int n_groups, float* normals, double* sums, float* metrics,
+                         double* mean_acc, polcue_stream_t stream) {
+    return eval_pass(gt, pred, inst, K, B, H, W, min_d, max_d, group_ids, n_groups, normals, sums, metrics, mean_acc, nullptr, nullptr, stream);
+}
+
+int polcue_eval_pass_peer_f32(const float* gt, const float* pred, const uint8_t* inst, const float* K, int B, int H, int W, float min_d,
+                              float max_d, const int* group_ids, int n_groups, float* normals, double* sums, float* metrics,
+                              double* mean_acc, polcue_peer* peer, double* mean_acc_all, polcue_stream_t stream) {
+    if (!peer) return POLCUE_EINVAL;
+    return eval_pass(gt, pred, inst, K, B, H, W, min_d, max_d, group_ids, n_groups, normals, sums, metrics, mean_acc, peer, mean_acc_all, stream);
 }
 
 }  // extern "C"

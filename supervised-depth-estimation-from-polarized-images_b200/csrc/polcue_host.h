@@ -27,9 +27,18 @@ struct polcue_lut {
     size_t bytes() const { return blob.size() * sizeof(float4); }
 };
 
+struct polcue_peer {
+    int world = 1, rank = 0, device = -1;
+    bool connected = false;
+    void* block[POLCUE_PEER_MAX_RANKS] = {};   // block[r]: rank r's PeerBlock (peer.cuh) as mapped here; block[rank] is this rank's own
+};
+
 namespace polcue {
 
 extern std::atomic<unsigned long long> g_launches;
+
+struct PeerParams;                                            // peer.cuh
+bool peer_params(const polcue_peer* peer, PeerParams& pp);    // peer.cu: false unless the peer is connected
 
 inline int launch_status() {
     g_launches.fetch_add(1, std::memory_order_relaxed);

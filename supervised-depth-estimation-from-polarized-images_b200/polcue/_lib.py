@@ -88,6 +88,13 @@ _SIGNATURES = {
                                                   C.c_int, _f64p, _f32p, _vp]),
     "polcue_eval_pass_f32": (C.c_int, [_f32p, _f32p, _u8p, _f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_int),
                                       C.c_int, _f32p, _f64p, _f32p, _f64p, _vp]),
+    "polcue_eval_pass_peer_f32": (C.c_int, [_f32p, _f32p, _u8p, _f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_int),
+                                           C.c_int, _f32p, _f64p, _f32p, _f64p, _vp, _f64p, _vp]),
+    "polcue_peer_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_vp), _vp]),
+    "polcue_peer_connect": (C.c_int, [_vp, _vp]),
+    "polcue_peer_allreduce_f64": (C.c_int, [_vp, _f64p, C.c_int, _f64p, _vp]),
+    "polcue_peer_status": (C.c_int, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
+    "polcue_peer_destroy": (C.c_int, [_vp]),
     "polcue_channel_stats_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_size_t]),
     "polcue_channel_stats_f32": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_size_t, _vp, _f64p, _vp]),
 }

@@ -706,13 +706,15 @@ def depth_errors_groups(gt, pred, inst, min_depth, max_depth, group_ids):
     return sums, metrics
 
 
-def eval_pass(gt, pred, inst, camera_matrix, min_depth, max_depth, group_ids, want_normals=True, out=None):
+def eval_pass(gt, pred, inst, camera_matrix, min_depth, max_depth, group_ids, want_normals=True, out=None, peer=None):
     """One evaluation pass over this rank's images with no host work between the launches (BASELINE configs[4]): the GT
     depth->normals stencil, every mask group's per-image metrics, and `mean_acc` = {n_images, sum over images of the
     per-image metrics} (float64 [1 + G * 7]) -- all-reduce it and divide for the reference's mean over images
     (trainer.py:1426).  gt / pred: B x H x W float32, inst: uint8, camera_matrix: B x 3 x 3.
     `out` may hold the tensors of a previous call (a fixed set of buffers makes the pass CUDA-graph capturable).
-    Returns dict(normals [B,3,H,W] or None, sums [B,G,8], metrics [B,G,7], mean_acc [1 + 7 G])."""
+    `peer` (a `polcue.dist.PeerExchange`): the last kernel also sums `mean_acc` over all ranks through NVLink peer memory
+    into `mean_acc_all` -- the collective of a sharded evaluation costs no extra launch; every rank must make the call.
+    Returns dict(normals [B,3,H,W] or None, sums [B,G,8], metrics [B,G,7], mean_acc [1 + 7 G] (, mean_acc_all [1 + 7 G]))."""
     gt = _need_cuda(gt, "gt", torch.float32)
     pred = _need_cuda(pred, "pred", torch.float32)
     if gt.dim() != 3 or pred.shape != gt.shape:
@@ -747,9 +749,15 @@ def eval_pass(gt, pred, inst, camera_matrix, min_depth, max_depth, group_ids, wa
     acc = buf("mean_acc", (1 + 7 * g,), torch.float64)
     arr = (C.c_int * g)(*ids)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().polcue_eval_pass_f32(_ptr(gt), _ptr(pred), _ptr(inst), _ptr(k), b, h, w, float(min_depth), float(max_depth),
-                                                   arr, g, _ptr(normals), _ptr(sums), _ptr(metrics), _ptr(acc), _stream(gt)),
-                   "polcue_eval_pass_f32")
+        if peer is not None:
+            acc_all = buf("mean_acc_all", (1 + 7 * g,), torch.float64)
+            _lib.check(_lib.lib().polcue_eval_pass_peer_f32(_ptr(gt), _ptr(pred), _ptr(inst), _ptr(k), b, h, w, float(min_depth),
+                                                            float(max_depth), arr, g, _ptr(normals), _ptr(sums), _ptr(metrics), _ptr(acc),
+                                                            peer.handle, _ptr(acc_all), _stream(gt)), "polcue_eval_pass_peer_f32")
+        else:
+            _lib.check(_lib.lib().polcue_eval_pass_f32(_ptr(gt), _ptr(pred), _ptr(inst), _ptr(k), b, h, w, float(min_depth),
+                                                       float(max_depth), arr, g, _ptr(normals), _ptr(sums), _ptr(metrics), _ptr(acc),
+                                                       _stream(gt)), "polcue_eval_pass_f32")
     if not want_normals:
         out["normals"] = None
     return out

@@ -163,26 +163,45 @@ def cfg4_loader(rank, world, dev, reps=200, with_encoders=True):
 def cfg5_eval(rank, world, dev, images=120, reps=200, check=False, graph=True):
     """BASELINE configs[4]: per rank its contiguous shard of `images` 320x480 images -> GT depth->normals stencil +
     per-image masked compute_depth_errors for the range mask and every material level (11 groups, one launch) ->
-    accumulators of the mean over images; one all-reduce of 1 + 11 x 7 float64.  `polcue_eval_pass_f32`: three launches,
-    no host work in between; timed eagerly and replayed from a CUDA graph (the 120-image pass is launch-latency sized)."""
+    accumulators of the mean over images; one sum over ranks of 1 + 11 x 7 float64.  `polcue_eval_pass_peer_f32`: three
+    launches, the last of which also exchanges the accumulators over NVLink peer memory; no host work in between; timed
+    eagerly, replayed from a CUDA graph (the 120-image pass is launch-latency sized), and with NCCL's all-reduce instead."""
     lo, hi = D.shard_range(images, rank, world)
     n_local = hi - lo
     groups = [None] + list(synth.MATERIAL_LEVELS)
+    n_acc = 1 + 7 * len(groups)
     if n_local > 0:
         gt, pred, inst, k = (torch.from_numpy(a).to(dev) for a in synth.gen_depth_batch(lo, n_local))
     bufs = {}
+    peer, peer_note = None, None
+    if world > 1:
+        try:
+            peer = D.PeerExchange(dev)                         # NVLink peer-memory exchange (one node); raises on every rank or on none
+        except RuntimeError as e:
+            peer_note = str(e)
+    zeros, zeros_out = torch.zeros(n_acc, dtype=torch.float64, device=dev), torch.zeros(n_acc, dtype=torch.float64, device=dev)
 
     def local_pass():
         nonlocal bufs
         if n_local > 0:
             bufs = ops.eval_pass(gt, pred, inst, k, 0.1, 2.0, groups, out=bufs)
             return bufs["mean_acc"]
-        return torch.zeros(1 + 7 * len(groups), dtype=torch.float64, device=dev)
+        return zeros
+
+    def evaluate_nccl():
+        acc = local_pass().clone()
+        D.all_reduce_sums(acc)                                # library all-reduce of 78 float64: a launch + a protocol round trip
+        return acc
 
     def evaluate():
-        acc = local_pass().clone()
-        D.all_reduce_sums(acc)                                # the one collective: 78 float64
-        return acc
+        """The product path: the sum over ranks happens inside the pass's last kernel (polcue_eval_pass_peer_f32)."""
+        nonlocal bufs
+        if peer is None:
+            return evaluate_nccl() if world > 1 else local_pass()
+        if n_local > 0:
+            bufs = ops.eval_pass(gt, pred, inst, k, 0.1, 2.0, groups, out=bufs, peer=peer)
+            return bufs["mean_acc_all"]
+        return peer.all_reduce(zeros, out=zeros_out)          # a rank without images still takes part
 
     def timed(fn, n):
         for _ in range(5):
@@ -197,23 +216,29 @@ def cfg5_eval(rank, world, dev, images=120, reps=200, check=False, graph=True):
         torch.cuda.synchronize()
         return D.max_over_ranks(a.elapsed_time(e) / n, dev)
 
-    acc = evaluate()
+    acc = evaluate().clone()
+    acc_nccl = evaluate_nccl()
+    torch.cuda.synchronize()
+    assert torch.allclose(acc, acc_nccl, rtol=1e-13, atol=0, equal_nan=True), (acc, acc_nccl)   # same sum, rank order vs NCCL's order
     means = (acc[1:] / acc[0]).reshape(len(groups), 7)
     ms_eager = timed(evaluate, reps)
+    ms_nccl = timed(evaluate_nccl, reps) if world > 1 else None
     ms_local = timed(local_pass, reps)
     ms_graph = None
-    if graph and n_local > 0:
+    if graph and (world == 1 or peer is not None):
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            local_pass()
-            torch.cuda.synchronize()
             with torch.cuda.graph(g, stream=side):
-                local_pass()
+                evaluate()                                     # the exchange is captured with the pass
         torch.cuda.current_stream(dev).wait_stream(side)
         ms_graph = timed(g.replay, reps)
-        assert torch.equal(bufs["mean_acc"], local_pass())     # the replay wrote the same accumulators
+        torch.cuda.synchronize()
+        assert torch.equal(evaluate().clone(), acc)            # replays and eager calls give the same (rank-ordered) sums
+    if peer is not None:
+        made, failed = peer.status()
+        assert failed == 0, f"peer exchange {failed} timed out"
     px = n_local * synth.TRAIN_H * synth.TRAIN_W
     bytes_alg = px * (16 + 9)                                  # stencil 4 R + 12 W, metrics 4 + 4 + 1 R (gt is read by both kernels)
     chk = (bufs["normals"].double().sum().reshape(1) if n_local > 0 else torch.zeros(1, dtype=torch.float64, device=dev))
@@ -221,8 +246,11 @@ def cfg5_eval(rank, world, dev, images=120, reps=200, check=False, graph=True):
     res = {"workload": f"cfg5: evaluation path, {images} synthetic 320x480 images over {world} GPU(s): GT depth->normals + per-image "
                        "masked depth errors for 11 mask groups + mean over images (polcue_eval_pass_f32, 3 launches) + 1 all-reduce",
            "images": images, "n_gpus": world, "scaling": "strong", "ms_per_pass": ms_eager, "value": images / (ms_eager * 1e-3),
-           "unit": "images/s", "ms_local_launches_only": ms_local, "ms_local_cuda_graph_replay": ms_graph,
-           "roofline_frac_of_local_pass": bytes_alg / ((ms_graph or ms_local) * 1e-3) / 1e9 / hbm_peak(),
+           "unit": "images/s", "collective": ("sum of %d float64 over NVLink peer memory inside the pass's last kernel (polcue_eval_pass_peer_f32), "
+                                              "rank-ordered; checked against the NCCL all-reduce" % n_acc) if peer is not None else
+                                             ("NCCL all-reduce (peer memory unavailable: %s)" % peer_note if world > 1 else "none (one rank)"),
+           "ms_per_pass_cuda_graph_replay": ms_graph, "ms_per_pass_with_nccl_all_reduce": ms_nccl, "ms_local_launches_only": ms_local,
+           "roofline_frac_of_pass": bytes_alg / ((ms_graph or ms_eager) * 1e-3) / 1e9 / hbm_peak(),
            "abs_rel_all": float(means[0, 0]), "a1_all": float(means[0, 4]), "normals_checksum": float(chk[0])}
     if check and rank == 0:
         from oracle import polcue_oracle as O                  # the checker (test infrastructure), never timed
@@ -238,4 +266,6 @@ def cfg5_eval(rank, world, dev, images=120, reps=200, check=False, graph=True):
         res["parity"] = (f"sharded mean over images == unsharded oracle for {len(groups)} mask groups, worst relative difference "
                          f"{worst:.1e} ({time.perf_counter() - t0:.1f} s on the CPU)")
         res["parity_ok"] = True
+    if peer is not None:
+        peer.close()
     return res
