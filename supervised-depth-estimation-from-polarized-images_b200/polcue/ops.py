@@ -706,7 +706,7 @@ def depth_errors_groups(gt, pred, inst, min_depth, max_depth, group_ids):
     return sums, metrics
 
 
-def eval_pass(gt, pred, inst, camera_matrix, min_depth, max_depth, group_ids, want_normals=True, out=None, peer=None):
+def eval_pass(gt, pred, inst, camera_matrix, min_depth, max_depth, group_ids, want_normals=True, out=None, peer=None, _prepare_only=False):
     """One evaluation pass over this rank's images with no host work between the launches (BASELINE configs[4]): the GT
     depth->normals stencil, every mask group's per-image metrics, and `mean_acc` = {n_images, sum over images of the
     per-image metrics} (float64 [1 + G * 7]) -- all-reduce it and divide for the reference's mean over images
@@ -748,19 +748,42 @@ def eval_pass(gt, pred, inst, camera_matrix, min_depth, max_depth, group_ids, wa
     metrics = buf("metrics", (b, g, 7), torch.float32)
     acc = buf("mean_acc", (1 + 7 * g,), torch.float64)
     arr = (C.c_int * g)(*ids)
-    with torch.cuda.device(dev):
-        if peer is not None:
-            acc_all = buf("mean_acc_all", (1 + 7 * g,), torch.float64)
-            _lib.check(_lib.lib().polcue_eval_pass_peer_f32(_ptr(gt), _ptr(pred), _ptr(inst), _ptr(k), b, h, w, float(min_depth),
-                                                            float(max_depth), arr, g, _ptr(normals), _ptr(sums), _ptr(metrics), _ptr(acc),
-                                                            peer.handle, _ptr(acc_all), _stream(gt)), "polcue_eval_pass_peer_f32")
-        else:
-            _lib.check(_lib.lib().polcue_eval_pass_f32(_ptr(gt), _ptr(pred), _ptr(inst), _ptr(k), b, h, w, float(min_depth),
-                                                       float(max_depth), arr, g, _ptr(normals), _ptr(sums), _ptr(metrics), _ptr(acc),
-                                                       _stream(gt)), "polcue_eval_pass_f32")
+    head = (_ptr(gt), _ptr(pred), _ptr(inst), _ptr(k), b, h, w, float(min_depth), float(max_depth), arr, g, _ptr(normals), _ptr(sums),
+            _ptr(metrics), _ptr(acc))
+    if peer is not None:
+        acc_all = buf("mean_acc_all", (1 + 7 * g,), torch.float64)
+        fn, name, args = _lib.lib().polcue_eval_pass_peer_f32, "polcue_eval_pass_peer_f32", head + (peer.handle, _ptr(acc_all))
+    else:
+        fn, name, args = _lib.lib().polcue_eval_pass_f32, "polcue_eval_pass_f32", head
     if not want_normals:
         out["normals"] = None
+    if _prepare_only:
+        return out, fn, name, args, (gt, pred, inst, k)
+    with torch.cuda.device(dev):
+        _lib.check(fn(*args, _stream(gt)), name)
     return out
+
+
+class EvalPass:
+    """`eval_pass` with its arguments validated, its buffers allocated and its C call bound ONCE: `run()` only enqueues the
+    three launches (a few microseconds of host time instead of ~40 for the checks, buffer look-ups and context managers of
+    `eval_pass`) -- the 120-image evaluation pass of the reference is launch-latency sized, and a shard of it even more so.
+    The inputs are captured by reference: refill `gt` / `pred` / `inst` / `camera_matrix` in place between runs.
+    `run()` must be called with the inputs' device current (`torch.cuda.set_device`); results are in `.out` (see `eval_pass`)."""
+
+    def __init__(self, gt, pred, inst, camera_matrix, min_depth, max_depth, group_ids, want_normals=True, peer=None):
+        self.out, self._fn, self._name, self._args, self._inputs = eval_pass(gt, pred, inst, camera_matrix, min_depth, max_depth, group_ids,
+                                                                             want_normals=want_normals, peer=peer, _prepare_only=True)
+        self.device = gt.device
+        self._peer = peer                                  # keeps the exchange block alive as long as the bound call
+
+    def run(self):
+        if torch.cuda.current_device() != self.device.index:
+            raise RuntimeError(f"EvalPass.run: make {self.device} the current device first")
+        rc = self._fn(*self._args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            _lib.check(rc, self._name)
+        return self.out
 
 
 def metrics_from_sums(sums):

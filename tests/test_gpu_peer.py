@@ -33,7 +33,17 @@ def test_single_rank_exchange_is_the_identity_counts_its_calls_and_rejects_bad_a
     for key in ("normals", "sums", "metrics", "mean_acc"):
         assert torch.equal(plain[key], fused[key]), key
     assert torch.equal(fused["mean_acc_all"], plain["mean_acc"])
-    assert peer.status() == (3, 0)
+    # the prepared launcher binds arguments and buffers once; inputs are captured by reference
+    prepared = ops.EvalPass(gt, pred, inst, k, 0.1, 2.0, groups, peer=peer)
+    got = prepared.run()
+    for key in ("normals", "sums", "metrics", "mean_acc"):
+        assert torch.equal(plain[key], got[key]), key
+    assert torch.equal(got["mean_acc_all"], plain["mean_acc"])
+    pred.mul_(1.01)
+    again = ops.eval_pass(gt, pred, inst, k, 0.1, 2.0, groups)
+    got = prepared.run()
+    assert torch.equal(got["mean_acc_all"], again["mean_acc"]) and not torch.equal(again["mean_acc"], plain["mean_acc"])
+    assert peer.status() == (5, 0)
     peer.close()
     peer.close()                                   # idempotent
 

@@ -181,12 +181,13 @@ def cfg5_eval(rank, world, dev, images=120, reps=200, check=False, graph=True):
             peer_note = str(e)
     zeros, zeros_out = torch.zeros(n_acc, dtype=torch.float64, device=dev), torch.zeros(n_acc, dtype=torch.float64, device=dev)
 
+    # prepared launchers (ops.EvalPass): arguments checked and buffers bound once, a run only enqueues the three launches
+    plain = ops.EvalPass(gt, pred, inst, k, 0.1, 2.0, groups) if n_local > 0 else None
+    fused = ops.EvalPass(gt, pred, inst, k, 0.1, 2.0, groups, peer=peer) if (n_local > 0 and peer is not None) else None
+    bufs = (fused or plain).out if n_local > 0 else {}
+
     def local_pass():
-        nonlocal bufs
-        if n_local > 0:
-            bufs = ops.eval_pass(gt, pred, inst, k, 0.1, 2.0, groups, out=bufs)
-            return bufs["mean_acc"]
-        return zeros
+        return plain.run()["mean_acc"] if plain is not None else zeros
 
     def evaluate_nccl():
         acc = local_pass().clone()
@@ -195,13 +196,19 @@ def cfg5_eval(rank, world, dev, images=120, reps=200, check=False, graph=True):
 
     def evaluate():
         """The product path: the sum over ranks happens inside the pass's last kernel (polcue_eval_pass_peer_f32)."""
-        nonlocal bufs
         if peer is None:
             return evaluate_nccl() if world > 1 else local_pass()
-        if n_local > 0:
-            bufs = ops.eval_pass(gt, pred, inst, k, 0.1, 2.0, groups, out=bufs, peer=peer)
-            return bufs["mean_acc_all"]
+        if fused is not None:
+            return fused.run()["mean_acc_all"]
         return peer.all_reduce(zeros, out=zeros_out)          # a rank without images still takes part
+
+    def evaluate_unprepared():
+        """the same through ops.eval_pass (argument checks and buffer look-ups on every call)"""
+        nonlocal bufs
+        if n_local > 0 and (peer is not None or world == 1):
+            bufs = ops.eval_pass(gt, pred, inst, k, 0.1, 2.0, groups, out=bufs, peer=peer)
+            return bufs["mean_acc_all" if peer is not None else "mean_acc"]
+        return evaluate()
 
     def timed(fn, n):
         for _ in range(5):
@@ -222,20 +229,27 @@ def cfg5_eval(rank, world, dev, images=120, reps=200, check=False, graph=True):
     assert torch.allclose(acc, acc_nccl, rtol=1e-13, atol=0, equal_nan=True), (acc, acc_nccl)   # same sum, rank order vs NCCL's order
     means = (acc[1:] / acc[0]).reshape(len(groups), 7)
     ms_eager = timed(evaluate, reps)
+    ms_unprepared = timed(evaluate_unprepared, reps)
     ms_nccl = timed(evaluate_nccl, reps) if world > 1 else None
     ms_local = timed(local_pass, reps)
-    ms_graph = None
-    if graph and (world == 1 or peer is not None):
+    def replayed(fn):
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             with torch.cuda.graph(g, stream=side):
-                evaluate()                                     # the exchange is captured with the pass
+                fn()
         torch.cuda.current_stream(dev).wait_stream(side)
-        ms_graph = timed(g.replay, reps)
+        return timed(g.replay, reps)
+
+    ms_graph = ms_graph_local = us_exchange = None
+    if graph and (world == 1 or peer is not None):
+        ms_graph = replayed(evaluate)                          # the exchange is captured with the pass
         torch.cuda.synchronize()
         assert torch.equal(evaluate().clone(), acc)            # replays and eager calls give the same (rank-ordered) sums
+        if peer is not None:
+            ms_graph_local = replayed(local_pass)
+            us_exchange = 1e3 * replayed(lambda: peer.all_reduce(zeros, out=zeros_out))   # the exchange alone: launch + one NVLink trip
     if peer is not None:
         made, failed = peer.status()
         assert failed == 0, f"peer exchange {failed} timed out"
@@ -249,7 +263,8 @@ def cfg5_eval(rank, world, dev, images=120, reps=200, check=False, graph=True):
            "unit": "images/s", "collective": ("sum of %d float64 over NVLink peer memory inside the pass's last kernel (polcue_eval_pass_peer_f32), "
                                               "rank-ordered; checked against the NCCL all-reduce" % n_acc) if peer is not None else
                                              ("NCCL all-reduce (peer memory unavailable: %s)" % peer_note if world > 1 else "none (one rank)"),
-           "ms_per_pass_cuda_graph_replay": ms_graph, "ms_per_pass_with_nccl_all_reduce": ms_nccl, "ms_local_launches_only": ms_local,
+           "ms_per_pass_cuda_graph_replay": ms_graph, "ms_per_pass_through_ops_eval_pass": ms_unprepared, "ms_per_pass_with_nccl_all_reduce": ms_nccl, "ms_local_launches_only": ms_local,
+           "ms_local_cuda_graph_replay": ms_graph_local, "us_peer_exchange_alone_graph_replay": us_exchange,
            "roofline_frac_of_pass": bytes_alg / ((ms_graph or ms_eager) * 1e-3) / 1e9 / hbm_peak(),
            "abs_rel_all": float(means[0, 0]), "a1_all": float(means[0, 4]), "normals_checksum": float(chk[0])}
     if check and rank == 0:
