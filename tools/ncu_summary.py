@@ -21,6 +21,7 @@ METRICS = [
     ("sm__inst_issued.avg.pct_of_peak_sustained_active", "issue %", 1.0),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %", 1.0),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma %", 1.0),
+    ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma pipe cycles % (a packed FFMA2/FADD2/FMUL2 holds the pipe two cycles)", 1.0),
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu %", 1.0),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu %", 1.0),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu %", 1.0),
@@ -59,7 +60,7 @@ def main():
         for key, label, _ in METRICS:
             if key in idx:
                 print(f"| {label} (`{key}`) | {r[idx[key]]} | {units[idx[key]]} |")
-        if k < len(px) and "smsp__inst_executed.sum" in idx:
+        if k < len(px) and px[k] > 0 and "smsp__inst_executed.sum" in idx:
             print(f"| thread-instructions per pixel | {float(r[idx['smsp__inst_executed.sum']].replace(',', '')) * 32 / px[k]:.1f} | at {px[k]:.0f} px |")
         print()
 
