@@ -74,15 +74,29 @@ __device__ __forceinline__ void stage_tile(float (*tile)[kLBoxW], const float* p
 struct Cam {
     float inv_fx, cx, inv_fy, cy;
 };
-__device__ __forceinline__ Cam load_cam(const float* K, int b) {
+// The four intrinsics are REQUESTED at the top of a kernel (cam_fetch) and turned into reciprocals after the tile's barrier
+// (cam_finish): fetched after the barrier, every warp of the CTA sat out an L2 round trip there (7 % of the backward's stall samples).
+struct CamRaw {
+    float fx, cx, fy, cy;
+};
+__device__ __forceinline__ CamRaw cam_fetch(const float* K, int b) {
     const float* k = K + (size_t)b * 9;
+    CamRaw r;
+    r.fx = __ldg(k + 0);
+    r.cx = __ldg(k + 2);
+    r.fy = __ldg(k + 4);
+    r.cy = __ldg(k + 5);
+    return r;
+}
+__device__ __forceinline__ Cam cam_finish(const CamRaw& r) {
     Cam c;
-    c.inv_fx = 1.0f / __ldg(k + 0);
-    c.cx = __ldg(k + 2);
-    c.inv_fy = 1.0f / __ldg(k + 4);
-    c.cy = __ldg(k + 5);
+    c.inv_fx = 1.0f / r.fx;
+    c.cx = r.cx;
+    c.inv_fy = 1.0f / r.fy;
+    c.cy = r.cy;
     return c;
 }
+__device__ __forceinline__ Cam load_cam(const float* K, int b) { return cam_finish(cam_fetch(K, b)); }
 
 // 8 x gradients of xyz at tile-local pixel (ty, tx) (image pixel (y0+ty, x0+tx)), same arithmetic as stencil.cu.
 __device__ __forceinline__ void gradients(const float (*tile)[kLBoxW], int ty, int tx, int x, int y, int H, int W, const Cam& cam,
@@ -191,7 +205,7 @@ __device__ __forceinline__ float normalize3(const float (&n)[3], float (&u)[3]) 
 __device__ __forceinline__ float cosine_from_dots(float ab, float aa, float bb, float& inv_den, bool& clamped) {
     const float den2 = __fmul_rn(aa, bb);
     clamped = den2 <= 1e-16f;
-    inv_den = clamped ? 1e8f : rsqrtf(den2);
+    inv_den = clamped ? 1e8f : rsqrt_approx(den2);   // den2 > 1e-16 here: a normal number, the same MUFU.RSQ result rsqrtf() returns without its denormal fix-up
     return __fmul_rn(ab, inv_den);
 }
 __device__ __forceinline__ float cosine(const float (&a)[3], const float (&b)[3], float& inv_den, float& ab, float& bb,
@@ -216,7 +230,8 @@ __device__ __forceinline__ float cosine_pairs(const f32x2 (&n)[3], const float (
 //   linear, otherwise project out b and divide by |n| (= multiply by inv);   n = gu x gv  =>  gu_bar = gv x n_bar, gv_bar = n_bar x gu.
 __device__ __forceinline__ void adjoint_tail(const float (&a)[3], const float (&bn)[3], float inv, const float (&up)[3], const float (&vp)[3],
                                              float k, float inv_den, float ab, float bb, bool clamped, float (&gub)[3], float (&gvb)[3]) {
-    const float w_b = clamped ? 0.0f : __fdiv_rn(__fmul_rn(ab, inv_den), fmaxf(bb, 1e-30f));
+    // (MUFU reciprocal, 1 ulp: |b|^2 is 1 to rounding unless the normalisation was capped; the IEEE division was 7 % of the backward's instructions)
+    const float w_b = clamped ? 0.0f : __fmul_rn(__fmul_rn(ab, inv_den), rcp_approx(fmaxf(bb, 1e-30f)));
     float g[3], nb[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) g[c] = fmaf(-w_b, bn[c], __fmul_rn(a[c], inv_den));
@@ -517,6 +532,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel
     __shared__ double red[kLossThreads / 32][3];
     const int b = blockIdx.z, x0 = blockIdx.x * kPW, y0 = blockIdx.y * kPH;
     const size_t hw = (size_t)p.H * p.W;
+    const CamRaw cam_raw = cam_fetch(p.K, b);
     // the caller's mask of the tile rides along with the depth tile (requested before the tile's loads are consumed), so
     // no global load is left inside the arithmetic loop
     float4 mreg[kPH / 8];
@@ -534,7 +550,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel
         for (int k = 0; k < kPH / 8; ++k) *reinterpret_cast<float4*>(&M[(threadIdx.x >> 5) + 8 * k][4 * (threadIdx.x & 31)]) = mreg[k];
     }
     __syncthreads();
-    const Cam cam = load_cam(p.K, b);
+    const Cam cam = cam_finish(cam_raw);
     const int tx0 = 4 * (threadIdx.x & 31), x = x0 + tx0;
     f32x2 fx6[6];
 #pragma unroll
@@ -664,12 +680,15 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_pairs_kernel
     const size_t hw = (size_t)p.H * p.W;
     const float* Gt = p.gt + b * hw;
     const float* Pr = p.pred + b * hw;
+    const CamRaw cam_raw = cam_fetch(p.K, b);                      // requested before the tile, used after its barrier
+    const float go = __ldg(p.grad_out), gl1 = (L1 && p.grad_l1) ? __ldg(p.grad_l1) : 0.0f;
+    const double msum = __ldg(p.sums2 + 1);
     // ---- stage rows y0 - 2 .. y0 + kBwdH + 1, columns x0 - 2 .. x0 + 129 (replicate padding by clamping) ----
     stage_pairs<kBwdH, 2, 3, kBPitch>(T, Gt, Pr, p.H, p.W, x0, y0);
     __syncthreads();
-    const Cam cam = load_cam(p.K, b);
-    const float scale = -__ldg(p.grad_out) / (float)p.sums2[1];    // -grad_out / sum(mask)
-    const float l1_scale = (L1 && p.grad_l1) ? __ldg(p.grad_l1) / (float)p.sums2[1] : 0.0f;
+    const Cam cam = cam_finish(cam_raw);
+    const float scale = -go / (float)msum;    // -grad_out / sum(mask)
+    const float l1_scale = (L1 && p.grad_l1) ? gl1 / (float)msum : 0.0f;
 
     // ---- phase 1: adjoints of the two gradients at every pixel of the tile and its 1-pixel ring ----
     {
