@@ -42,11 +42,16 @@ struct StencilParams {
 
 // Normals of rows ty0, ty0 + 8, ... of the tile for the four pixels starting at image column xb.
 // tile[r][kColOff + c] holds depth(y0 - 1 + r, x0 + c) with replicate padding already applied.
-__device__ __forceinline__ void stencil_rows(const StencilParams& p, const float (*tile)[kBoxW], int b, int x0, int y0) {
-    const size_t hw = (size_t)p.H * p.W;
+// kraw: (fx, cx, fy, cy) of image b, requested by the caller BEFORE it waits for the tile (fetched afterwards, every warp
+// of the CTA sat out an L2 round trip between the tile's arrival and its first arithmetic).
+__device__ __forceinline__ float4 fetch_intrinsics(const StencilParams& p, int b) {
     const float* k = p.K + (size_t)b * 9;
-    const float inv_fx = 1.0f / __ldg(k + 0), cx = __ldg(k + 2);
-    const float inv_fy = 1.0f / __ldg(k + 4), cy = __ldg(k + 5);
+    return make_float4(__ldg(k + 0), __ldg(k + 2), __ldg(k + 4), __ldg(k + 5));
+}
+__device__ __forceinline__ void stencil_rows(const StencilParams& p, const float (*tile)[kBoxW], int b, int x0, int y0, const float4 kraw) {
+    const size_t hw = (size_t)p.H * p.W;
+    const float inv_fx = 1.0f / kraw.x, cx = kraw.y;
+    const float inv_fy = 1.0f / kraw.z, cy = kraw.w;
     const int ty0 = threadIdx.x / (kTW / 4), tx = threadIdx.x - ty0 * (kTW / 4);
     const int xb = x0 + 4 * tx;
     if (xb >= p.W) return;
@@ -140,6 +145,7 @@ __global__ void __launch_bounds__(kStencilThreads) depth_to_normals_tma_kernel(c
     __shared__ uint64_t bar;
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const float4 kraw = fetch_intrinsics(p, b);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(kStencilThreads) depth_to_normals_tma_kernel(c
         }
         __syncthreads();
     }
-    stencil_rows(p, tile, b, x0, y0);
+    stencil_rows(p, tile, b, x0, y0, kraw);
 }
 
 // ---- manually staged variant (any width / alignment) ----------------------------------------------
@@ -180,6 +186,7 @@ __global__ void __launch_bounds__(kStencilThreads) depth_to_normals_kernel(const
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
     const float* z = p.depth + (size_t)b * p.H * p.W;
+    const float4 kraw = fetch_intrinsics(p, b);
     for (int i = threadIdx.x; i < kBoxH * (kTW + 2); i += kStencilThreads) {
         const int r = i / (kTW + 2), c = i - r * (kTW + 2);      // c = 0 is image column x0 - 1
         const int yy = min(max(y0 + r - 1, 0), p.H - 1);
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(kStencilThreads) depth_to_normals_kernel(const
         tile[r][kColOff - 1 + c] = __ldg(z + (size_t)yy * p.W + xx);
     }
     __syncthreads();
-    stencil_rows(p, tile, b, x0, y0);
+    stencil_rows(p, tile, b, x0, y0, kraw);
 }
 
 std::atomic<unsigned long long> g_tma_launches{0};
