@@ -295,7 +295,12 @@ POLCUE_API int polcue_depth_errors_f32(const float* gt, const float* pred, size_
 /* Per-image masked evaluation of Trainer.compute_depth_losses_from_list (manydepth/trainer.py:1376-1428):
  * mask = gt > min_d && gt < max_d [&& inst == inst_id], pred clamped to [min_d, max_d].
  * inst: B x px uint8 instance-id map or NULL (then inst_id is ignored).
- * sums: B x 8 doubles; metrics: B x 7 floats or NULL.  One block-group per image, no workspace. */
+ * sums: B x 8 doubles; metrics: B x 7 floats or NULL.  One thread-block cluster per image, no workspace.
+ * The cluster size (1..8 CTAs per image) follows the batch: the largest that still fits one wave on the device, fewer CTAs
+ * per image for batches of several waves.  The pixel counts (sums[0..3]) are exact integers for every size; the float sums
+ * follow the per-thread summation order, so they are bitwise reproducible from run to run for the same batch size, image
+ * size and GPU model, and agree to float32 rounding (~1e-7 relative) between launch geometries.  The same holds for the
+ * *_scaled, *_groups and eval_pass entry points below. */
 POLCUE_API int polcue_depth_errors_images_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px,
                                    float min_d, float max_d, int inst_id, double* sums, float* metrics,
                                    polcue_stream_t stream);

@@ -29,7 +29,7 @@ namespace {
 
 constexpr int kMetricThreads = 256;
 constexpr int kMaxMetricBlocks = 148 * 16;
-constexpr int kCluster = 8;  // CTAs per image in the per-image kernel (portable cluster size)
+constexpr int kMaxCluster = 8;  // most CTAs per image (portable cluster size); every launch picks its size, see pick_cluster
 
 struct Acc {
     float f[4];  // d^2, (log2 hi - log2 lo)^2, |d|/gt, d^2/gt
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kMetricThreads) depth_errors_kernel(const floa
 }
 
 // ------------------------------------------------------------------------------------------
-// per image, masked: one cluster of kCluster CTAs per image, DSMEM reduction into CTA rank 0
+// per image, masked: one cluster of 1..8 CTAs per image (pick_cluster), DSMEM reduction into CTA rank 0
 // ------------------------------------------------------------------------------------------
 struct ImageParams {
     const float* gt;
@@ -244,11 +244,10 @@ __device__ __forceinline__ void acc_masked(Acc& a, const ImageParams& p, int wan
 }
 
 template <bool EXT, bool INST>
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThreads)
-    depth_errors_images_kernel(const ImageParams p) {
+__global__ void __launch_bounds__(kMetricThreads) depth_errors_images_kernel(const ImageParams p) {   // cluster (c, 1, 1): a launch attribute
     __shared__ double warp_rows[kMetricThreads / 32][8];
     cg::cluster_group cluster = cg::this_cluster();
-    const unsigned rank = cluster.block_rank();
+    const unsigned rank = cluster.block_rank(), n_rank = cluster.num_blocks();
     const size_t b = blockIdx.y;
     const int want_id = p.inst ? p.group_ids[0] : -1;
     const float* gt = p.gt + b * p.px;
@@ -259,7 +258,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     Acc a;
     acc_clear(a);
     Acc64 s{};
-    const size_t tid = (size_t)rank * kMetricThreads + threadIdx.x, stride = (size_t)kCluster * kMetricThreads;
+    const size_t tid = (size_t)rank * kMetricThreads + threadIdx.x, stride = (size_t)n_rank * kMetricThreads;
     int since = 0;
     if (p.vec4) {
         // the loads of the next group are issued before the current one is reduced (the top stall of this kernel was the
@@ -307,7 +306,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     cluster.sync();  // every CTA's row 0 is final and visible cluster-wide
     if (rank == 0 && threadIdx.x < 8) {
         double v = 0.0;
-        for (unsigned r = 0; r < kCluster; ++r) {
+        for (unsigned r = 0; r < n_rank; ++r) {
             const double* remote = cluster.map_shared_rank(&warp_rows[0][0], r);
             v += remote[threadIdx.x];
         }
@@ -549,12 +548,11 @@ struct GroupParams {
 };
 
 template <bool ALL>   // ALL: the "all" group (range mask only) is among the requested groups
-__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThreads)
-    depth_errors_groups_kernel(const __grid_constant__ GroupParams p) {
+__global__ void __launch_bounds__(kMetricThreads) depth_errors_groups_kernel(const __grid_constant__ GroupParams p) {   // cluster (c, 1, 1): a launch attribute
     extern __shared__ __align__(16) float table[];          // [n_groups][kGroupRows][kMetricThreads], see run_flush
     __shared__ double cta_tot[16][8];
     cg::cluster_group cluster = cg::this_cluster();
-    const unsigned rank = cluster.block_rank();
+    const unsigned rank = cluster.block_rank(), n_rank = cluster.num_blocks();
     const size_t b = blockIdx.y;
     const float* gt = p.gt + b * p.px;
     const float* pred = p.pred + b * p.px;
@@ -580,7 +578,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
         }
         run_add(mat, c, ALL ? true : slot != 0xFF);
     };
-    const size_t tid = (size_t)rank * kMetricThreads + threadIdx.x, stride = (size_t)kCluster * kMetricThreads;
+    const size_t tid = (size_t)rank * kMetricThreads + threadIdx.x, stride = (size_t)n_rank * kMetricThreads;
     if (p.vec4) {
         // The per-thread table limits this kernel to ~2 CTAs per SM, so memory latency is hidden inside the thread:
         // the loads of the next group are issued before the current one is reduced (1.70 -> 2.25 TB/s; a deeper
@@ -654,7 +652,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kMetricThread
     if (rank == 0 && threadIdx.x < p.n_groups * 8) {
         const int slot = threadIdx.x >> 3, k = threadIdx.x & 7;
         double v = 0.0;
-        for (unsigned r = 0; r < kCluster; ++r) v += cluster.map_shared_rank(&cta_tot[0][0], r)[slot * 8 + k];
+        for (unsigned r = 0; r < n_rank; ++r) v += cluster.map_shared_rank(&cta_tot[0][0], r)[slot * 8 + k];
         if (!ALL || slot != p.all_slot) p.sums[(b * p.n_groups + slot) * 8 + k] = v;
         cta_tot[slot][k] = v;       // rank 0's own copy has been read by this same thread already
     }
@@ -713,6 +711,73 @@ __global__ void __launch_bounds__(1024) image_mean_acc_peer_kernel(const __grid_
     if (k < n) acc_all[k] = total;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// CTAs per image.  Both per-image kernels pay a fixed price per CTA (the table / accumulator fold and two cluster
+// barriers), so the best cluster size depends on how the batch fills the machine (tools/probes/cluster_sweep.py, B200,
+// 320 x 480 images, 11 groups: 8 CTAs per image 69 us at 120 images and 856 us at 1920; 3 CTAs 57 us; 2 CTAs 618 us):
+//   * the batch fits one wave at some size: the LARGEST such size (shortest critical path, no second wave);
+//   * it does not: 4 per image while the images alone still fit one wave (a 1.1-wave launch is the worst case),
+//     2 per image beyond that (many waves: the fixed price per CTA is what is left to save).
+// The per-thread summation order follows the size, so the float sums of an image are reproducible run to run for the
+// same launch geometry (batch size, image size, GPU model) and agree to rounding (1e-7) across geometries; the counts
+// are exact integers in every case.
+// ------------------------------------------------------------------------------------------
+int cta_capacity(const void* kernel, size_t smem) {       // CTAs of this kernel resident on the current device (cached)
+    struct Entry {
+        const void* kernel;
+        size_t smem;
+        int dev, capacity;
+    };
+    static std::mutex mutex;
+    static Entry cache[32];
+    static int used = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    std::lock_guard<std::mutex> lock(mutex);
+    for (int i = 0; i < used; ++i)
+        if (cache[i].kernel == kernel && cache[i].smem == smem && cache[i].dev == dev) return cache[i].capacity;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kMetricThreads, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return device_info().sms;
+    }
+    const int capacity = device_info().sms * per_sm;
+    if (used < 32) cache[used++] = Entry{kernel, smem, dev, capacity};
+    return capacity;
+}
+int pick_cluster(int B, int capacity, bool fine, size_t px) {
+    int c = 2;
+    if ((long long)B * 8 <= capacity) c = 8;
+    else if (fine && (long long)B * 6 <= capacity) c = 6;
+    else if ((long long)B * 4 <= capacity) c = 4;
+    else if (fine && (long long)B * 3 <= capacity) c = 3;
+    else if (B <= capacity) c = 4;
+    while (c < kMaxCluster && px / ((size_t)c * kMetricThreads) + 8 > 65535) c = c < 4 ? c + 1 : (c == 4 ? 6 : 8);   // 16-bit per-thread counts (run_flush)
+    return c;
+}
+template <typename Params>
+int launch_clustered(void (*kernel)(const Params), const Params& p, int cluster, int B, size_t smem, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)cluster, (unsigned)B, 1);
+    cfg.blockDim = dim3(kMetricThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)cluster;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return (int)e;
+    }
+    return launch_status();
+}
+
 }  // namespace
 }  // namespace polcue
 
@@ -763,11 +828,10 @@ static int launch_images(const float* gt, const float* pred, const uint8_t* inst
     p.vec4 = (px % 4 == 0) && (((reinterpret_cast<uintptr_t>(gt) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(inst) & 3) == 0);
     const bool ext = pred_scale || clamp_first || (inst && p.want_hi != p.group_ids[0]);
-    const dim3 grid(kCluster, B, 1);
-    if (ext) depth_errors_images_kernel<true, true><<<grid, kMetricThreads, 0, (cudaStream_t)stream>>>(p);
-    else if (inst && p.group_ids[0] >= 0) depth_errors_images_kernel<false, true><<<grid, kMetricThreads, 0, (cudaStream_t)stream>>>(p);
-    else depth_errors_images_kernel<false, false><<<grid, kMetricThreads, 0, (cudaStream_t)stream>>>(p);
-    return launch_status();
+    auto kern = ext ? depth_errors_images_kernel<true, true>
+                    : ((inst && p.group_ids[0] >= 0) ? depth_errors_images_kernel<false, true> : depth_errors_images_kernel<false, false>);
+    const int cluster = pick_cluster(B, cta_capacity(reinterpret_cast<const void*>(kern), 0), false, 0);
+    return launch_clustered(kern, p, cluster, B, 0, (cudaStream_t)stream);
 }
 
 int polcue_depth_errors_images_f32(const float* gt, const float* pred, const uint8_t* inst, int B, size_t px, float min_d,
@@ -840,13 +904,13 @@ int polcue_depth_errors_groups_f32(const float* gt, const float* pred, const uin
     p.metrics = metrics;
     p.vec4 = (px % 4 == 0) && (((reinterpret_cast<uintptr_t>(gt) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0) &&
              ((reinterpret_cast<uintptr_t>(inst) & 3) == 0);
-    if (px / ((size_t)kCluster * kMetricThreads) + 8 > 65535) return POLCUE_E2BIG;   // 16-bit per-thread counts (run_flush)
+    if (px / ((size_t)kMaxCluster * kMetricThreads) + 8 > 65535) return POLCUE_E2BIG;   // 16-bit per-thread counts (run_flush)
     const size_t smem = (size_t)n_groups * kGroupRows * kMetricThreads * sizeof(float);
     auto kern = p.all_slot >= 0 ? depth_errors_groups_kernel<true> : depth_errors_groups_kernel<false>;
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<dim3(kCluster, B, 1), kMetricThreads, smem, (cudaStream_t)stream>>>(p);
-    return launch_status();
+    const int cluster = pick_cluster(B, cta_capacity(reinterpret_cast<const void*>(kern), smem), true, px);
+    return launch_clustered(kern, p, cluster, B, smem, (cudaStream_t)stream);
 }
 
 namespace {
