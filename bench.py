@@ -236,7 +236,9 @@ def pcie_probe(dev, h_in, d_in, h_out, d_out, D, reps=3):
     d2h_bytes = sum(t.numel() * t.element_size() for t in h_out.values())
     h2d_bytes = h_in.numel() * h_in.element_size()
 
-    def run(do_in, do_out):
+    s_out2 = torch.cuda.Stream(dev)
+
+    def run(do_in, do_out, split=False):
         torch.cuda.synchronize()
         D.barrier()
         best = float("inf")
@@ -246,17 +248,27 @@ def pcie_probe(dev, h_in, d_in, h_out, d_out, D, reps=3):
             if do_in:
                 with torch.cuda.stream(s_in):
                     d_in.copy_(h_in, non_blocking=True)
-            if do_out:
+            if do_out and not split:
                 with torch.cuda.stream(s_out):
                     for key, t in h_out.items():
                         t.copy_(d_out[key], non_blocking=True)
+            elif do_out:                                        # the same bytes as frame-sized pieces alternating between two streams
+                k = 0                                           # (how the host pipeline returns its chunks)
+                for key, t in h_out.items():
+                    for f in range(t.shape[0]):
+                        with torch.cuda.stream(s_out if k % 2 == 0 else s_out2):
+                            t[f].copy_(d_out[key][f], non_blocking=True)
+                        k += 1
             torch.cuda.synchronize()
             best = min(best, time.perf_counter() - t0)
         return D.max_over_ranks(best, dev)
 
     run(True, True)                                             # warm-up
     t_in, t_out, t_both = run(True, False), run(False, True), run(True, True)
-    return {"h2d_gbs_alone": h2d_bytes / t_in / 1e9, "d2h_gbs_alone": d2h_bytes / t_out / 1e9,
+    t_out_split = run(False, True, split=True)
+    return {"h2d_gbs_alone": h2d_bytes / t_in / 1e9, "d2h_gbs_alone": d2h_bytes / min(t_out, t_out_split) / 1e9,
+            "d2h_gbs_alone_whole_tensors_one_stream": d2h_bytes / t_out / 1e9,
+            "d2h_gbs_alone_frame_pieces_two_streams": d2h_bytes / t_out_split / 1e9,
             "duplex_ms_for_one_step": t_both * 1e3, "d2h_gbs_duplex": d2h_bytes / t_both / 1e9,
             "h2d_bytes": h2d_bytes, "d2h_bytes": d2h_bytes}
 
@@ -417,8 +429,9 @@ def run_polcue_arm(args, rank, local_rank, world):
                              "frac": 44 * out_px / (e2e_ms * 1e-3) / 1e9 / pcie["d2h_gbs_alone"],
                              "probe": pcie, "ranks_copying_concurrently": world,
                              "host_numa_node_of_gpu": int(_lib.lib().polcue_host_numa_node(local_rank)),
-                             "note": "peak = best plain cudaMemcpyAsync of the step's device->host bytes with nothing else running on "
-                                     "this GPU's link, all ranks copying concurrently; the probe also times both directions at once"}},
+                             "note": "peak = best plain cudaMemcpyAsync of the step's device->host bytes (whole tensors on one stream, or "
+                                     "frame-sized pieces on two) with nothing else running on this GPU's link, all ranks copying "
+                                     "concurrently; the probe also times both directions at once"}},
         "e2e_device_resident_outputs": {
             "value": world * B * MPIX_PER_FRAME / (res_ms * 1e-3), "unit": "Mpix/s", "ms_per_step": res_ms, "steps": e2e_steps,
             "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": 13 * 8,
