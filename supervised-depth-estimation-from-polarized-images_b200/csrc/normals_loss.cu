@@ -9,6 +9,9 @@
 // and the masked sums; 12 B read per pixel) and the backward is ONE kernel that recomputes the window quantities
 // instead of storing them (12 B read + 4 B written per pixel).
 //
+// Forward: the two cross products in a cancellation-free form (scaled_normals4 below: half the FP operations of the
+// reference's operation order, which the stencil kernel and the backward keep), the cosine from the unnormalised vectors.
+//
 // Backward, per image (depth_to_normals as in stencil.cu, with the unnormalised Sobel taps s = (1,2,1), d = (-1,0,1):
 // gu = sum_ab s[a] d[b] P(p+(a,b)), gv = sum_ab d[a] s[b] P(p+(a,b)), P = (fx(u) Z, fy(v) Z, Z), n = gu x gv, b = n/|n|):
 //     k_p   = -grad_out * m_p / sum(m)
@@ -328,6 +331,127 @@ __global__ void __launch_bounds__(kFoldThreads) loss_fold_kernel(const double* _
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------
+// FORWARD stencil in cancellation-free form.  The loss only needs the DIRECTION of the two cross products, and both
+// kernels above (stencil.cu's arithmetic) spend most of their FP work forming fx(u) Z and fy(v) Z per window column
+// only to difference them again.  With fx(u + b) = fx(u) + b / f_x (clamped coordinates: b in {-1, 0, 1} becomes the
+// weights w below) the gradients of P = (fx Z, fy Z, Z) are
+//     gu = G r + (A / f_x, Cu / f_y, 0),   gv = V r + (Cv / f_x, B / f_y, 0),   r = (fx(u), fy(v), 1)
+// with, from the vertical column combinations S2 = Z0 + 2 Z1 + Z2, D2 = Z2 - Z0 (rows y-1, y, y+1) and the row-weighted
+// T = wp Z2 + wm Z0, D = wp Z2 - wm Z0 (wm = [y > 0], wp = [y < H-1]: replicated rows carry no fy step):
+//     G  = S2[x+1] - S2[x-1]                     V  = D2[x-1] + 2 D2[x] + D2[x+1]          (the z components of gu, gv)
+//     A  = wr S2[x+1] + wl S2[x-1]               B  = T[x-1] + 2 T[x] + T[x+1]
+//     Cu = D[x+1] - D[x-1]                       Cv = wr D2[x+1] - wl D2[x-1]              (wl = [x > 0], wr = [x < W-1])
+// and the cross product, scaled by the positive constant f_x f_y (which the cosine does not see), is
+//     m = f_x f_y (gu x gv) = ( f_x (V Cu - G B),  f_y (G Cv - V A),  -fx(u) m_x - fy(v) m_y + A B - Cu Cv ).
+// 35 instead of 66 FP operations per pixel and field, and none of the differences of nearly equal products that make
+// the reference's float32 normals noisy: the result is closer to the float64 oracle than the reference's own float32
+// (tests: the loss against the float64 oracle; the stencil KERNEL keeps the reference's operation order).
+// The clamps of F.normalize (|n| >= 1e-12) and of cosine_similarity (|a||b| >= 1e-8) only matter for |n| < 1e-12, i.e.
+// q = |m|^2 < qthr: those pixels (zero-depth holes) take the explicit path of cos_scaled.
+// Templated on the lane type: float (scalar kernel) and f32x2 (GT and prediction in the two lanes) run the identical
+// operation sequence, so the two kernels agree bit for bit.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float vadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float vsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float vmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+__device__ __forceinline__ f32x2 vadd(f32x2 a, f32x2 b) { return add2(a, b); }
+__device__ __forceinline__ f32x2 vsub(f32x2 a, f32x2 b) { return sub2(a, b); }
+__device__ __forceinline__ f32x2 vmul(f32x2 a, f32x2 b) { return mul2(a, b); }
+__device__ __forceinline__ f32x2 vfma(f32x2 a, f32x2 b, f32x2 c) { return fma2(a, b, c); }
+__device__ __forceinline__ f32x2 vneg(f32x2 a) { return neg2(a); }
+template <typename V> __device__ __forceinline__ V vdup(float c);
+template <> __device__ __forceinline__ float vdup<float>(float c) { return c; }
+template <> __device__ __forceinline__ f32x2 vdup<f32x2>(float c) { return dup2(c); }
+
+struct FwdCam {
+    float nfX, nfY;            // -f_x, -f_y
+    float cx, inv_fx, cy, inv_fy;
+    float kap, qthr;           // |n_ref| 1e12 = |m| kap (n_ref = the reference's cross product = m / (64 f_x f_y)); qthr = kap^-2
+};
+__device__ __forceinline__ FwdCam fwd_cam(const CamRaw& r) {
+    FwdCam c;
+    c.nfX = -r.fx;
+    c.nfY = -r.fy;
+    c.cx = r.cx;
+    c.cy = r.cy;
+    c.inv_fx = 1.0f / r.fx;
+    c.inv_fy = 1.0f / r.fy;
+    c.kap = (1e12f / 64.0f) * c.inv_fx * c.inv_fy;
+    c.qthr = 1.0f / (c.kap * c.kap);
+    return c;
+}
+
+// m of the four pixels at window columns 1..4 (Z[r][c] = depth at row y - 1 + r, column x - 1 + c, replicate padding applied).
+// GENERAL = false: x is a multiple of 4 and so is W, so only pixel 0 can sit on the left image border and only pixel 3 on
+// the right one (wl = weight of pixel 0's left neighbour, wr = weight of pixel 3's right neighbour); GENERAL = true: any
+// pixel may (wls[j], wrs[j]).  With all weights 1 both forms round identically.
+// BORDER_ROW (first / last image row, a warp-uniform case the callers branch on): T and D take the row weights; elsewhere
+// they are the plain column sums, which keeps the common path free of the extra live values.
+template <typename V, bool GENERAL, bool BORDER_ROW>
+__device__ __forceinline__ void scaled_normals4(const V (&Z)[3][6], V wm, V wp, const V (&wls)[4], const V (&wrs)[4],
+                                                V nfX, V nfY, const V (&nfx0)[4], V nfy0, V (&m)[3][4]) {
+    const V two = vdup<V>(2.0f);
+    const V pfX = vneg(nfX), nwl0 = vneg(wls[0]);      // loop-invariant for the callers (hoisted)
+    V S2[6], D2[6], T[6], D[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const V t = vadd(Z[0][c], Z[2][c]);
+        S2[c] = vfma(two, Z[1][c], t);
+        D2[c] = vsub(Z[2][c], Z[0][c]);
+        if constexpr (BORDER_ROW) {
+            const V lo = vmul(wm, Z[0][c]);
+            T[c] = vfma(wp, Z[2][c], lo);
+            D[c] = vfma(wp, Z[2][c], vneg(lo));
+        } else {
+            T[c] = t;
+            D[c] = D2[c];
+        }
+    }
+    // (differences are formed in the sign each product needs: a packed negation is two LOP3 on the half-rate ALU pipe)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const V nG = vsub(S2[j], S2[j + 2]);
+        const V Vz = vfma(two, D2[j + 1], vadd(D2[j], D2[j + 2]));
+        const V B = vfma(two, T[j + 1], vadd(T[j], T[j + 2]));
+        const V Cu = vsub(D[j + 2], D[j]), nCu = vsub(D[j], D[j + 2]);
+        V A, Cv;
+        if constexpr (GENERAL) {
+            A = vfma(wrs[j], S2[j + 2], vmul(wls[j], S2[j]));
+            Cv = vfma(wrs[j], D2[j + 2], vmul(vneg(wls[j]), D2[j]));
+        } else if (j == 0) {
+            A = vfma(wls[0], S2[0], S2[2]);
+            Cv = vfma(nwl0, D2[0], D2[2]);
+        } else if (j == 3) {
+            A = vfma(wrs[3], S2[5], S2[3]);
+            Cv = vfma(wrs[3], D2[5], vmul(vdup<V>(-1.0f), D2[3]));
+        } else {
+            A = vadd(S2[j + 2], S2[j]);
+            Cv = BORDER_ROW ? vsub(D2[j + 2], D2[j]) : Cu;
+        }
+        const V mx = vmul(pfX, vfma(Vz, Cu, vmul(nG, B)));              //  f_x (V Cu - G B)
+        const V my = vmul(nfY, vfma(nG, Cv, vmul(Vz, A)));              // -f_y (V A - G Cv)
+        m[0][j] = mx;
+        m[1][j] = my;
+        m[2][j] = vfma(nfx0[j], mx, vfma(nfy0, my, vfma(nCu, Cv, vmul(A, B))));
+    }
+}
+
+// cos(n_gt, n_pred) as the reference forms it -- F.normalize(eps 1e-12), then cosine_similarity(eps 1e-8) -- from the scaled
+// cross products: ab = <m_a, m_b>, qa = |m_a|^2, qb = |m_b|^2.
+__device__ __forceinline__ float cos_scaled(float ab, float qa, float qb, const FwdCam& fc) {
+    const float ra = rsqrt_approx(qa), rb = rsqrt_approx(qb);
+    float c = __fmul_rn(ab, __fmul_rn(ra, rb));
+    if (fminf(qa, qb) < fc.qthr) {     // |n| < 1e-12 for one of the two (a zero-depth hole): a^ = n 1e12, |a^| < 1
+        const float sa = qa > 0.0f ? ra : 0.0f, sb = qb > 0.0f ? rb : 0.0f;
+        const float na = fminf(1.0f, __fmul_rn(__fmul_rn(qa, sa), fc.kap)), nb = fminf(1.0f, __fmul_rn(__fmul_rn(qb, sb), fc.kap));
+        c = __fmul_rn(__fmul_rn(ab, __fmul_rn(sa, sb)), fminf(1.0f, __fmul_rn(__fmul_rn(na, nb), 1e8f)));
+    }
+    return c;
+}
+
 // L1 = true adds the supervised depth loss of the same block of the trainer (trainer.py:1246):
 //     supervised_depth_loss = (|gt - pred| * mask).sum() / mask.sum()
 // Scalar kernel: any width / alignment (the packed kernel below serves rows that are 16-byte multiples).
@@ -341,42 +465,47 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const
     stage_tile<kFwdH>(tg, p.gt + b * hw, p.H, p.W, x0, y0);
     stage_tile<kFwdH>(tp, p.pred + b * hw, p.H, p.W, x0, y0);
     __syncthreads();
-    const Cam cam = load_cam(p.K, b);
+    const FwdCam fc = fwd_cam(cam_fetch(p.K, b));
     float s = 0.0f, m = 0.0f, l1 = 0.0f;   // at most 16 pixels per thread: float32 partials, float64 from the warp level on
     for (int i = threadIdx.x; i < (kLW / 4) * kFwdH; i += kLossThreads) {
         const int ty = i / (kLW / 4), tx0 = 4 * (i - ty * (kLW / 4));
         const int x = x0 + tx0, y = y0 + ty;
         if (x >= p.W || y >= p.H) continue;
-        float gu[3][4], gv[3][4], a4[3][4], b4[3][4];
-        gradients4(tg, ty, tx0, x, y, p.H, p.W, cam, gu, gv);
+        float wls[4], wrs[4], nfx0[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float u[3] = {gu[0][j], gu[1][j], gu[2][j]}, v[3] = {gv[0][j], gv[1][j], gv[2][j]};
-            float n[3], un[3];
-            cross_rn(u, v, n);
-            normalize3(n, un);
-            a4[0][j] = un[0]; a4[1][j] = un[1]; a4[2][j] = un[2];
+            wls[j] = (x + j == 0) ? 0.0f : 1.0f;
+            wrs[j] = (x + j == p.W - 1) ? 0.0f : 1.0f;
+            nfx0[j] = -(((float)(x + j) - fc.cx) * fc.inv_fx);
         }
-        gradients4(tp, ty, tx0, x, y, p.H, p.W, cam, gu, gv);
+        const bool border_row = (y == 0) | (y == p.H - 1);
+        const float wm = y > 0 ? 1.0f : 0.0f, wp = y < p.H - 1 ? 1.0f : 0.0f, nfy0 = -(((float)y - fc.cy) * fc.inv_fy);
+        float Zg[3][6], Zp[3][6], mg[3][4], mp[3][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float u[3] = {gu[0][j], gu[1][j], gu[2][j]}, v[3] = {gv[0][j], gv[1][j], gv[2][j]};
-            float n[3], un[3];
-            cross_rn(u, v, n);
-            normalize3(n, un);
-            b4[0][j] = un[0]; b4[1][j] = un[1]; b4[2][j] = un[2];
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                Zg[r][c] = tg[kLRow + ty + r - 1][kLCol + tx0 + c - 1];
+                Zp[r][c] = tp[kLRow + ty + r - 1][kLCol + tx0 + c - 1];
+            }
+        if (border_row) {
+            scaled_normals4<float, true, true>(Zg, wm, wp, wls, wrs, fc.nfX, fc.nfY, nfx0, nfy0, mg);
+            scaled_normals4<float, true, true>(Zp, wm, wp, wls, wrs, fc.nfX, fc.nfY, nfx0, nfy0, mp);
+        } else {
+            scaled_normals4<float, true, false>(Zg, wm, wp, wls, wrs, fc.nfX, fc.nfY, nfx0, nfy0, mg);
+            scaled_normals4<float, true, false>(Zp, wm, wp, wls, wrs, fc.nfX, fc.nfY, nfx0, nfy0, mp);
         }
         float fs = 0.0f, fm = 0.0f, fl = 0.0f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (x + j < p.W) {
-                const float zg = tg[kLRow + ty][kLCol + tx0 + j];
+                const float zg = Zg[1][1 + j];
                 const float mk = mask_value<L1>(p, b * hw + (size_t)y * p.W + x + j, zg);
-                if constexpr (L1) fl = fmaf(fabsf(__fsub_rn(zg, tp[kLRow + ty][kLCol + tx0 + j])), mk, fl);
-                const float a[3] = {a4[0][j], a4[1][j], a4[2][j]}, bb3[3] = {b4[0][j], b4[1][j], b4[2][j]};
-                float inv_den, ab, bb;
-                bool clamped;
-                const float c = cosine(a, bb3, inv_den, ab, bb, clamped);
+                if constexpr (L1) fl = fmaf(fabsf(__fsub_rn(zg, Zp[1][1 + j])), mk, fl);
+                const float qa = fmaf(mg[0][j], mg[0][j], fmaf(mg[1][j], mg[1][j], __fmul_rn(mg[2][j], mg[2][j])));
+                const float qb = fmaf(mp[0][j], mp[0][j], fmaf(mp[1][j], mp[1][j], __fmul_rn(mp[2][j], mp[2][j])));
+                const float ab = fmaf(mg[0][j], mp[0][j], fmaf(mg[1][j], mp[1][j], __fmul_rn(mg[2][j], mp[2][j])));
+                const float c = cos_scaled(ab, qa, qb, fc);
                 fs = fmaf(__fsub_rn(2.0f, c), mk, fs);
                 fm += mk;
             }
@@ -550,11 +679,15 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel
         for (int k = 0; k < kPH / 8; ++k) *reinterpret_cast<float4*>(&M[(threadIdx.x >> 5) + 8 * k][4 * (threadIdx.x & 31)]) = mreg[k];
     }
     __syncthreads();
-    const Cam cam = cam_finish(cam_raw);
+    const FwdCam fc = fwd_cam(cam_raw);
     const int tx0 = 4 * (threadIdx.x & 31), x = x0 + tx0;
-    f32x2 fx6[6];
+    const f32x2 one = dup2(1.0f);
+    const f32x2 wls[4] = {dup2(x == 0 ? 0.0f : 1.0f), one, one, one};                 // W % 4 == 0: only pixel 0 / pixel 3 of a group
+    const f32x2 wrs[4] = {one, one, one, dup2(x + 3 == p.W - 1 ? 0.0f : 1.0f)};       // can sit on the left / right image border
+    const f32x2 nfX = dup2(fc.nfX), nfY = dup2(fc.nfY);
+    f32x2 nfx0[4];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) fx6[c] = dup2(((float)min(max(x + c - 1, 0), p.W - 1) - cam.cx) * cam.inv_fx);
+    for (int j = 0; j < 4; ++j) nfx0[j] = dup2(-(((float)(x + j) - fc.cx) * fc.inv_fx));
     float s = 0.0f, m = 0.0f, l1 = 0.0f;   // at most 16 pixels per thread
     if (x < p.W) {
 #pragma unroll 1
@@ -566,30 +699,39 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel
                 const float4 mv = *reinterpret_cast<const float4*>(&M[ty][tx0]);
                 mk4[0] = mv.x; mk4[1] = mv.y; mk4[2] = mv.z; mk4[3] = mv.w;
             }
-            f32x2 fy3[3];
+            const bool border_row = (y == 0) | (y == p.H - 1);
+            const f32x2 wm = dup2(y > 0 ? 1.0f : 0.0f), wp = dup2(y < p.H - 1 ? 1.0f : 0.0f);
+            const f32x2 nfy0 = dup2(-(((float)y - fc.cy) * fc.inv_fy));
+            f32x2 Z[3][6], mm[3][4];
+            {   // the 3 x 6 window of (gt, pred) pairs: three swizzled 16-byte units per row (tile column c lives at pair index c + 1)
+                const float2* top = &T[ty][0];
+                const int u0 = swz_pair(tx0), u1 = swz_pair(tx0 + 2), u2 = swz_pair(tx0 + 4);
 #pragma unroll
-            for (int r = 0; r < 3; ++r) fy3[r] = dup2(((float)min(max(y + r - 1, 0), p.H - 1) - cam.cy) * cam.inv_fy);
-            f32x2 gu[3][4], gv[3][4], centre[4];
-            gradients4_pairs(&T[ty][0], tx0, kPPitch, fx6, fy3, gu, gv, centre);
+                for (int r = 0; r < 3; ++r) {
+                    const float2* row = top + r * kPPitch;
+                    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(row + u0), bq = *reinterpret_cast<const ulonglong2*>(row + u1),
+                                     c = *reinterpret_cast<const ulonglong2*>(row + u2);
+                    Z[r][0] = a.x; Z[r][1] = a.y; Z[r][2] = bq.x; Z[r][3] = bq.y; Z[r][4] = c.x; Z[r][5] = c.y;
+                }
+            }
+            if (border_row) scaled_normals4<f32x2, false, true>(Z, wm, wp, wls, wrs, nfX, nfY, nfx0, nfy0, mm);
+            else scaled_normals4<f32x2, false, false>(Z, wm, wp, wls, wrs, nfX, nfY, nfx0, nfy0, mm);
             float fs = 0.0f, fm = 0.0f, fl = 0.0f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const f32x2 u[3] = {gu[0][j], gu[1][j], gu[2][j]}, v[3] = {gv[0][j], gv[1][j], gv[2][j]};
-                f32x2 n[3];
-                unit_normals_pairs(u, v, n);
-                float a[3], bb3[3];
-                unpk2(n[0], a[0], bb3[0]);
-                unpk2(n[1], a[1], bb3[1]);
-                unpk2(n[2], a[2], bb3[2]);
                 float zg, zp;
-                unpk2(centre[j], zg, zp);
+                unpk2(Z[1][1 + j], zg, zp);
                 float mk;
                 if constexpr (L1) mk = (zg >= p.min_d && zg <= p.max_d) ? 1.0f : 0.0f;
                 else mk = mk4[j];
                 if constexpr (L1) fl = fmaf(fabsf(__fsub_rn(zg, zp)), mk, fl);
-                float inv_den, ab, bb;
-                bool clamped;
-                const float c = cosine_pairs(n, a, bb3, inv_den, ab, bb, clamped);
+                float qa, qb, a[3], bb3[3];
+                unpk2(fma2(mm[0][j], mm[0][j], fma2(mm[1][j], mm[1][j], mul2(mm[2][j], mm[2][j]))), qa, qb);
+                unpk2(mm[0][j], a[0], bb3[0]);
+                unpk2(mm[1][j], a[1], bb3[1]);
+                unpk2(mm[2][j], a[2], bb3[2]);
+                const float ab = fmaf(a[0], bb3[0], fmaf(a[1], bb3[1], __fmul_rn(a[2], bb3[2])));
+                const float c = cos_scaled(ab, qa, qb, fc);
                 fs = fmaf(__fsub_rn(2.0f, c), mk, fs);
                 fm += mk;
             }

@@ -784,8 +784,8 @@ def test_normals_loss_matches_composition_of_public_ops_and_is_deterministic():
     cos = torch.nn.functional.cosine_similarity(n_gt.double(), n_pred.double(), dim=1).unsqueeze(1)
     ref = ((2 - cos) * args[3]).sum() / args[3].sum()
     assert abs(float(loss) - float(ref)) < 1e-6
-    # the normals inside the loss kernels are the stencil kernel's, bit for bit (every rounding of the stencil is pinned in
-    # the source): a float32 re-evaluation of the cosine from the public op's normals reproduces the kernel's sums closely
+    # (the forward kernel evaluates the stencil in a cancellation-free form, the public op in the reference's operation
+    # order: a float64 re-evaluation of the cosine from the public op's float32 normals agrees to 1e-6)
     for misalign in (False, True):
         d = _misaligned(args[0]) if misalign else args[0]
         assert torch.equal(ops.depth_to_normals(d, args[2]), n_gt)
