@@ -9,21 +9,18 @@
 // and the masked sums; 12 B read per pixel) and the backward is ONE kernel that recomputes the window quantities
 // instead of storing them (12 B read + 4 B written per pixel).
 //
-// Forward: the two cross products in a cancellation-free form (scaled_normals4 below: half the FP operations of the
-// reference's operation order, which the stencil kernel and the backward keep), the cosine from the unnormalised vectors.
-//
-// Backward, per image (depth_to_normals as in stencil.cu, with the unnormalised Sobel taps s = (1,2,1), d = (-1,0,1):
-// gu = sum_ab s[a] d[b] P(p+(a,b)), gv = sum_ab d[a] s[b] P(p+(a,b)), P = (fx(u) Z, fy(v) Z, Z), n = gu x gv, b = n/|n|):
-//     k_p   = -grad_out * m_p / sum(m)
-//     n_bar = k_p (g - <g,b> b) / |n|,   g = dcos/db = a/D - <a,b> b / (D |b|^2),  D = max(|a||b|, 1e-8)
-//     gu_bar = gv x n_bar,  gv_bar = n_bar x gu
-//     Zbar(q) = fx(q) A_0(q) + fy(q) A_1(q) + A_2(q),
-//     A_c(q)  = sum_{i,j in {-1,0,1}} Sv[i] Du[j] gu_bar_c(q+(i,j)) + Dv[i] Su[j] gv_bar_c(q+(i,j))
-// where the per-axis weights fold the replicate padding back onto border pixels:
-//     S[-1] = S[+1] = 1, D[-1] = +1, D[+1] = -1, S[0] = 2 + [q == 0] + [q == last], D[0] = [q == last] - [q == 0].
-// Phase 1 of the backward kernel writes gu_bar, gv_bar of the tile + 1-pixel ring to shared memory, phase 2 gathers.
+// Both kernels evaluate the stencil in a CANCELLATION-FREE form (the derivation is at scaled_normals4 / adjoint_terms below):
+// the gradients of P = (fx(u) Z, fy(v) Z, Z) are written through six small window functionals G, V, A, B, Cu, Cv of the
+// depth, f_x f_y (gu x gv) is a handful of products of them, and the backward propagates to those six functionals
+// (separable 3 x 3 tap patterns, gathered in a second phase through shared memory) instead of to the six gradient
+// components -- half the FP operations of the reference's operation order (which stencil.cu, the public
+// depth_to_normals, keeps) and none of its differences of nearly equal products.
+//     k_p   = -grad_out * mask_p / sum(mask)
+//     m_bar = k_p (g - <g,b> b) / |m|,   g = dcos/db = a/D - <a,b> b / (D |b|^2),  D = max(|a||b|, 1e-8),  b = m/|m| (clamps as the reference)
+// Phase 1 of the backward kernel writes the six adjoints of the tile + 1-pixel ring to shared memory, phase 2 gathers.
 // Two kernel families: packed (rows that are 16-byte multiples: GT and prediction in the two lanes of packed FP32
-// instructions, interleaved shared tile) and scalar (any width / alignment); both stage their tiles by hand.
+// instructions, interleaved shared tile) and scalar (any width / alignment); both stage their tiles by hand and run the
+// same operation sequence per lane, so they agree bit for bit.
 #include "polcue_device.cuh"
 #include "polcue_host.h"
 
@@ -74,11 +71,8 @@ __device__ __forceinline__ void stage_tile(float (*tile)[kLBoxW], const float* p
     }
 }
 
-struct Cam {
-    float inv_fx, cx, inv_fy, cy;
-};
 // The four intrinsics are REQUESTED at the top of a kernel (cam_fetch) and turned into reciprocals after the tile's barrier
-// (cam_finish): fetched after the barrier, every warp of the CTA sat out an L2 round trip there (7 % of the backward's stall samples).
+// (fwd_cam): fetched after the barrier, every warp of the CTA sat out an L2 round trip there (7 % of the backward's stall samples).
 struct CamRaw {
     float fx, cx, fy, cy;
 };
@@ -90,117 +84,6 @@ __device__ __forceinline__ CamRaw cam_fetch(const float* K, int b) {
     r.fy = __ldg(k + 4);
     r.cy = __ldg(k + 5);
     return r;
-}
-__device__ __forceinline__ Cam cam_finish(const CamRaw& r) {
-    Cam c;
-    c.inv_fx = 1.0f / r.fx;
-    c.cx = r.cx;
-    c.inv_fy = 1.0f / r.fy;
-    c.cy = r.cy;
-    return c;
-}
-__device__ __forceinline__ Cam load_cam(const float* K, int b) { return cam_finish(cam_fetch(K, b)); }
-
-// 8 x gradients of xyz at tile-local pixel (ty, tx) (image pixel (y0+ty, x0+tx)), same arithmetic as stencil.cu.
-__device__ __forceinline__ void gradients(const float (*tile)[kLBoxW], int ty, int tx, int x, int y, int H, int W, const Cam& cam,
-                                          float (&gu)[3], float (&gv)[3]) {
-    float fx3[3], fy3[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        fx3[k] = ((float)min(max(x + k - 1, 0), W - 1) - cam.cx) * cam.inv_fx;
-        fy3[k] = ((float)min(max(y + k - 1, 0), H - 1) - cam.cy) * cam.inv_fy;
-    }
-    float Z[3][3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) Z[r][c] = tile[kLRow + ty + r - 1][kLCol + tx + c - 1];
-    // The stencil arithmetic is DEFINED here, rounding by rounding (no compiler-chosen contraction), and repeated verbatim by
-    // gradients4, the packed twins below and stencil.cu, so every kernel gives the same bits:
-    //   S2 = fma(2, Z1, Z0 + Z2), D2 = Z2 - Z0                     vertical smoothing / difference of Z per column
-    //   X: P = fl(fx S2), Q = fl(fx D2);  gu_x = P[+1] - P[-1];  gv_x = fma(2, Q[0], Q[-1] + Q[+1])
-    //   Y: lo = fl(fy[-1] Z0), hi = fl(fy[+1] Z2), S1 = fma(fy[+1], Z2, fma(2 fy[0], Z1, lo)), D1 = hi - lo;
-    //      gu_y = S1[+1] - S1[-1];  gv_y = fma(2, D1[0], D1[-1] + D1[+1])
-    //   Z: gu_z = S2[+1] - S2[-1];  gv_z = fma(2, D2[0], D2[-1] + D2[+1])
-    // Products that feed a difference are rounded separately, so replicated rows / columns (image borders, one-pixel-wide
-    // images) and parallel gradients cancel to exact zeros.
-    float S2[3], D2[3], S1[3], D1[3], P[3], Q[3];
-    const float fy1x2 = 2.0f * fy3[1];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        S2[c] = fmaf(2.0f, Z[1][c], __fadd_rn(Z[0][c], Z[2][c]));
-        D2[c] = __fsub_rn(Z[2][c], Z[0][c]);
-        P[c] = __fmul_rn(fx3[c], S2[c]);
-        Q[c] = __fmul_rn(fx3[c], D2[c]);
-        const float lo = __fmul_rn(fy3[0], Z[0][c]);
-        S1[c] = fmaf(fy3[2], Z[2][c], fmaf(fy1x2, Z[1][c], lo));
-        D1[c] = __fsub_rn(__fmul_rn(fy3[2], Z[2][c]), lo);
-    }
-    gu[0] = __fsub_rn(P[2], P[0]);
-    gv[0] = fmaf(2.0f, Q[1], __fadd_rn(Q[0], Q[2]));
-    gu[1] = __fsub_rn(S1[2], S1[0]);
-    gv[1] = fmaf(2.0f, D1[1], __fadd_rn(D1[0], D1[2]));
-    gu[2] = __fsub_rn(S2[2], S2[0]);
-    gv[2] = fmaf(2.0f, D2[1], __fadd_rn(D2[0], D2[2]));
-}
-
-// The same for four consecutive pixels starting at tile-local column tx0 (a multiple of 4): the 3 x 6 window is read
-// as one LDS.128 + two LDS.32 per row and its column sums are shared by the four pixels (as stencil.cu does).
-__device__ __forceinline__ void gradients4(const float (*tile)[kLBoxW], int ty, int tx0, int x, int y, int H, int W, const Cam& cam,
-                                           float (&gu)[3][4], float (&gv)[3][4]) {
-    float fx6[6], fy3[3];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) fx6[c] = ((float)min(max(x + c - 1, 0), W - 1) - cam.cx) * cam.inv_fx;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) fy3[r] = ((float)min(max(y + r - 1, 0), H - 1) - cam.cy) * cam.inv_fy;
-    float Z[3][6];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const float* row = &tile[kLRow + ty + r - 1][kLCol + tx0];
-        const float4 mid = *reinterpret_cast<const float4*>(row);
-        Z[r][0] = row[-1];
-        Z[r][1] = mid.x; Z[r][2] = mid.y; Z[r][3] = mid.z; Z[r][4] = mid.w;
-        Z[r][5] = row[4];
-    }
-    float S2[6], D2[6], S1[6], D1[6], P[6], Q[6];
-    const float fy1x2 = 2.0f * fy3[1];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        S2[c] = fmaf(2.0f, Z[1][c], __fadd_rn(Z[0][c], Z[2][c]));
-        D2[c] = __fsub_rn(Z[2][c], Z[0][c]);
-        P[c] = __fmul_rn(fx6[c], S2[c]);
-        Q[c] = __fmul_rn(fx6[c], D2[c]);
-        const float lo = __fmul_rn(fy3[0], Z[0][c]);
-        S1[c] = fmaf(fy3[2], Z[2][c], fmaf(fy1x2, Z[1][c], lo));
-        D1[c] = __fsub_rn(__fmul_rn(fy3[2], Z[2][c]), lo);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        gu[0][j] = __fsub_rn(P[j + 2], P[j]);
-        gv[0][j] = fmaf(2.0f, Q[j + 1], __fadd_rn(Q[j], Q[j + 2]));
-        gu[1][j] = __fsub_rn(S1[j + 2], S1[j]);
-        gv[1][j] = fmaf(2.0f, D1[j + 1], __fadd_rn(D1[j], D1[j + 2]));
-        gu[2][j] = __fsub_rn(S2[j + 2], S2[j]);
-        gv[2][j] = fmaf(2.0f, D2[j + 1], __fadd_rn(D2[j], D2[j + 2]));
-    }
-}
-
-// products rounded separately (never contracted): parallel vectors cancel to an exact zero vector
-__device__ __forceinline__ void cross_rn(const float (&a)[3], const float (&b)[3], float (&n)[3]) {
-    n[0] = __fsub_rn(__fmul_rn(a[1], b[2]), __fmul_rn(a[2], b[1]));
-    n[1] = __fsub_rn(__fmul_rn(a[2], b[0]), __fmul_rn(a[0], b[2]));
-    n[2] = __fsub_rn(__fmul_rn(a[0], b[1]), __fmul_rn(a[1], b[0]));
-}
-
-constexpr float kInvCap = 1.0f / (64.0f * 1e-12f);   // n here is 64 x the reference's cross product (see stencil.cu)
-
-// unit (or capped) normal and the factor it was scaled by
-__device__ __forceinline__ float normalize3(const float (&n)[3], float (&u)[3]) {
-    const float inv = fminf(rsqrt_approx(fmaf(n[0], n[0], fmaf(n[1], n[1], __fmul_rn(n[2], n[2])))), kInvCap);
-    u[0] = __fmul_rn(n[0], inv);
-    u[1] = __fmul_rn(n[1], inv);
-    u[2] = __fmul_rn(n[2], inv);
-    return inv;
 }
 
 // cos = <a,b> / max(|a||b|, 1e-8)   (torch 1.7.1 F.cosine_similarity: w12 * rsqrt(clamp_min(w1 w2, eps^2)))
@@ -218,55 +101,6 @@ __device__ __forceinline__ float cosine(const float (&a)[3], const float (&b)[3]
     bb = fmaf(b[0], b[0], fmaf(b[1], b[1], __fmul_rn(b[2], b[2])));
     return cosine_from_dots(ab, aa, bb, inv_den, clamped);
 }
-// the same from the packed unit normals n (lane 0 = a, lane 1 = b): (aa, bb) cost three packed instructions instead of six
-__device__ __forceinline__ float cosine_pairs(const f32x2 (&n)[3], const float (&a)[3], const float (&b)[3], float& inv_den, float& ab,
-                                              float& bb, bool& clamped) {
-    ab = fmaf(a[0], b[0], fmaf(a[1], b[1], __fmul_rn(a[2], b[2])));
-    float aa;
-    unpk2(fma2(n[0], n[0], fma2(n[1], n[1], mul2(n[2], n[2]))), aa, bb);
-    return cosine_from_dots(ab, aa, bb, inv_den, clamped);
-}
-
-// The adjoint arithmetic after the cosine, with every rounding spelled out (no compiler-chosen contraction) so that the
-// scalar and the packed kernel produce the same bits:
-//   g = dcos/db: above the eps clamp a/D - <a,b> b / (D |b|^2), inside it a / eps;   b = n * inv: the capped normalisation is
-//   linear, otherwise project out b and divide by |n| (= multiply by inv);   n = gu x gv  =>  gu_bar = gv x n_bar, gv_bar = n_bar x gu.
-__device__ __forceinline__ void adjoint_tail(const float (&a)[3], const float (&bn)[3], float inv, const float (&up)[3], const float (&vp)[3],
-                                             float k, float inv_den, float ab, float bb, bool clamped, float (&gub)[3], float (&gvb)[3]) {
-    // (MUFU reciprocal, 1 ulp: |b|^2 is 1 to rounding unless the normalisation was capped; the IEEE division was 7 % of the backward's instructions)
-    const float w_b = clamped ? 0.0f : __fmul_rn(__fmul_rn(ab, inv_den), rcp_approx(fmaxf(bb, 1e-30f)));
-    float g[3], nb[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) g[c] = fmaf(-w_b, bn[c], __fmul_rn(a[c], inv_den));
-    const float gb = (inv >= kInvCap) ? 0.0f : fmaf(g[0], bn[0], fmaf(g[1], bn[1], __fmul_rn(g[2], bn[2])));
-    const float ki = __fmul_rn(k, inv);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) nb[c] = __fmul_rn(ki, fmaf(-gb, bn[c], g[c]));
-    gub[0] = fmaf(vp[1], nb[2], -__fmul_rn(vp[2], nb[1]));
-    gub[1] = fmaf(vp[2], nb[0], -__fmul_rn(vp[0], nb[2]));
-    gub[2] = fmaf(vp[0], nb[1], -__fmul_rn(vp[1], nb[0]));
-    gvb[0] = fmaf(nb[1], up[2], -__fmul_rn(nb[2], up[1]));
-    gvb[1] = fmaf(nb[2], up[0], -__fmul_rn(nb[0], up[2]));
-    gvb[2] = fmaf(nb[0], up[1], -__fmul_rn(nb[1], up[0]));
-}
-
-// Adjoints of the predicted-depth gradients of one pixel: (gu, gv) of the GT tile -> a; of the prediction -> b, n;
-// k = -grad_out m / sum(m).  See the derivation in the file header.
-__device__ __forceinline__ void adjoint_px(const float (&ug)[3], const float (&vg)[3], const float (&up)[3], const float (&vp)[3],
-                                           float k, float (&gub)[3], float (&gvb)[3]) {
-    gub[0] = gub[1] = gub[2] = gvb[0] = gvb[1] = gvb[2] = 0.0f;
-    if (k == 0.0f) return;
-    float n[3], a[3], bn[3];
-    cross_rn(ug, vg, n);
-    normalize3(n, a);
-    cross_rn(up, vp, n);
-    const float inv = normalize3(n, bn);
-    float inv_den, ab, bb;
-    bool clamped;
-    cosine(a, bn, inv_den, ab, bb, clamped);
-    adjoint_tail(a, bn, inv, up, vp, k, inv_den, ab, bb, clamped, gub, gvb);
-}
-
 // mask of one pixel: the caller's float mask, or the supervised range test on the GT depth (trainer.py:1241-1242)
 template <bool RANGE>   // RANGE is what the supervised (L1) entry points use; the plain ones read the caller's mask
 __device__ __forceinline__ float mask_value(const LossParams& p, size_t idx, float gt_depth) {
@@ -384,58 +218,87 @@ __device__ __forceinline__ FwdCam fwd_cam(const CamRaw& r) {
     return c;
 }
 
-// m of the four pixels at window columns 1..4 (Z[r][c] = depth at row y - 1 + r, column x - 1 + c, replicate padding applied).
-// GENERAL = false: x is a multiple of 4 and so is W, so only pixel 0 can sit on the left image border and only pixel 3 on
-// the right one (wl = weight of pixel 0's left neighbour, wr = weight of pixel 3's right neighbour); GENERAL = true: any
-// pixel may (wls[j], wrs[j]).  With all weights 1 both forms round identically.
+// Column combinations of a 3 x N window (Z[r][c] = depth at row y - 1 + r, column first + c, replicate padding applied).
 // BORDER_ROW (first / last image row, a warp-uniform case the callers branch on): T and D take the row weights; elsewhere
-// they are the plain column sums, which keeps the common path free of the extra live values.
+// they are the plain column sums (same bits as the weighted form with both weights 1), which keeps the common path short.
+template <typename V, int N>
+struct StencilCols {
+    V S2[N], D2[N], T[N], D[N];
+};
+template <typename V, int N, bool BORDER_ROW>
+__device__ __forceinline__ void stencil_columns(const V (&Z)[3][N], V wm, V wp, StencilCols<V, N>& s) {
+    const V two = vdup<V>(2.0f);
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        const V t = vadd(Z[0][c], Z[2][c]);
+        s.S2[c] = vfma(two, Z[1][c], t);
+        s.D2[c] = vsub(Z[2][c], Z[0][c]);
+        if constexpr (BORDER_ROW) {
+            const V lo = vmul(wm, Z[0][c]);
+            s.T[c] = vfma(wp, Z[2][c], lo);
+            s.D[c] = vfma(wp, Z[2][c], vneg(lo));
+        } else {
+            s.T[c] = t;
+            s.D[c] = s.D2[c];
+        }
+    }
+}
+
+// The six functionals and m of the pixel at window column j + 1.  `mode`: which of the pixel's horizontal neighbours may
+// be a replicated image border (a compile-time constant at every call site): kWNone: neither; kWLeft / kWRight: wl / wr
+// is its weight; kWBoth: both (the general form).  With weights 1 every form rounds identically.
+// (Differences are formed in the sign each product needs: a packed negation is two LOP3 on the half-rate ALU pipe.)
+enum { kWNone = 0, kWLeft = 1, kWRight = 2, kWBoth = 3 };
+template <typename V>
+struct PixelTerms {
+    V nG, Vz, A, B, Cu, Cv;    // -G, V, A, B, Cu, Cv of the file comment above
+    V m[3];
+};
+template <typename V, bool BORDER_ROW, int N>
+__device__ __forceinline__ PixelTerms<V> pixel_terms(const StencilCols<V, N>& s, int j, int mode, V wl, V nwl, V wr, V pfX, V nfY,
+                                                     V nfx0, V nfy0) {
+    const V two = vdup<V>(2.0f);
+    PixelTerms<V> t;
+    t.nG = vsub(s.S2[j], s.S2[j + 2]);
+    t.Vz = vfma(two, s.D2[j + 1], vadd(s.D2[j], s.D2[j + 2]));
+    t.B = vfma(two, s.T[j + 1], vadd(s.T[j], s.T[j + 2]));
+    t.Cu = vsub(s.D[j + 2], s.D[j]);
+    const V nCu = vsub(s.D[j], s.D[j + 2]);
+    if (mode == kWBoth) {
+        t.A = vfma(wr, s.S2[j + 2], vmul(wl, s.S2[j]));
+        t.Cv = vfma(wr, s.D2[j + 2], vmul(nwl, s.D2[j]));
+    } else if (mode == kWLeft) {
+        t.A = vfma(wl, s.S2[j], s.S2[j + 2]);
+        t.Cv = vfma(nwl, s.D2[j], s.D2[j + 2]);
+    } else if (mode == kWRight) {
+        t.A = vfma(wr, s.S2[j + 2], s.S2[j]);
+        t.Cv = vfma(wr, s.D2[j + 2], vmul(vdup<V>(-1.0f), s.D2[j]));
+    } else {
+        t.A = vadd(s.S2[j + 2], s.S2[j]);
+        t.Cv = BORDER_ROW ? vsub(s.D2[j + 2], s.D2[j]) : t.Cu;
+    }
+    t.m[0] = vmul(pfX, vfma(t.Vz, t.Cu, vmul(t.nG, t.B)));              //  f_x (V Cu - G B)
+    t.m[1] = vmul(nfY, vfma(t.nG, t.Cv, vmul(t.Vz, t.A)));              // -f_y (V A - G Cv)
+    t.m[2] = vfma(nfx0, t.m[0], vfma(nfy0, t.m[1], vfma(nCu, t.Cv, vmul(t.A, t.B))));
+    return t;
+}
+
+// m of the four pixels at window columns 1..4 of a 3 x 6 window.  GENERAL = false: x is a multiple of 4 and so is W, so
+// only pixel 0 can sit on the left image border and only pixel 3 on the right one (wls[0], wrs[3]); GENERAL = true: any
+// pixel may (wls[j], wrs[j]).
 template <typename V, bool GENERAL, bool BORDER_ROW>
 __device__ __forceinline__ void scaled_normals4(const V (&Z)[3][6], V wm, V wp, const V (&wls)[4], const V (&wrs)[4],
                                                 V nfX, V nfY, const V (&nfx0)[4], V nfy0, V (&m)[3][4]) {
-    const V two = vdup<V>(2.0f);
     const V pfX = vneg(nfX), nwl0 = vneg(wls[0]);      // loop-invariant for the callers (hoisted)
-    V S2[6], D2[6], T[6], D[6];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        const V t = vadd(Z[0][c], Z[2][c]);
-        S2[c] = vfma(two, Z[1][c], t);
-        D2[c] = vsub(Z[2][c], Z[0][c]);
-        if constexpr (BORDER_ROW) {
-            const V lo = vmul(wm, Z[0][c]);
-            T[c] = vfma(wp, Z[2][c], lo);
-            D[c] = vfma(wp, Z[2][c], vneg(lo));
-        } else {
-            T[c] = t;
-            D[c] = D2[c];
-        }
-    }
-    // (differences are formed in the sign each product needs: a packed negation is two LOP3 on the half-rate ALU pipe)
+    StencilCols<V, 6> s;
+    stencil_columns<V, 6, BORDER_ROW>(Z, wm, wp, s);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const V nG = vsub(S2[j], S2[j + 2]);
-        const V Vz = vfma(two, D2[j + 1], vadd(D2[j], D2[j + 2]));
-        const V B = vfma(two, T[j + 1], vadd(T[j], T[j + 2]));
-        const V Cu = vsub(D[j + 2], D[j]), nCu = vsub(D[j], D[j + 2]);
-        V A, Cv;
-        if constexpr (GENERAL) {
-            A = vfma(wrs[j], S2[j + 2], vmul(wls[j], S2[j]));
-            Cv = vfma(wrs[j], D2[j + 2], vmul(vneg(wls[j]), D2[j]));
-        } else if (j == 0) {
-            A = vfma(wls[0], S2[0], S2[2]);
-            Cv = vfma(nwl0, D2[0], D2[2]);
-        } else if (j == 3) {
-            A = vfma(wrs[3], S2[5], S2[3]);
-            Cv = vfma(wrs[3], D2[5], vmul(vdup<V>(-1.0f), D2[3]));
-        } else {
-            A = vadd(S2[j + 2], S2[j]);
-            Cv = BORDER_ROW ? vsub(D2[j + 2], D2[j]) : Cu;
-        }
-        const V mx = vmul(pfX, vfma(Vz, Cu, vmul(nG, B)));              //  f_x (V Cu - G B)
-        const V my = vmul(nfY, vfma(nG, Cv, vmul(Vz, A)));              // -f_y (V A - G Cv)
-        m[0][j] = mx;
-        m[1][j] = my;
-        m[2][j] = vfma(nfx0[j], mx, vfma(nfy0, my, vfma(nCu, Cv, vmul(A, B))));
+        const int mode = GENERAL ? kWBoth : (j == 0 ? kWLeft : (j == 3 ? kWRight : kWNone));
+        const PixelTerms<V> t = pixel_terms<V, BORDER_ROW, 6>(s, j, mode, wls[j], GENERAL ? vneg(wls[j]) : nwl0, wrs[j], pfX, nfY, nfx0[j], nfy0);
+        m[0][j] = t.m[0];
+        m[1][j] = t.m[1];
+        m[2][j] = t.m[2];
     }
 }
 
@@ -450,6 +313,81 @@ __device__ __forceinline__ float cos_scaled(float ab, float qa, float qb, const 
         c = __fmul_rn(__fmul_rn(ab, __fmul_rn(sa, sb)), fminf(1.0f, __fmul_rn(__fmul_rn(na, nb), 1e8f)));
     }
     return c;
+}
+
+// BACKWARD in the same form.  With m = (f_x (V Cu - G B), f_y (G Cv - V A), -fx m_x - fy m_y + A B - Cu Cv) and m_bar = dL/dm
+// (from the cosine and the two clamped normalisations, exactly as the reference's autograd forms it), the adjoints of the
+// six window functionals of the PREDICTED depth at one pixel are, with px = f_x (m_bar_x - fx m_bar_z), py = f_y (m_bar_y - fy m_bar_z):
+//     G_bar = py Cv - px B    V_bar = px Cu - py A    A_bar = m_bar_z B - py V
+//     B_bar = m_bar_z A - px G    Cu_bar = px V - m_bar_z Cv    Cv_bar = py G - m_bar_z Cu
+// and each functional is a separable 3 x 3 tap pattern of Z: rows x columns = G: s x d, V: d x s, A: s x e, B: e x s,
+// Cu: d' x d, Cv: d x d', with s = (1, 2, 1), d = (-1, 0, 1) (replicate padding folds their outer taps onto border
+// pixels) and the weighted e = (w-, 0, w+), d' = (-w-, 0, w+), whose weights cancel the folded taps exactly: in gather
+// form, for the output pixel q and F = 0 outside the image,
+//     s: F(q-1) + F(q+1) + (2 + [q first] + [q last]) F(q)      d: F(q-1) - F(q+1) + ([q last] - [q first]) F(q)
+//     e: F(q-1) + F(q+1)                                        d': F(q-1) - F(q+1).
+// Phase 1 stores the six adjoints of every pixel of the tile + 1-pixel ring, phase 2 gathers: rows first, then
+//     Zbar(q) = U(q-1) + W(q+1) + Dh0 Xd(q) + Sh0 Xs(q),   Xd = Rs(G_bar) + Rd'(Cu_bar),  Xs = Rd(V_bar) + Re(B_bar),
+//     P1 = Xd + Rd(Cv_bar),  P2 = Xs + Rs(A_bar),  U = P1 + P2,  W = P2 - P1         (R = the row combinations above).
+// (Checked against float64 autograd of the reference formulation: tests, and tools/probes/bwd_terms_proto.py.)
+struct Adj6 {
+    float G, A, V, Cv, B, Cu;
+};
+__device__ __forceinline__ Adj6 adjoint_terms(const float (&mg)[3], const float (&mp)[3], float qg, float qp, float nG, float Vz, float A,
+                                              float B, float Cu, float Cv, float k, float fx0, float fy0, const FwdCam& fc) {
+    Adj6 o{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (k == 0.0f) return o;
+    // a = n_gt / max(|n_gt|, 1e-12), b = n_pred / max(|n_pred|, 1e-12) in terms of m = 64 f_x f_y n
+    const float inv_a = fminf(rsqrt_approx(qg), fc.kap), inv_b = fminf(rsqrt_approx(qp), fc.kap);
+    float a[3], bn[3], mb[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        a[c] = __fmul_rn(mg[c], inv_a);
+        bn[c] = __fmul_rn(mp[c], inv_b);
+    }
+    const float ki = __fmul_rn(k, inv_b);
+    if (fminf(qg, qp) >= fc.qthr) {
+        // neither normalisation is capped: a and b are unit vectors, the eps clamp of the cosine is far away, and
+        // m_bar = k (a - <a,b> b) / |m|
+        const float c = fmaf(a[0], bn[0], fmaf(a[1], bn[1], __fmul_rn(a[2], bn[2])));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) mb[i] = __fmul_rn(ki, fmaf(-c, bn[i], a[i]));
+    } else {
+        // a zero-depth hole under one of the two windows: the reference's clamps decide.  g = dcos/db: above the eps clamp
+        // a/D - <a,b> b / (D |b|^2), inside it a / eps;  b = m inv_b: the capped normalisation is linear, otherwise project
+        // out b and divide by |m|
+        float inv_den, ab, bb;
+        bool clamped;
+        cosine(a, bn, inv_den, ab, bb, clamped);
+        const float w_b = clamped ? 0.0f : __fmul_rn(__fmul_rn(ab, inv_den), rcp_approx(fmaxf(bb, 1e-30f)));
+        float g[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g[c] = fmaf(-w_b, bn[c], __fmul_rn(a[c], inv_den));
+        const float gb = (inv_b >= fc.kap) ? 0.0f : fmaf(g[0], bn[0], fmaf(g[1], bn[1], __fmul_rn(g[2], bn[2])));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) mb[c] = __fmul_rn(ki, fmaf(-gb, bn[c], g[c]));
+    }
+    const float mz = mb[2];
+    const float px = __fmul_rn(-fc.nfX, fmaf(-fx0, mz, mb[0]));
+    const float py = __fmul_rn(-fc.nfY, fmaf(-fy0, mz, mb[1]));
+    const float G = -nG;
+    o.G = fmaf(py, Cv, -__fmul_rn(px, B));
+    o.V = fmaf(px, Cu, -__fmul_rn(py, A));
+    o.A = fmaf(mz, B, -__fmul_rn(py, Vz));
+    o.B = fmaf(mz, A, -__fmul_rn(px, G));
+    o.Cu = fmaf(px, Vz, -__fmul_rn(mz, Cv));
+    o.Cv = fmaf(py, G, -__fmul_rn(mz, Cu));
+    return o;
+}
+
+// Row combinations of one window column -> the four per-column values of the gather (see above).
+__device__ __forceinline__ void gather_column(float RsG, float RsA, float RdV, float RdCv, float ReB, float RdpCu, float& U, float& Wq,
+                                              float& Xd, float& Xs) {
+    Xd = __fadd_rn(RsG, RdpCu);
+    Xs = __fadd_rn(RdV, ReB);
+    const float p1 = __fadd_rn(Xd, RdCv), p2 = __fadd_rn(Xs, RsA);
+    U = __fadd_rn(p1, p2);
+    Wq = __fsub_rn(p2, p1);
 }
 
 // L1 = true adds the supervised depth loss of the same block of the trainer (trainer.py:1246):
@@ -598,61 +536,6 @@ __device__ __forceinline__ void stage_pairs(float2 (*T)[PITCH], const float* __r
     }
 }
 
-// 8 x gradients of xyz of both fields for the four pixels starting at tile column tx0 of tile row ty (shared row ty + 1):
-// lane 0 = GT, lane 1 = prediction.  Same arithmetic, per lane, as gradients4.
-// `top` = the shared row of image row y - 1 (`pitch` pairs per row), `p0` = the (even) pair index of column x - 1 in it.
-__device__ __forceinline__ void gradients4_pairs(const float2* top, int p0, int pitch, const f32x2 (&fx6)[6], const f32x2 (&fy3)[3],
-                                                 f32x2 (&gu)[3][4], f32x2 (&gv)[3][4], f32x2 (&centre)[4]) {
-    f32x2 Z[3][6];
-    const int u0 = swz_pair(p0), u1 = swz_pair(p0 + 2), u2 = swz_pair(p0 + 4);    // the window's three 16-byte units
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const float2* row = top + r * pitch;                                          // pairs of columns x - 1 .. x + 4
-        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(row + u0), b = *reinterpret_cast<const ulonglong2*>(row + u1),
-                         c = *reinterpret_cast<const ulonglong2*>(row + u2);
-        Z[r][0] = a.x; Z[r][1] = a.y; Z[r][2] = b.x; Z[r][3] = b.y; Z[r][4] = c.x; Z[r][5] = c.y;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) centre[j] = Z[1][1 + j];
-    f32x2 S2[6], D2[6], S1[6], D1[6], P[6], Q[6];
-    const f32x2 two = dup2(2.0f);
-    const f32x2 fy1x2 = mul2(two, fy3[1]);
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        S2[c] = fma2(two, Z[1][c], add2(Z[0][c], Z[2][c]));
-        D2[c] = sub2(Z[2][c], Z[0][c]);
-        P[c] = mul2(fx6[c], S2[c]);
-        Q[c] = mul2(fx6[c], D2[c]);
-        const f32x2 lo = mul2(fy3[0], Z[0][c]);
-        S1[c] = fma2(fy3[2], Z[2][c], fma2(fy1x2, Z[1][c], lo));
-        D1[c] = sub2_unfused(mul2(fy3[2], Z[2][c]), lo);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        gu[0][j] = sub2_unfused(P[j + 2], P[j]);
-        gv[0][j] = fma2(two, Q[j + 1], add2_unfused(Q[j], Q[j + 2]));
-        gu[1][j] = sub2(S1[j + 2], S1[j]);
-        gv[1][j] = fma2(two, D1[j + 1], add2(D1[j], D1[j + 2]));
-        gu[2][j] = sub2(S2[j + 2], S2[j]);
-        gv[2][j] = fma2(two, D2[j + 1], add2(D2[j], D2[j + 2]));
-    }
-}
-
-// cross_rn + normalize3 on both lanes; returns the scale factors (inv) of both lanes.
-__device__ __forceinline__ f32x2 unit_normals_pairs(const f32x2 (&u)[3], const f32x2 (&v)[3], f32x2 (&n)[3]) {
-    f32x2 c[3];
-    c[0] = sub2_unfused(mul2(u[1], v[2]), mul2(u[2], v[1]));
-    c[1] = sub2_unfused(mul2(u[2], v[0]), mul2(u[0], v[2]));
-    c[2] = sub2_unfused(mul2(u[0], v[1]), mul2(u[1], v[0]));
-    float qa, qb;
-    unpk2(fma2(c[0], c[0], fma2(c[1], c[1], mul2(c[2], c[2]))), qa, qb);
-    const f32x2 inv = pk2(fminf(rsqrt_approx(qa), kInvCap), fminf(rsqrt_approx(qb), kInvCap));
-    n[0] = mul2(c[0], inv);
-    n[1] = mul2(c[1], inv);
-    n[2] = mul2(c[2], inv);
-    return inv;
-}
-
 template <bool L1>
 __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel(const LossParams p) {
     extern __shared__ __align__(128) unsigned char fwd_smem[];          // the (gt, pred) tile, then the mask tile (plain variant)
@@ -755,69 +638,64 @@ constexpr int kBPitch = 136;                          // pairs per shared row; t
 constexpr int kBTileRows = kBwdH + 4;                 // rows y0 - 2 .. y0 + kBwdH + 1
 constexpr size_t kBwdPairsSmem = (size_t)(kBTileRows + 3 * kGH) * kBPitch * sizeof(float2);
 
-// 3 x 3 window, one pixel (the two ring columns): same arithmetic as `gradients`, both fields in the two lanes.
-__device__ __forceinline__ void gradients1_pairs(const float2* top, int p0, int pitch, int x, int y, int H, int W, const Cam& cam,
-                                                 f32x2 (&gu)[3], f32x2 (&gv)[3], f32x2& centre) {
-    f32x2 fx3[3], fy3[3];
+// Phase-1 work of one 4-pixel group: the (gt, pred) window `top` (shared row of image row y - 1; `p0` = even pair index of
+// column x - 1) -> the adjoints of the six functionals at the four pixels as three pair fields
+// PA = (G_bar, A_bar), PB = (V_bar, Cv_bar), PC = (B_bar, Cu_bar)   (paired by their ROW taps: s, d, and e / d').
+struct BwdConsts {            // per-thread constants of phase 1, kept as scalars (duplicated into lane pairs at their use:
+    float wl0, wr3, pfX, nfY; // registers are what limits this kernel to three CTAs per SM)
+    float nfx0[4];
+};
+template <bool L1, bool BORDER_ROW>
+__device__ __forceinline__ void bwd_group_pairs(const LossParams& p, const FwdCam& fc, const float2* top, int p0, int pitch, f32x2 wm,
+                                                f32x2 wp, const BwdConsts& k, f32x2 nfy0, float scale, const float (&mk4)[4],
+                                                float2* ga, float2* gb, float2* gc, int g0) {    // G rows of the three pair fields; g0: pair index of pixel 0
+    f32x2 Z[3][6];
+    const int u0 = swz_pair(p0), u1 = swz_pair(p0 + 2), u2 = swz_pair(p0 + 4);    // the window's three 16-byte units
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        fx3[k] = dup2(((float)min(max(x + k - 1, 0), W - 1) - cam.cx) * cam.inv_fx);
-        fy3[k] = dup2(((float)min(max(y + k - 1, 0), H - 1) - cam.cy) * cam.inv_fy);
+    for (int r = 0; r < 3; ++r) {
+        const float2* row = top + r * pitch;
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(row + u0), bq = *reinterpret_cast<const ulonglong2*>(row + u1),
+                         c = *reinterpret_cast<const ulonglong2*>(row + u2);
+        Z[r][0] = a.x; Z[r][1] = a.y; Z[r][2] = bq.x; Z[r][3] = bq.y; Z[r][4] = c.x; Z[r][5] = c.y;
     }
-    f32x2 Z[3][3];
+    StencilCols<f32x2, 6> s;
+    stencil_columns<f32x2, 6, BORDER_ROW>(Z, wm, wp, s);
+    float fy0, dummy;
+    unpk2(nfy0, dummy, fy0);
+    fy0 = -fy0;
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int j = 0; j < 4; ++j) {
+        const int mode = j == 0 ? kWLeft : (j == 3 ? kWRight : kWNone);
+        const PixelTerms<f32x2> t = pixel_terms<f32x2, BORDER_ROW, 6>(s, j, mode, dup2(k.wl0), dup2(-k.wl0), dup2(k.wr3), dup2(k.pfX), dup2(k.nfY),
+                                                                      dup2(k.nfx0[j]), nfy0);
+        float qg, qp, mg[3], mp[3], nG, Vz, A, B, Cu, Cv, zg, zp, nfx;
+        unpk2(fma2(t.m[0], t.m[0], fma2(t.m[1], t.m[1], mul2(t.m[2], t.m[2]))), qg, qp);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) Z[r][c] = *reinterpret_cast<const f32x2*>(top + r * pitch + swz_pair(p0 + c));
-    centre = Z[1][1];
-    f32x2 S2[3], D2[3], S1[3], D1[3];
-    const f32x2 two = dup2(2.0f);
-    const f32x2 fy1x2 = mul2(two, fy3[1]);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        S2[c] = fma2(two, Z[1][c], add2(Z[0][c], Z[2][c]));
-        D2[c] = sub2(Z[2][c], Z[0][c]);
-        const f32x2 lo = mul2(fy3[0], Z[0][c]);
-        S1[c] = fma2(fy3[2], Z[2][c], fma2(fy1x2, Z[1][c], lo));
-        D1[c] = sub2_unfused(mul2(fy3[2], Z[2][c]), lo);
+        for (int c = 0; c < 3; ++c) unpk2(t.m[c], mg[c], mp[c]);
+        unpk2(t.nG, dummy, nG);
+        unpk2(t.Vz, dummy, Vz);
+        unpk2(t.A, dummy, A);
+        unpk2(t.B, dummy, B);
+        unpk2(t.Cu, dummy, Cu);
+        unpk2(t.Cv, dummy, Cv);
+        unpk2(Z[1][1 + j], zg, zp);
+        nfx = k.nfx0[j];
+        float mk;
+        if constexpr (L1) mk = (zg >= p.min_d && zg <= p.max_d) ? 1.0f : 0.0f;
+        else mk = mk4[j];
+        const Adj6 o = adjoint_terms(mg, mp, qg, qp, nG, Vz, A, B, Cu, Cv, scale * mk, -nfx, fy0, fc);
+        const int gi = swz_pair(g0 + j);      // stored pixel by pixel: three 4-pixel output arrays would not fit the register budget
+        *reinterpret_cast<f32x2*>(ga + gi) = pk2(o.G, o.A);
+        *reinterpret_cast<f32x2*>(gb + gi) = pk2(o.V, o.Cv);
+        *reinterpret_cast<f32x2*>(gc + gi) = pk2(o.B, o.Cu);
     }
-    gu[0] = sub2_unfused(mul2(fx3[2], S2[2]), mul2(fx3[0], S2[0]));
-    gv[0] = fma2(two, mul2(fx3[1], D2[1]), add2_unfused(mul2(fx3[0], D2[0]), mul2(fx3[2], D2[2])));
-    gu[1] = sub2(S1[2], S1[0]);
-    gv[1] = fma2(two, D1[1], add2(D1[0], D1[2]));
-    gu[2] = sub2(S2[2], S2[0]);
-    gv[2] = fma2(two, D2[1], add2(D2[0], D2[2]));
-}
-
-// adjoint_px from the packed gradients of one pixel (lane 0 = GT, lane 1 = prediction).
-__device__ __forceinline__ void adjoint_pairs(const f32x2 (&gu)[3], const f32x2 (&gv)[3], float k, f32x2& A, f32x2& B, f32x2& C) {
-    A = B = C = 0ull;
-    if (k == 0.0f) return;
-    f32x2 n[3];
-    const f32x2 inv2 = unit_normals_pairs(gu, gv, n);
-    float a[3], bn[3], up[3], vp[3], tmp, inv;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        unpk2(n[c], a[c], bn[c]);
-        unpk2(gu[c], tmp, up[c]);
-        unpk2(gv[c], tmp, vp[c]);
-    }
-    unpk2(inv2, tmp, inv);
-    float inv_den, ab, bb;
-    bool clamped;
-    cosine_pairs(n, a, bn, inv_den, ab, bb, clamped);
-    float gub[3], gvb[3];
-    adjoint_tail(a, bn, inv, up, vp, k, inv_den, ab, bb, clamped, gub, gvb);
-    A = pk2(gub[0], gub[1]);
-    B = pk2(gvb[0], gvb[1]);
-    C = pk2(gub[2], gvb[2]);
 }
 
 template <bool L1>
 __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_pairs_kernel(const LossParams p) {
     extern __shared__ __align__(128) unsigned char bwd_smem[];
     float2 (*T)[kBPitch] = reinterpret_cast<float2 (*)[kBPitch]>(bwd_smem);                                     // (gt, pred) tile, halo 2
-    float2 (*G)[kGH][kBPitch] = reinterpret_cast<float2 (*)[kGH][kBPitch]>(bwd_smem + sizeof(float2) * kBTileRows * kBPitch);   // A, B, C
+    float2 (*G)[kGH][kBPitch] = reinterpret_cast<float2 (*)[kGH][kBPitch]>(bwd_smem + sizeof(float2) * kBTileRows * kBPitch);   // PA, PB, PC
     const int b = blockIdx.z, x0 = blockIdx.x * kLW, y0 = blockIdx.y * kBwdH;
     const size_t hw = (size_t)p.H * p.W;
     const float* Gt = p.gt + b * hw;
@@ -828,128 +706,123 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_pairs_kernel
     // ---- stage rows y0 - 2 .. y0 + kBwdH + 1, columns x0 - 2 .. x0 + 129 (replicate padding by clamping) ----
     stage_pairs<kBwdH, 2, 3, kBPitch>(T, Gt, Pr, p.H, p.W, x0, y0);
     __syncthreads();
-    const Cam cam = cam_finish(cam_raw);
+    const FwdCam fc = fwd_cam(cam_raw);
     const float scale = -go / (float)msum;    // -grad_out / sum(mask)
     const float l1_scale = (L1 && p.grad_l1) ? gl1 / (float)msum : 0.0f;
 
-    // ---- phase 1: adjoints of the two gradients at every pixel of the tile and its 1-pixel ring ----
+    // ---- phase 1: adjoints of the six functionals at every pixel of the tile and its 1-pixel ring ----
     {
         const int tx0 = 4 * (threadIdx.x & 31), x = x0 + tx0;
-        f32x2 fx6[6];
+        BwdConsts kc;
+        kc.wl0 = x == 0 ? 0.0f : 1.0f;
+        kc.wr3 = x + 3 == p.W - 1 ? 0.0f : 1.0f;
+        kc.pfX = -fc.nfX;
+        kc.nfY = fc.nfY;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) fx6[c] = dup2(((float)min(max(x + c - 1, 0), p.W - 1) - cam.cx) * cam.inv_fx);
+        for (int j = 0; j < 4; ++j) kc.nfx0[j] = -(((float)(x + j) - fc.cx) * fc.inv_fx);
 #pragma unroll 1
         for (int gy = threadIdx.x >> 5; gy < kGH; gy += kLossThreads / 32) {
             const int ty = gy - 1, y = y0 + ty;
-            f32x2 oa[4] = {0ull, 0ull, 0ull, 0ull}, ob[4] = {0ull, 0ull, 0ull, 0ull}, oc[4] = {0ull, 0ull, 0ull, 0ull};
+            float2 *ga = &G[0][gy][0], *gb = &G[1][gy][0], *gc = &G[2][gy][0];
             if (y >= 0 && y < p.H && x < p.W) {
-                f32x2 fy3[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) fy3[r] = dup2(((float)min(max(y + r - 1, 0), p.H - 1) - cam.cy) * cam.inv_fy);
-                f32x2 gu[3][4], gv[3][4], centre[4];
-                gradients4_pairs(&T[ty + 1][0], tx0 + 2, kBPitch, fx6, fy3, gu, gv, centre);
-                float mk4[4];
+                float mk4[4] = {0.f, 0.f, 0.f, 0.f};
                 if constexpr (!L1) {
                     const float4 mv = __ldg(reinterpret_cast<const float4*>(p.mask + b * hw + (size_t)y * p.W + x));
                     mk4[0] = mv.x; mk4[1] = mv.y; mk4[2] = mv.z; mk4[3] = mv.w;
                 }
+                const f32x2 wm = dup2(y > 0 ? 1.0f : 0.0f), wp = dup2(y < p.H - 1 ? 1.0f : 0.0f);
+                const f32x2 nfy0 = dup2(-(((float)y - fc.cy) * fc.inv_fy));
+                if ((y == 0) | (y == p.H - 1)) bwd_group_pairs<L1, true>(p, fc, &T[ty + 1][0], tx0 + 2, kBPitch, wm, wp, kc, nfy0, scale, mk4, ga, gb, gc, 3 + tx0);
+                else bwd_group_pairs<L1, false>(p, fc, &T[ty + 1][0], tx0 + 2, kBPitch, wm, wp, kc, nfy0, scale, mk4, ga, gb, gc, 3 + tx0);
+            } else {      // outside the image: no contribution (pairs 3 + tx0 .. 6 + tx0: half a unit, a whole unit, half of the next)
+                const int pa = swz_pair(3 + tx0), pb = swz_pair(4 + tx0), pc = swz_pair(6 + tx0);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float mk;
-                    if constexpr (L1) {
-                        float zg, zp;
-                        unpk2(centre[j], zg, zp);
-                        mk = (zg >= p.min_d && zg <= p.max_d) ? 1.0f : 0.0f;
-                    } else {
-                        mk = mk4[j];
-                    }
-                    const f32x2 u[3] = {gu[0][j], gu[1][j], gu[2][j]}, v[3] = {gv[0][j], gv[1][j], gv[2][j]};
-                    adjoint_pairs(u, v, scale * mk, oa[j], ob[j], oc[j]);
+                for (int f = 0; f < 3; ++f) {
+                    float2* row = f == 0 ? ga : (f == 1 ? gb : gc);
+                    *reinterpret_cast<f32x2*>(row + pa) = 0ull;
+                    *reinterpret_cast<ulonglong2*>(row + pb) = make_ulonglong2(0ull, 0ull);
+                    *reinterpret_cast<f32x2*>(row + pc) = 0ull;
                 }
-            }
-            // pairs 3 + tx0 .. 6 + tx0 of the row: the upper half of a unit, a whole unit, the lower half of the next
-            const int pa = swz_pair(3 + tx0), pb = swz_pair(4 + tx0), pc = swz_pair(6 + tx0);
-#pragma unroll
-            for (int f = 0; f < 3; ++f) {
-                const f32x2* o = f == 0 ? oa : (f == 1 ? ob : oc);
-                float2* row = &G[f][gy][0];
-                *reinterpret_cast<f32x2*>(row + pa) = o[0];
-                *reinterpret_cast<ulonglong2*>(row + pb) = make_ulonglong2(o[1], o[2]);
-                *reinterpret_cast<f32x2*>(row + pc) = o[3];
             }
         }
     }
-    for (int i = threadIdx.x; i < kGH * 2; i += kLossThreads) {     // the two ring columns, one pixel at a time
+    for (int i = threadIdx.x; i < kGH * 2; i += kLossThreads) {     // the two ring columns, one pixel at a time (general weights)
         const int gy = i >> 1, tx = (i & 1) ? kLW : -1;
         const int ty = gy - 1;
         const int x = x0 + tx, y = y0 + ty;
-        f32x2 A = 0ull, B = 0ull, C = 0ull;
+        f32x2 A2 = 0ull, B2 = 0ull, C2 = 0ull;
         if (x >= 0 && x < p.W && y >= 0 && y < p.H) {
-            f32x2 gu[3], gv[3], centre;
-            gradients1_pairs(&T[ty + 1][0], tx + 2, kBPitch, x, y, p.H, p.W, cam, gu, gv, centre);
-            float zg, zp;
-            unpk2(centre, zg, zp);
+            f32x2 Z[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Z[r][c] = *reinterpret_cast<const f32x2*>(&T[ty + 1 + r][swz_pair(tx + 2 + c)]);
+            StencilCols<f32x2, 3> s;
+            stencil_columns<f32x2, 3, true>(Z, dup2(y > 0 ? 1.0f : 0.0f), dup2(y < p.H - 1 ? 1.0f : 0.0f), s);
+            const float fx0 = ((float)x - fc.cx) * fc.inv_fx, fy0 = ((float)y - fc.cy) * fc.inv_fy;
+            const float wl = x == 0 ? 0.0f : 1.0f, wr = x == p.W - 1 ? 0.0f : 1.0f;
+            const PixelTerms<f32x2> t = pixel_terms<f32x2, true, 3>(s, 0, kWBoth, dup2(wl), dup2(-wl), dup2(wr), dup2(-fc.nfX), dup2(fc.nfY),
+                                                                    dup2(-fx0), dup2(-fy0));
+            float qg, qp, mg[3], mp[3], nG, Vz, A, B, Cu, Cv, zg, zp, dummy;
+            unpk2(fma2(t.m[0], t.m[0], fma2(t.m[1], t.m[1], mul2(t.m[2], t.m[2]))), qg, qp);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) unpk2(t.m[c], mg[c], mp[c]);
+            unpk2(t.nG, dummy, nG);
+            unpk2(t.Vz, dummy, Vz);
+            unpk2(t.A, dummy, A);
+            unpk2(t.B, dummy, B);
+            unpk2(t.Cu, dummy, Cu);
+            unpk2(t.Cv, dummy, Cv);
+            unpk2(Z[1][1], zg, zp);
             const float mk = mask_value<L1>(p, b * hw + (size_t)y * p.W + x, zg);
-            adjoint_pairs(gu, gv, scale * mk, A, B, C);
+            const Adj6 o = adjoint_terms(mg, mp, qg, qp, nG, Vz, A, B, Cu, Cv, scale * mk, fx0, fy0, fc);
+            A2 = pk2(o.G, o.A);
+            B2 = pk2(o.V, o.Cv);
+            C2 = pk2(o.B, o.Cu);
         }
-        *reinterpret_cast<f32x2*>(&G[0][gy][swz_pair(3 + tx)]) = A;
-        *reinterpret_cast<f32x2*>(&G[1][gy][swz_pair(3 + tx)]) = B;
-        *reinterpret_cast<f32x2*>(&G[2][gy][swz_pair(3 + tx)]) = C;
+        *reinterpret_cast<f32x2*>(&G[0][gy][swz_pair(3 + tx)]) = A2;
+        *reinterpret_cast<f32x2*>(&G[1][gy][swz_pair(3 + tx)]) = B2;
+        *reinterpret_cast<f32x2*>(&G[2][gy][swz_pair(3 + tx)]) = C2;
     }
     __syncthreads();
 
-    // ---- phase 2: gather, four pixels at a time ----
+    // ---- phase 2: gather, four pixels at a time: rows first (packed: both members of a pair field share their row taps) ----
     {
         const int tx0 = 4 * (threadIdx.x & 31), x = x0 + tx0;
         if (x >= p.W) return;
+        const f32x2 pm = pk2(1.0f, -1.0f);
 #pragma unroll 1
         for (int ty = threadIdx.x >> 5; ty < kBwdH; ty += kLossThreads / 32) {
             const int y = y0 + ty;
             if (y >= p.H) break;
-            const float Sv[3] = {1.0f, 2.0f + (y == 0) + (y == p.H - 1), 1.0f};
-            const float Dv[3] = {1.0f, (float)(y == p.H - 1) - (float)(y == 0), -1.0f};
-            f32x2 VA[6], VB[6], VC[6];      // vertical combinations: (VU_x, VU_y), (VV_x, VV_y), (VU_z, VV_z) of the six window columns
+            const f32x2 sv = dup2(2.0f + (y == 0) + (y == p.H - 1)), dv = dup2((float)(y == p.H - 1) - (float)(y == 0));
+            float U[6], Wq[6], Xd[6], Xs[6];
 #pragma unroll
-            for (int k6 = 0; k6 < 6; ++k6) VA[k6] = VB[k6] = VC[k6] = 0ull;
+            for (int h = 0; h < 3; ++h) {      // columns x - 1 .. x + 4 = pairs tx0 + 2 .. tx0 + 7 = three swizzled units
+                const int u = swz_pair(tx0 + 2 + 2 * h);
+                ulonglong2 w[3][3];            // [field][row above / at / below]
 #pragma unroll
-            for (int di = 0; di < 3; ++di) {
-                const f32x2 ws = dup2(Sv[di]), wd = dup2(Dv[di]), wsd = pk2(Sv[di], Dv[di]);
-                const float2* ra = &G[0][ty + di][0];      // columns x - 1 .. x + 4 = pairs tx0 + 2 .. tx0 + 7 = three swizzled units
-                const float2* rb = &G[1][ty + di][0];
-                const float2* rc = &G[2][ty + di][0];
+                for (int f = 0; f < 3; ++f)
 #pragma unroll
-                for (int h = 0; h < 3; ++h) {
-                    const int u = swz_pair(tx0 + 2 + 2 * h);
-                    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(ra + u), bq = *reinterpret_cast<const ulonglong2*>(rb + u),
-                                     c = *reinterpret_cast<const ulonglong2*>(rc + u);
-                    VA[2 * h] = fma2(ws, a.x, VA[2 * h]);
-                    VA[2 * h + 1] = fma2(ws, a.y, VA[2 * h + 1]);
-                    VB[2 * h] = fma2(wd, bq.x, VB[2 * h]);
-                    VB[2 * h + 1] = fma2(wd, bq.y, VB[2 * h + 1]);
-                    VC[2 * h] = fma2(wsd, c.x, VC[2 * h]);
-                    VC[2 * h + 1] = fma2(wsd, c.y, VC[2 * h + 1]);
+                    for (int di = 0; di < 3; ++di) w[f][di] = *reinterpret_cast<const ulonglong2*>(&G[f][ty + di][u]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const f32x2 au = e ? w[0][0].y : w[0][0].x, am = e ? w[0][1].y : w[0][1].x, ad = e ? w[0][2].y : w[0][2].x;
+                    const f32x2 bu = e ? w[1][0].y : w[1][0].x, bm = e ? w[1][1].y : w[1][1].x, bd = e ? w[1][2].y : w[1][2].x;
+                    const f32x2 cu = e ? w[2][0].y : w[2][0].x, cd = e ? w[2][2].y : w[2][2].x;
+                    float RsG, RsA, RdV, RdCv, ReB, RdpCu;
+                    unpk2(fma2(sv, am, add2(au, ad)), RsG, RsA);
+                    unpk2(fma2(dv, bm, sub2(bu, bd)), RdV, RdCv);
+                    unpk2(fma2(cd, pm, cu), ReB, RdpCu);
+                    gather_column(RsG, RsA, RdV, RdCv, ReB, RdpCu, U[2 * h + e], Wq[2 * h + e], Xd[2 * h + e], Xs[2 * h + e]);
                 }
             }
-            const float fyq = ((float)y - cam.cy) * cam.inv_fy;
             float res[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int xj = x + j;
-                const float Sh[3] = {1.0f, 2.0f + (xj == 0) + (xj == p.W - 1), 1.0f};
-                const float Dh[3] = {1.0f, (float)(xj == p.W - 1) - (float)(xj == 0), -1.0f};
-                f32x2 acc01 = 0ull;
-                float acc2 = 0.0f;
-#pragma unroll
-                for (int dj = 0; dj < 3; ++dj) {
-                    acc01 = fma2(dup2(Dh[dj]), VA[j + dj], fma2(dup2(Sh[dj]), VB[j + dj], acc01));
-                    float vu2, vv2;
-                    unpk2(VC[j + dj], vu2, vv2);
-                    acc2 = fmaf(Dh[dj], vu2, fmaf(Sh[dj], vv2, acc2));
-                }
-                float a0, a1;
-                unpk2(acc01, a0, a1);
-                const float fxq = ((float)xj - cam.cx) * cam.inv_fx;
-                res[j] = fmaf(fxq, a0, fmaf(fyq, a1, acc2));
+                const float sh0 = 2.0f + (xj == 0) + (xj == p.W - 1), dh0 = (float)(xj == p.W - 1) - (float)(xj == 0);
+                res[j] = fmaf(sh0, Xs[j + 1], fmaf(dh0, Xd[j + 1], __fadd_rn(U[j], Wq[j + 2])));
                 if constexpr (L1) {
                     float zg, zp;
                     unpk2(*reinterpret_cast<const f32x2*>(&T[ty + 2][swz_pair(3 + tx0 + j)]), zg, zp);
@@ -969,140 +842,98 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_pairs_kernel
     }
 }
 
-// 72 KB of shared memory per CTA: three CTAs per SM, so up to 85 registers per thread (no spills)
+// Scalar twin (any width / alignment): the same operation sequence per pixel as the packed kernel (general border weights,
+// which round identically), planar depth tiles and six planar adjoint fields 0: G_bar, 1: A_bar, 2: V_bar, 3: Cv_bar,
+// 4: B_bar, 5: Cu_bar.  72 KB of shared memory per CTA: three CTAs per SM.
+__device__ __forceinline__ Adj6 bwd_pixel_scalar(const LossParams& p, const FwdCam& fc, const float (*tg)[kLBoxW], const float (*tp)[kLBoxW],
+                                                 int ty, int tx, int x, int y, float k) {
+    float Zg[3][3], Zp[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Zg[r][c] = tg[kLRow + ty + r - 1][kLCol + tx + c - 1];
+            Zp[r][c] = tp[kLRow + ty + r - 1][kLCol + tx + c - 1];
+        }
+    const float wm = y > 0 ? 1.0f : 0.0f, wp = y < p.H - 1 ? 1.0f : 0.0f;
+    const float wl = x == 0 ? 0.0f : 1.0f, wr = x == p.W - 1 ? 0.0f : 1.0f;
+    const float fx0 = ((float)x - fc.cx) * fc.inv_fx, fy0 = ((float)y - fc.cy) * fc.inv_fy;
+    StencilCols<float, 3> sg, sp;
+    stencil_columns<float, 3, true>(Zg, wm, wp, sg);
+    stencil_columns<float, 3, true>(Zp, wm, wp, sp);
+    const PixelTerms<float> g = pixel_terms<float, true, 3>(sg, 0, kWBoth, wl, -wl, wr, -fc.nfX, fc.nfY, -fx0, -fy0);
+    const PixelTerms<float> t = pixel_terms<float, true, 3>(sp, 0, kWBoth, wl, -wl, wr, -fc.nfX, fc.nfY, -fx0, -fy0);
+    const float qg = fmaf(g.m[0], g.m[0], fmaf(g.m[1], g.m[1], __fmul_rn(g.m[2], g.m[2])));
+    const float qp = fmaf(t.m[0], t.m[0], fmaf(t.m[1], t.m[1], __fmul_rn(t.m[2], t.m[2])));
+    const float mg[3] = {g.m[0], g.m[1], g.m[2]}, mp[3] = {t.m[0], t.m[1], t.m[2]};
+    return adjoint_terms(mg, mp, qg, qp, t.nG, t.Vz, t.A, t.B, t.Cu, t.Cv, k, fx0, fy0, fc);
+}
+
 template <bool L1>
 __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_bwd_kernel(const LossParams p) {
-    // dynamic shared memory: two halo'd depth tiles and the six adjoint fields of the tile + 1-pixel ring (46 KB)
     extern __shared__ __align__(128) unsigned char bwd_smem[];
     float (*tg)[kLBoxW] = reinterpret_cast<float (*)[kLBoxW]>(bwd_smem);
     float (*tp)[kLBoxW] = reinterpret_cast<float (*)[kLBoxW]>(bwd_smem + kLTilePad);
-    float (*G)[kGH][kGPitch] = reinterpret_cast<float (*)[kGH][kGPitch]>(bwd_smem + 2 * kLTilePad);   // gu_bar xyz, gv_bar xyz
+    float (*G)[kGH][kGPitch] = reinterpret_cast<float (*)[kGH][kGPitch]>(bwd_smem + 2 * kLTilePad);   // the six adjoint fields
     const int b = blockIdx.z, x0 = blockIdx.x * kLW, y0 = blockIdx.y * kBwdH;
     const size_t hw = (size_t)p.H * p.W;
     stage_tile<kBwdH>(tg, p.gt + b * hw, p.H, p.W, x0, y0);
     stage_tile<kBwdH>(tp, p.pred + b * hw, p.H, p.W, x0, y0);
     __syncthreads();
-    const Cam cam = load_cam(p.K, b);
+    const FwdCam fc = fwd_cam(cam_fetch(p.K, b));
     const float scale = -__ldg(p.grad_out) / (float)p.sums2[1];    // -grad_out / sum(mask)
     const float l1_scale = (L1 && p.grad_l1) ? __ldg(p.grad_l1) / (float)p.sums2[1] : 0.0f;
 
-    // phase 1: adjoint of the two gradients at every pixel of the tile and its 1-pixel ring.
-    // Core columns go four pixels at a time (shared 3 x 6 windows), the two ring columns one pixel at a time.
-    for (int i = threadIdx.x; i < kGH * (kLW / 4); i += kLossThreads) {
-        const int gy = i / (kLW / 4), tx0 = 4 * (i - gy * (kLW / 4));
-        const int ty = gy - 1, x = x0 + tx0, y = y0 + ty;
-        float out[6][4];
-#pragma unroll
-        for (int c = 0; c < 6; ++c)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) out[c][j] = 0.0f;
-        if (y >= 0 && y < p.H && x < p.W) {
-            float gug[3][4], gvg[3][4], gup[3][4], gvp[3][4];
-            gradients4(tg, ty, tx0, x, y, p.H, p.W, cam, gug, gvg);
-            gradients4(tp, ty, tx0, x, y, p.H, p.W, cam, gup, gvp);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (x + j < p.W) {
-                    const float k = scale * mask_value<L1>(p, b * hw + (size_t)y * p.W + x + j, tg[kLRow + ty][kLCol + tx0 + j]);
-                    const float ug[3] = {gug[0][j], gug[1][j], gug[2][j]}, vg[3] = {gvg[0][j], gvg[1][j], gvg[2][j]};
-                    const float up[3] = {gup[0][j], gup[1][j], gup[2][j]}, vp[3] = {gvp[0][j], gvp[1][j], gvp[2][j]};
-                    float gub[3], gvb[3];
-                    adjoint_px(ug, vg, up, vp, k, gub, gvb);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        out[c][j] = gub[c];
-                        out[3 + c][j] = gvb[c];
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 6; ++c)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) G[c][gy][kGCol + tx0 + j] = out[c][j];
-    }
-    for (int i = threadIdx.x; i < kGH * 2; i += kLossThreads) {
-        const int gy = i >> 1, tx = (i & 1) ? kLW : -1;
-        const int ty = gy - 1, gx = kGCol + tx;
-        const int x = x0 + tx, y = y0 + ty;
-        float gub[3] = {0.f, 0.f, 0.f}, gvb[3] = {0.f, 0.f, 0.f};
+    // phase 1: the six adjoints at every pixel of the tile and its 1-pixel ring (G column kGCol + tx, tx = -1 .. kLW)
+    for (int i = threadIdx.x; i < kGH * (kLW + 2); i += kLossThreads) {
+        const int gy = i / (kLW + 2), tx = i - gy * (kLW + 2) - 1;
+        const int ty = gy - 1, x = x0 + tx, y = y0 + ty;
+        Adj6 o{0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
         if (x >= 0 && x < p.W && y >= 0 && y < p.H) {
             const float k = scale * mask_value<L1>(p, b * hw + (size_t)y * p.W + x, tg[kLRow + ty][kLCol + tx]);
-            float ug[3], vg[3], up[3], vp[3];
-            gradients(tg, ty, tx, x, y, p.H, p.W, cam, ug, vg);
-            gradients(tp, ty, tx, x, y, p.H, p.W, cam, up, vp);
-            adjoint_px(ug, vg, up, vp, k, gub, gvb);
+            o = bwd_pixel_scalar(p, fc, tg, tp, ty, tx, x, y, k);
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            G[c][gy][gx] = gub[c];
-            G[3 + c][gy][gx] = gvb[c];
-        }
+        const int gx = kGCol + tx;
+        G[0][gy][gx] = o.G;
+        G[1][gy][gx] = o.A;
+        G[2][gy][gx] = o.V;
+        G[3][gy][gx] = o.Cv;
+        G[4][gy][gx] = o.B;
+        G[5][gy][gx] = o.Cu;
     }
     __syncthreads();
 
-    // phase 2: gather the adjoint stencil four pixels at a time; the replicate padding is folded onto border pixels
-    // by the per-axis weights (file header).  Vertical combinations first (shared by the four pixels), then horizontal.
-    for (int i = threadIdx.x; i < (kLW / 4) * kBwdH; i += kLossThreads) {
-        const int ty = i / (kLW / 4), tx0 = 4 * (i - ty * (kLW / 4));
-        const int x = x0 + tx0, y = y0 + ty;
+    // phase 2: gather, one pixel per thread and step: rows first, then the four per-column values of the three window columns
+    for (int i = threadIdx.x; i < kLW * kBwdH; i += kLossThreads) {
+        const int ty = i / kLW, tx = i - ty * kLW;
+        const int x = x0 + tx, y = y0 + ty;
         if (x >= p.W || y >= p.H) continue;
-        const float Sv[3] = {1.0f, 2.0f + (y == 0) + (y == p.H - 1), 1.0f};
-        const float Dv[3] = {1.0f, (float)(y == p.H - 1) - (float)(y == 0), -1.0f};
-        float VU[3][6], VV[3][6];
+        const float sv0 = 2.0f + (y == 0) + (y == p.H - 1), dv0 = (float)(y == p.H - 1) - (float)(y == 0);
+        float U[3], Wq[3], Xd[3], Xs[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 3; ++c) {
+            const int gx = kGCol + tx + c - 1;
+            float u[6], m[6], d[6];
 #pragma unroll
-            for (int k6 = 0; k6 < 6; ++k6) VU[c][k6] = VV[c][k6] = 0.0f;
-#pragma unroll
-        for (int di = 0; di < 3; ++di)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float* ru = &G[c][ty + di][kGCol + tx0];
-                const float* rv = &G[3 + c][ty + di][kGCol + tx0];
-                const float4 mu = *reinterpret_cast<const float4*>(ru), mv = *reinterpret_cast<const float4*>(rv);
-                const float wu[6] = {ru[-1], mu.x, mu.y, mu.z, mu.w, ru[4]};
-                const float wv[6] = {rv[-1], mv.x, mv.y, mv.z, mv.w, rv[4]};
-#pragma unroll
-                for (int k6 = 0; k6 < 6; ++k6) {
-                    VU[c][k6] = fmaf(Sv[di], wu[k6], VU[c][k6]);
-                    VV[c][k6] = fmaf(Dv[di], wv[k6], VV[c][k6]);
-                }
+            for (int f = 0; f < 6; ++f) {
+                u[f] = G[f][ty][gx];
+                m[f] = G[f][ty + 1][gx];
+                d[f] = G[f][ty + 2][gx];
             }
-        const float fyq = ((float)y - cam.cy) * cam.inv_fy;
-        float res[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int xj = x + j;
-            const float Sh[3] = {1.0f, 2.0f + (xj == 0) + (xj == p.W - 1), 1.0f};
-            const float Dh[3] = {1.0f, (float)(xj == p.W - 1) - (float)(xj == 0), -1.0f};
-            float A[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float acc = 0.0f;
-#pragma unroll
-                for (int dj = 0; dj < 3; ++dj) acc = fmaf(Dh[dj], VU[c][j + dj], fmaf(Sh[dj], VV[c][j + dj], acc));
-                A[c] = acc;
-            }
-            const float fxq = ((float)xj - cam.cx) * cam.inv_fx;
-            res[j] = fmaf(fxq, A[0], fmaf(fyq, A[1], A[2]));
-            if constexpr (L1) {     // d/dpred of sum |gt - pred| m / sum m: sign(pred - gt) m / sum m (sign(0) = 0, as torch.abs)
-                if (xj < p.W) {
-                    const float zg = tg[kLRow + ty][kLCol + tx0 + j], zp = tp[kLRow + ty][kLCol + tx0 + j];
-                    const float mk = mask_value<L1>(p, b * hw + (size_t)y * p.W + xj, zg);
-                    const float sgn = (zp > zg) ? 1.0f : ((zp < zg) ? -1.0f : 0.0f);
-                    res[j] = fmaf(l1_scale * mk, sgn, res[j]);
-                }
-            }
+            const float RsG = fmaf(sv0, m[0], __fadd_rn(u[0], d[0])), RsA = fmaf(sv0, m[1], __fadd_rn(u[1], d[1]));
+            const float RdV = fmaf(dv0, m[2], __fsub_rn(u[2], d[2])), RdCv = fmaf(dv0, m[3], __fsub_rn(u[3], d[3]));
+            const float ReB = fmaf(d[4], 1.0f, u[4]), RdpCu = fmaf(d[5], -1.0f, u[5]);
+            gather_column(RsG, RsA, RdV, RdCv, ReB, RdpCu, U[c], Wq[c], Xd[c], Xs[c]);
         }
-        float* o = p.grad_pred + b * hw + (size_t)y * p.W + x;
-        if (x + 3 < p.W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-            *reinterpret_cast<float4*>(o) = make_float4(res[0], res[1], res[2], res[3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (x + j < p.W) o[j] = res[j];
+        const float sh0 = 2.0f + (x == 0) + (x == p.W - 1), dh0 = (float)(x == p.W - 1) - (float)(x == 0);
+        float res = fmaf(sh0, Xs[1], fmaf(dh0, Xd[1], __fadd_rn(U[0], Wq[2])));
+        if constexpr (L1) {     // d/dpred of sum |gt - pred| m / sum m: sign(pred - gt) m / sum m (sign(0) = 0, as torch.abs)
+            const float zg = tg[kLRow + ty][kLCol + tx], zp = tp[kLRow + ty][kLCol + tx];
+            const float mk = mask_value<L1>(p, b * hw + (size_t)y * p.W + x, zg);
+            const float sgn = (zp > zg) ? 1.0f : ((zp < zg) ? -1.0f : 0.0f);
+            res = fmaf(l1_scale * mk, sgn, res);
         }
+        p.grad_pred[b * hw + (size_t)y * p.W + x] = res;
     }
 }
 
