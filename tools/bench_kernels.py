@@ -153,6 +153,22 @@ def main():
             emit("loss/normals_fwd", f"depth_gt, depth_pred, mask f32 [{n_img},1,{h},{w}] -> loss (C ABI)", 12 * npx, fwd, small)
             emit("loss/normals_bwd", f"-> d loss / d depth_pred f32 [{n_img},1,{h},{w}] (C ABI)", 16 * npx, bwd, small)
 
+            # the trainer's own call (trainer.py:1240-1251): range mask derived from the GT tile, L1 depth loss folded in; no mask tensor
+            sums3 = torch.empty(3, dtype=torch.float64, device=dev)
+            losses2 = torch.empty(2, device=dev)
+            gtc = gt[:, None].contiguous()
+
+            def sup_fwd():
+                assert L.polcue_supervised_losses_fwd_f32(gtc.data_ptr(), pd.data_ptr(), k.data_ptr(), C.c_float(0.1), C.c_float(2.0), n_img, h, w,
+                                                          wsb.data_ptr(), sums3.data_ptr(), losses2.data_ptr(), st) == 0
+
+            def sup_bwd():
+                assert L.polcue_supervised_losses_bwd_f32(gtc.data_ptr(), pd.data_ptr(), k.data_ptr(), C.c_float(0.1), C.c_float(2.0), n_img, h, w,
+                                                          sums3.data_ptr(), one.data_ptr(), one.data_ptr(), gradp.data_ptr(), st) == 0
+            emit("loss/supervised_fwd", f"depth_gt (with zero-depth holes), depth_pred f32 [{n_img},1,{h},{w}] -> normals loss + L1 depth loss (C ABI)",
+                 8 * npx, sup_fwd, small)
+            emit("loss/supervised_bwd", f"-> d (both losses) / d depth_pred f32 [{n_img},1,{h},{w}] (C ABI)", 12 * npx, sup_bwd, small)
+
             def fwd_bwd():
                 predd.grad = None
                 ops.normals_loss(smooth, predd, k, maskf).backward()
