@@ -257,6 +257,9 @@ POLCUE_API int polcue_depth_to_normals_f32(const float* depth, const float* K, i
  *      fixed order, so results are bitwise reproducible).
  * bwd: grad_pred (B x 1 x H x W) = d(loss)/d(depth_pred) * grad_out, with sums2 from the forward call and grad_out a
  *      DEVICE float scalar.  depth_gt and mask receive no gradient (they are data).
+ * Both kernels evaluate the stencil in a cancellation-free form scaled by f_x f_y: |64 f_x f_y n|^2 must stay
+ * finite in float32, i.e. depths up to ~1e7 in whatever unit (metres in the reference); the clamps of F.normalize and
+ * cosine_similarity are reproduced for |n| < 1e-12 (zero-depth holes).
  * ------------------------------------------------------------------------------------------- */
 POLCUE_API size_t polcue_normals_loss_workspace_bytes(void);
 POLCUE_API int polcue_normals_loss_fwd_f32(const float* depth_gt, const float* depth_pred, const float* K, const float* mask,
