@@ -28,7 +28,7 @@ namespace polcue {
 namespace {
 
 constexpr int kLW = 128, kLossThreads = 256;
-constexpr int kFwdH = 32, kBwdH = 14;                        // tile heights: forward keeps two depth tiles, backward also six adjoint fields;
+constexpr int kFwdH = 32, kBwdH = 14;                        // tile heights: the forward keeps the depth tile(s), the backward also six adjoint fields;
                                                              // 14 + 2 ring rows = 16 rows x 32 pixel groups = two full rounds of 256 threads in phase 1
 constexpr int kHalo = 2;
 constexpr int kLBoxW = kLW + 8;                              // interior at column 4, row 2
@@ -458,8 +458,8 @@ __global__ void __launch_bounds__(kLossThreads, 4) normals_loss_fwd_kernel(const
 // ---------------------------------------------------------------------------------------------------------------
 // Packed forward (rows that are 16-byte multiples).  The GT and the predicted depth go through the IDENTICAL stencil,
 // so they ride in the two lanes of Blackwell's packed FP32 instructions (FFMA2 / FADD2 / FMUL2: the scalar FLOP rate
-// in half the issue slots, tools/probes/int_pipe_probe.cu): every lane runs exactly the operation sequence of
-// gradients4 / cross_rn / normalize3 above, so losses are bit-identical to the scalar kernel's.  The tile is staged
+// in half the issue slots, tools/probes/int_pipe_probe.cu): every lane runs exactly the operation sequence of the
+// scalar kernel (the same templated core), so losses are bit-identical to the scalar kernel's.  The tile is staged
 // INTERLEAVED -- shared element = (gt, pred) of one pixel -- so one LDS.128 delivers two ready-made lane pairs and a
 // thread's 3 x 6 window of both fields costs 9 loads (18 in the planar layout).  Staging is by hand (coalesced
 // 16-byte global loads, replicate padding by clamped coordinates); TMA cannot interleave two tensors.
@@ -628,11 +628,11 @@ __global__ void __launch_bounds__(kLossThreads, 3) normals_loss_fwd_pairs_kernel
 
 // ---------------------------------------------------------------------------------------------------------------
 // Packed backward (rows that are 16-byte multiples).  Phase 1 runs the two stencils of every pixel of the tile + ring
-// in the two lanes of packed FP32 instructions (as the packed forward does) and stores the six adjoint fields as three
-// PAIR fields A = (gu_bar_x, gu_bar_y), B = (gv_bar_x, gv_bar_y), C = (gu_bar_z, gv_bar_z); phase 2 gathers them with
-// packed instructions too: the vertical combinations of A / B / C are independent chains per lane, and the horizontal
-// chain  acc = fma(Dh, VU, fma(Sh, VV, acc))  of components x and y runs in the two lanes of one register pair.  Every
-// lane performs exactly the operation sequence of the scalar kernel below: gradients are bit-identical to it.
+// in the two lanes of packed FP32 instructions (as the packed forward does), forms the six adjoints of the prediction's
+// functionals per pixel (adjoint_terms, scalar: only one lane needs it) and stores them as three PAIR fields paired by
+// their row taps, PA = (G_bar, A_bar), PB = (V_bar, Cv_bar), PC = (B_bar, Cu_bar); phase 2 forms the row combinations of
+// both members of a pair in packed instructions, then four values per window column (gather_column) and the output.
+// Every lane performs exactly the operation sequence of the scalar kernel below: gradients are bit-identical to it.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kBPitch = 136;                          // pairs per shared row; tile column c lives at index c + 3 (c = -2 .. 129)
 constexpr int kBTileRows = kBwdH + 4;                 // rows y0 - 2 .. y0 + kBwdH + 1
