@@ -227,3 +227,21 @@ def test_depth_to_normals_oracle_against_kornia_outputs():
         well = np.isfinite(bound) & (bound < 1e6) & ~dead
         assert np.abs(got - ref).transpose(0, 2, 3, 1)[well].max(initial=0.0) < 1e-12 * max(1.0, float(bound[well].max(initial=1.0))), name
         assert (ref.transpose(0, 2, 3, 1)[dead] == 0).all() and (got.transpose(0, 2, 3, 1)[dead] == 0).all(), name
+
+
+def test_six_functional_form_of_the_normals_loss_equals_the_reference_formulation():
+    """The loss kernels evaluate the stencil through six window functionals (G, V, A, B, Cu, Cv; csrc/normals_loss.cu) instead of
+    the reference's gradients of (fx Z, fy Z, Z).  The float64 restatement of that form -- forward, adjoints, and the gather
+    with the replicate-padding folds, tools/probes/bwd_terms_proto.py -- must agree with float64 autograd of the reference
+    formulation (oracle.normals_loss_torch, manydepth/trainer.py:1298-1309) to rounding on every shape, borders and 2-pixel
+    images included."""
+    import importlib.util
+    import sys
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "probes", "bwd_terms_proto.py")
+    spec = importlib.util.spec_from_file_location("bwd_terms_proto", path)
+    proto = importlib.util.module_from_spec(spec)
+    sys.modules["bwd_terms_proto"] = proto
+    spec.loader.exec_module(proto)
+    for seed, (h, w) in enumerate(((7, 9), (2, 2), (12, 16), (3, 4), (2, 9), (9, 2), (5, 33))):
+        d_loss, d_grad = proto.compare_with_autograd(h, w, seed)
+        assert d_loss < 1e-13 and d_grad < 1e-12, ((h, w), d_loss, d_grad)

@@ -1,13 +1,12 @@
 """CPU prototype (numpy float64) of the normals-loss backward in the cancellation-free form used by csrc/normals_loss.cu:
 forward m = f_x f_y (gu x gv) from the six window functionals (G, V, A, B, Cu, Cv), their adjoints, and the gather with the
 replicate-padding folds -- checked against float64 autograd of the reference formulation (oracle.normals_loss_torch).
-  python tools/probes/bwd_terms_proto.py      (prints differences at the 1e-15 level; images with H = 1 or W = 1 are degenerate)
+  python tools/probes/bwd_terms_proto.py      (prints differences at the 1e-15 level; images with H = 1 or W = 1 are degenerate: m = 0, the clamped branch of the kernels)
 """
 import sys, numpy as np, torch
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import polcue_oracle as O
-rng = np.random.default_rng(0)
 
 def fwd_terms(Z, K):
     H, W = Z.shape
@@ -61,7 +60,10 @@ def loss_and_grad(Zg, Zq, K, mask):
             + cols(rows(Cub,"d'"),'d') + cols(rows(Cvb,'d'),"d'"))
     return loss, Zbar
 
-for (H, W) in ((7, 9), (1, 8), (5, 1), (2, 2), (12, 16), (3, 4)):
+def compare_with_autograd(H, W, seed=0):
+    """(loss difference, max gradient difference relative to the largest gradient) between the six-functional form and
+    float64 autograd of the reference formulation, on a random smooth surface with a random mask."""
+    rng = np.random.default_rng(seed)
     K = np.array([[520.0*W/640, 0, W/2 - 0.3], [0, 515.0*H/480, H/2 + 0.2], [0, 0, 1]])
     yy, xx = np.mgrid[0:H, 0:W]
     Zg = 0.8 + 0.1*np.sin(xx/3.0) + 0.05*np.cos(yy/2.0) + 0.01*rng.standard_normal((H, W))
@@ -73,4 +75,9 @@ for (H, W) in ((7, 9), (1, 8), (5, 1), (2, 2), (12, 16), (3, 4)):
     ref = O.normals_loss_torch(t(Zg), zq, torch.from_numpy(K)[None], t(mask))
     ref.backward()
     g_ref = zq.grad[0, 0].numpy()
-    print((H, W), 'loss diff', abs(loss - float(ref)), 'grad max rel diff', np.abs(grad - g_ref).max() / (np.abs(g_ref).max() + 1e-30))
+    return abs(loss - float(ref.detach())), np.abs(grad - g_ref).max() / (np.abs(g_ref).max() + 1e-30)
+
+
+if __name__ == "__main__":
+    for (H, W) in ((7, 9), (2, 2), (12, 16), (3, 4), (2, 9), (9, 2)):
+        print((H, W), "loss diff %.1e, gradient diff %.1e of its scale" % compare_with_autograd(H, W))
